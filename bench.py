@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on BASELINE cfg 2.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: under torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+metric   chain-steps x observations / second.  One chain-step = one (mcmciter, pidx)
+         schedule element for one chain = one full-data log-likelihood evaluation
+         (reference: src/run.jl:257).
+step     one MCMC iteration of cfg 2 = its 2 random-walk updates for all chains, i.e.
+         2 * C * N chain-step x observation units.
+value    device-resident throughput: K steps timed with CUDA events on the library's own
+         stream, L2 flushed (untimed) before every step, max over ranks.
+e2e      the whole cfg 2 job through the reference-facing API `run_(mcmc, M, data, theta0)`
+         with host buffers: observation upload, every block launch, and the copy of every
+         history row back to the host are inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_OBS = 1_000_000
+CHAINS_PER_GPU = 4096
+NU = 2
+
+
+def cfg2_data():
+    return 1.5 + 2.0 * np.random.default_rng(2).standard_normal(N_OBS)
+
+
+def cfg2_updates(em):
+    mk = lambda: em.AdaptationUnifRW([0.0], adapt_every_k_steps=50, target_accpt_rate=0.234,
+                                     scale=5e-4, min=1e-7, max=1e7, offset=100.0)
+    return [em.RandomWalkUpdate(em.UniformRandomWalk([5e-3]), [1], adpt=mk()),
+            em.RandomWalkUpdate(em.UniformRandomWalk([5e-3], [True]), [2],
+                                prior=em.ImproperPosPrior(), adpt=mk())]
+
+
+def cfg2_theta_init(x, n_chains, offset=0):
+    rng = np.random.default_rng(3)
+    z = rng.standard_normal((2, offset + n_chains))[:, offset:]
+    th = np.empty((2, n_chains))
+    th[0] = x.mean() + 0.01 * z[0]
+    th[1] = x.var(ddof=1) * np.exp(0.01 * z[1])
+    return th
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [v.strip() for v in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(smax)) if smax else None,
+                "power_w_max": float(max(power)) if power else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+def steps_for(em, _abi, it0, n_iters):
+    """ABI step array for iterations it0 .. it0 + n_iters - 1 of the 2-update schedule."""
+    arr = (_abi.Step * (n_iters * NU))()
+    k = 0
+    for it in range(it0, it0 + n_iters):
+        for pj in range(NU):
+            arr[k].mcmciter = it
+            arr[k].pidx = pj
+            first = (it == 1 and pj == 0)
+            arr[k].prev_pidx = -1 if first else (pj - 1 if pj else NU - 1)
+            arr[k].prev_mcmciter = 0 if first else (it if pj else it - 1)
+            k += 1
+    return arr
+
+
+def make_ws(em, x, n_chains, chain_offset, device, **bk):
+    from extensiblemcmc_jl_b200.mcmc import init_
+    ups = cfg2_updates(em)
+    mcmc = em.MCMC(ups, backend=em.CUDAMCMCBackend(n_chains=n_chains, device=device, seed=3,
+                                                   chain_offset=chain_offset, history="none", **bk))
+    init_(mcmc, 1, dict(P=em.GsnTargetLaw([0.0]), obs=x), cfg2_theta_init(x, n_chains, chain_offset))
+    return mcmc.workspace
+
+
+def timed_steps(ws, _abi, C, K, W, flush=True):
+    """W warm-up + K timed steps (one MCMC iteration each); returns summed device ms."""
+    import ctypes
+    lib, h = ws.lib, ws.handle
+    it = 1
+    for _ in range(W):
+        ws._ck(lib.extmcmc_run_block(h, steps_for(None, _abi, it, 1), NU)); it += 1
+    ws.sync()
+    total = 0.0
+    ms = ctypes.c_float()
+    for _ in range(K):
+        if flush:
+            ws._ck(lib.extmcmc_flush_l2(h))
+        arr = steps_for(None, _abi, it, 1)
+        ws._ck(lib.extmcmc_timer_start(h))
+        ws._ck(lib.extmcmc_run_block(h, arr, NU))
+        ws._ck(lib.extmcmc_timer_stop(h, ctypes.byref(ms)))
+        total += ms.value
+        it += 1
+    ws.sync()
+    return total
+
+
+def run_ours(args):
+    import ctypes
+    import torch
+    import extensiblemcmc_jl_b200 as em
+    from extensiblemcmc_jl_b200 import _abi
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the GPU path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    K, Wm = args.steps, max(args.warmup, 3)
+    C = CHAINS_PER_GPU
+    x = cfg2_data()
+    peaks, peak_src = measured_peaks()
+
+    # ---- value: device-resident, CUDA-graph blocks, L2 flushed between steps ----------
+    ws = make_ws(em, x, C, rank * C, local, block_len=NU, use_graphs=True)
+    variant = ws.lib.extmcmc_sweep_variant_name(ws.handle).decode()
+    sampler = ClockSampler(local)
+    barrier()
+    l0 = ws.lib.extmcmc_launch_count(ws.handle)
+    timed_steps(ws, _abi, C, 0, Wm)                # warm-up (graph capture, clocks)
+    l1 = ws.lib.extmcmc_launch_count(ws.handle)
+    sampler.start()
+    barrier()
+    ms_total = timed_steps(ws, _abi, C, K, 0)
+    barrier()
+    clocks = sampler.stop()
+    launches = int(ws.lib.extmcmc_launch_count(ws.handle) - l1)
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    units = float(world) * C * K * NU * N_OBS
+    value = units / (ms_total * 1e-3)
+    fp64_peak = ctypes.c_double()
+    ws._ck(ws.lib.extmcmc_measure_fp64_peak(ws.handle, ctypes.byref(fp64_peak)))
+    ws.close()
+
+    # ---- roofline of the dominant kernel: every sweep launch bracketed by events ------
+    wsi = make_ws(em, x, C, rank * C, local, block_len=NU, use_graphs=False, instrument=True)
+    timed_steps(wsi, _abi, C, 0, Wm)
+    msw, nl = ctypes.c_float(), ctypes.c_int64()
+    wsi._ck(wsi.lib.extmcmc_get_sweep_time(wsi.handle, ctypes.byref(msw), ctypes.byref(nl)))
+    step_ms_instr = timed_steps(wsi, _abi, C, min(K, 50), 0)
+    wsi._ck(wsi.lib.extmcmc_get_sweep_time(wsi.handle, ctypes.byref(msw), ctypes.byref(nl)))
+    sweep_ms = msw.value / max(nl.value, 1)
+    sweep_share = msw.value / step_ms_instr if step_ms_instr > 0 else None
+    wsi.close()
+    flops = 3.0 * C * N_OBS                      # 1 SUB + 1 FMA per chain x observation
+    ach_tf = flops / (sweep_ms * 1e-3) / 1e12
+    roofline = {
+        "kernel": variant, "bound": "fp64", "achieved": ach_tf, "peak": fp64_peak.value,
+        "unit": "TFLOP/s", "frac": ach_tf / fp64_peak.value if fp64_peak.value else None,
+        "peak_source": "FP64 FMA micro-benchmark run in this process (not in MEASURED_PEAKS.json)",
+        # 2 FP64 issue slots (DADD + DFMA) per pair; the FMA-rate peak counts 2 flop per slot
+        "issue_frac": (2.0 * C * N_OBS / (sweep_ms * 1e-3)) / (fp64_peak.value * 1e12 / 2.0) if fp64_peak.value else None,
+        "avg_launch_ms": sweep_ms, "launches_timed": int(nl.value), "share_of_step": sweep_share,
+        "traffic": None,
+        "hbm": {"achieved": 8.0 * N_OBS / (sweep_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                "unit": "GB/s", "frac": 8.0 * N_OBS / (sweep_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                "peak_source": peak_src + " (MEASURED_PEAKS.json)" if peak_src == "measured" else "fallback"},
+    }
+
+    # ---- the HBM-bound regime of the same kernel family (cfg 5 shape on one GPU) ------
+    roofline_hbm = None
+    if rank == 0 and not args.skip_hbm:
+        n5, c5 = 1 << 28, 8                       # 2 GiB of observations, 8 chains
+        ups = cfg2_updates(em)
+        from extensiblemcmc_jl_b200.mcmc import init_
+        m5 = em.MCMC(ups, backend=em.CUDAMCMCBackend(n_chains=c5, device=local, seed=6, history="none",
+                                                     block_len=NU, use_graphs=False, instrument=True))
+        init_(m5, 1, dict(P=em.GsnTargetLaw([0.0]), obs=em.DeviceGeneratedObs(n5, 1.5, 2.0, 6)),
+              np.repeat(np.array([[1.5], [4.0]]), c5, axis=1))
+        w5 = m5.workspace
+        for _ in range(3):
+            w5.eval_loglik()
+        w5._ck(w5.lib.extmcmc_get_sweep_time(w5.handle, ctypes.byref(msw), ctypes.byref(nl)))
+        for _ in range(10):
+            w5.eval_loglik()
+        w5._ck(w5.lib.extmcmc_get_sweep_time(w5.handle, ctypes.byref(msw), ctypes.byref(nl)))
+        t5 = msw.value / max(nl.value, 1)
+        gbs = 8.0 * n5 / (t5 * 1e-3) / 1e9
+        roofline_hbm = {"kernel": w5.lib.extmcmc_sweep_variant_name(w5.handle).decode(),
+                        "workload": f"cfg5 shape on 1 GPU: C={c5}, N=2^28 (2 GiB > L2)", "bound": "hbm",
+                        "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": gbs / peaks["hbm_gbs"], "avg_launch_ms": t5,
+                        "peak_source": peak_src, "traffic": None}
+        w5.close()
+
+    # ---- e2e: the whole job through run_() with host buffers --------------------------
+    M = args.e2e_iters
+    th0 = cfg2_theta_init(x, C, rank * C)
+
+    def job(m_iters):
+        mcmc = em.MCMC(cfg2_updates(em), backend=em.CUDAMCMCBackend(
+            n_chains=C, device=local, seed=3, chain_offset=rank * C, block_len=128))
+        return em.run_(mcmc, m_iters, dict(P=em.GsnTargetLaw([0.0]), obs=x), th0)
+
+    w_, _ = job(8); w_.close()                   # warm-up of the API path
+    barrier()
+    t0 = time.perf_counter()
+    ws_e, lws_e = job(M)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    t = torch.tensor([wall], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    wall = float(t.item())
+    e2e_value = float(world) * C * M * NU * N_OBS / wall
+    h2d = (8.0 * N_OBS + 8.0 * 2 * C) / M
+    d2h = NU * C * (2 * 2 * 8 + 2 * 8 + 1)
+    ess_per_sec = None
+    if rank == 0 and M >= 400:
+        tr = ws_e.sub_ws.state_history[M // 2:, 1][:, :, ::8]      # post warm-up, every 8th chain
+        ess = em.ess_geyer(tr).min(axis=0)                          # min over params, per chain
+        ess_per_sec = float(ess.mean() * C * world / wall)
+    acc_rate = float(np.mean([l.acceptance_history.mean() for l in lws_e]))
+    ws_e.close()
+
+    # ---- CPU baseline: the oracle (a port of the reference's algorithm), 1 core -------
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        cpu = cpu_oracle_rate(x, n_chains=8, n_iters=args.cpu_iters, n_threads=1)
+        cpu["sample"] = (f"{cpu.pop('chains')} chains x {cpu.pop('iters')} iterations of cfg2 "
+                         f"(N=1e6, 2 updates), single thread, oracle = CPU restatement of "
+                         f"ExtensibleMCMC.jl's algorithm (Julia unavailable)")
+
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    out = {
+        "metric": "chain-steps x obs/sec", "value": value, "unit": "chain-step*obs/s",
+        "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms_total / K,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "BASELINE cfg2: 4096 chains/GPU x iid Gaussian likelihood, N=1e6 obs, "
+                               "2 adaptive uniform random-walk updates per iteration",
+                   "chains_per_gpu": C, "n_obs": N_OBS, "updates_per_step": NU,
+                   "parallelism": f"chains sharded over {world} GPU(s), observations replicated, no collective",
+                   "l2": "flushed (320 MiB write, untimed) before every timed step",
+                   "timing": "CUDA events on the library stream per step, summed; max over ranks"},
+        "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": "chain-step*obs/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "iters": M, "wall_s": wall,
+                "what": "run_(mcmc, M, data, theta0): obs upload + all blocks + every history row copied to host"},
+        "ess_per_sec": ess_per_sec, "accept_rate": acc_rate,
+        "gpu_launches": launches, "clocks": clocks,
+    }
+    print(json.dumps(out))
+
+
+def cpu_oracle_rate(x, n_chains, n_iters, n_threads):
+    import extensiblemcmc_jl_b200 as em
+    from oracle import oracle as orc
+    ups = cfg2_updates(em)
+    o = orc.Oracle(em.GsnTargetLaw([0.0]), ups, x, cfg2_theta_init(x, n_chains), n_chains, seed=3)
+    steps = list(em.MCMCSchedule(n_iters, NU))
+    t0 = time.perf_counter()
+    o.run(steps, n_threads=n_threads, record=False)
+    dt = time.perf_counter() - t0
+    return {"value": n_chains * n_iters * NU * float(len(x)) / dt, "unit": "chain-step*obs/s",
+            "cores": n_threads, "kind": "port", "chains": n_chains, "iters": n_iters, "wall_s": dt}
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU algorithm (oracle port; Julia is not in the
+    image) on all host threads, bounded sample of the same workload per step."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    import extensiblemcmc_jl_b200 as em
+    from oracle import oracle as orc
+    nthr = os.cpu_count() or 1
+    x = cfg2_data()
+    n_chains = 2 * nthr                       # per step: 2 chains per thread x 1 iteration x N=1e6
+    ups = cfg2_updates(em)
+    o = orc.Oracle(em.GsnTargetLaw([0.0]), ups, x, cfg2_theta_init(x, n_chains), n_chains, seed=3)
+    K, Wm = args.steps, max(args.warmup, 1)
+    K = min(K, 40)
+    sched = list(em.MCMCSchedule(Wm + K, NU))
+    o.run(sched[:Wm * NU], n_threads=nthr, record=False)
+    t0 = time.perf_counter()
+    o.run(sched[Wm * NU:], n_threads=nthr, record=False)
+    dt = time.perf_counter() - t0
+    value = n_chains * K * NU * float(N_OBS) / dt
+    sample = (f"{n_chains} chains x 1 iteration of cfg2 (N=1e6, 2 updates) per step, {K} steps, "
+              f"{nthr} threads; oracle = CPU restatement of ExtensibleMCMC.jl's algorithm (Julia unavailable)")
+    print(json.dumps({
+        "impl": "reference", "metric": "chain-steps x obs/sec", "value": value, "unit": "chain-step*obs/s",
+        "n_gpus": args.gpus, "steps": K, "warmup": Wm, "ms_per_step": dt / K * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "BASELINE cfg2 (bounded sample): iid Gaussian likelihood, N=1e6 obs, "
+                               "2 adaptive uniform random-walk updates per iteration", "n_obs": N_OBS},
+        "cpu_baseline": {"value": value, "unit": "chain-step*obs/s", "cores": nthr, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "chain-step*obs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-iters", type=int, default=2000, help="iterations of the end-to-end job (BASELINE cfg2: 2000)")
+    ap.add_argument("--cpu-iters", type=int, default=150)
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-hbm", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,820 @@
+// C ABI of libextmcmc_cuda.so (include/extmcmc.h): handle lifetime, device-resident
+// workspaces, the block driver that replaces __run! (src/run.jl:64-83) with one CUDA
+// graph launch per block of schedule elements, read-back, measurement helpers and the
+// NCCL exchange of per-chain partial sums under observation sharding.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/extmcmc.h"
+#include "dev_state.cuh"
+#include "step_kernels.h"
+#include "sweep.h"
+
+using namespace extmcmc;
+
+namespace {
+
+std::string g_create_error;
+
+// NCCL is resolved at run time so that the library loads (and the single-GPU path
+// works) without it, and so that a process that already loaded an NCCL (torch) shares it.
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                              cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool load(std::string &err) {
+        if (lib) return true;
+        lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) { err = std::string("cannot load libnccl: ") + dlerror(); return false; }
+        GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+        AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+        CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+        GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+        if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) {
+            err = "libnccl lacks required symbols";
+            return false;
+        }
+        return true;
+    }
+} g_nccl;
+
+struct Slot {
+    StepDesc *h_descs = nullptr;  // pinned
+    StepDesc *d_descs = nullptr;
+    int cap = 0;
+    cudaEvent_t done = nullptr;
+    bool in_flight = false;
+};
+
+}  // namespace
+
+struct extmcmc_handle {
+    extmcmc_config_t cfg{};
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    DevState d{};
+    std::vector<DevUpdate> upd_host;
+    std::vector<bool> upd_set;
+    bool upd_dirty = true;
+    double *obs_dev = nullptr;
+    int64_t n_obs_local = 0;
+    bool state_set = false;
+    SweepPlan plan{};
+    bool plan_valid = false;
+    Slot slot[2];
+    int next_slot = 0;
+    std::map<long long, cudaGraphExec_t> graphs;
+    // schedule bookkeeping for the rolling acceptance rate (chain_statistics.jl:53-64)
+    int64_t seq_next = 0;
+    std::vector<int64_t> ra_iter;   // [NU] mcmciter at which the update last ran (0 = never)
+    std::vector<int64_t> acc_tag;   // [NU][W] mcmciter stored in the ring slot (0 = never)
+    // replay staging
+    double *rp_prop = nullptr, *rp_exp = nullptr;
+    size_t rp_prop_cap = 0, rp_exp_cap = 0;
+    // instrumentation
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pending, ev_free;
+    float sweep_ms = 0.f;
+    int64_t sweep_launches = 0;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    int64_t launches = 0;
+    double *flush_buf = nullptr;
+    int64_t flush_n = 0;
+    double *scratch_ll = nullptr;  // [C]
+    // multi-rank
+    ncclComm_t comm = nullptr;
+    int64_t *n_obs_dev = nullptr;
+    bool n_total_known = false;
+    std::vector<void *> allocs;
+};
+
+namespace {
+
+#define CK(h, call)                                                                      \
+    do {                                                                                 \
+        cudaError_t e_ = (call);                                                         \
+        if (e_ != cudaSuccess) {                                                         \
+            (h)->err = std::string(#call) + ": " + cudaGetErrorString(e_);               \
+            return e_ == cudaErrorMemoryAllocation ? EXTMCMC_EOOM : EXTMCMC_ECUDA;       \
+        }                                                                                \
+    } while (0)
+
+#define NK(h, call)                                                                      \
+    do {                                                                                 \
+        ncclResult_t r_ = (call);                                                        \
+        if (r_ != ncclSuccess) {                                                         \
+            (h)->err = std::string(#call) + ": " +                                       \
+                       (g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "nccl error"); \
+            return EXTMCMC_ENCCL;                                                        \
+        }                                                                                \
+    } while (0)
+
+int32_t fail(extmcmc_t h, int32_t code, const std::string &msg) {
+    if (h) h->err = msg; else g_create_error = msg;
+    return code;
+}
+
+template <typename T>
+int32_t dev_alloc(extmcmc_t h, T **out, size_t n) {
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
+    if (e != cudaSuccess) {
+        h->err = std::string("cudaMalloc: ") + cudaGetErrorString(e);
+        return EXTMCMC_EOOM;
+    }
+    h->allocs.push_back(p);
+    *out = (T *)p;
+    return EXTMCMC_OK;
+}
+
+void invalidate_graphs(extmcmc_t h) {
+    for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second);
+    h->graphs.clear();
+}
+
+int32_t ensure_plan(extmcmc_t h) {
+    if (h->plan_valid) return EXTMCMC_OK;
+    if (h->cfg.law != EXTMCMC_LAW_GSN_IID_1D)
+        return fail(h, EXTMCMC_EUNSUPPORTED, "law not implemented on the GPU path");
+    h->plan = plan_sweep_gsn1d(h->d.C, h->n_obs_local, h->cfg.sweep_variant, h->num_sms);
+    h->d.S = h->plan.S;
+    int32_t rc = dev_alloc(h, &h->d.partial, (size_t)h->plan.S * h->d.C);
+    if (rc) return rc;
+    h->plan_valid = true;
+    invalidate_graphs(h);
+    return EXTMCMC_OK;
+}
+
+int32_t upload_updates(extmcmc_t h) {
+    if (!h->upd_dirty) return EXTMCMC_OK;
+    CK(h, cudaMemcpyAsync(h->d.upd, h->upd_host.data(), sizeof(DevUpdate) * h->upd_host.size(),
+                          cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    h->upd_dirty = false;
+    return EXTMCMC_OK;
+}
+
+int32_t ensure_total_obs(extmcmc_t h) {
+    if (h->n_total_known) return EXTMCMC_OK;
+    if (h->cfg.shard_mode == EXTMCMC_SHARD_OBS && h->cfg.world_size > 1) {
+        if (!h->comm) return fail(h, EXTMCMC_EINVAL, "EXTMCMC_SHARD_OBS needs extmcmc_comm_init first");
+        int64_t n = h->n_obs_local;
+        CK(h, cudaMemcpyAsync(h->n_obs_dev, &n, sizeof n, cudaMemcpyHostToDevice, h->stream));
+        NK(h, g_nccl.AllReduce(h->n_obs_dev, h->n_obs_dev, 1, ncclInt64, ncclSum, h->comm, h->stream));
+        CK(h, cudaMemcpyAsync(&n, h->n_obs_dev, sizeof n, cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaStreamSynchronize(h->stream));
+        h->d.n_obs_total = n;
+    } else {
+        h->d.n_obs_total = h->n_obs_local;
+    }
+    h->n_total_known = true;
+    invalidate_graphs(h);
+    return EXTMCMC_OK;
+}
+
+bool obs_sharded(extmcmc_t h) {
+    return h->cfg.shard_mode == EXTMCMC_SHARD_OBS && h->cfg.world_size > 1;
+}
+
+// One likelihood sweep of lawc[0] (+ cross-rank reduction when observations are sharded).
+int32_t enqueue_sweep(extmcmc_t h, bool instrument) {
+    std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+    if (instrument) {
+        if (!h->ev_free.empty()) { ev = h->ev_free.back(); h->ev_free.pop_back(); }
+        else { CK(h, cudaEventCreate(&ev.first)); CK(h, cudaEventCreate(&ev.second)); }
+        CK(h, cudaEventRecord(ev.first, h->stream));
+    }
+    launch_sweep_gsn1d(h->plan, h->obs_dev, h->n_obs_local, h->d.lawc, h->d.C, h->d.partial, h->stream);
+    h->launches += h->plan.launches;
+    if (instrument) {
+        CK(h, cudaEventRecord(ev.second, h->stream));
+        h->ev_pending.push_back(ev);
+    }
+    if (obs_sharded(h)) {
+        launch_reduce_partials(h->d, h->stream);
+        h->launches += 1;
+        NK(h, g_nccl.AllReduce(h->d.ssum, h->d.ssum, (size_t)h->d.C, ncclFloat64, ncclSum, h->comm,
+                               h->stream));
+    }
+    return EXTMCMC_OK;
+}
+
+int32_t enqueue_steps(extmcmc_t h, const StepDesc *d_descs, int n_steps, bool instrument) {
+    for (int k = 0; k < n_steps; ++k) {
+        launch_propose(h->d, d_descs, k, h->stream);
+        int32_t rc = enqueue_sweep(h, instrument);
+        if (rc) return rc;
+        launch_accept(h->d, d_descs, k, h->stream);
+        h->launches += 2;
+    }
+    CK(h, cudaGetLastError());
+    return EXTMCMC_OK;
+}
+
+int32_t collect_events(extmcmc_t h) {
+    for (auto &ev : h->ev_pending) {
+        float ms = 0.f;
+        CK(h, cudaEventElapsedTime(&ms, ev.first, ev.second));
+        h->sweep_ms += ms;
+        h->sweep_launches += 1;
+        h->ev_free.push_back(ev);
+    }
+    h->ev_pending.clear();
+    return EXTMCMC_OK;
+}
+
+int32_t run_block_impl(extmcmc_t h, const extmcmc_step_t *steps, int32_t n_steps, int rng_mode,
+                       int32_t p_u_max, const double *proposals, const double *exp_draws) {
+    if (!h) return EXTMCMC_EINVAL;
+    if (n_steps < 0 || (n_steps > 0 && !steps)) return fail(h, EXTMCMC_EINVAL, "bad steps");
+    if (n_steps == 0) return EXTMCMC_OK;
+    if (!h->obs_dev) return fail(h, EXTMCMC_EINVAL, "no observations uploaded");
+    if (!h->state_set) return fail(h, EXTMCMC_EINVAL, "extmcmc_set_state not called");
+    for (int u = 0; u < h->cfg.n_updates; ++u)
+        if (!h->upd_set[u]) return fail(h, EXTMCMC_EINVAL, "update " + std::to_string(u) + " not set");
+    if (n_steps > h->cfg.history_window)
+        return fail(h, EXTMCMC_EINVAL, "block longer than history_window");
+    for (int s = 0; s < n_steps; ++s)
+        if (steps[s].pidx < 0 || steps[s].pidx >= h->cfg.n_updates || steps[s].mcmciter < 1)
+            return fail(h, EXTMCMC_EINVAL, "step out of range");
+    CK(h, cudaSetDevice(h->cfg.device));
+    int32_t rc;
+    if ((rc = ensure_plan(h))) return rc;
+    if ((rc = upload_updates(h))) return rc;
+    if ((rc = ensure_total_obs(h))) return rc;
+
+    if (h->d.rng_mode != rng_mode) { h->d.rng_mode = rng_mode; invalidate_graphs(h); }
+    if (rng_mode == EXTMCMC_RNG_REPLAY) {
+        if (!proposals || !exp_draws || p_u_max < 1) return fail(h, EXTMCMC_EINVAL, "replay buffers missing");
+        for (int s = 0; s < n_steps; ++s)
+            if (h->upd_host[steps[s].pidx].n_coords > p_u_max)
+                return fail(h, EXTMCMC_EINVAL, "p_u_max smaller than an update's n_coords");
+        const size_t np = (size_t)n_steps * p_u_max * h->d.C, ne = (size_t)n_steps * h->d.C;
+        CK(h, cudaStreamSynchronize(h->stream));
+        if (np > h->rp_prop_cap) {
+            if (h->rp_prop) cudaFree(h->rp_prop);
+            CK(h, cudaMalloc(&h->rp_prop, np * sizeof(double)));
+            h->rp_prop_cap = np;
+        }
+        if (ne > h->rp_exp_cap) {
+            if (h->rp_exp) cudaFree(h->rp_exp);
+            CK(h, cudaMalloc(&h->rp_exp, ne * sizeof(double)));
+            h->rp_exp_cap = ne;
+        }
+        CK(h, cudaMemcpy(h->rp_prop, proposals, np * sizeof(double), cudaMemcpyHostToDevice));
+        CK(h, cudaMemcpy(h->rp_exp, exp_draws, ne * sizeof(double), cudaMemcpyHostToDevice));
+        h->d.rp_prop = h->rp_prop;
+        h->d.rp_exp = h->rp_exp;
+        h->d.p_u_max = p_u_max;
+    }
+
+    // descriptor slot (double-buffered so the host can prepare block k+1 while k runs)
+    const int si = h->next_slot;
+    Slot &sl = h->slot[si];
+    h->next_slot ^= 1;
+    if (sl.in_flight) { CK(h, cudaEventSynchronize(sl.done)); sl.in_flight = false; }
+    if (sl.cap < n_steps) {
+        if (sl.h_descs) cudaFreeHost(sl.h_descs);
+        if (sl.d_descs) cudaFree(sl.d_descs);
+        for (auto it = h->graphs.begin(); it != h->graphs.end();) {
+            if ((it->first & 1) == si) { cudaGraphExecDestroy(it->second); it = h->graphs.erase(it); }
+            else ++it;
+        }
+        const int cap = std::max(n_steps, 64);
+        CK(h, cudaMallocHost(&sl.h_descs, sizeof(StepDesc) * cap));
+        CK(h, cudaMalloc(&sl.d_descs, sizeof(StepDesc) * cap));
+        sl.cap = cap;
+    }
+    const int W = h->d.W, NU = h->cfg.n_updates;
+    for (int s = 0; s < n_steps; ++s) {
+        StepDesc &sd = sl.h_descs[s];
+        const int u = steps[s].pidx;
+        const int64_t it = steps[s].mcmciter;
+        sd.mcmciter = it;
+        sd.seq = h->seq_next + s;
+        sd.stat_n = sd.seq + 1;  // GenericChainStats.N starts at 1 (chain_statistics.jl:34)
+        sd.pidx = u;
+        sd.first = steps[s].prev_pidx < 0 ? 1 : 0;
+        const int64_t prev_it = it - 1 > 1 ? it - 1 : 1;
+        sd.ra_prev_valid = (h->ra_iter[u] == prev_it && prev_it != it) ? 1 : 0;
+        int64_t &tag = h->acc_tag[(size_t)u * W + (size_t)(it % W)];
+        sd.acc_out_valid = (it > W && tag == it - W) ? 1 : 0;
+        sd.replay_row = s;
+        sd.pad_ = 0;
+        h->ra_iter[u] = it;
+        tag = it;
+        (void)NU;
+    }
+
+    const bool instrument = h->cfg.instrument != 0;
+    const bool use_graph = h->cfg.use_graphs && !instrument && rng_mode == EXTMCMC_RNG_PHILOX;
+    if (!use_graph) {
+        CK(h, cudaMemcpyAsync(sl.d_descs, sl.h_descs, sizeof(StepDesc) * n_steps,
+                              cudaMemcpyHostToDevice, h->stream));
+        if ((rc = enqueue_steps(h, sl.d_descs, n_steps, instrument))) return rc;
+    } else {
+        const long long key = ((long long)n_steps << 1) | si;
+        auto it = h->graphs.find(key);
+        if (it == h->graphs.end()) {
+            const int64_t launches_before = h->launches;
+            cudaGraph_t g = nullptr;
+            CK(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+            cudaError_t e1 = cudaMemcpyAsync(sl.d_descs, sl.h_descs, sizeof(StepDesc) * n_steps,
+                                             cudaMemcpyHostToDevice, h->stream);
+            int32_t rc2 = e1 == cudaSuccess ? enqueue_steps(h, sl.d_descs, n_steps, false) : EXTMCMC_ECUDA;
+            cudaError_t e2 = cudaStreamEndCapture(h->stream, &g);
+            h->launches = launches_before;
+            if (rc2 || e2 != cudaSuccess || !g) {
+                if (g) cudaGraphDestroy(g);
+                return fail(h, EXTMCMC_ECUDA, "CUDA graph capture failed: " + h->err);
+            }
+            cudaGraphExec_t ge = nullptr;
+            cudaError_t e3 = cudaGraphInstantiate(&ge, g, 0);
+            cudaGraphDestroy(g);
+            if (e3 != cudaSuccess)
+                return fail(h, EXTMCMC_ECUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e3));
+            it = h->graphs.emplace(key, ge).first;
+        }
+        CK(h, cudaGraphLaunch(it->second, h->stream));
+        h->launches += (int64_t)n_steps * (2 + h->plan.launches + (obs_sharded(h) ? 1 : 0));
+    }
+    CK(h, cudaEventRecord(sl.done, h->stream));
+    sl.in_flight = true;
+    h->seq_next += n_steps;
+    return EXTMCMC_OK;
+}
+
+}  // namespace
+
+// =====================================================================================
+extern "C" {
+
+int32_t extmcmc_abi_version(void) { return EXTMCMC_ABI_VERSION; }
+
+const char *extmcmc_last_error(extmcmc_t h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int32_t extmcmc_create(const extmcmc_config_t *cfg, extmcmc_t *out) {
+    if (!cfg || !out) return fail(nullptr, EXTMCMC_EINVAL, "null argument");
+    *out = nullptr;
+    if (cfg->abi_version != EXTMCMC_ABI_VERSION) return fail(nullptr, EXTMCMC_EINVAL, "ABI version mismatch");
+    if (cfg->n_chains < 1 || cfg->n_params < 1 || cfg->n_updates < 1 || cfg->history_window < 1)
+        return fail(nullptr, EXTMCMC_EINVAL, "n_chains, n_params, n_updates, history_window must be >= 1");
+    if (cfg->n_updates > 65535) return fail(nullptr, EXTMCMC_EINVAL, "n_updates must be < 65536");
+    switch (cfg->law) {
+    case EXTMCMC_LAW_GSN_IID_1D:
+        if (cfg->obs_dim != 1 || cfg->n_params != 2)
+            return fail(nullptr, EXTMCMC_EINVAL, "GSN_IID_1D needs obs_dim = 1, n_params = 2");
+        break;
+    default:
+        // the reference's convention for a missing method: error("... not implemented")
+        return fail(nullptr, EXTMCMC_EUNSUPPORTED, "target law not implemented on the GPU path");
+    }
+    if (cfg->stats_mode < 0 || cfg->stats_mode > 2) return fail(nullptr, EXTMCMC_EINVAL, "bad stats_mode");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, EXTMCMC_ECUDA,
+                    std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count = 0"));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, EXTMCMC_EINVAL, "bad device ordinal");
+
+    extmcmc_handle *h = new extmcmc_handle();
+    h->cfg = *cfg;
+    auto bail = [&](int32_t rc) { g_create_error = h->err; extmcmc_destroy(h); return rc; };
+#define CKC(call)                                                                        \
+    do {                                                                                 \
+        cudaError_t e_ = (call);                                                         \
+        if (e_ != cudaSuccess) {                                                         \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                 \
+            return bail(e_ == cudaErrorMemoryAllocation ? EXTMCMC_EOOM : EXTMCMC_ECUDA); \
+        }                                                                                \
+    } while (0)
+    CKC(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CKC(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10) {
+        h->err = "libextmcmc_cuda is built for sm_100a (B200) only; found sm_" +
+                 std::to_string(prop.major) + std::to_string(prop.minor);
+        return bail(EXTMCMC_EUNSUPPORTED);
+    }
+    h->num_sms = prop.multiProcessorCount;
+    CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CKC(cudaEventCreate(&h->t0));
+    CKC(cudaEventCreate(&h->t1));
+    for (auto &sl : h->slot) CKC(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    CKC(sweep_gsn1d_init());
+
+    DevState &d = h->d;
+    const int64_t C = cfg->n_chains;
+    const int p = cfg->n_params, NU = cfg->n_updates;
+    d.C = C; d.chain_offset = cfg->chain_offset; d.p = p; d.NU = NU;
+    d.W = cfg->roll_window > 0 ? cfg->roll_window : 100;
+    d.H = cfg->history_window;
+    d.law = cfg->law; d.stats_mode = cfg->stats_mode; d.rng_mode = EXTMCMC_RNG_PHILOX;
+    d.p_u_max = 1; d.seed = cfg->seed;
+    d.use_ssum = (cfg->shard_mode == EXTMCMC_SHARD_OBS && cfg->world_size > 1) ? 1 : 0;
+    int32_t rc = 0;
+    const size_t covn = cfg->stats_mode == 0 ? (size_t)p * p : (cfg->stats_mode == 1 ? (size_t)p : 0);
+    if ((rc = dev_alloc(h, &d.theta, (size_t)p * C)) || (rc = dev_alloc(h, &d.ll, (size_t)C)) ||
+        (rc = dev_alloc(h, &d.prop_loc, (size_t)kMaxCoords * C)) ||
+        (rc = dev_alloc(h, &d.prop_full, (size_t)p * C)) ||
+        (rc = dev_alloc(h, &d.lawc, (size_t)kMaxLawConst * C)) ||
+        (rc = dev_alloc(h, &d.n_used, (size_t)C)) || (rc = dev_alloc(h, &d.ssum, (size_t)C)) ||
+        (rc = dev_alloc(h, &d.mean, (size_t)p * C)) || (rc = dev_alloc(h, &d.cov, covn * C)) ||
+        (rc = dev_alloc(h, &d.h_theta, (size_t)d.H * p * C)) ||
+        (rc = dev_alloc(h, &d.h_prop, (size_t)d.H * p * C)) ||
+        (rc = dev_alloc(h, &d.h_ll, (size_t)d.H * C)) || (rc = dev_alloc(h, &d.h_llp, (size_t)d.H * C)) ||
+        (rc = dev_alloc(h, &d.h_acc, (size_t)d.H * C)) || (rc = dev_alloc(h, &d.err_flag, 1)) ||
+        (rc = dev_alloc(h, &d.upd, (size_t)NU)) || (rc = dev_alloc(h, &h->scratch_ll, (size_t)C)) ||
+        (rc = dev_alloc(h, &h->n_obs_dev, 1)))
+        return bail(rc);
+    CKC(cudaMemset(d.err_flag, 0, sizeof(int32_t)));
+    h->upd_host.assign(NU, DevUpdate{});
+    h->upd_set.assign(NU, false);
+    h->ra_iter.assign(NU, 0);
+    h->acc_tag.assign((size_t)NU * d.W, 0);
+    *out = h;
+    return EXTMCMC_OK;
+#undef CKC
+}
+
+int32_t extmcmc_destroy(extmcmc_t h) {
+    if (!h) return EXTMCMC_OK;
+    cudaSetDevice(h->cfg.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    invalidate_graphs(h);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    for (void *p : h->allocs) cudaFree(p);
+    if (h->obs_dev) cudaFree(h->obs_dev);
+    if (h->rp_prop) cudaFree(h->rp_prop);
+    if (h->rp_exp) cudaFree(h->rp_exp);
+    if (h->flush_buf) cudaFree(h->flush_buf);
+    for (auto &sl : h->slot) {
+        if (sl.h_descs) cudaFreeHost(sl.h_descs);
+        if (sl.d_descs) cudaFree(sl.d_descs);
+        if (sl.done) cudaEventDestroy(sl.done);
+    }
+    for (auto &ev : h->ev_pending) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    for (auto &ev : h->ev_free) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    if (h->t0) cudaEventDestroy(h->t0);
+    if (h->t1) cudaEventDestroy(h->t1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return EXTMCMC_OK;
+}
+
+static int32_t install_obs(extmcmc_t h, int64_t n_obs) {
+    // padded to an even count (+ one spare pair): the sweep's bulk copies move 16 B units
+    if (h->obs_dev) { cudaFree(h->obs_dev); h->obs_dev = nullptr; }
+    const size_t padded = ((size_t)n_obs + 3) & ~(size_t)1;
+    CK(h, cudaMalloc(&h->obs_dev, padded * sizeof(double)));
+    CK(h, cudaMemsetAsync(h->obs_dev, 0, padded * sizeof(double), h->stream));
+    h->n_obs_local = n_obs;
+    h->plan_valid = false;
+    h->n_total_known = false;
+    return EXTMCMC_OK;
+}
+
+int32_t extmcmc_upload_obs(extmcmc_t h, const double *obs, int64_t n_obs, int32_t obs_dim,
+                           const double *y) {
+    if (!h) return EXTMCMC_EINVAL;
+    if (!obs || n_obs < 1) return fail(h, EXTMCMC_EINVAL, "need at least one observation");
+    if (obs_dim != h->cfg.obs_dim) return fail(h, EXTMCMC_EINVAL, "obs_dim differs from the configuration");
+    (void)y;
+    CK(h, cudaSetDevice(h->cfg.device));
+    CK(h, cudaStreamSynchronize(h->stream));
+    int32_t rc = install_obs(h, n_obs);
+    if (rc) return rc;
+    CK(h, cudaMemcpyAsync(h->obs_dev, obs, (size_t)n_obs * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return EXTMCMC_OK;
+}
+
+int32_t extmcmc_generate_obs_normal(extmcmc_t h, int64_t first, int64_t n_obs, double mean, double sd,
+                                    uint64_t seed) {
+    if (!h) return EXTMCMC_EINVAL;
+    if (n_obs < 1 || first < 0 || !(sd > 0.0)) return fail(h, EXTMCMC_EINVAL, "bad generate_obs arguments");
+    if (h->cfg.obs_dim != 1) return fail(h, EXTMCMC_EUNSUPPORTED, "generate_obs_normal needs obs_dim = 1");
+    CK(h, cudaSetDevice(h->cfg.device));
+    CK(h, cudaStreamSynchronize(h->stream));
+    int32_t rc = install_obs(h, n_obs);
+    if (rc) return rc;
+    launch_generate_obs_normal(h->obs_dev, first, n_obs, mean, sd, seed, h->num_sms, h->stream);
+    h->launches += 1;
+    CK(h, cudaGetLastError());
+    CK(h, cudaStreamSynchronize(h->stream));
+    return EXTMCMC_OK;
+}
+
+int32_t extmcmc_set_update(extmcmc_t h, int32_t u, const extmcmc_update_t *upd) {
+    if (!h || !upd) return EXTMCMC_EINVAL;
+    if (u < 0 || u >= h->cfg.n_updates) return fail(h, EXTMCMC_EINVAL, "update index out of range");
+    if (upd->kernel != EXTMCMC_KERNEL_RW_UNIFORM)
+        return fail(h, EXTMCMC_EUNSUPPORTED, "transition kernel not implemented on the GPU path");
+    if (upd->prior < EXTMCMC_PRIOR_IMPROPER || upd->prior > EXTMCMC_PRIOR_UNIFORM)
+        return fail(h, EXTMCMC_EUNSUPPORTED, "prior not implemented on the GPU path");
+    if (upd->adapt.kind != EXTMCMC_ADAPT_NONE && upd->adapt.kind != EXTMCMC_ADAPT_UNIF_RW)
+        return fail(h, EXTMCMC_EUNSUPPORTED, "adaptation not implemented on the GPU path");
+    if (upd->n_coords < 1 || upd->n_coords > kMaxCoords)
+        return fail(h, EXTMCMC_EUNSUPPORTED, "1 <= n_coords <= 16 for random-walk updates");
+    if (!upd->coords || !upd->step) return fail(h, EXTMCMC_EINVAL, "coords/step missing");
+    if (upd->n_prior_params > kMaxPriorParams || (upd->n_prior_params > 0 && !upd->prior_params))
+        return fail(h, EXTMCMC_EINVAL, "bad prior parameters");
+    if ((upd->prior == EXTMCMC_PRIOR_NORMAL || upd->prior == EXTMCMC_PRIOR_GAMMA ||
+         upd->prior == EXTMCMC_PRIOR_UNIFORM) && upd->n_prior_params < 2)
+        return fail(h, EXTMCMC_EINVAL, "prior needs two parameters");
+    if (upd->adapt.kind == EXTMCMC_ADAPT_UNIF_RW && upd->adapt.adapt_every_k_steps < 1)
+        return fail(h, EXTMCMC_EINVAL, "adapt_every_k_steps must be >= 1");
+    CK(h, cudaSetDevice(h->cfg.device));
+    const int64_t C = h->d.C;
+    const int W = h->d.W;
+    DevUpdate &t = h->upd_host[u];
+    const bool fresh = !h->upd_set[u];
+    if (!fresh && t.n_coords != upd->n_coords) return fail(h, EXTMCMC_EINVAL, "cannot change n_coords of an update");
+    t.kernel = upd->kernel; t.n_coords = upd->n_coords; t.prior = upd->prior;
+    t.adapt_kind = upd->adapt.kind;
+    for (int i = 0; i < upd->n_coords; ++i) {
+        if (upd->coords[i] < 0 || upd->coords[i] >= h->cfg.n_params)
+            return fail(h, EXTMCMC_EINVAL, "coordinate out of range");
+        if (!(upd->step[i] > 0.0))  // UniformRandomWalk: @assert all(eps .> 0.0), random_walk.jl:50
+            return fail(h, EXTMCMC_EINVAL, "eps must be > 0");
+        t.coords[i] = upd->coords[i];
+        t.pos[i] = upd->pos ? upd->pos[i] : 0;
+    }
+    for (int i = 0; i < kMaxPriorParams; ++i)
+        t.prior_params[i] = i < upd->n_prior_params ? upd->prior_params[i] : 0.0;
+    t.adapt_every_k = upd->adapt.adapt_every_k_steps;
+    t.target = upd->adapt.target_accpt_rate; t.scale = upd->adapt.scale;
+    t.vmin = upd->adapt.min; t.vmax = upd->adapt.max; t.offset = upd->adapt.offset;
+    int32_t rc = 0;
+    if (fresh) {
+        if ((rc = dev_alloc(h, &t.eps, (size_t)upd->n_coords * C)) ||
+            (rc = dev_alloc(h, &t.adapt_prop, (size_t)C)) || (rc = dev_alloc(h, &t.adapt_acc, (size_t)C)) ||
+            (rc = dev_alloc(h, &t.tot_prop, (size_t)C)) || (rc = dev_alloc(h, &t.tot_acc, (size_t)C)) ||
+            (rc = dev_alloc(h, &t.ra_val, (size_t)C)) || (rc = dev_alloc(h, &t.acc_ring, (size_t)W * C)))
+            return rc;
+    }
+    // broadcast the initial step size to every chain, zero the counters
+    std::vector<double> eps0((size_t)upd->n_coords * C);
+    for (int i = 0; i < upd->n_coords; ++i) std::fill_n(eps0.begin() + (size_t)i * C, C, upd->step[i]);
+    CK(h, cudaStreamSynchronize(h->stream));
+    CK(h, cudaMemcpy(t.eps, eps0.data(), eps0.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(h, cudaMemset(t.adapt_prop, 0, sizeof(int32_t) * C));
+    CK(h, cudaMemset(t.adapt_acc, 0, sizeof(int32_t) * C));
+    CK(h, cudaMemset(t.tot_prop, 0, sizeof(int64_t) * C));
+    CK(h, cudaMemset(t.tot_acc, 0, sizeof(int64_t) * C));
+    CK(h, cudaMemset(t.ra_val, 0, sizeof(double) * C));
+    CK(h, cudaMemset(t.acc_ring, 0, (size_t)W * C));
+    h->upd_set[u] = true;
+    h->upd_dirty = true;
+    return EXTMCMC_OK;
+}
+
+int32_t extmcmc_set_state(extmcmc_t h, const double *theta) {
+    if (!h || !theta) return EXTMCMC_EINVAL;
+    CK(h, cudaSetDevice(h->cfg.device));
+    CK(h, cudaStreamSynchronize(h->stream));
+    const DevState &d = h->d;
+    const int64_t C = d.C;
+    CK(h, cudaMemcpy(d.theta, theta, sizeof(double) * d.p * C, cudaMemcpyHostToDevice));
+    std::vector<double> ninf((size_t)C, -INFINITY);  // StandardLocalSubworkspace.ll, workspaces.jl:425
+    CK(h, cudaMemcpy(d.ll, ninf.data(), sizeof(double) * C, cudaMemcpyHostToDevice));
+    CK(h, cudaMemset(d.mean, 0, sizeof(double) * d.p * C));
+    const size_t covn = d.stats_mode == 0 ? (size_t)d.p * d.p : (d.stats_mode == 1 ? (size_t)d.p : 0);
+    if (covn) CK(h, cudaMemset(d.cov, 0, sizeof(double) * covn * C));
+    CK(h, cudaMemset(d.err_flag, 0, sizeof(int32_t)));
+    for (int u = 0; u < h->cfg.n_updates; ++u) {
+        if (!h->upd_set[u]) continue;
+        DevUpdate &t = h->upd_host[u];
+        CK(h, cudaMemset(t.adapt_prop, 0, sizeof(int32_t) * C));
+        CK(h, cudaMemset(t.adapt_acc, 0, sizeof(int32_t) * C));
+        CK(h, cudaMemset(t.tot_prop, 0, sizeof(int64_t) * C));
+        CK(h, cudaMemset(t.tot_acc, 0, sizeof(int64_t) * C));
+        CK(h, cudaMemset(t.ra_val, 0, sizeof(double) * C));
+        CK(h, cudaMemset(t.acc_ring, 0, (size_t)d.W * C));
+    }
+    h->seq_next = 0;
+    std::fill(h->ra_iter.begin(), h->ra_iter.end(), 0);
+    std::fill(h->acc_tag.begin(), h->acc_tag.end(), 0);
+    h->state_set = true;
+    return EXTMCMC_OK;
+}
+
+int32_t extmcmc_comm_unique_id(uint8_t id_out[128]) {
+    std::string err;
+    if (!id_out) return EXTMCMC_EINVAL;
+    if (!g_nccl.load(err)) return fail(nullptr, EXTMCMC_ENCCL, err);
+    ncclUniqueId id;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    if (g_nccl.GetUniqueId(&id) != ncclSuccess) return fail(nullptr, EXTMCMC_ENCCL, "ncclGetUniqueId failed");
+    std::memcpy(id_out, &id, 128);
+    return EXTMCMC_OK;
+}
+
+int32_t extmcmc_comm_init(extmcmc_t h, const uint8_t id_in[128]) {
+    if (!h || !id_in) return EXTMCMC_EINVAL;
+    if (h->comm) return fail(h, EXTMCMC_EINVAL, "communicator already initialised");
+    if (!g_nccl.load(h->err)) return EXTMCMC_ENCCL;
+    CK(h, cudaSetDevice(h->cfg.device));
+    ncclUniqueId id;
+    std::memcpy(&id, id_in, 128);
+    NK(h, g_nccl.CommInitRank(&h->comm, h->cfg.world_size, id, h->cfg.rank));
+    h->n_total_known = false;
+    return EXTMCMC_OK;
+}
+
+int32_t extmcmc_run_block(extmcmc_t h, const extmcmc_step_t *steps, int32_t n_steps) {
+    return run_block_impl(h, steps, n_steps, EXTMCMC_RNG_PHILOX, 0, nullptr, nullptr);
+}
+
+int32_t extmcmc_run_block_replay(extmcmc_t h, const extmcmc_step_t *steps, int32_t n_steps,
+                                 int32_t p_u_max, const double *proposals, const double *exp_draws) {
+    return run_block_impl(h, steps, n_steps, EXTMCMC_RNG_REPLAY, p_u_max, proposals, exp_draws);
+}
+
+int32_t extmcmc_sync(extmcmc_t h) {
+    if (!h) return EXTMCMC_EINVAL;
+    CK(h, cudaSetDevice(h->cfg.device));
+    CK(h, cudaStreamSynchronize(h->stream));
+    int32_t rc = collect_events(h);
+    if (rc) return rc;
+    int32_t flag = 0;
+    CK(h, cudaMemcpy(&flag, h->d.err_flag, sizeof flag, cudaMemcpyDeviceToHost));
+    if (flag) {
+        CK(h, cudaMemset(h->d.err_flag, 0, sizeof flag));
+        return fail(h, EXTMCMC_EDOMAIN,
+                    "a chain proposed parameters outside the law's domain (e.g. variance <= 0); "
+                    "the proposal was rejected");
+    }
+    return EXTMCMC_OK;
+}
+
+int32_t extmcmc_get_state(extmcmc_t h, double *theta, double *ll) {
+    if (!h) return EXTMCMC_EINVAL;
+    CK(h, cudaSetDevice(h->cfg.device));
+    CK(h, cudaStreamSynchronize(h->stream));
+    if (theta) CK(h, cudaMemcpy(theta, h->d.theta, sizeof(double) * h->d.p * h->d.C, cudaMemcpyDeviceToHost));
+    if (ll) CK(h, cudaMemcpy(ll, h->d.ll, sizeof(double) * h->d.C, cudaMemcpyDeviceToHost));
+    return EXTMCMC_OK;
+}
+
+int32_t extmcmc_get_history(extmcmc_t h, int64_t seq_lo, int64_t seq_hi, double *theta,
+                            double *theta_prop, double *ll, double *ll_prop, uint8_t *accepted) {
+    if (!h) return EXTMCMC_EINVAL;
+    if (seq_lo < 0 || seq_hi < seq_lo || seq_hi > h->seq_next) return fail(h, EXTMCMC_EINVAL, "bad history range");
+    if (seq_lo < h->seq_next - h->d.H) return fail(h, EXTMCMC_ESTALE, "history rows already overwritten");
+    CK(h, cudaSetDevice(h->cfg.device));
+    CK(h, cudaStreamSynchronize(h->stream));
+    const DevState &d = h->d;
+    const int64_t C = d.C, H = d.H;
+    int64_t row = 0;
+    for (int64_t s = seq_lo; s < seq_hi;) {
+        const int64_t slot = s % H;
+        const int64_t n = std::min<int64_t>(seq_hi - s, H - slot);  // contiguous run in the ring
+        const size_t rp = (size_t)d.p * C;
+        if (theta) CK(h, cudaMemcpy(theta + row * rp, d.h_theta + slot * rp, sizeof(double) * n * rp, cudaMemcpyDeviceToHost));
+        if (theta_prop) CK(h, cudaMemcpy(theta_prop + row * rp, d.h_prop + slot * rp, sizeof(double) * n * rp, cudaMemcpyDeviceToHost));
+        if (ll) CK(h, cudaMemcpy(ll + row * C, d.h_ll + slot * C, sizeof(double) * n * C, cudaMemcpyDeviceToHost));
+        if (ll_prop) CK(h, cudaMemcpy(ll_prop + row * C, d.h_llp + slot * C, sizeof(double) * n * C, cudaMemcpyDeviceToHost));
+        if (accepted) CK(h, cudaMemcpy(accepted + row * C, d.h_acc + slot * C, (size_t)n * C, cudaMemcpyDeviceToHost));
+        s += n;
+        row += n;
+    }
+    return EXTMCMC_OK;
+}
+
+int32_t extmcmc_get_stats(extmcmc_t h, double *mean, double *cov, double *rolling_ar,
+                          int64_t *n_accept, int64_t *n_prop) {
+    if (!h) return EXTMCMC_EINVAL;
+    CK(h, cudaSetDevice(h->cfg.device));
+    CK(h, cudaStreamSynchronize(h->stream));
+    const DevState &d = h->d;
+    const int64_t C = d.C;
+    if (mean) {
+        if (d.stats_mode == 2) return fail(h, EXTMCMC_EINVAL, "running moments disabled (stats_mode = 2)");
+        CK(h, cudaMemcpy(mean, d.mean, sizeof(double) * d.p * C, cudaMemcpyDeviceToHost));
+    }
+    if (cov) {
+        if (d.stats_mode == 2) return fail(h, EXTMCMC_EINVAL, "running moments disabled (stats_mode = 2)");
+        const size_t covn = d.stats_mode == 0 ? (size_t)d.p * d.p : (size_t)d.p;
+        CK(h, cudaMemcpy(cov, d.cov, sizeof(double) * covn * C, cudaMemcpyDeviceToHost));
+    }
+    for (int u = 0; u < h->cfg.n_updates; ++u) {
+        if (!h->upd_set[u]) return fail(h, EXTMCMC_EINVAL, "update not set");
+        const DevUpdate &t = h->upd_host[u];
+        if (rolling_ar) CK(h, cudaMemcpy(rolling_ar + (size_t)u * C, t.ra_val, sizeof(double) * C, cudaMemcpyDeviceToHost));
+        if (n_accept) CK(h, cudaMemcpy(n_accept + (size_t)u * C, t.tot_acc, sizeof(int64_t) * C, cudaMemcpyDeviceToHost));
+        if (n_prop) CK(h, cudaMemcpy(n_prop + (size_t)u * C, t.tot_prop, sizeof(int64_t) * C, cudaMemcpyDeviceToHost));
+    }
+    return EXTMCMC_OK;
+}
+
+int32_t extmcmc_get_eps(extmcmc_t h, int32_t u, double *eps) {
+    if (!h || !eps) return EXTMCMC_EINVAL;
+    if (u < 0 || u >= h->cfg.n_updates || !h->upd_set[u]) return fail(h, EXTMCMC_EINVAL, "update not set");
+    CK(h, cudaSetDevice(h->cfg.device));
+    CK(h, cudaStreamSynchronize(h->stream));
+    const DevUpdate &t = h->upd_host[u];
+    CK(h, cudaMemcpy(eps, t.eps, sizeof(double) * t.n_coords * h->d.C, cudaMemcpyDeviceToHost));
+    return EXTMCMC_OK;
+}
+
+int32_t extmcmc_eval_loglik(extmcmc_t h, double *ll_out) {
+    if (!h || !ll_out) return EXTMCMC_EINVAL;
+    if (!h->obs_dev || !h->state_set) return fail(h, EXTMCMC_EINVAL, "observations and state required");
+    CK(h, cudaSetDevice(h->cfg.device));
+    int32_t rc;
+    if ((rc = ensure_plan(h))) return rc;
+    if ((rc = ensure_total_obs(h))) return rc;
+    launch_prepare_current(h->d, h->stream);
+    if ((rc = enqueue_sweep(h, h->cfg.instrument != 0))) return rc;
+    if (!obs_sharded(h)) { launch_reduce_partials(h->d, h->stream); h->launches += 1; }
+    launch_finalize_loglik(h->d, h->scratch_ll, h->stream);
+    h->launches += 2;
+    CK(h, cudaGetLastError());
+    CK(h, cudaMemcpyAsync(ll_out, h->scratch_ll, sizeof(double) * h->d.C, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return EXTMCMC_OK;
+}
+
+int32_t extmcmc_timer_start(extmcmc_t h) {
+    if (!h) return EXTMCMC_EINVAL;
+    CK(h, cudaEventRecord(h->t0, h->stream));
+    return EXTMCMC_OK;
+}
+
+int32_t extmcmc_timer_stop(extmcmc_t h, float *ms_out) {
+    if (!h || !ms_out) return EXTMCMC_EINVAL;
+    CK(h, cudaEventRecord(h->t1, h->stream));
+    CK(h, cudaEventSynchronize(h->t1));
+    CK(h, cudaEventElapsedTime(ms_out, h->t0, h->t1));
+    return EXTMCMC_OK;
+}
+
+int32_t extmcmc_get_sweep_time(extmcmc_t h, float *ms_total, int64_t *n_launches) {
+    if (!h) return EXTMCMC_EINVAL;
+    CK(h, cudaStreamSynchronize(h->stream));
+    int32_t rc = collect_events(h);
+    if (rc) return rc;
+    if (ms_total) *ms_total = h->sweep_ms;
+    if (n_launches) *n_launches = h->sweep_launches;
+    h->sweep_ms = 0.f;
+    h->sweep_launches = 0;
+    return EXTMCMC_OK;
+}
+
+int64_t extmcmc_launch_count(extmcmc_t h) { return h ? h->launches : 0; }
+
+int32_t extmcmc_flush_l2(extmcmc_t h) {
+    if (!h) return EXTMCMC_EINVAL;
+    CK(h, cudaSetDevice(h->cfg.device));
+    if (!h->flush_buf) {
+        h->flush_n = (int64_t)(320ll << 20) / 8;  // 320 MiB > 126 MB L2
+        CK(h, cudaMalloc(&h->flush_buf, (size_t)h->flush_n * 8));
+    }
+    launch_flush_l2(h->flush_buf, h->flush_n, h->num_sms, h->stream);
+    CK(h, cudaGetLastError());
+    return EXTMCMC_OK;
+}
+
+int32_t extmcmc_measure_fp64_peak(extmcmc_t h, double *tflops_out) {
+    if (!h || !tflops_out) return EXTMCMC_EINVAL;
+    CK(h, cudaSetDevice(h->cfg.device));
+    const int iters = 20000;
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        CK(h, cudaEventRecord(h->t0, h->stream));
+        launch_fp64_peak(h->scratch_ll, iters, h->num_sms, h->stream);
+        CK(h, cudaEventRecord(h->t1, h->stream));
+        CK(h, cudaEventSynchronize(h->t1));
+        float ms = 0.f;
+        CK(h, cudaEventElapsedTime(&ms, h->t0, h->t1));
+        const double flops = (double)h->num_sms * 8 * 256 * 8.0 * iters * 2.0;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    *tflops_out = best;
+    return EXTMCMC_OK;
+}
+
+const char *extmcmc_sweep_variant_name(extmcmc_t h) {
+    if (!h) return "";
+    if (!h->plan_valid && h->obs_dev) ensure_plan(h);
+    return h->plan_valid ? h->plan.name : "unplanned";
+}
+
+}  // extern "C"

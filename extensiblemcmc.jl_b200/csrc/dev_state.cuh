@@ -1,0 +1,87 @@
+// Device-resident chain state (SoA, chain fastest) and the per-step descriptor.
+//
+// Replaces the reference's host AoS-of-Vectors workspaces:
+//   StandardGlobalSubworkspace   src/workspaces.jl:157-180  (state, histories)
+//   StandardLocalSubworkspace    src/workspaces.jl:413-431  (local state, ll, ll_history)
+//   GenericLocalWorkspace        src/workspaces.jl:453-458  (acceptance_history)
+//   GenericChainStats            src/chain_statistics.jl:16-38
+//   UniformRandomWalk.eps / AdaptationUnifRW counters
+//                                src/transition_kernels/random_walk.jl:45-48,
+//                                src/transition_kernels/adaptation.jl:51-61
+#pragma once
+#include <cstdint>
+#include "../../include/extmcmc.h"
+
+namespace extmcmc {
+
+constexpr int kMaxCoords = 16;      // p_u limit of the scalar per-chain step kernels
+constexpr int kMaxPriorParams = 4;
+constexpr int kMaxLawConst = 4;     // per-chain law constants written by the proposal kernel
+
+// One update as the kernels see it (constant per run; lives in a device table).
+struct DevUpdate {
+    int32_t kernel, n_coords, prior, adapt_kind;
+    int32_t coords[kMaxCoords];
+    uint8_t pos[kMaxCoords];
+    double  prior_params[kMaxPriorParams];
+    int32_t adapt_every_k;
+    double  target, scale, vmin, vmax, offset;
+    double *eps;          // [n_coords][C] per-chain step size (rw.eps, adapted in place)
+    int32_t *adapt_prop;  // [C] AdaptationUnifRW.proposed
+    int32_t *adapt_acc;   // [C] AdaptationUnifRW.accepted
+    int64_t *tot_prop;    // [C] totals since set_state
+    int64_t *tot_acc;     // [C]
+    double  *ra_val;      // [C] latest rolling acceptance rate of this update
+    uint8_t *acc_ring;    // [W][C] acceptance bits of the last W iterations
+};
+
+// One schedule element (src/schedule.jl:56-66) plus what the host planner knows.
+struct StepDesc {
+    int64_t mcmciter;       // 1-based, enters compute_delta (adaptation.jl:312-319)
+    int64_t seq;            // executed-step sequence number since set_state
+    int64_t stat_n;         // GenericChainStats.N before this step (= seq + 1)
+    int32_t pidx;           // 0-based update index
+    int32_t first;          // prev_pidx === nothing: ll stays -Inf (run.jl:76,109)
+    int32_t ra_prev_valid;  // rolling_ar[max(1, iter-1)][pidx] was written (else 0.0)
+    int32_t acc_out_valid;  // acceptance_history[iter - W] of this update was written
+    int32_t replay_row;     // row of this step in the replay buffers
+    int32_t pad_;
+};
+
+struct DevState {
+    int64_t C;              // chains on this rank
+    int64_t chain_offset;   // global id of local chain 0
+    int64_t n_obs_total;    // N over all ranks (enters the log-likelihood constant)
+    int32_t p, NU, W, H;    // params, updates, rolling window, history ring length
+    int32_t law, stats_mode, rng_mode, p_u_max;
+    uint64_t seed;
+    // current state
+    double *theta;          // [p][C]
+    double *ll;             // [C] log-likelihood of the current state
+    // proposal of the step in flight
+    double *prop_loc;       // [kMaxCoords][C] local proposal theta°_loc
+    double *prop_full;      // [p][C] full proposal = theta with coords replaced (run.jl:237-239)
+    double *lawc;           // [kMaxLawConst][C] per-chain law constants of the proposal
+    uint32_t *n_used;       // [C] uniforms consumed by the proposal (next index = Exp draw)
+    // sweep output
+    double *partial;        // [S][C] per-segment partial sums
+    int32_t S;
+    double *ssum;           // [C] reduced (and, under obs sharding, all-reduced) sums
+    int32_t use_ssum;       // accept kernel reads ssum instead of partial
+    // chain statistics
+    double *mean;           // [p][C]
+    double *cov;            // [p*p][C] (stats_mode 0) or [p][C] diagonal (stats_mode 1)
+    // history ring, slot = seq % H
+    double *h_theta;        // [H][p][C]
+    double *h_prop;         // [H][p][C]
+    double *h_ll;           // [H][C]
+    double *h_llp;          // [H][C]
+    uint8_t *h_acc;         // [H][C]
+    // replay buffers (EXTMCMC_RNG_REPLAY)
+    const double *rp_prop;  // [rows][p_u_max][C]
+    const double *rp_exp;   // [rows][C]
+    int32_t *err_flag;      // sticky: a chain left the law's domain
+    DevUpdate *upd;         // [NU]
+};
+
+}  // namespace extmcmc

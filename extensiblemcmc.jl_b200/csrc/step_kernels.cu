@@ -1,0 +1,376 @@
+// K1 (proposal) and K3 (accept / commit / statistics / adaptation): one thread per
+// chain, everything SoA and coalesced across chains.  Compiled with -fmad=false: the
+// reference never contracts a*b+c, and the replay parity tests compare eps, running
+// moments and trajectories bit-for-bit against the CPU oracle.
+#include <cmath>
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "dev_state.cuh"
+#include "philox.cuh"
+#include "step_kernels.h"
+
+namespace extmcmc {
+
+namespace {
+constexpr double kLog2Pi = 1.8378770664093454835606594728112;
+
+// logpdf(prior, theta_loc) on the update's own coordinates (src/updates.jl:104,
+// src/priors.jl:18-39).
+__device__ __forceinline__ double log_prior(const DevUpdate &u, const double *th) {
+    const int n = u.n_coords;
+    switch (u.prior) {
+    case EXTMCMC_PRIOR_IMPROPER: return 0.0;  // priors.jl:19
+    case EXTMCMC_PRIOR_IMPROPER_POS: {        // -sum(log.(th)), priors.jl:26
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) s += log(th[i]);
+        return -s;
+    }
+    case EXTMCMC_PRIOR_NORMAL: {
+        const double m = u.prior_params[0], sd = u.prior_params[1];
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) {
+            const double z = (th[i] - m) / sd;
+            s += -(z * z + kLog2Pi) / 2.0 - log(sd);
+        }
+        return s;
+    }
+    case EXTMCMC_PRIOR_GAMMA: {
+        const double k = u.prior_params[0], sc = u.prior_params[1];
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) {
+            if (!(th[i] > 0.0)) return -INFINITY;
+            s += -lgamma(k) - k * log(sc) + (k - 1.0) * log(th[i]) - th[i] / sc;
+        }
+        return s;
+    }
+    case EXTMCMC_PRIOR_UNIFORM: {
+        const double a = u.prior_params[0], b = u.prior_params[1];
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) {
+            if (!(th[i] >= a && th[i] <= b)) return -INFINITY;
+            s += -log(b - a);
+        }
+        return s;
+    }
+    }
+    return NAN;
+}
+
+// logpdf(rw::UniformRandomWalk, from, to) (random_walk.jl:88-94): only positive-
+// constrained coordinates contribute, -log(2 eps_i) - log(to_i).
+__device__ __forceinline__ double log_q_unif(const DevUpdate &u, const double *eps, const double *to) {
+    double s = 0.0;
+    for (int i = 0; i < u.n_coords; ++i) {
+        const double t = u.pos[i] ? (-log(2.0 * eps[i]) - log(to[i])) : 0.0;
+        s = (i == 0) ? t : s + t;
+    }
+    return s;
+}
+
+// Per-chain law constants of a parameter vector; the sweep only needs lawc[0].
+//   GSN_IID_1D: lawc = { mu, c0 = -(log 2pi + 2 log sqrt(var))/2, 1/(2 var) },
+//   ll = N c0 - S/(2 var) with S = sum (x - mu)^2 (gsn_target.jl:15-29 for d = 1).
+__device__ __forceinline__ void law_prepare(const DevState &d, int64_t c, const double *full,
+                                            int64_t stride) {
+    if (d.law == EXTMCMC_LAW_GSN_IID_1D) {
+        const double mu = full[0], var = full[stride];
+        double c0, inv2;
+        if (!(var > 0.0) || isinf(var)) {
+            c0 = NAN; inv2 = NAN;
+            *d.err_flag = 1;
+        } else {
+            c0 = -(kLog2Pi + 2.0 * log(sqrt(var))) / 2.0;
+            inv2 = 0.5 / var;
+        }
+        d.lawc[c] = mu;
+        d.lawc[d.C + c] = c0;
+        d.lawc[2 * d.C + c] = inv2;
+    }
+}
+
+__device__ __forceinline__ double law_finalize(const DevState &d, int64_t c, double S) {
+    // N*c0 - S/(2 var)
+    return (double)d.n_obs_total * d.lawc[d.C + c] - S * d.lawc[2 * d.C + c];
+}
+}  // namespace
+
+// ---------------------------------------------------------------------------------
+// K1: proposal!  (src/updates.jl:191-196, rand(::UniformRandomWalk) random_walk.jl:65-73)
+//     + set_proposal! (src/run.jl:221-240): writes the full proposal and the law
+//     constants the sweep consumes.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+propose_kernel(DevState d, const StepDesc *__restrict__ descs, int k) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= d.C) return;
+    const StepDesc sd = descs[k];
+    const DevUpdate &u = d.upd[sd.pidx];
+    const int n = u.n_coords;
+    double th[kMaxCoords], prop[kMaxCoords];
+    for (int i = 0; i < n; ++i) th[i] = d.theta[(int64_t)u.coords[i] * d.C + c];
+
+    uint32_t used = 0;
+    if (d.rng_mode == EXTMCMC_RNG_REPLAY) {
+        for (int i = 0; i < n; ++i)
+            prop[i] = d.rp_prop[((int64_t)sd.replay_row * d.p_u_max + i) * d.C + c];
+    } else {
+        ChainStepStream rng(d.seed, (uint64_t)(d.chain_offset + c), sd.mcmciter, sd.pidx);
+        for (;;) {
+            for (int i = 0; i < n; ++i) {
+                const double r = rng.next();
+                const double e = u.eps[(int64_t)i * d.C + c];
+                const double a = -e, b = e;
+                const double U = a + (b - a) * r;  // rand(Uniform(-eps, eps))
+                prop[i] = u.pos[i] ? th[i] * exp(U) : th[i] + U;  // random_walk.jl:72
+            }
+            // whole-vector redraw while the prior is exactly -Inf (updates.jl:193-195)
+            if (!(log_prior(u, prop) == -INFINITY)) break;
+            if (rng.j > 60000u) break;
+        }
+        used = rng.j;
+    }
+    d.n_used[c] = used;
+    for (int i = 0; i < n; ++i) d.prop_loc[(int64_t)i * d.C + c] = prop[i];
+    // full proposal = current state with the update's coordinates replaced (run.jl:237-239)
+    for (int j = 0; j < d.p; ++j) d.prop_full[(int64_t)j * d.C + c] = d.theta[(int64_t)j * d.C + c];
+    for (int i = 0; i < n; ++i) d.prop_full[(int64_t)u.coords[i] * d.C + c] = prop[i];
+    law_prepare(d, c, d.prop_full + c, d.C);
+}
+
+// Law constants of the CURRENT state (extmcmc_eval_loglik).
+__global__ void __launch_bounds__(256) prepare_current_kernel(DevState d) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= d.C) return;
+    law_prepare(d, c, d.theta + c, d.C);
+}
+
+// ssum[c] = sum over segments, fixed order.
+__global__ void __launch_bounds__(256) reduce_partials_kernel(DevState d) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= d.C) return;
+    double s = 0.0;
+    for (int i = 0; i < d.S; ++i) s += d.partial[(int64_t)i * d.C + c];
+    d.ssum[c] = s;
+}
+
+__global__ void __launch_bounds__(256) finalize_loglik_kernel(DevState d, double *ll_out) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= d.C) return;
+    ll_out[c] = law_finalize(d, c, d.ssum[c]);
+}
+
+// ---------------------------------------------------------------------------------
+// K3: accept_reject! (src/run.jl:268-281) + register_accept_reject_results!
+//     (:299-335) + set_chain_param! (:312-320) + update_stats!
+//     (src/chain_statistics.jl:41-66) + update_adaptation! (src/run.jl:136-173,
+//     src/transition_kernels/adaptation.jl:273-329).
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= d.C) return;
+    const StepDesc sd = descs[k];
+    const DevUpdate &u = d.upd[sd.pidx];
+    const int n = u.n_coords;
+    const int64_t C = d.C;
+
+    double S;
+    if (d.use_ssum) {
+        S = d.ssum[c];
+    } else {
+        S = 0.0;
+        for (int i = 0; i < d.S; ++i) S += d.partial[(int64_t)i * C + c];
+    }
+    const double ll_prop = law_finalize(d, c, S);
+    // update_workspaces! (run.jl:101-112): ll of the previously executed update; on the
+    // very first element it is still the initial -Inf (workspaces.jl:425)
+    const double ll_cur = sd.first ? -INFINITY : d.ll[c];
+
+    double th[kMaxCoords], prop[kMaxCoords], eps[kMaxCoords];
+    for (int i = 0; i < n; ++i) {
+        th[i] = d.theta[(int64_t)u.coords[i] * C + c];
+        prop[i] = d.prop_loc[(int64_t)i * C + c];
+        eps[i] = u.eps[(int64_t)i * C + c];
+    }
+    // llr, strictly left to right (run.jl:271-277)
+    double llr = ll_prop - ll_cur;
+    llr = llr + log_q_unif(u, eps, th);    // theta° -> theta
+    llr = llr - log_q_unif(u, eps, prop);  // theta -> theta°
+    llr = llr + log_prior(u, prop);
+    llr = llr - log_prior(u, th);
+
+    double E;
+    if (d.rng_mode == EXTMCMC_RNG_REPLAY) {
+        E = d.rp_exp[(int64_t)sd.replay_row * C + c];
+    } else {
+        ChainStepStream rng(d.seed, (uint64_t)(d.chain_offset + c), sd.mcmciter, sd.pidx, d.n_used[c]);
+        E = -log(rng.next());  // rand(Exponential(1.0)), run.jl:278
+    }
+    const bool accepted = E > -llr;  // NaN compares false -> reject
+
+    const double ll_new = accepted ? ll_prop : ll_cur;
+    if (accepted)
+        for (int i = 0; i < n; ++i) d.theta[(int64_t)u.coords[i] * C + c] = prop[i];
+    d.ll[c] = ll_new;
+
+    // history row (state_history / state_proposal_history / ll_history / acceptance_history)
+    const int64_t slot = sd.seq % d.H;
+    for (int j = 0; j < d.p; ++j) {
+        d.h_theta[(slot * d.p + j) * C + c] = d.theta[(int64_t)j * C + c];
+        d.h_prop[(slot * d.p + j) * C + c] = d.prop_full[(int64_t)j * C + c];
+    }
+    d.h_ll[slot * C + c] = ll_new;
+    d.h_llp[slot * C + c] = ll_prop;
+    d.h_acc[slot * C + c] = accepted ? 1 : 0;
+
+    // update_stats! (chain_statistics.jl:46-51), verbatim arithmetic
+    const int64_t N = sd.stat_n;
+    if (d.stats_mode != 2) {
+        const double f_old = (double)(N - 1) / (double)N;
+        const double f_mean = (double)N / (double)(N + 1);
+        const double f_new = (double)(N + 1) / (double)N;
+        const int p = d.p;
+        if (d.stats_mode == 0) {
+            // covariance first (it needs the old mean), column by column
+            for (int b = 0; b < p; ++b) {
+                const double tb = d.theta[(int64_t)b * C + c];
+                const double mb_old = d.mean[(int64_t)b * C + c];
+                const double mb_new = mb_old * f_mean + tb / (double)(N + 1);
+                for (int a = 0; a < p; ++a) {
+                    const double ta = d.theta[(int64_t)a * C + c];
+                    const double ma_old = d.mean[(int64_t)a * C + c];
+                    const double ma_new = ma_old * f_mean + ta / (double)(N + 1);
+                    const int64_t idx = ((int64_t)(a + b * p)) * C + c;
+                    const double old_sum_sq = f_old * d.cov[idx] + ma_old * mb_old;
+                    const double new_sum_sq = old_sum_sq + (ta * tb) / (double)N;
+                    d.cov[idx] = new_sum_sq - f_new * (ma_new * mb_new);
+                }
+            }
+        } else {
+            for (int a = 0; a < p; ++a) {
+                const double ta = d.theta[(int64_t)a * C + c];
+                const double ma_old = d.mean[(int64_t)a * C + c];
+                const double ma_new = ma_old * f_mean + ta / (double)(N + 1);
+                const int64_t idx = (int64_t)a * C + c;
+                const double old_sum_sq = f_old * d.cov[idx] + ma_old * ma_old;
+                const double new_sum_sq = old_sum_sq + (ta * ta) / (double)N;
+                d.cov[idx] = new_sum_sq - f_new * (ma_new * ma_new);
+            }
+        }
+        for (int a = 0; a < p; ++a) {
+            const int64_t idx = (int64_t)a * C + c;
+            d.mean[idx] = d.mean[idx] * f_mean + d.theta[idx] / (double)(N + 1);
+        }
+    }
+    // rolling acceptance rate (chain_statistics.jl:53-64)
+    {
+        const int W = d.W;
+        const double ra_prev = sd.ra_prev_valid ? u.ra_val[c] : 0.0;
+        const int64_t rslot = sd.mcmciter % W;
+        const int acc_out = sd.acc_out_valid ? (int)u.acc_ring[rslot * C + c] : 0;
+        const int64_t mn = (int64_t)W < N ? (int64_t)W : N;
+        u.ra_val[c] = (ra_prev * (double)W + (double)((int)accepted - acc_out)) / (double)mn;
+        u.acc_ring[rslot * C + c] = accepted ? 1 : 0;
+    }
+
+    // update_adaptation! -- only the update whose turn it is registers (run.jl:176-177)
+    u.tot_prop[c] += 1;
+    u.tot_acc[c] += accepted ? 1 : 0;
+    if (u.adapt_kind == EXTMCMC_ADAPT_UNIF_RW) {
+        int32_t prop_n = u.adapt_prop[c] + 1;                      // register! :292-295
+        int32_t acc_n = u.adapt_acc[c] + (accepted ? 1 : 0);
+        if (prop_n >= u.adapt_every_k) {                           // time_to_update :302-304
+            const double r = (double)sd.mcmciter / (double)u.adapt_every_k - u.offset;
+            const double delta = u.scale / sqrt(r > 1.0 ? r : 1.0);  // compute_delta :312-319
+            const double a_r = (double)acc_n / (double)prop_n;       // acceptance_rate :242-244
+            prop_n = 0; acc_n = 0;                                   // reset! :263-266
+            const double sgn = (a_r > u.target) ? 1.0 : -1.0;
+            for (int i = 0; i < n; ++i) {                            // compute_eps :326-329
+                double e = eps[i] + sgn * delta;
+                e = e < u.vmax ? e : u.vmax;
+                e = e > u.vmin ? e : u.vmin;
+                u.eps[(int64_t)i * C + c] = e;
+            }
+        }
+        u.adapt_prop[c] = prop_n;
+        u.adapt_acc[c] = acc_n;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// utilities
+// ---------------------------------------------------------------------------------
+// x_i ~ N(mean, sd^2), i = global observation index; Box-Muller on the Philox stream
+// keyed by (seed; counter = i/2).  BASELINE cfg 5 generates 1e9 observations in place.
+__global__ void generate_obs_normal_kernel(double *obs, int64_t first, int64_t n, double mean,
+                                           double sd, uint64_t seed) {
+    const int64_t pair0 = first >> 1;
+    const int64_t n_pairs = ((first + n + 1) >> 1) - pair0;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_pairs;
+         q += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t pair = (uint64_t)(pair0 + q);
+        const Philox4 w = philox4x32_10((uint32_t)pair, (uint32_t)(pair >> 32), 0x0B5E0B5Eu, 0u,
+                                        (uint32_t)seed, (uint32_t)(seed >> 32));
+        const double u1 = u52_to_unit(w.w[0], w.w[1]), u2 = u52_to_unit(w.w[2], w.w[3]);
+        const double rad = sqrt(-2.0 * log(u1));
+        double sn, cs;
+        sincospi(2.0 * u2, &sn, &cs);
+        const int64_t i0 = (int64_t)(pair << 1), i1 = i0 + 1;
+        if (i0 >= first && i0 < first + n) obs[i0 - first] = mean + sd * (rad * cs);
+        if (i1 >= first && i1 < first + n) obs[i1 - first] = mean + sd * (rad * sn);
+    }
+}
+
+__global__ void flush_l2_kernel(double *buf, int64_t n, double v) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        buf[i] = v;
+}
+
+// Dependent-free FP64 FMA chains: 8 accumulators x iters per thread.
+__global__ void fp64_peak_kernel(double *out, int iters, double a, double b) {
+    double acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = (double)(threadIdx.x + i);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fma(acc[i], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += acc[i];
+    if (s == 123.456) out[0] = s;
+}
+
+// ---------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------
+static inline int blocks_for(int64_t C) { return (int)((C + 255) / 256); }
+
+void launch_propose(const DevState &d, const StepDesc *descs, int k, cudaStream_t st) {
+    propose_kernel<<<blocks_for(d.C), 256, 0, st>>>(d, descs, k);
+}
+void launch_accept(const DevState &d, const StepDesc *descs, int k, cudaStream_t st) {
+    accept_kernel<<<blocks_for(d.C), 256, 0, st>>>(d, descs, k);
+}
+void launch_prepare_current(const DevState &d, cudaStream_t st) {
+    prepare_current_kernel<<<blocks_for(d.C), 256, 0, st>>>(d);
+}
+void launch_reduce_partials(const DevState &d, cudaStream_t st) {
+    reduce_partials_kernel<<<blocks_for(d.C), 256, 0, st>>>(d);
+}
+void launch_finalize_loglik(const DevState &d, double *ll_out, cudaStream_t st) {
+    finalize_loglik_kernel<<<blocks_for(d.C), 256, 0, st>>>(d, ll_out);
+}
+void launch_generate_obs_normal(double *obs, int64_t first, int64_t n, double mean, double sd,
+                                uint64_t seed, int num_sms, cudaStream_t st) {
+    generate_obs_normal_kernel<<<num_sms * 8, 256, 0, st>>>(obs, first, n, mean, sd, seed);
+}
+void launch_flush_l2(double *buf, int64_t n, int num_sms, cudaStream_t st) {
+    flush_l2_kernel<<<num_sms * 8, 256, 0, st>>>(buf, n, 1.0);
+}
+void launch_fp64_peak(double *out, int iters, int num_sms, cudaStream_t st) {
+    fp64_peak_kernel<<<num_sms * 8, 256, 0, st>>>(out, iters, 1.0000001, 1e-9);
+}
+
+}  // namespace extmcmc

@@ -1,0 +1,17 @@
+// Host-side launchers of the per-chain step kernels (step_kernels.cu).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "dev_state.cuh"
+
+namespace extmcmc {
+void launch_propose(const DevState &d, const StepDesc *descs, int k, cudaStream_t st);
+void launch_accept(const DevState &d, const StepDesc *descs, int k, cudaStream_t st);
+void launch_prepare_current(const DevState &d, cudaStream_t st);
+void launch_reduce_partials(const DevState &d, cudaStream_t st);
+void launch_finalize_loglik(const DevState &d, double *ll_out, cudaStream_t st);
+void launch_generate_obs_normal(double *obs, int64_t first, int64_t n, double mean, double sd,
+                                uint64_t seed, int num_sms, cudaStream_t st);
+void launch_flush_l2(double *buf, int64_t n, int num_sms, cudaStream_t st);
+void launch_fp64_peak(double *out, int iters, int num_sms, cudaStream_t st);
+}  // namespace extmcmc

@@ -1,0 +1,26 @@
+// Host-side interface of the likelihood sweep kernels (sweep_gsn1d.cu).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace extmcmc {
+
+enum { SWEEP_VARIANT_AUTO = 0, SWEEP_VARIANT_CHAINS = 1, SWEEP_VARIANT_OBS = 2 };
+
+struct SweepPlan {
+    int variant;       // SWEEP_VARIANT_*
+    int R;             // chains per thread ("chains") or chains per CTA pass ("obs")
+    int groups;        // chain groups (grid.y for "chains", launches for "obs")
+    int S;             // observation segments = rows of partial[S][C]
+    int launches;      // kernel launches per sweep
+    const char *name;
+};
+
+SweepPlan plan_sweep_gsn1d(int64_t C, int64_t n_obs, int force_variant, int num_sms);
+cudaError_t sweep_gsn1d_init();
+// partial[S][C] <- per-segment sums of (x - mu_c)^2.  obs must be 16-byte aligned and
+// readable up to the next even observation index (the library pads its copy).
+void launch_sweep_gsn1d(const SweepPlan &pl, const double *obs, int64_t n_obs, const double *mu,
+                        int64_t C, double *partial, cudaStream_t st);
+
+}  // namespace extmcmc

@@ -1,0 +1,365 @@
+// K2 -- the hot loop: full-data Gaussian log-likelihood sweep for all chains.
+//
+// Replaces loglikelihood(P::GsnTargetLaw, observs) (src/example/gsn_target.jl:23-29,
+// reached through compute_ll! src/run.jl:251-260 and src/workspaces.jl:236-238),
+// which in the reference is a sequential per-observation logpdf(MvNormal) loop for
+// ONE chain.  Here every chain's sum  S_c = sum_i (x_i - mu_c)^2  is accumulated in
+// one pass over the shared observation set; the O(1)-per-chain-step constants
+// (-N/2 log(2 pi sigma^2), 1/(2 sigma^2)) are applied by the accept kernel.
+// Observations are streamed, not summarised: the sweep is the stand-in for a
+// general per-observation likelihood, so no sufficient-statistics shortcut is used.
+//
+// Data movement: each CTA streams its observation segment HBM/L2 -> shared memory
+// with 1-D TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on mbarriers, in a
+// multi-stage ring; nobody touches an observation through the LSU global path.
+//
+// Two mappings, chosen by the host from the shapes:
+//   "chains" (many chains, cfg 2): thread <-> R chains held in registers; every thread
+//       of the CTA reads the same observation pair from shared memory (a broadcast
+//       LDS.128 feeds 4R FP64 instructions), so the FP64 pipe is the only busy unit.
+//       grid = (segments, chain groups); per-segment partial sums go to partial[S][C].
+//   "obs" (few chains, huge N, cfg 5): thread <-> observations of the tile, all CB
+//       chains' accumulators in registers; a fixed-order shuffle + shared-memory
+//       block reduction ends each CTA.  HBM-bound: 8 bytes per observation per sweep.
+// Both are deterministic: fixed tiling, fixed reduction order, no atomics.
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "sweep.h"
+
+namespace extmcmc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion counted on an mbarrier.
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+
+// Segment s of S over n_obs observations, boundaries on even indices so that every
+// bulk copy starts 16-byte aligned.
+__device__ __forceinline__ void segment_bounds(int64_t n_obs, int s, int S, int64_t &lo, int64_t &hi) {
+    const int64_t n_pairs = (n_obs + 1) >> 1;
+    lo = 2 * ((int64_t)s * n_pairs / S);
+    hi = 2 * ((int64_t)(s + 1) * n_pairs / S);
+    if (hi > n_obs) hi = n_obs;
+}
+
+// ---------------------------------------------------------------------------------
+// "chains" mapping
+// ---------------------------------------------------------------------------------
+template <int R, int NT, int TILE, int STAGES>
+__global__ void __launch_bounds__(NT)
+sweep_gsn1d_chains_kernel(const double *__restrict__ obs, int64_t n_obs,
+                          const double *__restrict__ mu, int64_t C,
+                          double *__restrict__ partial, int S) {
+    __shared__ __align__(128) double tile[STAGES][TILE];
+    __shared__ __align__(8) uint64_t bar[STAGES];
+    const int tid = threadIdx.x;
+    const int seg = blockIdx.x;
+    const int64_t cbase = (int64_t)blockIdx.y * (NT * R);
+
+    int64_t lo, hi;
+    segment_bounds(n_obs, seg, S, lo, hi);
+    const int64_t len = hi - lo;
+    const int n_tiles = (int)((len + TILE - 1) / TILE);
+
+    double m[R], acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int64_t c = cbase + (int64_t)r * NT + tid;
+        m[r] = c < C ? mu[c] : 0.0;
+        acc[r] = 0.0;
+    }
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) mbar_init(&bar[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int t) {
+        const int st = t % STAGES;
+        const int64_t off = (int64_t)t * TILE;
+        const int cnt = (int)((len - off) < (int64_t)TILE ? (len - off) : (int64_t)TILE);
+        const uint32_t bytes = (uint32_t)((cnt + 1) >> 1) * 16u;  // padded device buffer
+        mbar_expect_tx(&bar[st], bytes);
+        bulk_g2s(&tile[st][0], obs + lo + off, bytes, &bar[st]);
+    };
+    if (tid == 0)
+        for (int t = 0; t < STAGES && t < n_tiles; ++t) issue(t);
+
+    for (int t = 0; t < n_tiles; ++t) {
+        const int st = t % STAGES;
+        mbar_wait(&bar[st], (uint32_t)(t / STAGES) & 1u);
+        const int64_t off = (int64_t)t * TILE;
+        const int cnt = (int)((len - off) < (int64_t)TILE ? (len - off) : (int64_t)TILE);
+        const double2 *xs = reinterpret_cast<const double2 *>(&tile[st][0]);
+        const int np = cnt >> 1;
+#pragma unroll 4
+        for (int i = 0; i < np; ++i) {
+            const double2 x = xs[i];  // same address in every thread: broadcast LDS.128
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const double d0 = x.x - m[r];
+                acc[r] = fma(d0, d0, acc[r]);
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const double d1 = x.y - m[r];
+                acc[r] = fma(d1, d1, acc[r]);
+            }
+        }
+        if (cnt & 1) {
+            const double x = tile[st][cnt - 1];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const double d0 = x - m[r];
+                acc[r] = fma(d0, d0, acc[r]);
+            }
+        }
+        __syncthreads();  // everyone is done with this stage before it is refilled
+        if (tid == 0 && t + STAGES < n_tiles) issue(t + STAGES);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int64_t c = cbase + (int64_t)r * NT + tid;
+        if (c < C) partial[(int64_t)seg * C + c] = acc[r];
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// "obs" mapping
+// ---------------------------------------------------------------------------------
+template <int CB, int NT, int TILE, int STAGES>
+__global__ void __launch_bounds__(NT)
+sweep_gsn1d_obs_kernel(const double *__restrict__ obs, int64_t n_obs,
+                       const double *__restrict__ mu, int64_t C, int64_t c_first,
+                       double *__restrict__ partial, int S) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *tile = reinterpret_cast<double *>(smem_raw);                    // [STAGES][TILE]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(tile + STAGES * TILE);     // [STAGES]
+    double *red = reinterpret_cast<double *>(bar + STAGES);                 // [NT/32][CB]
+    const int tid = threadIdx.x;
+    const int seg = blockIdx.x;
+
+    int64_t lo, hi;
+    segment_bounds(n_obs, seg, S, lo, hi);
+    const int64_t len = hi - lo;
+    const int n_tiles = (int)((len + TILE - 1) / TILE);
+
+    double m[CB], acc[CB];
+#pragma unroll
+    for (int c = 0; c < CB; ++c) {
+        m[c] = (c_first + c) < C ? mu[c_first + c] : 0.0;
+        acc[c] = 0.0;
+    }
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(&bar[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int t) {
+        const int st = t % STAGES;
+        const int64_t off = (int64_t)t * TILE;
+        const int cnt = (int)((len - off) < (int64_t)TILE ? (len - off) : (int64_t)TILE);
+        const uint32_t bytes = (uint32_t)((cnt + 1) >> 1) * 16u;
+        mbar_expect_tx(&bar[st], bytes);
+        bulk_g2s(tile + st * TILE, obs + lo + off, bytes, &bar[st]);
+    };
+    if (tid == 0)
+        for (int t = 0; t < STAGES && t < n_tiles; ++t) issue(t);
+
+    for (int t = 0; t < n_tiles; ++t) {
+        const int st = t % STAGES;
+        mbar_wait(&bar[st], (uint32_t)(t / STAGES) & 1u);
+        const int64_t off = (int64_t)t * TILE;
+        const int cnt = (int)((len - off) < (int64_t)TILE ? (len - off) : (int64_t)TILE);
+        const double2 *xs = reinterpret_cast<const double2 *>(tile + st * TILE);
+        if (cnt == TILE) {
+#pragma unroll
+            for (int k = 0; k < TILE / 2 / NT; ++k) {
+                const double2 x = xs[k * NT + tid];  // consecutive threads, consecutive 16 B
+#pragma unroll
+                for (int c = 0; c < CB; ++c) {
+                    const double d0 = x.x - m[c];
+                    acc[c] = fma(d0, d0, acc[c]);
+                    const double d1 = x.y - m[c];
+                    acc[c] = fma(d1, d1, acc[c]);
+                }
+            }
+        } else {
+            const int np = cnt >> 1;
+            for (int i = tid; i < np; i += NT) {
+                const double2 x = xs[i];
+#pragma unroll
+                for (int c = 0; c < CB; ++c) {
+                    const double d0 = x.x - m[c];
+                    acc[c] = fma(d0, d0, acc[c]);
+                    const double d1 = x.y - m[c];
+                    acc[c] = fma(d1, d1, acc[c]);
+                }
+            }
+            if ((cnt & 1) && tid == 0) {
+                const double x = tile[st * TILE + cnt - 1];
+#pragma unroll
+                for (int c = 0; c < CB; ++c) {
+                    const double d0 = x - m[c];
+                    acc[c] = fma(d0, d0, acc[c]);
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && t + STAGES < n_tiles) issue(t + STAGES);
+    }
+
+    // fixed-order block reduction: xor-shuffle tree inside each warp, then warp 0..W-1
+#pragma unroll
+    for (int c = 0; c < CB; ++c) {
+        double v = acc[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((tid & 31) == 0) red[(tid >> 5) * CB + c] = v;
+    }
+    __syncthreads();
+    if (tid < CB && (c_first + tid) < C) {
+        double v = 0.0;
+        for (int w = 0; w < NT / 32; ++w) v += red[w * CB + tid];
+        partial[(int64_t)seg * C + c_first + tid] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// host side: shape -> plan -> launch
+// ---------------------------------------------------------------------------------
+namespace {
+constexpr int kChainsNT = 128, kChainsTile = 1024, kChainsStages = 2;
+constexpr int kObsNT = 256, kObsTile = 2048, kObsStages = 4;
+constexpr size_t kObsSmem(int cb) {
+    return (size_t)kObsStages * kObsTile * 8 + kObsStages * 8 + (size_t)(kObsNT / 32) * cb * 8;
+}
+
+template <int R>
+void launch_chains(const SweepPlan &pl, const double *obs, int64_t n_obs, const double *mu,
+                   int64_t C, double *partial, cudaStream_t st) {
+    dim3 grid(pl.S, pl.groups);
+    sweep_gsn1d_chains_kernel<R, kChainsNT, kChainsTile, kChainsStages>
+        <<<grid, kChainsNT, 0, st>>>(obs, n_obs, mu, C, partial, pl.S);
+}
+template <int CB>
+cudaError_t prep_obs() {
+    return cudaFuncSetAttribute(sweep_gsn1d_obs_kernel<CB, kObsNT, kObsTile, kObsStages>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kObsSmem(CB));
+}
+template <int CB>
+void launch_obs(const SweepPlan &pl, const double *obs, int64_t n_obs, const double *mu, int64_t C,
+                double *partial, cudaStream_t st) {
+    for (int g = 0; g < pl.groups; ++g)
+        sweep_gsn1d_obs_kernel<CB, kObsNT, kObsTile, kObsStages>
+            <<<pl.S, kObsNT, kObsSmem(CB), st>>>(obs, n_obs, mu, C, (int64_t)g * CB, partial, pl.S);
+}
+}  // namespace
+
+SweepPlan plan_sweep_gsn1d(int64_t C, int64_t n_obs, int force_variant, int num_sms) {
+    SweepPlan pl{};
+    const int64_t n_pairs = (n_obs + 1) / 2;
+    bool chains = C > 32;
+    if (force_variant == SWEEP_VARIANT_CHAINS) chains = true;
+    if (force_variant == SWEEP_VARIANT_OBS) chains = false;
+    if (chains) {
+        // registers per thread: largest R that still leaves >= 2 chain groups' worth of
+        // CTAs to spread over the SMs
+        int R = 8;
+        while (R > 1 && C < (int64_t)kChainsNT * R) R >>= 1;
+        pl.variant = SWEEP_VARIANT_CHAINS;
+        pl.R = R;
+        pl.groups = (int)((C + (int64_t)kChainsNT * R - 1) / ((int64_t)kChainsNT * R));
+        const int target = num_sms * 4;  // 4 CTAs of 4 warps per SM
+        int S = (target + pl.groups - 1) / pl.groups;
+        const int64_t max_S = (n_pairs + 255) / 256;  // >= 512 observations per segment
+        if (S > max_S) S = (int)max_S;
+        if (S < 1) S = 1;
+        pl.S = S;
+        pl.launches = 1;
+        static const char *names[] = {"", "gsn1d_chains_R1", "gsn1d_chains_R2", "", "gsn1d_chains_R4",
+                                      "", "", "", "gsn1d_chains_R8"};
+        pl.name = names[R];
+    } else {
+        int CB = 1;
+        while (CB < C && CB < 32) CB <<= 1;
+        pl.variant = SWEEP_VARIANT_OBS;
+        pl.R = CB;
+        pl.groups = (int)((C + CB - 1) / CB);
+        int S = num_sms * 3;  // 3 CTAs x 64 KB of staging per SM
+        const int64_t max_S = (n_pairs + 1023) / 1024;  // >= one 2048-observation tile
+        if (S > max_S) S = (int)max_S;
+        if (S < 1) S = 1;
+        pl.S = S;
+        pl.launches = pl.groups;
+        pl.name = CB == 1 ? "gsn1d_obs_C1" : CB == 2 ? "gsn1d_obs_C2" : CB == 4 ? "gsn1d_obs_C4"
+                : CB == 8 ? "gsn1d_obs_C8" : CB == 16 ? "gsn1d_obs_C16" : "gsn1d_obs_C32";
+    }
+    return pl;
+}
+
+cudaError_t sweep_gsn1d_init() {
+    cudaError_t e;
+    if ((e = prep_obs<1>()) != cudaSuccess) return e;
+    if ((e = prep_obs<2>()) != cudaSuccess) return e;
+    if ((e = prep_obs<4>()) != cudaSuccess) return e;
+    if ((e = prep_obs<8>()) != cudaSuccess) return e;
+    if ((e = prep_obs<16>()) != cudaSuccess) return e;
+    if ((e = prep_obs<32>()) != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
+void launch_sweep_gsn1d(const SweepPlan &pl, const double *obs, int64_t n_obs, const double *mu,
+                        int64_t C, double *partial, cudaStream_t st) {
+    if (pl.variant == SWEEP_VARIANT_CHAINS) {
+        switch (pl.R) {
+        case 1: launch_chains<1>(pl, obs, n_obs, mu, C, partial, st); break;
+        case 2: launch_chains<2>(pl, obs, n_obs, mu, C, partial, st); break;
+        case 4: launch_chains<4>(pl, obs, n_obs, mu, C, partial, st); break;
+        default: launch_chains<8>(pl, obs, n_obs, mu, C, partial, st); break;
+        }
+    } else {
+        switch (pl.R) {
+        case 1: launch_obs<1>(pl, obs, n_obs, mu, C, partial, st); break;
+        case 2: launch_obs<2>(pl, obs, n_obs, mu, C, partial, st); break;
+        case 4: launch_obs<4>(pl, obs, n_obs, mu, C, partial, st); break;
+        case 8: launch_obs<8>(pl, obs, n_obs, mu, C, partial, st); break;
+        case 16: launch_obs<16>(pl, obs, n_obs, mu, C, partial, st); break;
+        default: launch_obs<32>(pl, obs, n_obs, mu, C, partial, st); break;
+        }
+    }
+}
+
+}  // namespace extmcmc

@@ -1,0 +1,65 @@
+"""Priors (src/priors.jl).  Evaluated on the device on the update's own coordinates only
+(src/run.jl:374-385, src/updates.jl:104).  Arbitrary `dist` objects cannot cross the C ABI:
+the enumerated families below are supported, anything else raises at workspace creation
+(the reference's convention for a missing method is error("... not implemented"))."""
+import numpy as np
+
+from . import _abi
+
+
+class Prior:                                          # priors.jl:4
+    def to_abi(self):
+        raise NotImplementedError(f"logpdf not implemented for prior {type(self).__name__} on the GPU path")
+
+
+class ImproperPrior(Prior):                           # priors.jl:18-19
+    def to_abi(self):
+        return _abi.PRIOR_IMPROPER, np.zeros(0)
+
+
+class ImproperPosPrior(Prior):                        # priors.jl:25-26
+    def to_abi(self):
+        return _abi.PRIOR_IMPROPER_POS, np.zeros(0)
+
+
+class Normal:
+    """Stand-in for Distributions.Normal(mu, sigma) inside StandardPrior."""
+    def __init__(self, mu=0.0, sigma=1.0):
+        self.mu, self.sigma = float(mu), float(sigma)
+
+
+class Gamma:
+    """Stand-in for Distributions.Gamma(shape, scale)."""
+    def __init__(self, shape=1.0, scale=1.0):
+        self.shape, self.scale = float(shape), float(scale)
+
+
+class Uniform:
+    """Stand-in for Distributions.Uniform(a, b)."""
+    def __init__(self, a=0.0, b=1.0):
+        self.a, self.b = float(a), float(b)
+
+
+class StandardPrior(Prior):                           # priors.jl:35-39
+    """StandardPrior(dist): `dist` is applied independently to each coordinate of the
+    update (an iid product)."""
+    def __init__(self, dist):
+        self.dist = dist
+
+    def to_abi(self):
+        d = self.dist
+        if isinstance(d, Normal):
+            return _abi.PRIOR_NORMAL, np.array([d.mu, d.sigma])
+        if isinstance(d, Gamma):
+            return _abi.PRIOR_GAMMA, np.array([d.shape, d.scale])
+        if isinstance(d, Uniform):
+            return _abi.PRIOR_UNIFORM, np.array([d.a, d.b])
+        raise NotImplementedError(
+            f"StandardPrior({type(d).__name__}) is not implemented on the GPU path "
+            "(supported: Normal, Gamma, Uniform)")
+
+
+class ProductPrior(Prior):                            # priors.jl:60-88
+    def __init__(self, dists, dims):
+        self.dists, self.dims = tuple(dists), tuple(dims)
+    # to_abi: inherited -> raises (device path: next round)

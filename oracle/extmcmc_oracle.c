@@ -1,0 +1,598 @@
+/*
+ * extmcmc_oracle.c -- CPU ORACLE (TEST INFRASTRUCTURE, NOT PRODUCT).
+ * See extmcmc_oracle.h for the parity status ("parity unpinned" for the step
+ * numerics; schedule + adaptation defaults pinned by the reference's tests).
+ *
+ * Every function cites the reference file:line (relative to the upstream
+ * ExtensibleMCMC.jl tree) whose behaviour it restates.  Compile with
+ * -O2 -ffp-contract=off: the reference (Julia) never contracts a*b+c into an
+ * FMA, and bit-exact replay against the GPU relies on that.
+ */
+#include "extmcmc_oracle.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <pthread.h>
+
+#define ORC_MAX_D 16 /* obs_dim limit of the general-d Gaussian law in the oracle */
+
+static __thread char g_err[512];
+static char g_err_global[512];
+static void set_err(const char *msg) {
+    snprintf(g_err, sizeof g_err, "%s", msg);
+    snprintf(g_err_global, sizeof g_err_global, "%s", msg);
+}
+const char *oracle_last_error(void) { return g_err_global; }
+
+/* ------------------------------------------------------------------------- */
+/* Philox4x32-10 (Salmon et al., SC'11; constants as in Random123 and in     */
+/* cuRAND's curand_philox4x32_x.h).  Counter layout of this project:         */
+/*   key = (seed lo32, seed hi32)                                            */
+/*   ctr = (chain lo32, chain hi32, mcmciter lo32, (pidx << 16) | block)     */
+/* The j-th uniform of a (chain, mcmciter, pidx) substream is lane j & 1 of  */
+/* block j >> 1: u = (k + 0.5) * 2^-52 with k the top 52 bits of the lane's  */
+/* 64-bit word (w[2l+1] << 32 | w[2l]), so u is in (0, 1) exactly.           */
+/* ------------------------------------------------------------------------- */
+#define PHILOX_M0 0xD2511F53u
+#define PHILOX_M1 0xCD9E8D57u
+#define PHILOX_W0 0x9E3779B9u
+#define PHILOX_W1 0xBB67AE85u
+
+void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
+    uint32_t k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)PHILOX_M0 * c0;
+        uint64_t p1 = (uint64_t)PHILOX_M1 * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += PHILOX_W0; k1 += PHILOX_W1;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+double oracle_uniform(uint64_t seed, uint64_t chain, int64_t mcmciter, int32_t pidx,
+                      uint32_t j) {
+    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    uint32_t ctr[4] = {(uint32_t)chain, (uint32_t)(chain >> 32), (uint32_t)mcmciter,
+                       ((uint32_t)pidx << 16) | (j >> 1)};
+    uint32_t w[4];
+    oracle_philox4x32_10(ctr, key, w);
+    uint32_t l = j & 1u;
+    uint64_t word = ((uint64_t)w[2 * l + 1] << 32) | w[2 * l];
+    uint64_t k = word >> 12;
+    return ((double)k + 0.5) * 0x1.0p-52;
+}
+
+/* ------------------------------------------------------------------------- */
+/* State                                                                     */
+/* ------------------------------------------------------------------------- */
+typedef struct {
+    int32_t kernel, n_coords, prior, n_prior_params;
+    int32_t *coords;
+    uint8_t *pos;
+    double prior_params[8];
+    extmcmc_adapt_t adapt;
+    int32_t step_len; /* doubles of step-size state per chain */
+    double *step0;    /* initial step-size state [step_len] */
+} orc_update_t;
+
+struct oracle_handle {
+    extmcmc_config_t cfg;
+    orc_update_t *upd;
+    double *obs; /* [n_obs][d] */
+    double *y;
+    int64_t n_obs;
+    int64_t C;
+    int32_t p, NU, W;
+    /* per chain, AoS by chain */
+    double *theta;      /* [C][p] */
+    double *ll;         /* [C]    */
+    double *mean;       /* [C][p] */
+    double *cov;        /* [C][p*p] column-major */
+    int64_t *statN;     /* [C]    */
+    double **step;      /* [NU] -> [C][step_len] */
+    int64_t *proposed;  /* [C][NU] adaptation counters (adaptation.jl:52-53) */
+    int64_t *accepted;  /* [C][NU] */
+    int64_t *tot_prop;  /* [C][NU] */
+    int64_t *tot_acc;   /* [C][NU] */
+    double *ra_val;     /* [C][NU] latest rolling_ar value */
+    int64_t *ra_iter;   /* [C][NU] mcmciter at which ra_val was written (0 = never) */
+    uint8_t *acc_ring;  /* [C][NU][W] */
+    int64_t *acc_tag;   /* [C][NU][W] mcmciter stored in the slot (0 = never) */
+    int32_t domain_err;
+};
+
+static void *xcalloc(size_t n, size_t s) {
+    void *p = calloc(n ? n : 1, s);
+    return p;
+}
+
+int32_t oracle_create(const extmcmc_config_t *cfg, const extmcmc_update_t *updates,
+                      const double *obs, int64_t n_obs, const double *y,
+                      const double *theta_init, oracle_t *out) {
+    if (!cfg || !updates || !out || !theta_init) { set_err("null argument"); return EXTMCMC_EINVAL; }
+    if (cfg->law != EXTMCMC_LAW_GSN_IID_1D && cfg->law != EXTMCMC_LAW_GSN_MV) {
+        set_err("oracle: law not implemented");
+        return EXTMCMC_EUNSUPPORTED;
+    }
+    int32_t d = cfg->obs_dim;
+    if (cfg->law == EXTMCMC_LAW_GSN_IID_1D && (d != 1 || cfg->n_params != 2)) {
+        set_err("GSN_IID_1D needs obs_dim = 1 and n_params = 2");
+        return EXTMCMC_EINVAL;
+    }
+    if (cfg->law == EXTMCMC_LAW_GSN_MV && (d < 1 || d > ORC_MAX_D || cfg->n_params != d * (d + 1))) {
+        set_err("GSN_MV needs n_params = d(d+1), 1 <= d <= 16");
+        return EXTMCMC_EINVAL;
+    }
+    if (cfg->n_params > 256 || cfg->n_params < 1 || cfg->n_chains < 1 || cfg->n_updates < 1) {
+        set_err("oracle: need 1 <= n_params <= 256, n_chains >= 1, n_updates >= 1");
+        return EXTMCMC_EINVAL;
+    }
+    for (int u = 0; u < cfg->n_updates; ++u)
+        if (updates[u].n_coords < 1 || updates[u].n_coords > 64) { set_err("oracle: 1 <= n_coords <= 64"); return EXTMCMC_EINVAL; }
+    struct oracle_handle *h = xcalloc(1, sizeof *h);
+    h->cfg = *cfg;
+    h->C = cfg->n_chains; h->p = cfg->n_params; h->NU = cfg->n_updates;
+    h->W = cfg->roll_window > 0 ? cfg->roll_window : 100;
+    h->n_obs = n_obs;
+    h->obs = xcalloc((size_t)n_obs * d, sizeof(double));
+    if (n_obs) memcpy(h->obs, obs, (size_t)n_obs * d * sizeof(double));
+    if (y) { h->y = xcalloc((size_t)n_obs, sizeof(double)); memcpy(h->y, y, (size_t)n_obs * sizeof(double)); }
+    int64_t C = h->C; int32_t p = h->p, NU = h->NU;
+    h->upd = xcalloc(NU, sizeof(orc_update_t));
+    h->step = xcalloc(NU, sizeof(double *));
+    for (int u = 0; u < NU; ++u) {
+        const extmcmc_update_t *s = &updates[u];
+        orc_update_t *t = &h->upd[u];
+        if (s->kernel != EXTMCMC_KERNEL_RW_UNIFORM) {
+            set_err("oracle: transition kernel not implemented");
+            oracle_destroy(h);
+            return EXTMCMC_EUNSUPPORTED;
+        }
+        if (s->prior < EXTMCMC_PRIOR_IMPROPER || s->prior > EXTMCMC_PRIOR_UNIFORM) {
+            /* reference: error("logpdf not implemented for prior ...") src/priors.jl:11-13 */
+            set_err("oracle: prior not implemented");
+            oracle_destroy(h);
+            return EXTMCMC_EUNSUPPORTED;
+        }
+        t->kernel = s->kernel; t->n_coords = s->n_coords; t->prior = s->prior;
+        t->n_prior_params = s->n_prior_params; t->adapt = s->adapt;
+        t->coords = xcalloc(s->n_coords, sizeof(int32_t));
+        t->pos = xcalloc(s->n_coords, 1);
+        for (int i = 0; i < s->n_coords; ++i) {
+            t->coords[i] = s->coords[i];
+            t->pos[i] = s->pos ? s->pos[i] : 0;
+            if (s->coords[i] < 0 || s->coords[i] >= p) { set_err("coord out of range"); oracle_destroy(h); return EXTMCMC_EINVAL; }
+            /* UniformRandomWalk asserts all(eps .> 0), random_walk.jl:50 */
+            if (!(s->step[i] > 0.0)) { set_err("eps must be > 0"); oracle_destroy(h); return EXTMCMC_EINVAL; }
+        }
+        for (int i = 0; i < s->n_prior_params && i < 8; ++i) t->prior_params[i] = s->prior_params[i];
+        t->step_len = s->n_coords;
+        t->step0 = xcalloc(t->step_len, sizeof(double));
+        memcpy(t->step0, s->step, t->step_len * sizeof(double));
+        h->step[u] = xcalloc((size_t)C * t->step_len, sizeof(double));
+        for (int64_t c = 0; c < C; ++c) memcpy(h->step[u] + c * t->step_len, t->step0, t->step_len * sizeof(double));
+    }
+    h->theta = xcalloc((size_t)C * p, sizeof(double));
+    h->ll = xcalloc((size_t)C, sizeof(double));
+    h->mean = xcalloc((size_t)C * p, sizeof(double));
+    h->cov = xcalloc((size_t)C * p * p, sizeof(double));
+    h->statN = xcalloc((size_t)C, sizeof(int64_t));
+    h->proposed = xcalloc((size_t)C * NU, sizeof(int64_t));
+    h->accepted = xcalloc((size_t)C * NU, sizeof(int64_t));
+    h->tot_prop = xcalloc((size_t)C * NU, sizeof(int64_t));
+    h->tot_acc = xcalloc((size_t)C * NU, sizeof(int64_t));
+    h->ra_val = xcalloc((size_t)C * NU, sizeof(double));
+    h->ra_iter = xcalloc((size_t)C * NU, sizeof(int64_t));
+    h->acc_ring = xcalloc((size_t)C * NU * h->W, 1);
+    h->acc_tag = xcalloc((size_t)C * NU * h->W, sizeof(int64_t));
+    for (int64_t c = 0; c < C; ++c) {
+        for (int k = 0; k < p; ++k) h->theta[c * p + k] = theta_init[(int64_t)k * C + c];
+        h->ll[c] = -INFINITY; /* StandardLocalSubworkspace: ll = -Inf, src/workspaces.jl:425 */
+        h->statN[c] = 1;      /* GenericChainStats: N = 1, mean = 0, cov = 0, chain_statistics.jl:29-35 */
+    }
+    *out = h;
+    return EXTMCMC_OK;
+}
+
+void oracle_destroy(oracle_t h) {
+    if (!h) return;
+    if (h->upd) for (int u = 0; u < h->NU; ++u) { free(h->upd[u].coords); free(h->upd[u].pos); free(h->upd[u].step0); }
+    if (h->step) for (int u = 0; u < h->NU; ++u) free(h->step[u]);
+    free(h->upd); free(h->step); free(h->obs); free(h->y); free(h->theta); free(h->ll);
+    free(h->mean); free(h->cov); free(h->statN); free(h->proposed); free(h->accepted);
+    free(h->tot_prop); free(h->tot_acc); free(h->ra_val); free(h->ra_iter);
+    free(h->acc_ring); free(h->acc_tag);
+    free(h);
+}
+
+/* ------------------------------------------------------------------------- */
+/* Target law: loglikelihood(P::GsnTargetLaw, observs)                       */
+/*   src/example/gsn_target.jl:23-29 -- ll = 0.0; for obs: ll += logpdf(P.P, obs) */
+/* with P.P = MvNormal(mu, Symmetric(triu(Sigma))) rebuilt by set_parameters! */
+/*   src/example/gsn_target.jl:15-21.                                        */
+/* logpdf(::MvNormal, x) is Distributions.jl (unpinned, absent): published   */
+/* form  c0 - sqmahal/2,  c0 = -(d*log(2pi) + logdet(Sigma))/2,              */
+/* logdet = 2*sum(log(diag(chol))), sqmahal = sum(abs2, L \ (x - mu)).        */
+/* Returns NaN (and *bad = 1) when Sigma is not positive definite; the       */
+/* reference throws PosDefException there.                                   */
+/* ------------------------------------------------------------------------- */
+static const double LOG2PI = 1.8378770664093454835606594728112; /* log(2*pi) */
+
+static double loglik_gsn_1d(const double *x, int64_t n, double mu, double var, int *bad) {
+    if (!(var > 0.0) || !isfinite(var)) { *bad = 1; return NAN; }
+    double s = sqrt(var);                       /* cholesky of the 1x1 Sigma */
+    double c0 = -(1.0 * LOG2PI + 2.0 * log(s)) / 2.0;
+    double ll = 0.0;
+    for (int64_t i = 0; i < n; ++i) {           /* sequential left-to-right sum */
+        double z = (x[i] - mu) / s;             /* L \ (x - mu) */
+        ll += c0 - (z * z) / 2.0;
+    }
+    return ll;
+}
+
+static double loglik_gsn_mv(const double *x, int64_t n, int d, const double *theta, int *bad) {
+    const double *mu = theta;
+    const double *Sg = theta + d; /* column-major d x d; only triu is used (Symmetric(triu(S))) */
+    double L[ORC_MAX_D * ORC_MAX_D];
+    memset(L, 0, sizeof L);
+    /* lower Cholesky factor of the symmetric matrix whose upper triangle is Sg's */
+    for (int j = 0; j < d; ++j) {
+        double s = Sg[j + j * d]; /* A[j][j] */
+        for (int k = 0; k < j; ++k) s -= L[j + k * d] * L[j + k * d];
+        if (!(s > 0.0) || !isfinite(s)) { *bad = 1; return NAN; }
+        double ljj = sqrt(s);
+        L[j + j * d] = ljj;
+        for (int i = j + 1; i < d; ++i) {
+            double a = Sg[j + i * d]; /* A[i][j] = A[j][i] = upper entry (row j, col i) */
+            for (int k = 0; k < j; ++k) a -= L[i + k * d] * L[j + k * d];
+            L[i + j * d] = a / ljj;
+        }
+    }
+    double logdet = 0.0;
+    for (int j = 0; j < d; ++j) logdet += log(L[j + j * d]);
+    logdet = 2.0 * logdet;
+    double c0 = -((double)d * LOG2PI + logdet) / 2.0;
+    double ll = 0.0;
+    for (int64_t i = 0; i < n; ++i) {
+        const double *xi = x + i * d;
+        double z[ORC_MAX_D];
+        double sq = 0.0;
+        for (int r = 0; r < d; ++r) { /* forward substitution L z = x - mu */
+            double a = xi[r] - mu[r];
+            for (int k = 0; k < r; ++k) a -= L[r + k * d] * z[k];
+            z[r] = a / L[r + r * d];
+            sq += z[r] * z[r];
+        }
+        ll += c0 - sq / 2.0;
+    }
+    return ll;
+}
+
+static double law_loglik(const struct oracle_handle *h, const double *theta, int *bad) {
+    if (h->cfg.law == EXTMCMC_LAW_GSN_IID_1D)
+        return loglik_gsn_1d(h->obs, h->n_obs, theta[0], theta[1], bad);
+    return loglik_gsn_mv(h->obs, h->n_obs, h->cfg.obs_dim, theta, bad);
+}
+
+/* ------------------------------------------------------------------------- */
+/* Priors: logpdf(prior, theta_loc) on the update's own coordinates only     */
+/*   src/updates.jl:104, src/run.jl:374-385, src/priors.jl:18-39             */
+/* ------------------------------------------------------------------------- */
+static double log_prior(const orc_update_t *u, const double *th) {
+    int n = u->n_coords;
+    switch (u->prior) {
+    case EXTMCMC_PRIOR_IMPROPER: /* logpdf(::ImproperPrior, th) = 0.0, priors.jl:19 */
+        return 0.0;
+    case EXTMCMC_PRIOR_IMPROPER_POS: { /* -sum(log.(th)), priors.jl:26 */
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) s += log(th[i]);
+        return -s;
+    }
+    case EXTMCMC_PRIOR_NORMAL: { /* StandardPrior(dist), priors.jl:35-39; Normal: -(z^2 + log2pi)/2 - log(s) */
+        double m = u->prior_params[0], sd = u->prior_params[1], s = 0.0;
+        for (int i = 0; i < n; ++i) { double z = (th[i] - m) / sd; s += -(z * z + LOG2PI) / 2.0 - log(sd); }
+        return s;
+    }
+    case EXTMCMC_PRIOR_GAMMA: { /* Gamma(k, scale): -lgamma(k) - k log(scale) + (k-1) log x - x/scale */
+        double k = u->prior_params[0], sc = u->prior_params[1], s = 0.0;
+        for (int i = 0; i < n; ++i) {
+            if (!(th[i] > 0.0)) return -INFINITY;
+            s += -lgamma(k) - k * log(sc) + (k - 1.0) * log(th[i]) - th[i] / sc;
+        }
+        return s;
+    }
+    case EXTMCMC_PRIOR_UNIFORM: { /* Uniform(a, b): -log(b - a) inside, -Inf outside */
+        double a = u->prior_params[0], b = u->prior_params[1], s = 0.0;
+        for (int i = 0; i < n; ++i) {
+            if (!(th[i] >= a && th[i] <= b)) return -INFINITY;
+            s += -log(b - a);
+        }
+        return s;
+    }
+    }
+    return NAN;
+}
+
+/* logpdf(rw::UniformRandomWalk, a, b): sum over i of pos[i] ? -log(2 eps_i) - log(b_i) : 0.0
+ *   src/transition_kernels/random_walk.jl:88-94 (mapreduce, left fold) */
+static double log_q_unif(const orc_update_t *u, const double *eps, const double *to) {
+    double s = 0.0;
+    for (int i = 0; i < u->n_coords; ++i) {
+        double t = u->pos[i] ? (-log(2.0 * eps[i]) - log(to[i])) : 0.0;
+        s = (i == 0) ? t : s + t;
+    }
+    return s;
+}
+
+/* ------------------------------------------------------------------------- */
+/* One schedule element for one chain: the body of __run! src/run.jl:70-82   */
+/* ------------------------------------------------------------------------- */
+typedef struct {
+    double *rec_prop, *rec_exp;
+    double *theta_hist, *prop_hist, *ll_hist, *llp_hist, *llr_hist;
+    uint8_t *acc_hist;
+    int32_t rng_mode, p_u_max;
+} orc_io_t;
+
+static void chain_step(struct oracle_handle *h, int64_t c, const extmcmc_step_t *st,
+                       int64_t s_idx, const orc_io_t *io) {
+    const int32_t p = h->p, NU = h->NU, W = h->W;
+    const int64_t C = h->C;
+    const int32_t u_idx = st->pidx;
+    const orc_update_t *u = &h->upd[u_idx];
+    const int n = u->n_coords;
+    double *theta = h->theta + c * p;
+    double *eps = h->step[u_idx] + c * u->step_len;
+    const uint64_t gchain = (uint64_t)(h->cfg.chain_offset + c);
+
+    /* update_workspaces! src/run.jl:101-112: local state <- global state[coords];
+     * local ll <- ll_history of the previously executed update (here: the carried
+     * ll); on the very first element prev is `nothing` and ll stays -Inf. */
+    double th_loc[64], th_prop[64];
+    for (int i = 0; i < n; ++i) th_loc[i] = theta[u->coords[i]];
+    double ll_cur = (st->prev_pidx < 0) ? -INFINITY : h->ll[c];
+    if (st->prev_pidx < 0) h->ll[c] = -INFINITY;
+
+    /* proposal! src/updates.jl:191-196 + rand(::UniformRandomWalk) random_walk.jl:65-73 */
+    uint32_t j = 0; /* index into this chain-step's uniform substream */
+    if (io->rng_mode == EXTMCMC_RNG_REPLAY) {
+        for (int i = 0; i < n; ++i)
+            th_prop[i] = io->rec_prop[((int64_t)s_idx * io->p_u_max + i) * C + c];
+    } else {
+        for (;;) {
+            for (int i = 0; i < n; ++i) {
+                double r = oracle_uniform(h->cfg.seed, gchain, st->mcmciter, u_idx, j++);
+                /* rand(Uniform(a, b)) = a + (b - a) * rand() with a = -eps, b = eps */
+                double a = -eps[i], b = eps[i];
+                double U = a + (b - a) * r;
+                /* theta .* (exp.(U).*pos .+ 1.0.*.!pos) .+ U.*.!pos, random_walk.jl:72 */
+                th_prop[i] = u->pos[i] ? th_loc[i] * exp(U) : th_loc[i] + U;
+            }
+            /* redraw the whole vector while the prior is exactly -Inf, updates.jl:193-195 */
+            if (!(log_prior(u, th_prop) == -INFINITY)) break;
+            if (j > 60000u) break; /* substream exhausted: keep the -Inf proposal (will be rejected) */
+        }
+    }
+    if (io->rec_prop && io->rng_mode != EXTMCMC_RNG_REPLAY)
+        for (int i = 0; i < n; ++i)
+            io->rec_prop[((int64_t)s_idx * io->p_u_max + i) * C + c] = th_prop[i];
+
+    /* set_proposal! src/run.jl:221-240: full proposal = global state with the
+     * update's coordinates replaced; pushed into P° (gsn_target.jl:15-21) */
+    double full_prop[256];
+    for (int k = 0; k < p; ++k) full_prop[k] = theta[k];
+    for (int i = 0; i < n; ++i) full_prop[u->coords[i]] = th_prop[i];
+
+    /* compute_ll! src/run.jl:251-260 -> loglikelihood(P°, obs) */
+    int bad = 0;
+    double ll_prop = law_loglik(h, full_prop, &bad);
+    if (bad) h->domain_err = 1;
+
+    /* accept_reject! src/run.jl:268-281; strict left-to-right association */
+    double llr = ll_prop - ll_cur;
+    llr = llr + log_q_unif(u, eps, th_loc);   /* ltd(Proposal): theta° -> theta, run.jl:360-367 */
+    llr = llr - log_q_unif(u, eps, th_prop);  /* ltd(Previous): theta -> theta°, run.jl:344-351 */
+    llr = llr + log_prior(u, th_prop);
+    llr = llr - log_prior(u, th_loc);
+    double E;
+    if (io->rng_mode == EXTMCMC_RNG_REPLAY) {
+        E = io->rec_exp[(int64_t)s_idx * C + c];
+    } else {
+        /* rand(Exponential(1.0)), run.jl:278, by inversion of the next uniform */
+        E = -log(oracle_uniform(h->cfg.seed, gchain, st->mcmciter, u_idx, j++));
+        if (io->rec_exp) io->rec_exp[(int64_t)s_idx * C + c] = E;
+    }
+    int accepted = E > -llr; /* NaN llr compares false => reject */
+
+    /* register_accept_reject_results! run.jl:329-335 and set_chain_param! run.jl:312-320 */
+    double ll_new = accepted ? ll_prop : ll_cur;
+    if (accepted) for (int i = 0; i < n; ++i) theta[u->coords[i]] = th_prop[i];
+    h->ll[c] = ll_new;
+    if (io->theta_hist) for (int k = 0; k < p; ++k) io->theta_hist[((int64_t)s_idx * p + k) * C + c] = theta[k];
+    if (io->prop_hist) for (int k = 0; k < p; ++k) io->prop_hist[((int64_t)s_idx * p + k) * C + c] = full_prop[k];
+    if (io->ll_hist) io->ll_hist[(int64_t)s_idx * C + c] = ll_new;
+    if (io->llp_hist) io->llp_hist[(int64_t)s_idx * C + c] = ll_prop;
+    if (io->llr_hist) io->llr_hist[(int64_t)s_idx * C + c] = llr;
+    if (io->acc_hist) io->acc_hist[(int64_t)s_idx * C + c] = (uint8_t)accepted;
+
+    /* update_stats! src/chain_statistics.jl:41-66 (verbatim arithmetic) */
+    {
+        double *mean = h->mean + c * p, *cov = h->cov + c * p * p;
+        int64_t N = h->statN[c];
+        double f_old = (double)(N - 1) / (double)N;
+        double f_mean = (double)N / (double)(N + 1);
+        double f_new = (double)(N + 1) / (double)N;
+        double old_mean[256];
+        for (int k = 0; k < p; ++k) old_mean[k] = mean[k];
+        for (int k = 0; k < p; ++k) mean[k] = old_mean[k] * f_mean + theta[k] / (double)(N + 1);
+        for (int b = 0; b < p; ++b)
+            for (int a = 0; a < p; ++a) {
+                double old_sum_sq = f_old * cov[a + b * p] + old_mean[a] * old_mean[b];
+                double new_sum_sq = old_sum_sq + (theta[a] * theta[b]) / (double)N;
+                cov[a + b * p] = new_sum_sq - f_new * (mean[a] * mean[b]);
+            }
+        int64_t it = st->mcmciter;
+        int64_t *ra_iter = h->ra_iter + c * NU;
+        double *ra_val = h->ra_val + c * NU;
+        /* ra_prev = rolling_ar[max(1, it-1)][pidx]; zeros unless written */
+        int64_t prev_it = it - 1 > 1 ? it - 1 : 1;
+        double ra_prev = (ra_iter[u_idx] == prev_it && prev_it != it) ? ra_val[u_idx] : 0.0;
+        uint8_t *ring = h->acc_ring + ((size_t)c * NU + u_idx) * W;
+        int64_t *tag = h->acc_tag + ((size_t)c * NU + u_idx) * W;
+        int slot = (int)(it % W);
+        int acc_out = 0;
+        /* acceptance_history[it - W] (undef memory in the reference if that update
+         * was excluded at it - W; the restatement reads false there) */
+        if (it > W && tag[slot] == it - W) acc_out = ring[slot];
+        int64_t mn = (int64_t)W < N ? (int64_t)W : N;
+        double ra = (ra_prev * (double)W + (double)(accepted - acc_out)) / (double)mn;
+        ra_val[u_idx] = ra; ra_iter[u_idx] = it;
+        ring[slot] = (uint8_t)accepted; tag[slot] = it;
+        h->statN[c] = N + 1;
+    }
+
+    /* update_adaptation! src/run.jl:136-173 (only the update whose turn it is
+     * registers, run.jl:176-177) -> register!/time_to_update/readjust!
+     * src/transition_kernels/adaptation.jl:273-329 */
+    h->tot_prop[c * NU + u_idx] += 1;
+    h->tot_acc[c * NU + u_idx] += accepted;
+    if (u->adapt.kind == EXTMCMC_ADAPT_UNIF_RW) {
+        int64_t *prop = &h->proposed[c * NU + u_idx], *acc = &h->accepted[c * NU + u_idx];
+        *acc += accepted; *prop += 1;                       /* register! :292-295 */
+        if (*prop >= u->adapt.adapt_every_k_steps) {        /* time_to_update :302-304 */
+            /* compute_delta :312-319 (Int / Int -> Float64 division) */
+            double r = (double)st->mcmciter / (double)u->adapt.adapt_every_k_steps - u->adapt.offset;
+            double delta = u->adapt.scale / sqrt(r > 1.0 ? r : 1.0);
+            double a_r = (*prop == 0) ? 0.0 : (double)*acc / (double)*prop; /* :242-244 */
+            *prop = 0; *acc = 0;                            /* reset! :263-266 */
+            double sgn = (a_r > u->adapt.target_accpt_rate) ? 1.0 : -1.0;
+            for (int i = 0; i < n; ++i) {                   /* compute_eps :326-329 */
+                double e = eps[i] + sgn * delta;
+                e = e < u->adapt.max ? e : u->adapt.max;    /* min(e, max) */
+                e = e > u->adapt.min ? e : u->adapt.min;    /* max(., min) */
+                eps[i] = e;
+            }
+        }
+    }
+}
+
+/* Chains are independent, so the optional thread pool hands out chain ids from
+ * a shared counter; results do not depend on the thread count. */
+typedef struct {
+    struct oracle_handle *h;
+    const extmcmc_step_t *steps;
+    int32_t n_steps;
+    const orc_io_t *io;
+    const double *theta_eval;
+    double *ll_out;
+    int64_t n_eval;
+    int any_bad;
+} run_job_t;
+
+typedef struct {
+    void (*fn)(void *, int64_t);
+    void *arg;
+    int64_t n;
+    int64_t next;
+    pthread_mutex_t mu;
+} pool_t;
+
+static void *pool_main(void *a) {
+    pool_t *pl = a;
+    for (;;) {
+        pthread_mutex_lock(&pl->mu);
+        int64_t c = pl->next < pl->n ? pl->next++ : -1;
+        pthread_mutex_unlock(&pl->mu);
+        if (c < 0) return NULL;
+        pl->fn(pl->arg, c);
+    }
+}
+
+static void parallel_chains(void (*fn)(void *, int64_t), void *arg, int64_t n, int n_threads) {
+    if (n_threads <= 1 || n <= 1) { for (int64_t c = 0; c < n; ++c) fn(arg, c); return; }
+    if (n_threads > 256) n_threads = 256;
+    pool_t pl = {fn, arg, n, 0, PTHREAD_MUTEX_INITIALIZER};
+    pthread_t th[256];
+    int started = 0;
+    for (int t = 0; t < n_threads; ++t) if (pthread_create(&th[started], NULL, pool_main, &pl) == 0) ++started;
+    if (started == 0) pool_main(&pl);
+    for (int t = 0; t < started; ++t) pthread_join(th[t], NULL);
+}
+
+static void run_worker(void *a, int64_t c) {
+    run_job_t *j = a;
+    for (int s = 0; s < j->n_steps; ++s) chain_step(j->h, c, &j->steps[s], s, j->io);
+}
+
+static void loglik_worker(void *a, int64_t c) {
+    run_job_t *j = a;
+    double th[256];
+    for (int k = 0; k < j->h->p; ++k) th[k] = j->theta_eval[(int64_t)k * j->n_eval + c];
+    int bad = 0;
+    j->ll_out[c] = law_loglik(j->h, th, &bad);
+    if (bad) j->any_bad = 1;
+}
+
+int32_t oracle_run_block(oracle_t h, const extmcmc_step_t *steps, int32_t n_steps,
+                         int32_t rng_mode, int32_t p_u_max,
+                         double *rec_proposals, double *rec_exp,
+                         double *theta_hist, double *theta_prop_hist,
+                         double *ll_hist, double *ll_prop_hist,
+                         uint8_t *accepted_hist, double *llr_hist, int32_t n_threads) {
+    if (!h || !steps) { set_err("null argument"); return EXTMCMC_EINVAL; }
+    if (rng_mode == EXTMCMC_RNG_REPLAY && (!rec_proposals || !rec_exp)) { set_err("replay needs buffers"); return EXTMCMC_EINVAL; }
+    for (int s = 0; s < n_steps; ++s) {
+        if (steps[s].pidx < 0 || steps[s].pidx >= h->NU) { set_err("pidx out of range"); return EXTMCMC_EINVAL; }
+        if (h->upd[steps[s].pidx].n_coords > p_u_max && (rec_proposals != NULL)) { set_err("p_u_max too small"); return EXTMCMC_EINVAL; }
+    }
+    orc_io_t io = {rec_proposals, rec_exp, theta_hist, theta_prop_hist, ll_hist,
+                   ll_prop_hist, llr_hist, accepted_hist, rng_mode, p_u_max};
+    run_job_t job = {h, steps, n_steps, &io, NULL, NULL, 0, 0};
+    parallel_chains(run_worker, &job, h->C, n_threads);
+    return h->domain_err ? EXTMCMC_EDOMAIN : EXTMCMC_OK;
+}
+
+int32_t oracle_get_state(oracle_t h, double *theta, double *ll) {
+    for (int64_t c = 0; c < h->C; ++c) {
+        if (theta) for (int k = 0; k < h->p; ++k) theta[(int64_t)k * h->C + c] = h->theta[c * h->p + k];
+        if (ll) ll[c] = h->ll[c];
+    }
+    return EXTMCMC_OK;
+}
+
+int32_t oracle_get_stats(oracle_t h, double *mean, double *cov, double *rolling_ar,
+                         int64_t *n_accept, int64_t *n_prop) {
+    int64_t C = h->C; int p = h->p, NU = h->NU;
+    for (int64_t c = 0; c < C; ++c) {
+        if (mean) for (int k = 0; k < p; ++k) mean[(int64_t)k * C + c] = h->mean[c * p + k];
+        if (cov) for (int k = 0; k < p * p; ++k) cov[(int64_t)k * C + c] = h->cov[c * p * p + k];
+        for (int u = 0; u < NU; ++u) {
+            if (rolling_ar) rolling_ar[(int64_t)u * C + c] = h->ra_val[c * NU + u];
+            if (n_accept) n_accept[(int64_t)u * C + c] = h->tot_acc[c * NU + u];
+            if (n_prop) n_prop[(int64_t)u * C + c] = h->tot_prop[c * NU + u];
+        }
+    }
+    return EXTMCMC_OK;
+}
+
+int32_t oracle_get_eps(oracle_t h, int32_t u, double *eps) {
+    if (u < 0 || u >= h->NU) return EXTMCMC_EINVAL;
+    int L = h->upd[u].step_len;
+    for (int64_t c = 0; c < h->C; ++c)
+        for (int i = 0; i < L; ++i) eps[(int64_t)i * h->C + c] = h->step[u][c * L + i];
+    return EXTMCMC_OK;
+}
+
+int32_t oracle_loglik(oracle_t h, const double *theta, int64_t n_eval, double *ll_out,
+                      int32_t n_threads) {
+    run_job_t job = {h, NULL, 0, NULL, theta, ll_out, n_eval, 0};
+    parallel_chains(loglik_worker, &job, n_eval, n_threads);
+    return job.any_bad ? EXTMCMC_EDOMAIN : EXTMCMC_OK;
+}

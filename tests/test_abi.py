@@ -1,0 +1,78 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/extmcmc.h declares;
+without a device the product fails loudly (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import extensiblemcmc_jl_b200 as em
+from extensiblemcmc_jl_b200 import _abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "extmcmc.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(extmcmc_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    lib = _abi.load()
+    names = _declared()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/extmcmc.h but not exported"
+        assert n in _abi.SIGNATURES, f"{n} has no ctypes signature"
+    assert set(_abi.SIGNATURES) == set(names)
+    assert lib.extmcmc_abi_version() == _abi.ABI_VERSION
+
+
+def test_struct_sizes_match_the_header():
+    # compile-time truth: sizes computed by gcc for the same header
+    import subprocess, tempfile
+    prog = r'''
+    #include <stdio.h>
+    #include "extmcmc.h"
+    int main(void){ printf("%zu %zu %zu %zu\n", sizeof(extmcmc_config_t), sizeof(extmcmc_update_t),
+                           sizeof(extmcmc_step_t), sizeof(extmcmc_adapt_t)); return 0; }'''
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(prog)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "t.c"), "-o", os.path.join(d, "t")])
+        out = subprocess.check_output([os.path.join(d, "t")]).split()
+    assert [int(v) for v in out] == [C.sizeof(_abi.Config), C.sizeof(_abi.Update), C.sizeof(_abi.Step), C.sizeof(_abi.Adapt)]
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-device failure mode")
+def test_no_device_fails_loudly():
+    mcmc = em.MCMC([em.RandomWalkUpdate(em.UniformRandomWalk([1.0]), [1])],
+                   backend=em.CUDAMCMCBackend(n_chains=4))
+    data = dict(P=em.GsnTargetLaw([0.0]), obs=np.zeros(10))
+    with pytest.raises(_abi.ExtMCMCError) as ei:
+        em.run_(mcmc, 10, data, [0.0, 1.0])
+    assert ei.value.code == _abi.ECUDA
+
+
+def test_unsupported_configurations_raise():
+    class MyLaw:
+        pass
+    with pytest.raises(NotImplementedError):
+        em.init_global_workspace(em.CUDAMCMCBackend(), 10, [], dict(P=MyLaw(), obs=[0.0]), [0.0])
+    with pytest.raises(NotImplementedError):
+        em.init_global_workspace(em.GenericMCMCBackend(), 10, [], dict(P=em.GsnTargetLaw([0.0]), obs=[0.0]), [0.0, 1.0])
+    with pytest.raises(TypeError):
+        em.MCMC([em.RandomWalkUpdate(em.UniformRandomWalk([1.0]), [1])])
+    with pytest.raises(NotImplementedError):
+        em.StandardPrior(object()).to_abi()
+    with pytest.raises(NotImplementedError):
+        em.MALAUpdate().to_abi(2)

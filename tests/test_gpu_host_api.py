@@ -1,0 +1,99 @@
+"""The reference-facing host API (MCMC / run! / callbacks / workspaces) on the GPU path."""
+import io
+import os
+
+import numpy as np
+import pytest
+
+import extensiblemcmc_jl_b200 as em
+from tests.parity import GpuSession
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(n_chains, M, **bk):
+    rng = np.random.default_rng(10)
+    x = 1.0 + 2.0 * rng.standard_normal(500)
+    mk = lambda: em.AdaptationUnifRW([0.0], adapt_every_k_steps=20, scale=0.05)
+    ups = [em.RandomWalkUpdate(em.UniformRandomWalk([0.5]), [1], adpt=mk()),
+           em.RandomWalkUpdate(em.UniformRandomWalk([0.5], [True]), [2], prior=em.ImproperPosPrior(), adpt=mk())]
+    mcmc = em.MCMC(ups, backend=em.CUDAMCMCBackend(n_chains=n_chains, seed=4, **bk))
+    return mcmc, ups, x
+
+
+def test_reference_smoke_shape():
+    # the reference's own "mcmc" testset shape (test/runtests.jl:87-114), d = 1 variant:
+    # 2 single-site uniform walks, 1000 iterations, one chain, no assertion on the values
+    mcmc, ups, x = _setup(1, 1000)
+    ws, lws = em.run_(mcmc, 1000, dict(P=em.GsnTargetLaw([0.0]), obs=x[:10]), [0.0, 1.0], [])
+    assert ws.sub_ws.state_history.shape == (1000, 2, 2, 1)
+    assert not np.isnan(ws.sub_ws.state_history).any()
+    assert len(lws) == 2 and lws[0].acceptance_history.shape == (1000, 1)
+    assert lws[0].acceptance_history[0, 0]                       # first proposal always accepted
+    ws.close()
+
+
+def test_run_matches_raw_abi_and_block_length_is_irrelevant():
+    outs = []
+    for bl in (7, 64):
+        mcmc, ups, x = _setup(32, 50, block_len=bl)
+        ws, lws = em.run_(mcmc, 50, dict(P=em.GsnTargetLaw([0.0]), obs=x), [0.0, 1.0])
+        outs.append((ws.sub_ws.state_history.copy(), lws[1].sub_ws.ll_history.copy(),
+                     lws[0].acceptance_history.copy(), ws.stats()))
+        ws.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    assert np.array_equal(outs[0][3]["mean"], outs[1][3]["mean"])
+    s = GpuSession(em.GsnTargetLaw([0.0]), ups, x, [0.0, 1.0], 32, seed=4, n_steps_hint=100)
+    r = s.run(list(em.MCMCSchedule(50, 2)))
+    assert np.array_equal(r["theta"].reshape(50, 2, 2, 32), outs[0][0])
+    assert np.array_equal(r["accepted"].reshape(50, 2, 32)[:, 0].astype(bool), outs[0][2])
+    s.close()
+
+
+def test_callbacks_and_csv(tmp_path):
+    mcmc, ups, x = _setup(3, 40, block_len=16)
+    buf = io.StringIO()
+    cbs = [em.SavingCallback(save_at_iters=[10, 25], filename="chain", path=str(tmp_path)),
+           em.REPLCallback(print_every_k_iter=20, file=buf)]
+    seen = []
+
+    class Probe(em.Callback):
+        def check_if_execute(self, step, flag):
+            return isinstance(flag, em.PostMCMCStep) and step.mcmciter == 13 and step.pidx == 1
+        def execute_(self, ws, lws, step, flag):
+            # at this point every earlier step must be mirrored on the host
+            h = ws.sub_ws.state_history
+            seen.append((not np.isnan(h[:12]).any(), not np.isnan(h[12, 0]).any(), np.isnan(h[12, 1]).all()))
+    ws, lws = em.run_(mcmc, 40, dict(P=em.GsnTargetLaw([0.0]), obs=x), [0.0, 1.0], cbs + [Probe()])
+    assert seen == [(True, True, True)]
+    out = buf.getvalue()
+    assert "Initializing an MCMC chain" in out and "20.1 RandomWalkUpdate" in out and "40.2" in out
+    files = sorted(os.listdir(tmp_path))
+    assert files == ["chain_chain0.csv", "chain_chain1.csv", "chain_chain2.csv"]
+    rows = open(tmp_path / "chain_chain1.csv").read().strip().split("\n")
+    # iterations 1..9 (save at 10), 10..24 (save at 25), then the end-of-run save from the last
+    # save point to M - 1 (callbacks.jl:223,234-239)
+    its = [int(r.split(",")[0]) for r in rows]
+    assert its[0] == 1 and its[-1] == 39 and len(rows) == 2 * 39
+    f = rows[0].split("!")
+    assert f[0].strip() == "1, 1," and len(f) == 6
+    th = [float(v) for v in f[1].split(",") if v.strip()]
+    assert th == list(ws.sub_ws.state_history[0, 0, :, 1])
+    assert f[5].strip() in ("true,", "false,")
+    ws.close()
+
+
+def test_reschedule_from_a_callback():
+    mcmc, ups, x = _setup(8, 12, block_len=5)
+
+    class Drop(em.Callback):
+        def check_if_execute(self, step, flag):
+            return isinstance(flag, em.PostMCMCStep) and step.mcmciter == 4 and step.pidx == 1
+        def execute_(self, ws, lws, step, flag):
+            em.reschedule_(mcmc.schedule, 0, [2])
+    ws, lws = em.run_(mcmc, 12, dict(P=em.GsnTargetLaw([0.0]), obs=x), [0.0, 1.0], [Drop()])
+    h = ws.sub_ws.state_history
+    # update 2 still runs at (4, 2) (the next state was already computed, schedule.jl:56-66)
+    assert not np.isnan(h[3, 1]).any() and np.isnan(h[4:, 1]).all() and not np.isnan(h[:, 0]).any()
+    assert (ws.stats()["n_prop"][:, 0] == [12, 4]).all()
+    ws.close()
