@@ -112,6 +112,8 @@ SIGNATURES = {
     "extmcmc_sync": (C.c_int32, [Handle]),
     "extmcmc_get_state": (C.c_int32, [Handle, c_double_p, c_double_p]),
     "extmcmc_get_history": (C.c_int32, [Handle, C.c_int64, C.c_int64, c_double_p, c_double_p, c_double_p, c_double_p, c_uint8_p]),
+    "extmcmc_history_fetch_begin": (C.c_int32, [Handle, C.c_int64, C.c_int64]),
+    "extmcmc_history_fetch_end": (C.c_int32, [Handle, c_double_p, c_double_p, c_double_p, c_double_p, c_uint8_p]),
     "extmcmc_get_stats": (C.c_int32, [Handle, c_double_p, c_double_p, c_double_p, c_int64_p, c_int64_p]),
     "extmcmc_get_eps": (C.c_int32, [Handle, C.c_int32, c_double_p]),
     "extmcmc_eval_loglik": (C.c_int32, [Handle, c_double_p]),

@@ -97,6 +97,13 @@ struct extmcmc_handle {
     double *flush_buf = nullptr;
     int64_t flush_n = 0;
     double *scratch_ll = nullptr;  // [C]
+    // asynchronous history fetch
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t fetch_ready = nullptr, fetch_done = nullptr;
+    unsigned char *stage = nullptr;   // pinned
+    size_t stage_cap = 0;
+    int64_t fetch_lo = 0, fetch_hi = 0;
+    bool fetch_active = false;
     // multi-rank
     ncclComm_t comm = nullptr;
     int64_t *n_obs_dev = nullptr;
@@ -414,6 +421,9 @@ int32_t extmcmc_create(const extmcmc_config_t *cfg, extmcmc_t *out) {
     }
     h->num_sms = prop.multiProcessorCount;
     CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CKC(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    CKC(cudaEventCreateWithFlags(&h->fetch_ready, cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&h->fetch_done, cudaEventDisableTiming));
     CKC(cudaEventCreate(&h->t0));
     CKC(cudaEventCreate(&h->t1));
     for (auto &sl : h->slot) CKC(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
@@ -473,6 +483,10 @@ int32_t extmcmc_destroy(extmcmc_t h) {
     for (auto &ev : h->ev_free) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     if (h->t0) cudaEventDestroy(h->t0);
     if (h->t1) cudaEventDestroy(h->t1);
+    if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+    if (h->fetch_ready) cudaEventDestroy(h->fetch_ready);
+    if (h->fetch_done) cudaEventDestroy(h->fetch_done);
+    if (h->stage) cudaFreeHost(h->stage);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return EXTMCMC_OK;
@@ -609,6 +623,7 @@ int32_t extmcmc_set_state(extmcmc_t h, const double *theta) {
         CK(h, cudaMemset(t.acc_ring, 0, (size_t)d.W * C));
     }
     h->seq_next = 0;
+    if (h->fetch_active) { cudaEventSynchronize(h->fetch_done); h->fetch_active = false; }
     std::fill(h->ra_iter.begin(), h->ra_iter.end(), 0);
     std::fill(h->acc_tag.begin(), h->acc_tag.end(), 0);
     h->state_set = true;
@@ -695,6 +710,70 @@ int32_t extmcmc_get_history(extmcmc_t h, int64_t seq_lo, int64_t seq_hi, double 
         s += n;
         row += n;
     }
+    return EXTMCMC_OK;
+}
+
+// rows [lo, hi) of a ring array with row_bytes per row -> dst (contiguous), on stream st
+static int32_t copy_ring_rows(extmcmc_t h, void *dst, const void *ring, size_t row_bytes, int64_t lo,
+                              int64_t hi, cudaStream_t st) {
+    const int64_t H = h->d.H;
+    int64_t row = 0;
+    for (int64_t s = lo; s < hi;) {
+        const int64_t slot = s % H;
+        const int64_t n = std::min<int64_t>(hi - s, H - slot);
+        CK(h, cudaMemcpyAsync((char *)dst + row * row_bytes, (const char *)ring + slot * row_bytes,
+                              (size_t)n * row_bytes, cudaMemcpyDeviceToHost, st));
+        s += n;
+        row += n;
+    }
+    return EXTMCMC_OK;
+}
+
+int32_t extmcmc_history_fetch_begin(extmcmc_t h, int64_t seq_lo, int64_t seq_hi) {
+    if (!h) return EXTMCMC_EINVAL;
+    if (h->fetch_active) return fail(h, EXTMCMC_EINVAL, "a history fetch is already outstanding");
+    if (seq_lo < 0 || seq_hi < seq_lo || seq_hi > h->seq_next) return fail(h, EXTMCMC_EINVAL, "bad history range");
+    if (seq_lo < h->seq_next - h->d.H) return fail(h, EXTMCMC_ESTALE, "history rows already overwritten");
+    CK(h, cudaSetDevice(h->cfg.device));
+    const DevState &d = h->d;
+    const size_t n = (size_t)(seq_hi - seq_lo), C = (size_t)d.C, rp = (size_t)d.p * C * 8;
+    const size_t need = n * (2 * rp + 2 * C * 8 + C);
+    if (need > h->stage_cap) {
+        CK(h, cudaStreamSynchronize(h->copy_stream));
+        if (h->stage) cudaFreeHost(h->stage);
+        h->stage = nullptr; h->stage_cap = 0;
+        CK(h, cudaMallocHost(&h->stage, need));
+        h->stage_cap = need;
+    }
+    CK(h, cudaEventRecord(h->fetch_ready, h->stream));
+    CK(h, cudaStreamWaitEvent(h->copy_stream, h->fetch_ready, 0));
+    unsigned char *st = h->stage;
+    int32_t rc;
+    if ((rc = copy_ring_rows(h, st, d.h_theta, rp, seq_lo, seq_hi, h->copy_stream))) return rc;
+    if ((rc = copy_ring_rows(h, st + n * rp, d.h_prop, rp, seq_lo, seq_hi, h->copy_stream))) return rc;
+    if ((rc = copy_ring_rows(h, st + 2 * n * rp, d.h_ll, C * 8, seq_lo, seq_hi, h->copy_stream))) return rc;
+    if ((rc = copy_ring_rows(h, st + 2 * n * rp + n * C * 8, d.h_llp, C * 8, seq_lo, seq_hi, h->copy_stream))) return rc;
+    if ((rc = copy_ring_rows(h, st + 2 * n * rp + 2 * n * C * 8, d.h_acc, C, seq_lo, seq_hi, h->copy_stream))) return rc;
+    CK(h, cudaEventRecord(h->fetch_done, h->copy_stream));
+    h->fetch_lo = seq_lo; h->fetch_hi = seq_hi;
+    h->fetch_active = true;
+    return EXTMCMC_OK;
+}
+
+int32_t extmcmc_history_fetch_end(extmcmc_t h, double *theta, double *theta_prop, double *ll,
+                                  double *ll_prop, uint8_t *accepted) {
+    if (!h) return EXTMCMC_EINVAL;
+    if (!h->fetch_active) return fail(h, EXTMCMC_EINVAL, "no history fetch outstanding");
+    CK(h, cudaEventSynchronize(h->fetch_done));
+    h->fetch_active = false;
+    const DevState &d = h->d;
+    const size_t n = (size_t)(h->fetch_hi - h->fetch_lo), C = (size_t)d.C, rp = (size_t)d.p * C * 8;
+    const unsigned char *st = h->stage;
+    if (theta) std::memcpy(theta, st, n * rp);
+    if (theta_prop) std::memcpy(theta_prop, st + n * rp, n * rp);
+    if (ll) std::memcpy(ll, st + 2 * n * rp, n * C * 8);
+    if (ll_prop) std::memcpy(ll_prop, st + 2 * n * rp + n * C * 8, n * C * 8);
+    if (accepted) std::memcpy(accepted, st + 2 * n * rp + 2 * n * C * 8, n * C);
     return EXTMCMC_OK;
 }
 

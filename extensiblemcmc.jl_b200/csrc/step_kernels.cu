@@ -144,13 +144,44 @@ __global__ void __launch_bounds__(256) prepare_current_kernel(DevState d) {
     law_prepare(d, c, d.theta + c, d.C);
 }
 
-// ssum[c] = sum over segments, fixed order.
-__global__ void __launch_bounds__(256) reduce_partials_kernel(DevState d) {
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= d.C) return;
+// Fixed-order reduction of partial[S][C] over the segments.  A 256-thread CTA owns 32
+// chains; slice j (0..7) adds segments j, j+8, j+16, ... (8 independent loads in flight per
+// thread), then the 8 slice sums are combined in slice order.  The order depends only on
+// S, never on timing, so results are reproducible run to run.
+constexpr int kRedChains = 32, kRedSlices = 8;
+
+__device__ __forceinline__ double reduce_segments(const DevState &d, double *sh /*[8][32]*/) {
+    const int lane_c = threadIdx.x & (kRedChains - 1);
+    const int slice = threadIdx.x >> 5;
+    const int64_t c = (int64_t)blockIdx.x * kRedChains + lane_c;
     double s = 0.0;
-    for (int i = 0; i < d.S; ++i) s += d.partial[(int64_t)i * d.C + c];
-    d.ssum[c] = s;
+    if (c < d.C) {
+        const double *p = d.partial + c;
+        int i = slice;
+        for (; i + 3 * kRedSlices < d.S; i += 4 * kRedSlices) {
+            const double a0 = p[(int64_t)i * d.C];
+            const double a1 = p[(int64_t)(i + kRedSlices) * d.C];
+            const double a2 = p[(int64_t)(i + 2 * kRedSlices) * d.C];
+            const double a3 = p[(int64_t)(i + 3 * kRedSlices) * d.C];
+            s += a0; s += a1; s += a2; s += a3;
+        }
+        for (; i < d.S; i += kRedSlices) s += p[(int64_t)i * d.C];
+    }
+    sh[slice * kRedChains + lane_c] = s;
+    __syncthreads();
+    double tot = 0.0;
+    if (slice == 0) {
+#pragma unroll
+        for (int j = 0; j < kRedSlices; ++j) tot += sh[j * kRedChains + lane_c];
+    }
+    return tot;  // valid in threads with slice == 0
+}
+
+__global__ void __launch_bounds__(256) reduce_partials_kernel(DevState d) {
+    __shared__ double sh[kRedSlices * kRedChains];
+    const double tot = reduce_segments(d, sh);
+    const int64_t c = (int64_t)blockIdx.x * kRedChains + (threadIdx.x & (kRedChains - 1));
+    if ((threadIdx.x >> 5) == 0 && c < d.C) d.ssum[c] = tot;
 }
 
 __global__ void __launch_bounds__(256) finalize_loglik_kernel(DevState d, double *ll_out) {
@@ -167,20 +198,20 @@ __global__ void __launch_bounds__(256) finalize_loglik_kernel(DevState d, double
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k) {
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= d.C) return;
+    // 256 threads = 32 chains x 8 reduction slices; slice 0 carries on with the chain
+    __shared__ double sh[kRedSlices * kRedChains];
+    const int64_t c = (int64_t)blockIdx.x * kRedChains + (threadIdx.x & (kRedChains - 1));
+    double S;
+    if (d.use_ssum) {
+        S = c < d.C ? d.ssum[c] : 0.0;
+    } else {
+        S = reduce_segments(d, sh);
+    }
+    if ((threadIdx.x >> 5) != 0 || c >= d.C) return;
     const StepDesc sd = descs[k];
     const DevUpdate &u = d.upd[sd.pidx];
     const int n = u.n_coords;
     const int64_t C = d.C;
-
-    double S;
-    if (d.use_ssum) {
-        S = d.ssum[c];
-    } else {
-        S = 0.0;
-        for (int i = 0; i < d.S; ++i) S += d.partial[(int64_t)i * C + c];
-    }
     const double ll_prop = law_finalize(d, c, S);
     // update_workspaces! (run.jl:101-112): ll of the previously executed update; on the
     // very first element it is still the initial -Inf (workspaces.jl:425)
@@ -350,14 +381,15 @@ static inline int blocks_for(int64_t C) { return (int)((C + 255) / 256); }
 void launch_propose(const DevState &d, const StepDesc *descs, int k, cudaStream_t st) {
     propose_kernel<<<blocks_for(d.C), 256, 0, st>>>(d, descs, k);
 }
+static inline int red_blocks_for(int64_t C) { return (int)((C + kRedChains - 1) / kRedChains); }
 void launch_accept(const DevState &d, const StepDesc *descs, int k, cudaStream_t st) {
-    accept_kernel<<<blocks_for(d.C), 256, 0, st>>>(d, descs, k);
+    accept_kernel<<<red_blocks_for(d.C), 256, 0, st>>>(d, descs, k);
 }
 void launch_prepare_current(const DevState &d, cudaStream_t st) {
     prepare_current_kernel<<<blocks_for(d.C), 256, 0, st>>>(d);
 }
 void launch_reduce_partials(const DevState &d, cudaStream_t st) {
-    reduce_partials_kernel<<<blocks_for(d.C), 256, 0, st>>>(d);
+    reduce_partials_kernel<<<red_blocks_for(d.C), 256, 0, st>>>(d);
 }
 void launch_finalize_loglik(const DevState &d, double *ll_out, cudaStream_t st) {
     finalize_loglik_kernel<<<blocks_for(d.C), 256, 0, st>>>(d, ll_out);

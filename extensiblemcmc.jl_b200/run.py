@@ -34,7 +34,9 @@ def run_(mcmc, num_mcmc_steps, data, theta_init, callbacks=(), **kwargs):
 
 
 def _flush(ws, local_wss, block):
-    """Ship one block of schedule elements to the device and mirror its history rows."""
+    """Ship one block of schedule elements to the device (asynchronous) and start the
+    copy-back of its history rows; while the GPU runs it, the previous block's rows are
+    moved from the pinned staging area into the host histories."""
     if not block:
         return
     n = len(block)
@@ -45,44 +47,61 @@ def _flush(ws, local_wss, block):
         arr[k].pidx = s.pidx - 1
         arr[k].prev_pidx = (s.prev_pidx - 1) if s.prev_pidx is not None else -1
     ws._ck(ws.lib.extmcmc_run_block(ws.handle, arr, n))
-    ws.pending.append((ws.seq_launched, list(block)))
+    seq_lo = ws.seq_launched
     ws.seq_launched += n
+    if ws.keep_history:
+        _finish_fetch(ws, local_wss)                       # rows of the previous block
+        ws._ck(ws.lib.extmcmc_history_fetch_begin(ws.handle, seq_lo, seq_lo + n))
+        ws.fetching = list(block)
+
+
+def _finish_fetch(ws, local_wss):
+    block = ws.fetching
+    if block is None:
+        return
+    ws.fetching = None
+    lib, n, p, Cn, NU = ws.lib, len(block), ws.p, ws.C, ws.NU
+    it = np.fromiter((s.mcmciter - 1 for s in block), dtype=np.int64, count=n)
+    pj = np.fromiter((s.pidx - 1 for s in block), dtype=np.int64, count=n)
+    flat = it * NU + pj
+    sh, sph = ws.sub_ws.state_history, ws.sub_ws.state_proposal_history
+    if np.array_equal(flat, flat[0] + np.arange(n)):
+        # dense block: the rows are consecutive in the [M][NU] host arrays -- copy straight in
+        f0 = int(flat[0])
+        sl = lambda a: a.reshape((-1,) + a.shape[2:])[f0:f0 + n]
+        th, thp, l, lp, acc = sl(sh), sl(sph), sl(ws.ll_all), sl(ws.llp_all), sl(ws.acc_all)
+        ws._ck(lib.extmcmc_history_fetch_end(ws.handle, _abi.dptr(th), _abi.dptr(thp), _abi.dptr(l),
+                                             _abi.dptr(lp), acc.ctypes.data_as(_abi.c_uint8_p)))
+    else:
+        th = np.empty((n, p, Cn)); thp = np.empty((n, p, Cn))
+        l = np.empty((n, Cn)); lp = np.empty((n, Cn))
+        acc = np.empty((n, Cn), dtype=np.uint8)
+        ws._ck(lib.extmcmc_history_fetch_end(ws.handle, _abi.dptr(th), _abi.dptr(thp), _abi.dptr(l),
+                                             _abi.dptr(lp), acc.ctypes.data_as(_abi.c_uint8_p)))
+        sh[it, pj] = th
+        sph[it, pj] = thp
+        ws.ll_all[it, pj] = l
+        ws.llp_all[it, pj] = lp
+        ws.acc_all[it, pj] = acc
+    ws.executed[it, pj] = True
+    # "current" values of every local workspace = its last executed step in this block
+    last = {}
+    for k, s in enumerate(block):
+        last[s.pidx - 1] = k
+    for j, k in last.items():
+        lw = local_wss[j]
+        idx = np.asarray(ws.updates[j].coords) - 1
+        lw.sub_ws.state[:] = th[k][idx]
+        lw.sub_ws_prop.state[:] = thp[k][idx]
+        lw.sub_ws.ll[0] = l[k]
+        lw.sub_ws_prop.ll[0] = lp[k]
+    ws.sub_ws.state = np.array(th[n - 1])
 
 
 def _drain(ws, local_wss):
-    """Copy the history rows of all launched blocks back (blocks until they finished)."""
-    lib = ws.lib
-    for seq_lo, block in ws.pending:
-        n = len(block)
-        if ws.keep_history:
-            p, Cn = ws.p, ws.C
-            th = np.empty((n, p, Cn)); thp = np.empty((n, p, Cn))
-            l = np.empty((n, Cn)); lp = np.empty((n, Cn))
-            acc = np.empty((n, Cn), dtype=np.uint8)
-            ws._ck(lib.extmcmc_get_history(ws.handle, seq_lo, seq_lo + n, _abi.dptr(th), _abi.dptr(thp),
-                                           _abi.dptr(l), _abi.dptr(lp), acc.ctypes.data_as(_abi.c_uint8_p)))
-            it = np.fromiter((s.mcmciter - 1 for s in block), dtype=np.int64, count=n)
-            pj = np.fromiter((s.pidx - 1 for s in block), dtype=np.int64, count=n)
-            ws.sub_ws.state_history[it, pj] = th
-            ws.sub_ws.state_proposal_history[it, pj] = thp
-            for j in np.unique(pj):
-                m = pj == j
-                lw = local_wss[j]
-                lw.sub_ws.ll_history[it[m], 0] = l[m]
-                lw.sub_ws_prop.ll_history[it[m], 0] = lp[m]
-                lw.acceptance_history[it[m]] = acc[m].astype(bool)
-            last = {}
-            for k, s in enumerate(block):
-                last[s.pidx - 1] = k
-            for j, k in last.items():
-                lw = local_wss[j]
-                idx = np.asarray(ws.updates[j].coords) - 1
-                lw.sub_ws.state[:] = th[k][idx]
-                lw.sub_ws_prop.state[:] = thp[k][idx]
-                lw.sub_ws.ll[0] = l[k]
-                lw.sub_ws_prop.ll[0] = lp[k]
-            ws.sub_ws.state = th[-1].copy()
-    ws.pending.clear()
+    """Host-visible point: every launched step has finished and is mirrored on the host."""
+    if ws.keep_history:
+        _finish_fetch(ws, local_wss)
     ws.sync()              # raises on a domain error (the reference would have thrown)
     if not ws.keep_history:
         ws.refresh_state()
@@ -92,7 +111,7 @@ def __run_(global_ws, local_wss, updates, schedule, callbacks):
     """__run!(global_ws, local_wss, updates, schedule, callbacks) -- run.jl:64-83."""
     ws = global_ws
     ws.updates = updates
-    ws.pending = []
+    ws.fetching = None
     ws.seq_launched = 0
     block = []
     for step in schedule:
@@ -111,7 +130,9 @@ def __run_(global_ws, local_wss, updates, schedule, callbacks):
                 cb.execute_(ws, local_wss, step, POSTSTEP)
         elif len(block) >= ws.block_len:
             _flush(ws, local_wss, block); block = []
-            if len(ws.pending) >= 2:          # ring holds two blocks: drain the older one(s)
-                _drain(ws, local_wss)
     _flush(ws, local_wss, block)
     _drain(ws, local_wss)
+    if ws.keep_history and not ws.executed.all():
+        never = ~ws.executed
+        ws.sub_ws.state_history[never] = np.nan
+        ws.sub_ws.state_proposal_history[never] = np.nan

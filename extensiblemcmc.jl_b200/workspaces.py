@@ -71,8 +71,11 @@ class _GlobalSub:
         self.data = data
         self.state = None                                     # [p, C], refreshed at block ends
         if keep:
-            self.state_history = np.full((M, NU, p, C), np.nan)
-            self.state_proposal_history = np.full((M, NU, p, C), np.nan)
+            # rows are written block by block as they arrive from the device; rows of
+            # schedule elements that never ran are NaN-filled at the end of run_ (the
+            # reference leaves them `undef`, src/workspaces.jl:171)
+            self.state_history = np.empty((M, NU, p, C))
+            self.state_proposal_history = np.empty((M, NU, p, C))
         else:
             self.state_history = self.state_proposal_history = None
         self.stats = None
@@ -156,7 +159,13 @@ class CUDAGlobalWorkspace(GlobalWorkspace):
         self.keep_history = backend.history == "full"
         self.sub_ws = _GlobalSub(self.M, self.NU, self.p, self.C, data, self.keep_history)
         self.sub_ws.state = self.theta_init.copy()
-        self.seq_done = 0          # executed update steps already mirrored on the host
+        if self.keep_history:
+            # one contiguous array per quantity, [M][NU][C]; the local workspaces hold views
+            self.ll_all = np.zeros((self.M, self.NU, self.C))            # workspaces.jl:426 (zeros)
+            self.llp_all = np.zeros((self.M, self.NU, self.C))
+            self.acc_all = np.zeros((self.M, self.NU, self.C), dtype=np.uint8)
+            self.executed = np.zeros((self.M, self.NU), dtype=bool)
+        self._n_local = 0
         self.local_wss = None
 
     # ---- plumbing ----------------------------------------------------------------
@@ -225,10 +234,10 @@ class DeviceGeneratedObs:
 class _LocalSub:
     """Counterpart of StandardLocalSubworkspace (src/workspaces.jl:413-431)."""
 
-    def __init__(self, p_u, C, M, keep):
+    def __init__(self, p_u, C, ll_hist_view):
         self.state = np.full((p_u, C), np.nan)
         self.ll = np.full((1, C), -np.inf)                      # workspaces.jl:425
-        self.ll_history = np.zeros((M, 1, C)) if keep else None  # workspaces.jl:426
+        self.ll_history = ll_hist_view                          # [M, 1, C] view (workspaces.jl:426)
 
 
 class CUDALocalWorkspace(LocalWorkspace):
@@ -237,12 +246,14 @@ class CUDALocalWorkspace(LocalWorkspace):
     def __init__(self, updt, global_ws, M):
         p_u = len(updt.coords)
         keep = global_ws.keep_history
-        self.sub_ws = _LocalSub(p_u, global_ws.C, M, keep)
-        self.sub_ws_prop = _LocalSub(p_u, global_ws.C, M, keep)         # sub_ws°
+        j = global_ws._n_local
+        global_ws._n_local += 1
+        self.sub_ws = _LocalSub(p_u, global_ws.C, global_ws.ll_all[:, j:j + 1] if keep else None)
+        self.sub_ws_prop = _LocalSub(p_u, global_ws.C, global_ws.llp_all[:, j:j + 1] if keep else None)  # sub_ws°
         idx = np.asarray(updt.coords) - 1
         self.sub_ws.state[:] = global_ws.theta_init[idx]
         self.sub_ws_prop.state[:] = global_ws.theta_init[idx]
-        self.acceptance_history = np.zeros((M, global_ws.C), dtype=bool) if keep else None
+        self.acceptance_history = global_ws.acc_all[:, j].view(np.bool_) if keep else None
         self.updt_name = type(updt).__name__
 
 

@@ -239,6 +239,16 @@ int32_t extmcmc_get_state(extmcmc_t h, double *theta /* [p][C] */,
 int32_t extmcmc_get_history(extmcmc_t h, int64_t seq_lo, int64_t seq_hi,
                             double *theta, double *theta_prop, double *ll,
                             double *ll_prop, uint8_t *accepted);
+/* Asynchronous pair for overlapping the copy-back of block k with the execution of
+ * block k+1 (callbacks fire only at save/print intervals, src/callbacks.jl:198-202,
+ * 300-304, so histories need to reach the host only there).  _begin enqueues the
+ * device->pinned-staging copy of rows [seq_lo, seq_hi) on a copy stream, ordered
+ * after everything queued so far; _end waits for it and scatters the staging area
+ * into the caller's buffers (same layouts as extmcmc_get_history).  One fetch may
+ * be outstanding at a time. */
+int32_t extmcmc_history_fetch_begin(extmcmc_t h, int64_t seq_lo, int64_t seq_hi);
+int32_t extmcmc_history_fetch_end(extmcmc_t h, double *theta, double *theta_prop,
+                                  double *ll, double *ll_prop, uint8_t *accepted);
 /* GenericChainStats (src/chain_statistics.jl:16-66), per chain:
  * mean[p][C], cov[p][p][C] (column-major p x p, chain fastest),
  * rolling_ar[NU][C] (latest value per update), n_accept/n_prop[NU][C] totals. */
