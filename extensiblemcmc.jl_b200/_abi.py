@@ -119,6 +119,8 @@ SIGNATURES = {
     "extmcmc_eval_loglik": (C.c_int32, [Handle, c_double_p]),
     "extmcmc_timer_start": (C.c_int32, [Handle]),
     "extmcmc_timer_stop": (C.c_int32, [Handle, C.POINTER(C.c_float)]),
+    "extmcmc_event_record": (C.c_int32, [Handle, C.c_int32]),
+    "extmcmc_event_elapsed": (C.c_int32, [Handle, C.c_int32, C.c_int32, C.POINTER(C.c_float)]),
     "extmcmc_get_sweep_time": (C.c_int32, [Handle, C.POINTER(C.c_float), c_int64_p]),
     "extmcmc_launch_count": (C.c_int64, [Handle]),
     "extmcmc_flush_l2": (C.c_int32, [Handle]),

@@ -93,6 +93,7 @@ struct extmcmc_handle {
     float sweep_ms = 0.f;
     int64_t sweep_launches = 0;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
+    std::vector<cudaEvent_t> ev_pool;
     int64_t launches = 0;
     double *flush_buf = nullptr;
     int64_t flush_n = 0;
@@ -223,12 +224,14 @@ int32_t enqueue_sweep(extmcmc_t h, bool instrument) {
 }
 
 int32_t enqueue_steps(extmcmc_t h, const StepDesc *d_descs, int n_steps, bool instrument) {
+    // propose(0); then per element: sweep, accept(k) [+ propose(k+1) fused in the same kernel]
+    launch_propose(h->d, d_descs, 0, h->stream);
+    h->launches += 1;
     for (int k = 0; k < n_steps; ++k) {
-        launch_propose(h->d, d_descs, k, h->stream);
         int32_t rc = enqueue_sweep(h, instrument);
         if (rc) return rc;
-        launch_accept(h->d, d_descs, k, h->stream);
-        h->launches += 2;
+        launch_accept(h->d, d_descs, k, k + 1 < n_steps ? 1 : 0, h->stream);
+        h->launches += 1;
     }
     CK(h, cudaGetLastError());
     return EXTMCMC_OK;
@@ -359,7 +362,7 @@ int32_t run_block_impl(extmcmc_t h, const extmcmc_step_t *steps, int32_t n_steps
             it = h->graphs.emplace(key, ge).first;
         }
         CK(h, cudaGraphLaunch(it->second, h->stream));
-        h->launches += (int64_t)n_steps * (2 + h->plan.launches + (obs_sharded(h) ? 1 : 0));
+        h->launches += 1 + (int64_t)n_steps * (1 + h->plan.launches + (obs_sharded(h) ? 1 : 0));
     }
     CK(h, cudaEventRecord(sl.done, h->stream));
     sl.in_flight = true;
@@ -483,6 +486,7 @@ int32_t extmcmc_destroy(extmcmc_t h) {
     for (auto &ev : h->ev_free) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     if (h->t0) cudaEventDestroy(h->t0);
     if (h->t1) cudaEventDestroy(h->t1);
+    for (cudaEvent_t e : h->ev_pool) if (e) cudaEventDestroy(e);
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
     if (h->fetch_ready) cudaEventDestroy(h->fetch_ready);
     if (h->fetch_done) cudaEventDestroy(h->fetch_done);
@@ -842,6 +846,25 @@ int32_t extmcmc_timer_stop(extmcmc_t h, float *ms_out) {
     CK(h, cudaEventRecord(h->t1, h->stream));
     CK(h, cudaEventSynchronize(h->t1));
     CK(h, cudaEventElapsedTime(ms_out, h->t0, h->t1));
+    return EXTMCMC_OK;
+}
+
+int32_t extmcmc_event_record(extmcmc_t h, int32_t idx) {
+    if (!h) return EXTMCMC_EINVAL;
+    if (idx < 0 || idx >= 8192) return fail(h, EXTMCMC_EINVAL, "event index out of range");
+    if ((size_t)idx >= h->ev_pool.size()) h->ev_pool.resize((size_t)idx + 1, nullptr);
+    if (!h->ev_pool[idx]) CK(h, cudaEventCreate(&h->ev_pool[idx]));
+    CK(h, cudaEventRecord(h->ev_pool[idx], h->stream));
+    return EXTMCMC_OK;
+}
+
+int32_t extmcmc_event_elapsed(extmcmc_t h, int32_t i0, int32_t i1, float *ms_out) {
+    if (!h || !ms_out) return EXTMCMC_EINVAL;
+    if (i0 < 0 || i1 < 0 || (size_t)i0 >= h->ev_pool.size() || (size_t)i1 >= h->ev_pool.size() ||
+        !h->ev_pool[i0] || !h->ev_pool[i1])
+        return fail(h, EXTMCMC_EINVAL, "event not recorded");
+    CK(h, cudaEventSynchronize(h->ev_pool[i1]));
+    CK(h, cudaEventElapsedTime(ms_out, h->ev_pool[i0], h->ev_pool[i1]));
     return EXTMCMC_OK;
 }
 

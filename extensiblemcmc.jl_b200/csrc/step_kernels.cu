@@ -99,11 +99,7 @@ __device__ __forceinline__ double law_finalize(const DevState &d, int64_t c, dou
 //     + set_proposal! (src/run.jl:221-240): writes the full proposal and the law
 //     constants the sweep consumes.
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-propose_kernel(DevState d, const StepDesc *__restrict__ descs, int k) {
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= d.C) return;
-    const StepDesc sd = descs[k];
+__device__ __forceinline__ void propose_chain(const DevState &d, const StepDesc &sd, int64_t c) {
     const DevUpdate &u = d.upd[sd.pidx];
     const int n = u.n_coords;
     double th[kMaxCoords], prop[kMaxCoords];
@@ -135,6 +131,13 @@ propose_kernel(DevState d, const StepDesc *__restrict__ descs, int k) {
     for (int j = 0; j < d.p; ++j) d.prop_full[(int64_t)j * d.C + c] = d.theta[(int64_t)j * d.C + c];
     for (int i = 0; i < n; ++i) d.prop_full[(int64_t)u.coords[i] * d.C + c] = prop[i];
     law_prepare(d, c, d.prop_full + c, d.C);
+}
+
+__global__ void __launch_bounds__(256)
+propose_kernel(DevState d, const StepDesc *__restrict__ descs, int k) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= d.C) return;
+    propose_chain(d, descs[k], c);
 }
 
 // Law constants of the CURRENT state (extmcmc_eval_loglik).
@@ -197,7 +200,7 @@ __global__ void __launch_bounds__(256) finalize_loglik_kernel(DevState d, double
 //     src/transition_kernels/adaptation.jl:273-329).
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k) {
+accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fuse_next) {
     // 256 threads = 32 chains x 8 reduction slices; slice 0 carries on with the chain
     __shared__ double sh[kRedSlices * kRedChains];
     const int64_t c = (int64_t)blockIdx.x * kRedChains + (threadIdx.x & (kRedChains - 1));
@@ -326,6 +329,9 @@ accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k) {
         u.adapt_prop[c] = prop_n;
         u.adapt_acc[c] = acc_n;
     }
+    // proposal of the NEXT schedule element of this block, fused here: the chain's thread
+    // already holds its freshly committed state, and one launch per update step is saved
+    if (fuse_next) propose_chain(d, descs[k + 1], c);
 }
 
 // ---------------------------------------------------------------------------------
@@ -382,8 +388,8 @@ void launch_propose(const DevState &d, const StepDesc *descs, int k, cudaStream_
     propose_kernel<<<blocks_for(d.C), 256, 0, st>>>(d, descs, k);
 }
 static inline int red_blocks_for(int64_t C) { return (int)((C + kRedChains - 1) / kRedChains); }
-void launch_accept(const DevState &d, const StepDesc *descs, int k, cudaStream_t st) {
-    accept_kernel<<<red_blocks_for(d.C), 256, 0, st>>>(d, descs, k);
+void launch_accept(const DevState &d, const StepDesc *descs, int k, int fuse_next, cudaStream_t st) {
+    accept_kernel<<<red_blocks_for(d.C), 256, 0, st>>>(d, descs, k, fuse_next);
 }
 void launch_prepare_current(const DevState &d, cudaStream_t st) {
     prepare_current_kernel<<<blocks_for(d.C), 256, 0, st>>>(d);

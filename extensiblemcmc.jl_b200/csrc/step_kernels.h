@@ -6,7 +6,7 @@
 
 namespace extmcmc {
 void launch_propose(const DevState &d, const StepDesc *descs, int k, cudaStream_t st);
-void launch_accept(const DevState &d, const StepDesc *descs, int k, cudaStream_t st);
+void launch_accept(const DevState &d, const StepDesc *descs, int k, int fuse_next, cudaStream_t st);
 void launch_prepare_current(const DevState &d, cudaStream_t st);
 void launch_reduce_partials(const DevState &d, cudaStream_t st);
 void launch_finalize_loglik(const DevState &d, double *ll_out, cudaStream_t st);

@@ -265,6 +265,11 @@ int32_t extmcmc_eval_loglik(extmcmc_t h, double *ll_out);
 /* CUDA-event stopwatch on the handle's stream. */
 int32_t extmcmc_timer_start(extmcmc_t h);
 int32_t extmcmc_timer_stop(extmcmc_t h, float *ms_out);
+/* Event pool on the handle's stream (idx in [0, 8192)): record now / elapsed ms between
+ * two recorded events (synchronises on the later one).  Lets a caller time many
+ * asynchronous blocks without a host sync in between. */
+int32_t extmcmc_event_record(extmcmc_t h, int32_t idx);
+int32_t extmcmc_event_elapsed(extmcmc_t h, int32_t idx_start, int32_t idx_stop, float *ms_out);
 /* With cfg.instrument: accumulated device time and launch count of the
  * likelihood sweep kernel since the last call (resets the accumulators). */
 int32_t extmcmc_get_sweep_time(extmcmc_t h, float *ms_total, int64_t *n_launches);
