@@ -238,7 +238,9 @@ def run_ours(args):
         # 2 FP64 issue slots (DADD + DFMA) per pair; the FMA-rate peak counts 2 flop per slot
         "issue_frac": (2.0 * C * N_OBS / (sweep_ms * 1e-3)) / (fp64_peak.value * 1e12 / 2.0) if fp64_peak.value else None,
         "avg_launch_ms": sweep_ms, "launches_timed": int(nl.value), "share_of_step": sweep_share,
-        "traffic": None,
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture of this
+        # kernel at this shape (profiles/README_r01.md); algorithmic bytes = 8e6
+        "traffic": 8.046592e6,
         "hbm": {"achieved": 8.0 * N_OBS / (sweep_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
                 "unit": "GB/s", "frac": 8.0 * N_OBS / (sweep_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                 "peak_source": peak_src + " (MEASURED_PEAKS.json)" if peak_src == "measured" else "fallback"},
@@ -267,7 +269,9 @@ def run_ours(args):
                         "workload": f"cfg5 shape on 1 GPU: C={c5}, N=2^28 (2 GiB > L2)", "bound": "hbm",
                         "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                         "frac": gbs / peaks["hbm_gbs"], "avg_launch_ms": t5,
-                        "peak_source": peak_src, "traffic": None}
+                        "peak_source": peak_src,
+                        # ncu --set full (profiles/README_r01.md): 2.147561e9 read + 4.2e6 write
+                        "traffic": 2.151769e9, "algorithmic_bytes": 8.0 * n5}
         w5.close()
 
     # ---- e2e: the whole job through run_() with host buffers --------------------------
@@ -334,6 +338,76 @@ def run_ours(args):
     print(json.dumps(out))
 
 
+def run_cfg5(args):
+    """Secondary workload (BASELINE cfg 5): one dataset of N observations generated on the
+    device, sharded by observations over the ranks; C = 8 replicated chains; the per-chain
+    partial sums are all-reduced (NCCL) once per update step.  Strong scaling in N."""
+    import torch
+    import extensiblemcmc_jl_b200 as em
+    from extensiblemcmc_jl_b200 import _abi, parallel as par
+    from extensiblemcmc_jl_b200.mcmc import init_
+    rank, world, local = par.env_rank_world()
+    torch.cuda.set_device(local)
+    dist = None
+    cid = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        cid = par.exchange_comm_id(dist)
+    n_total, C = args.n_obs, 8
+    first, cnt = par.shard_obs(n_total, rank, world)
+    mk = lambda: em.AdaptationUnifRW([0.0], adapt_every_k_steps=50, target_accpt_rate=0.234,
+                                     scale=5e-4 / 30, min=1e-7 / 30, max=1e7, offset=100.0)
+    ups = [em.RandomWalkUpdate(em.UniformRandomWalk([5e-3 / 30]), [1], adpt=mk()),
+           em.RandomWalkUpdate(em.UniformRandomWalk([5e-3 / 30], [True]), [2], prior=em.ImproperPosPrior(), adpt=mk())]
+    bk = par.backend_for_rank(rank, world, local, C, shard="obs" if world > 1 else "chains", comm_id=cid,
+                              seed=6, history="none", block_len=NU, use_graphs=True)
+    if world == 1:
+        bk = em.CUDAMCMCBackend(n_chains=C, device=local, seed=6, history="none", block_len=NU, use_graphs=True)
+    mcmc = em.MCMC(ups, backend=bk)
+    init_(mcmc, 1, dict(P=em.GsnTargetLaw([0.0]), obs=em.DeviceGeneratedObs(cnt, 1.5, 2.0, 6, first)),
+          np.repeat(np.array([[1.5], [4.0]]), C, axis=1))
+    ws = mcmc.workspace
+    K, Wm = args.steps, max(args.warmup, 3)
+    sampler = ClockSampler(local)
+    timed_steps(ws, _abi, C, 0, Wm, flush=False)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    l0 = ws.lib.extmcmc_launch_count(ws.handle)
+    ms_total = timed_steps(ws, _abi, C, K, 0, flush=False)
+    launches = int(ws.lib.extmcmc_launch_count(ws.handle) - l0)
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.barrier()
+    ms_total = float(t.item())
+    variant = ws.lib.extmcmc_sweep_variant_name(ws.handle).decode()
+    ws.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    peaks, peak_src = measured_peaks()
+    sweep_s = ms_total * 1e-3 / (K * NU)
+    gbs = 8.0 * cnt / sweep_s / 1e9
+    print(json.dumps({
+        "metric": "chain-steps x obs/sec", "value": C * K * NU * float(n_total) / (ms_total * 1e-3),
+        "unit": "chain-step*obs/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms_total / K,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"BASELINE cfg5: N={n_total:.3g} Gaussian observations generated on device, sharded "
+                               f"by observations over {world} GPU(s), C=8 replicated chains, NCCL all-reduce of "
+                               "partial sums per update step", "l2": "inputs larger than L2, no flush"},
+        "roofline": {"kernel": variant, "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": gbs / peaks["hbm_gbs"], "peak_source": peak_src,
+                     "note": "per-GPU bytes of one update step / whole update-step time (sweep + reduce + all-reduce + accept)",
+                     "traffic": None},
+        "gpu_launches": launches, "clocks": clocks}))
+
+
 def cpu_oracle_rate(x, n_chains, n_iters, n_threads):
     import extensiblemcmc_jl_b200 as em
     from oracle import oracle as orc
@@ -392,9 +466,13 @@ def main():
     ap.add_argument("--cpu-iters", type=int, default=150)
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-hbm", action="store_true")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg5"])
+    ap.add_argument("--n-obs", type=int, default=1_000_000_000, help="cfg5 only: total observations")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "cfg5":
+        run_cfg5(args)
     else:
         run_ours(args)
 
