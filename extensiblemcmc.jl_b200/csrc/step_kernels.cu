@@ -94,13 +94,31 @@ __device__ __forceinline__ double law_finalize(const DevState &d, int64_t c, dou
 }
 }  // namespace
 
+// The schedule element and its update entry are read by every thread dozens of times;
+// stage them in shared memory once per CTA (a dependent chain of global loads otherwise).
+struct StepCtx {
+    StepDesc sd;
+    DevUpdate u;
+};
+__device__ __forceinline__ void load_step_ctx(StepCtx *ctx, const DevState &d, const StepDesc *descs, int k) {
+    static_assert(sizeof(StepDesc) % 4 == 0 && sizeof(DevUpdate) % 4 == 0, "word copies");
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(descs + k);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(&ctx->sd);
+    for (int i = threadIdx.x; i < (int)(sizeof(StepDesc) / 4); i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+    const uint32_t *us = reinterpret_cast<const uint32_t *>(d.upd + ctx->sd.pidx);
+    uint32_t *ud = reinterpret_cast<uint32_t *>(&ctx->u);
+    for (int i = threadIdx.x; i < (int)(sizeof(DevUpdate) / 4); i += blockDim.x) ud[i] = us[i];
+    __syncthreads();
+}
+
 // ---------------------------------------------------------------------------------
 // K1: proposal!  (src/updates.jl:191-196, rand(::UniformRandomWalk) random_walk.jl:65-73)
 //     + set_proposal! (src/run.jl:221-240): writes the full proposal and the law
 //     constants the sweep consumes.
 // ---------------------------------------------------------------------------------
-__device__ __forceinline__ void propose_chain(const DevState &d, const StepDesc &sd, int64_t c) {
-    const DevUpdate &u = d.upd[sd.pidx];
+__device__ __forceinline__ void propose_chain(const DevState &d, const StepDesc &sd, const DevUpdate &u,
+                                              int64_t c) {
     const int n = u.n_coords;
     double th[kMaxCoords], prop[kMaxCoords];
     for (int i = 0; i < n; ++i) th[i] = d.theta[(int64_t)u.coords[i] * d.C + c];
@@ -135,9 +153,11 @@ __device__ __forceinline__ void propose_chain(const DevState &d, const StepDesc 
 
 __global__ void __launch_bounds__(256)
 propose_kernel(DevState d, const StepDesc *__restrict__ descs, int k) {
+    __shared__ StepCtx ctx;
+    load_step_ctx(&ctx, d, descs, k);
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= d.C) return;
-    propose_chain(d, descs[k], c);
+    propose_chain(d, ctx.sd, ctx.u, c);
 }
 
 // Law constants of the CURRENT state (extmcmc_eval_loglik).
@@ -151,11 +171,16 @@ __global__ void __launch_bounds__(256) prepare_current_kernel(DevState d) {
 // chains; slice j (0..7) adds segments j, j+8, j+16, ... (8 independent loads in flight per
 // thread), then the 8 slice sums are combined in slice order.  The order depends only on
 // S, never on timing, so results are reproducible run to run.
-constexpr int kRedChains = 32, kRedSlices = 8;
+// SL = 8 slices when there are many segments (cfg 2: S = 148), SL = 1 (plain thread per
+// chain, every thread stays busy in the accept phase) when S is small.
+constexpr int kRedThreads = 256;
 
-__device__ __forceinline__ double reduce_segments(const DevState &d, double *sh /*[8][32]*/) {
-    const int lane_c = threadIdx.x & (kRedChains - 1);
-    const int slice = threadIdx.x >> 5;
+
+template <int kRedSlices>
+__device__ __forceinline__ double reduce_segments(const DevState &d, double *sh /*[SL][256/SL]*/) {
+    constexpr int kRedChains = kRedThreads / kRedSlices;
+    const int lane_c = threadIdx.x % kRedChains;
+    const int slice = threadIdx.x / kRedChains;
     const int64_t c = (int64_t)blockIdx.x * kRedChains + lane_c;
     double s = 0.0;
     if (c < d.C) {
@@ -170,6 +195,7 @@ __device__ __forceinline__ double reduce_segments(const DevState &d, double *sh 
         }
         for (; i < d.S; i += kRedSlices) s += p[(int64_t)i * d.C];
     }
+    if (kRedSlices == 1) return s;
     sh[slice * kRedChains + lane_c] = s;
     __syncthreads();
     double tot = 0.0;
@@ -180,11 +206,13 @@ __device__ __forceinline__ double reduce_segments(const DevState &d, double *sh 
     return tot;  // valid in threads with slice == 0
 }
 
+template <int SL>
 __global__ void __launch_bounds__(256) reduce_partials_kernel(DevState d) {
-    __shared__ double sh[kRedSlices * kRedChains];
-    const double tot = reduce_segments(d, sh);
-    const int64_t c = (int64_t)blockIdx.x * kRedChains + (threadIdx.x & (kRedChains - 1));
-    if ((threadIdx.x >> 5) == 0 && c < d.C) d.ssum[c] = tot;
+    __shared__ double sh[kRedThreads];
+    constexpr int kRedChains = kRedThreads / SL;
+    const double tot = reduce_segments<SL>(d, sh);
+    const int64_t c = (int64_t)blockIdx.x * kRedChains + (threadIdx.x % kRedChains);
+    if ((threadIdx.x / kRedChains) == 0 && c < d.C) d.ssum[c] = tot;
 }
 
 __global__ void __launch_bounds__(256) finalize_loglik_kernel(DevState d, double *ll_out) {
@@ -199,20 +227,25 @@ __global__ void __launch_bounds__(256) finalize_loglik_kernel(DevState d, double
 //     (src/chain_statistics.jl:41-66) + update_adaptation! (src/run.jl:136-173,
 //     src/transition_kernels/adaptation.jl:273-329).
 // ---------------------------------------------------------------------------------
+template <int SL>
 __global__ void __launch_bounds__(256)
 accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fuse_next) {
-    // 256 threads = 32 chains x 8 reduction slices; slice 0 carries on with the chain
-    __shared__ double sh[kRedSlices * kRedChains];
-    const int64_t c = (int64_t)blockIdx.x * kRedChains + (threadIdx.x & (kRedChains - 1));
+    // 256 threads = (256/SL) chains x SL reduction slices; slice 0 carries on with the chain
+    constexpr int kRedChains = kRedThreads / SL;
+    __shared__ double sh[kRedThreads];
+    __shared__ StepCtx ctx, ctx_next;
+    load_step_ctx(&ctx, d, descs, k);
+    if (fuse_next) load_step_ctx(&ctx_next, d, descs, k + 1);
+    const int64_t c = (int64_t)blockIdx.x * kRedChains + (threadIdx.x % kRedChains);
     double S;
     if (d.use_ssum) {
         S = c < d.C ? d.ssum[c] : 0.0;
     } else {
-        S = reduce_segments(d, sh);
+        S = reduce_segments<SL>(d, sh);
     }
-    if ((threadIdx.x >> 5) != 0 || c >= d.C) return;
-    const StepDesc sd = descs[k];
-    const DevUpdate &u = d.upd[sd.pidx];
+    if ((threadIdx.x / kRedChains) != 0 || c >= d.C) return;
+    const StepDesc &sd = ctx.sd;
+    const DevUpdate &u = ctx.u;
     const int n = u.n_coords;
     const int64_t C = d.C;
     const double ll_prop = law_finalize(d, c, S);
@@ -331,7 +364,7 @@ accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fuse_ne
     }
     // proposal of the NEXT schedule element of this block, fused here: the chain's thread
     // already holds its freshly committed state, and one launch per update step is saved
-    if (fuse_next) propose_chain(d, descs[k + 1], c);
+    if (fuse_next) propose_chain(d, ctx_next.sd, ctx_next.u, c);
 }
 
 // ---------------------------------------------------------------------------------
@@ -387,15 +420,25 @@ static inline int blocks_for(int64_t C) { return (int)((C + 255) / 256); }
 void launch_propose(const DevState &d, const StepDesc *descs, int k, cudaStream_t st) {
     propose_kernel<<<blocks_for(d.C), 256, 0, st>>>(d, descs, k);
 }
-static inline int red_blocks_for(int64_t C) { return (int)((C + kRedChains - 1) / kRedChains); }
+static inline int red_blocks_for(int64_t C, int sl) {
+    const int ch = kRedThreads / sl;
+    return (int)((C + ch - 1) / ch);
+}
+static inline int slices_for(const DevState &d) { return (!d.use_ssum && d.S > 16) ? 8 : 1; }
 void launch_accept(const DevState &d, const StepDesc *descs, int k, int fuse_next, cudaStream_t st) {
-    accept_kernel<<<red_blocks_for(d.C), 256, 0, st>>>(d, descs, k, fuse_next);
+    if (slices_for(d) == 8)
+        accept_kernel<8><<<red_blocks_for(d.C, 8), 256, 0, st>>>(d, descs, k, fuse_next);
+    else
+        accept_kernel<1><<<red_blocks_for(d.C, 1), 256, 0, st>>>(d, descs, k, fuse_next);
 }
 void launch_prepare_current(const DevState &d, cudaStream_t st) {
     prepare_current_kernel<<<blocks_for(d.C), 256, 0, st>>>(d);
 }
 void launch_reduce_partials(const DevState &d, cudaStream_t st) {
-    reduce_partials_kernel<<<red_blocks_for(d.C), 256, 0, st>>>(d);
+    if (d.S > 16)
+        reduce_partials_kernel<8><<<red_blocks_for(d.C, 8), 256, 0, st>>>(d);
+    else
+        reduce_partials_kernel<1><<<red_blocks_for(d.C, 1), 256, 0, st>>>(d);
 }
 void launch_finalize_loglik(const DevState &d, double *ll_out, cudaStream_t st) {
     finalize_loglik_kernel<<<blocks_for(d.C), 256, 0, st>>>(d, ll_out);
