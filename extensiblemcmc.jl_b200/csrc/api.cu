@@ -158,9 +158,12 @@ void invalidate_graphs(extmcmc_t h) {
 
 int32_t ensure_plan(extmcmc_t h) {
     if (h->plan_valid) return EXTMCMC_OK;
-    if (h->cfg.law != EXTMCMC_LAW_GSN_IID_1D)
+    if (h->cfg.law == EXTMCMC_LAW_GSN_IID_1D)
+        h->plan = plan_sweep_gsn1d(h->d.C, h->n_obs_local, h->cfg.sweep_variant, h->num_sms);
+    else if (h->cfg.law == EXTMCMC_LAW_GSN_MV)
+        h->plan = plan_sweep_gsnmv(h->cfg.obs_dim, h->d.C, h->n_obs_local, h->cfg.sweep_variant, h->num_sms);
+    else
         return fail(h, EXTMCMC_EUNSUPPORTED, "law not implemented on the GPU path");
-    h->plan = plan_sweep_gsn1d(h->d.C, h->n_obs_local, h->cfg.sweep_variant, h->num_sms);
     h->d.S = h->plan.S;
     int32_t rc = dev_alloc(h, &h->d.partial, (size_t)h->plan.S * h->d.C);
     if (rc) return rc;
@@ -208,7 +211,10 @@ int32_t enqueue_sweep(extmcmc_t h, bool instrument) {
         else { CK(h, cudaEventCreate(&ev.first)); CK(h, cudaEventCreate(&ev.second)); }
         CK(h, cudaEventRecord(ev.first, h->stream));
     }
-    launch_sweep_gsn1d(h->plan, h->obs_dev, h->n_obs_local, h->d.lawc, h->d.C, h->d.partial, h->stream);
+    if (h->cfg.law == EXTMCMC_LAW_GSN_IID_1D)
+        launch_sweep_gsn1d(h->plan, h->obs_dev, h->n_obs_local, h->d.lawc, h->d.C, h->d.partial, h->stream);
+    else
+        launch_sweep_gsnmv(h->plan, h->obs_dev, h->n_obs_local, h->d.lawc, h->d.C, h->d.partial, h->stream);
     h->launches += h->plan.launches;
     if (instrument) {
         CK(h, cudaEventRecord(ev.second, h->stream));
@@ -391,6 +397,12 @@ int32_t extmcmc_create(const extmcmc_config_t *cfg, extmcmc_t *out) {
         if (cfg->obs_dim != 1 || cfg->n_params != 2)
             return fail(nullptr, EXTMCMC_EINVAL, "GSN_IID_1D needs obs_dim = 1, n_params = 2");
         break;
+    case EXTMCMC_LAW_GSN_MV:
+        if (cfg->obs_dim < 2 || cfg->obs_dim > kMaxObsDim)
+            return fail(nullptr, EXTMCMC_EUNSUPPORTED, "GSN_MV on the GPU path needs 2 <= obs_dim <= 8 (d = 1: GSN_IID_1D)");
+        if (cfg->n_params != cfg->obs_dim * (cfg->obs_dim + 1))
+            return fail(nullptr, EXTMCMC_EINVAL, "GSN_MV needs n_params = d (d + 1)");
+        break;
     default:
         // the reference's convention for a missing method: error("... not implemented")
         return fail(nullptr, EXTMCMC_EUNSUPPORTED, "target law not implemented on the GPU path");
@@ -440,13 +452,15 @@ int32_t extmcmc_create(const extmcmc_config_t *cfg, extmcmc_t *out) {
     d.H = cfg->history_window;
     d.law = cfg->law; d.stats_mode = cfg->stats_mode; d.rng_mode = EXTMCMC_RNG_PHILOX;
     d.p_u_max = 1; d.seed = cfg->seed;
+    d.obs_dim = cfg->obs_dim;
+    d.lawc_k = cfg->law == EXTMCMC_LAW_GSN_IID_1D ? 3 : cfg->obs_dim + cfg->obs_dim * (cfg->obs_dim + 1) / 2 + 1;
     d.use_ssum = (cfg->shard_mode == EXTMCMC_SHARD_OBS && cfg->world_size > 1) ? 1 : 0;
     int32_t rc = 0;
     const size_t covn = cfg->stats_mode == 0 ? (size_t)p * p : (cfg->stats_mode == 1 ? (size_t)p : 0);
     if ((rc = dev_alloc(h, &d.theta, (size_t)p * C)) || (rc = dev_alloc(h, &d.ll, (size_t)C)) ||
         (rc = dev_alloc(h, &d.prop_loc, (size_t)kMaxCoords * C)) ||
         (rc = dev_alloc(h, &d.prop_full, (size_t)p * C)) ||
-        (rc = dev_alloc(h, &d.lawc, (size_t)kMaxLawConst * C)) ||
+        (rc = dev_alloc(h, &d.lawc, (size_t)d.lawc_k * C)) ||
         (rc = dev_alloc(h, &d.n_used, (size_t)C)) || (rc = dev_alloc(h, &d.ssum, (size_t)C)) ||
         (rc = dev_alloc(h, &d.mean, (size_t)p * C)) || (rc = dev_alloc(h, &d.cov, covn * C)) ||
         (rc = dev_alloc(h, &d.h_theta, (size_t)d.H * p * C)) ||
@@ -497,9 +511,9 @@ int32_t extmcmc_destroy(extmcmc_t h) {
 }
 
 static int32_t install_obs(extmcmc_t h, int64_t n_obs) {
-    // padded to an even count (+ one spare pair): the sweep's bulk copies move 16 B units
+    // padded to an even count of doubles (+ one spare pair): the sweep's bulk copies move 16 B units
     if (h->obs_dev) { cudaFree(h->obs_dev); h->obs_dev = nullptr; }
-    const size_t padded = ((size_t)n_obs + 3) & ~(size_t)1;
+    const size_t padded = ((size_t)n_obs * (size_t)h->cfg.obs_dim + 3) & ~(size_t)1;
     CK(h, cudaMalloc(&h->obs_dev, padded * sizeof(double)));
     CK(h, cudaMemsetAsync(h->obs_dev, 0, padded * sizeof(double), h->stream));
     h->n_obs_local = n_obs;
@@ -518,7 +532,7 @@ int32_t extmcmc_upload_obs(extmcmc_t h, const double *obs, int64_t n_obs, int32_
     CK(h, cudaStreamSynchronize(h->stream));
     int32_t rc = install_obs(h, n_obs);
     if (rc) return rc;
-    CK(h, cudaMemcpyAsync(h->obs_dev, obs, (size_t)n_obs * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(h->obs_dev, obs, (size_t)n_obs * obs_dim * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
     return EXTMCMC_OK;
 }

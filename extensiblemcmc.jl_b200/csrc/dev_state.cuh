@@ -16,7 +16,7 @@ namespace extmcmc {
 
 constexpr int kMaxCoords = 16;      // p_u limit of the scalar per-chain step kernels
 constexpr int kMaxPriorParams = 4;
-constexpr int kMaxLawConst = 4;     // per-chain law constants written by the proposal kernel
+constexpr int kMaxObsDim = 8;       // general-d Gaussian law on the device: d <= 8
 
 // One update as the kernels see it (constant per run; lives in a device table).
 struct DevUpdate {
@@ -54,6 +54,7 @@ struct DevState {
     int64_t n_obs_total;    // N over all ranks (enters the log-likelihood constant)
     int32_t p, NU, W, H;    // params, updates, rolling window, history ring length
     int32_t law, stats_mode, rng_mode, p_u_max;
+    int32_t obs_dim, lawc_k;  // observation dimension; per-chain law constants in lawc
     uint64_t seed;
     // current state
     double *theta;          // [p][C]
@@ -61,7 +62,7 @@ struct DevState {
     // proposal of the step in flight
     double *prop_loc;       // [kMaxCoords][C] local proposal theta°_loc
     double *prop_full;      // [p][C] full proposal = theta with coords replaced (run.jl:237-239)
-    double *lawc;           // [kMaxLawConst][C] per-chain law constants of the proposal
+    double *lawc;           // [lawc_k][C] per-chain law constants of the proposal
     uint32_t *n_used;       // [C] uniforms consumed by the proposal (next index = Exp draw)
     // sweep output
     double *partial;        // [S][C] per-segment partial sums

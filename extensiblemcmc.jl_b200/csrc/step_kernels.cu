@@ -67,9 +67,12 @@ __device__ __forceinline__ double log_q_unif(const DevUpdate &u, const double *e
     return s;
 }
 
-// Per-chain law constants of a parameter vector; the sweep only needs lawc[0].
+// Per-chain law constants of a parameter vector.
 //   GSN_IID_1D: lawc = { mu, c0 = -(log 2pi + 2 log sqrt(var))/2, 1/(2 var) },
-//   ll = N c0 - S/(2 var) with S = sum (x - mu)^2 (gsn_target.jl:15-29 for d = 1).
+//               ll = N c0 - S/(2 var),  S = sum (x - mu)^2     (gsn_target.jl:15-29, d = 1)
+//   GSN_MV(d):  lawc = { mu[d], W = inv(L) lower-tri row-major, c0 },  Sigma = L L' built from the
+//               UPPER triangle of the d x d block of theta (Symmetric(triu(S)), gsn_target.jl:19);
+//               ll = N c0 - S/2,  S = sum |W (x - mu)|^2,  c0 = -(d log 2pi + 2 sum log L_ii)/2
 __device__ __forceinline__ void law_prepare(const DevState &d, int64_t c, const double *full,
                                             int64_t stride) {
     if (d.law == EXTMCMC_LAW_GSN_IID_1D) {
@@ -85,12 +88,50 @@ __device__ __forceinline__ void law_prepare(const DevState &d, int64_t c, const 
         d.lawc[c] = mu;
         d.lawc[d.C + c] = c0;
         d.lawc[2 * d.C + c] = inv2;
+    } else if (d.law == EXTMCMC_LAW_GSN_MV) {
+        const int n = d.obs_dim;
+        double L[kMaxObsDim * kMaxObsDim], W[kMaxObsDim * kMaxObsDim];
+        bool bad = false;
+        // A[i][j] (i >= j) = theta[n + j + i*n]: entry (row j, col i) of the column-major block
+        for (int j = 0; j < n && !bad; ++j) {
+            double s = full[(int64_t)(n + j + j * n) * stride];
+            for (int k = 0; k < j; ++k) s -= L[j * n + k] * L[j * n + k];
+            if (!(s > 0.0) || isinf(s)) { bad = true; break; }
+            const double ljj = sqrt(s);
+            L[j * n + j] = ljj;
+            for (int i = j + 1; i < n; ++i) {
+                double a = full[(int64_t)(n + j + i * n) * stride];
+                for (int k = 0; k < j; ++k) a -= L[i * n + k] * L[j * n + k];
+                L[i * n + j] = a / ljj;
+            }
+        }
+        double logdet = 0.0;
+        if (!bad) {
+            // W = inv(L): forward substitution column by column
+            for (int j = 0; j < n; ++j) {
+                W[j * n + j] = 1.0 / L[j * n + j];
+                for (int i = j + 1; i < n; ++i) {
+                    double a = 0.0;
+                    for (int k = j; k < i; ++k) a -= L[i * n + k] * W[k * n + j];
+                    W[i * n + j] = a / L[i * n + i];
+                }
+                logdet += log(L[j * n + j]);
+            }
+        } else {
+            *d.err_flag = 1;
+        }
+        for (int j = 0; j < n; ++j) d.lawc[(int64_t)j * d.C + c] = full[(int64_t)j * stride];
+        int w = 0;
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j <= i; ++j, ++w) d.lawc[(int64_t)(n + w) * d.C + c] = bad ? NAN : W[i * n + j];
+        d.lawc[(int64_t)(d.lawc_k - 1) * d.C + c] = bad ? NAN : -((double)n * kLog2Pi + 2.0 * logdet) / 2.0;
     }
 }
 
 __device__ __forceinline__ double law_finalize(const DevState &d, int64_t c, double S) {
-    // N*c0 - S/(2 var)
-    return (double)d.n_obs_total * d.lawc[d.C + c] - S * d.lawc[2 * d.C + c];
+    if (d.law == EXTMCMC_LAW_GSN_IID_1D)  // N*c0 - S/(2 var)
+        return (double)d.n_obs_total * d.lawc[d.C + c] - S * d.lawc[2 * d.C + c];
+    return (double)d.n_obs_total * d.lawc[(int64_t)(d.lawc_k - 1) * d.C + c] - S / 2.0;
 }
 }  // namespace
 

@@ -13,6 +13,7 @@ struct SweepPlan {
     int groups;        // chain groups (grid.y for "chains", launches for "obs")
     int S;             // observation segments = rows of partial[S][C]
     int launches;      // kernel launches per sweep
+    int D;             // observation dimension (general-d Gaussian law)
     const char *name;
 };
 
@@ -21,6 +22,12 @@ cudaError_t sweep_gsn1d_init();
 // partial[S][C] <- per-segment sums of (x - mu_c)^2.  obs must be 16-byte aligned and
 // readable up to the next even observation index (the library pads its copy).
 void launch_sweep_gsn1d(const SweepPlan &pl, const double *obs, int64_t n_obs, const double *mu,
+                        int64_t C, double *partial, cudaStream_t st);
+
+// General-d GsnTargetLaw: lawc = [mu(d), W = inv(chol(Sigma)) lower-tri row-major, c0],
+// obs row-major [n_obs][d], readable up to the next 16-byte boundary.
+SweepPlan plan_sweep_gsnmv(int d, int64_t C, int64_t n_obs, int force_variant, int num_sms);
+void launch_sweep_gsnmv(const SweepPlan &pl, const double *obs, int64_t n_obs, const double *lawc,
                         int64_t C, double *partial, cudaStream_t st);
 
 }  // namespace extmcmc

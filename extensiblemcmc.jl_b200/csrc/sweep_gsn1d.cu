@@ -25,43 +25,9 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 #include "sweep.h"
+#include "tma.cuh"
 
 namespace extmcmc {
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) {
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_fence_init() {
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-                 "r"(bytes)
-                 : "memory");
-}
-// 1-D TMA bulk copy global -> shared, completion counted on an mbarrier.
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-            smem_u32(dst)),
-        "l"(src), "r"(bytes), "r"(smem_u32(bar))
-        : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    } while (!done);
-}
 
 // Segment s of S over n_obs observations, boundaries on even indices so that every
 // bulk copy starts 16-byte aligned.
@@ -295,18 +261,21 @@ SweepPlan plan_sweep_gsn1d(int64_t C, int64_t n_obs, int force_variant, int num_
     if (force_variant == SWEEP_VARIANT_CHAINS) chains = true;
     if (force_variant == SWEEP_VARIANT_OBS) chains = false;
     if (chains) {
-        // registers per thread: largest R that still leaves >= 2 chain groups' worth of
-        // CTAs to spread over the SMs
-        int R = 8;
-        while (R > 1 && C < (int64_t)kChainsNT * R) R >>= 1;
+        // chains per thread: the largest R in {8,4,2,1} that still yields >= 2 CTAs per SM
+        // (small N limits the number of segments, so small problems trade registers for CTAs)
+        const int64_t max_S = (n_pairs + 255) / 256;  // >= 512 observations per segment
+        int R = 8, S = 1, groups = 1;
+        for (;; R >>= 1) {
+            groups = (int)((C + (int64_t)kChainsNT * R - 1) / ((int64_t)kChainsNT * R));
+            S = (num_sms * 4 + groups - 1) / groups;
+            if (S > max_S) S = (int)max_S;
+            if (S < 1) S = 1;
+            const bool fits = C >= (int64_t)kChainsNT * R;      // no mostly-empty thread tiles
+            if (R == 1 || (fits && (int64_t)groups * S >= 2 * num_sms)) break;
+        }
         pl.variant = SWEEP_VARIANT_CHAINS;
         pl.R = R;
-        pl.groups = (int)((C + (int64_t)kChainsNT * R - 1) / ((int64_t)kChainsNT * R));
-        const int target = num_sms * 4;  // 4 CTAs of 4 warps per SM
-        int S = (target + pl.groups - 1) / pl.groups;
-        const int64_t max_S = (n_pairs + 255) / 256;  // >= 512 observations per segment
-        if (S > max_S) S = (int)max_S;
-        if (S < 1) S = 1;
+        pl.groups = groups;
         pl.S = S;
         pl.launches = 1;
         static const char *names[] = {"", "gsn1d_chains_R1", "gsn1d_chains_R2", "", "gsn1d_chains_R4",

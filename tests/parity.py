@@ -168,9 +168,9 @@ def compare_histories(o, g, tie_tol=1e-12):
 
 
 def replay_compare(x, n_chains, n_iters, seed=1, updates=None, theta_init=None, exclude=(),
-                   block=None, check_state=True, **cfg_kw):
+                   block=None, check_state=True, law=None, **cfg_kw):
     """Oracle (own Philox stream, recording) vs GPU (replaying) on the same inputs."""
-    law = em.GsnTargetLaw([0.0], [[1.0]])
+    law = law if law is not None else em.GsnTargetLaw([0.0], [[1.0]])
     updates = updates if updates is not None else cfg2_updates(eps0=0.05, scale=5e-3, k=10, offset=2.0)
     theta_init = theta_init if theta_init is not None else theta_init_for(x, n_chains)
     steps = list(em.MCMCSchedule(n_iters, len(updates), exclude))

@@ -223,7 +223,7 @@ def test_unsupported_requests_raise():
     lib = _abi.load()
     cfg = _abi.Config()
     cfg.abi_version, cfg.n_chains, cfg.n_params, cfg.n_updates = _abi.ABI_VERSION, 4, 6, 1
-    cfg.law, cfg.obs_dim, cfg.history_window = _abi.LAW_GSN_MV, 2, 4
+    cfg.law, cfg.obs_dim, cfg.history_window = 99, 2, 4
     import ctypes as C
     h = _abi.Handle()
     assert lib.extmcmc_create(C.byref(cfg), C.byref(h)) == _abi.EUNSUPPORTED
