@@ -258,6 +258,8 @@ SweepPlan plan_sweep_gsn1d(int64_t C, int64_t n_obs, int force_variant, int num_
     SweepPlan pl{};
     const int64_t n_pairs = (n_obs + 1) / 2;
     bool chains = C > 32;
+    int force_R = 0;  // force_variant 11, 12, 14, 18: "chains" mapping with R = 1, 2, 4, 8 (tests)
+    if (force_variant > 10) { force_R = force_variant - 10; force_variant = SWEEP_VARIANT_CHAINS; }
     if (force_variant == SWEEP_VARIANT_CHAINS) chains = true;
     if (force_variant == SWEEP_VARIANT_OBS) chains = false;
     if (chains) {
@@ -271,7 +273,8 @@ SweepPlan plan_sweep_gsn1d(int64_t C, int64_t n_obs, int force_variant, int num_
             if (S > max_S) S = (int)max_S;
             if (S < 1) S = 1;
             const bool fits = C >= (int64_t)kChainsNT * R;      // no mostly-empty thread tiles
-            if (R == 1 || (fits && (int64_t)groups * S >= 2 * num_sms)) break;
+            if (force_R ? R == force_R : (R == 1 || (fits && (int64_t)groups * S >= 2 * num_sms))) break;
+            if (R == 1) break;
         }
         pl.variant = SWEEP_VARIANT_CHAINS;
         pl.R = R;

@@ -169,7 +169,8 @@ typedef struct extmcmc_config {
     int32_t  use_graphs;      /* 1: run_block replays a captured CUDA graph        */
     int32_t  instrument;      /* 1: bracket every likelihood sweep launch with
                                  CUDA events (see extmcmc_get_sweep_time)          */
-    int32_t  sweep_variant;   /* 0 = auto; else force a sweep kernel variant       */
+    int32_t  sweep_variant;   /* 0 = auto; 1 = "chains" mapping, 2 = "obs" mapping;
+                                 11/12/14/18 = "chains" with 1/2/4/8 chains per thread */
     int32_t  stats_mode;      /* 0 = running mean + full covariance per chain (the
                                  reference's GenericChainStats); 1 = mean + diagonal
                                  of the covariance only; 2 = no running moments     */

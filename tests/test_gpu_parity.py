@@ -35,17 +35,19 @@ def _assert_clean(rep):
     assert 0.02 < rep["accept_rate"] < 0.98, rep
 
 
-@pytest.mark.parametrize("n_chains,n_obs,n_iters,variant", [
-    (64, 10000, 60, "gsn1d_chains_R1"),       # BASELINE minimum slice (C=64, N=1e4)
-    (300, 3001, 40, "gsn1d_chains_R2"),       # odd N, ragged chain group
-    (700, 5000, 25, "gsn1d_chains_R4"),
-    (1100, 2050, 25, "gsn1d_chains_R8"),      # 2 chain groups, second one ragged
-    (5, 20001, 60, "gsn1d_obs_C8"),           # few chains: observation-mapped kernel
-    (1, 4097, 120, "gsn1d_obs_C1"),           # the reference's shape: one chain
-    (20, 9000, 40, "gsn1d_obs_C32"),
+@pytest.mark.parametrize("n_chains,n_obs,n_iters,force,variant", [
+    (64, 10000, 60, 0, "gsn1d_chains_R1"),     # BASELINE minimum slice (C=64, N=1e4)
+    (300, 3001, 40, 12, "gsn1d_chains_R2"),    # odd N, ragged chain group
+    (700, 5000, 25, 14, "gsn1d_chains_R4"),
+    (1100, 2050, 25, 18, "gsn1d_chains_R8"),   # 2 chain groups, second one ragged
+    (2100, 60000, 12, 0, "gsn1d_chains_R8"),   # what the planner itself picks for a mid-size problem
+    (5, 20001, 60, 0, "gsn1d_obs_C8"),         # few chains: observation-mapped kernel
+    (1, 4097, 120, 0, "gsn1d_obs_C1"),         # the reference's shape: one chain
+    (20, 9000, 40, 0, "gsn1d_obs_C32"),
 ])
-def test_replay_parity(n_chains, n_obs, n_iters, variant):
-    rep = replay_compare(_data(n_obs, seed=n_chains), n_chains, n_iters, seed=n_chains + 1)
+def test_replay_parity(n_chains, n_obs, n_iters, force, variant):
+    rep = replay_compare(_data(n_obs, seed=n_chains), n_chains, n_iters, seed=n_chains + 1,
+                         sweep_variant=force)
     assert rep["variant"] == variant
     _assert_clean(rep)
 
