@@ -100,7 +100,13 @@ class HaarioTypeAdaptation(Adaptation):
         self.adapt_every_k_steps = int(adapt_every_k_steps)
         self.scale = float(scale)
         self.N, self.M = 1, 0
+        self._default_f = f is None
         self.f = f if f is not None else (lambda x, y, z: x)
 
     def to_abi(self):
+        if not self._default_f:
+            raise NotImplementedError(
+                "HaarioTypeAdaptation with a user closure f(lambda, N, iter) cannot cross the C ABI; "
+                "only the default f = (x, y, z) -> x (constant lambda) is implemented on the GPU path")
+        # NB the reference's readjust! ignores `scale` and uses 2.38^2 / length(rw) (adaptation.jl:423)
         return _abi.Adapt(_abi.ADAPT_HAARIO, self.adapt_every_k_steps, 0.0, self.scale, 0.0, 0.0, 0.0)

@@ -85,6 +85,7 @@ struct extmcmc_handle {
     int64_t seq_next = 0;
     std::vector<int64_t> ra_iter;   // [NU] mcmciter at which the update last ran (0 = never)
     std::vector<int64_t> acc_tag;   // [NU][W] mcmciter stored in the ring slot (0 = never)
+    std::vector<int64_t> haario_M;  // [NU] HaarioTypeAdaptation.M (own-turn counter, adaptation.jl:378)
     // replay staging
     double *rp_prop = nullptr, *rp_exp = nullptr;
     size_t rp_prop_cap = 0, rp_exp_cap = 0;
@@ -332,7 +333,11 @@ int32_t run_block_impl(extmcmc_t h, const extmcmc_step_t *steps, int32_t n_steps
         int64_t &tag = h->acc_tag[(size_t)u * W + (size_t)(it % W)];
         sd.acc_out_valid = (it > W && tag == it - W) ? 1 : 0;
         sd.replay_row = s;
-        sd.pad_ = 0;
+        sd.haario_ready = 0;
+        if (h->upd_host[u].adapt_kind == EXTMCMC_ADAPT_HAARIO) {
+            // register_only_on_my_turn(::Val{true}, ::Haario): M += 1; time_to_update: M >= k -> M = 0
+            if (++h->haario_M[u] >= h->upd_host[u].adapt_every_k) { sd.haario_ready = 1; h->haario_M[u] = 0; }
+        }
         h->ra_iter[u] = it;
         tag = it;
         (void)NU;
@@ -475,6 +480,7 @@ int32_t extmcmc_create(const extmcmc_config_t *cfg, extmcmc_t *out) {
     h->upd_set.assign(NU, false);
     h->ra_iter.assign(NU, 0);
     h->acc_tag.assign((size_t)NU * d.W, 0);
+    h->haario_M.assign(NU, 0);
     *out = h;
     return EXTMCMC_OK;
 #undef CKC
@@ -556,21 +562,27 @@ int32_t extmcmc_generate_obs_normal(extmcmc_t h, int64_t first, int64_t n_obs, d
 int32_t extmcmc_set_update(extmcmc_t h, int32_t u, const extmcmc_update_t *upd) {
     if (!h || !upd) return EXTMCMC_EINVAL;
     if (u < 0 || u >= h->cfg.n_updates) return fail(h, EXTMCMC_EINVAL, "update index out of range");
-    if (upd->kernel != EXTMCMC_KERNEL_RW_UNIFORM)
+    const bool gauss = upd->kernel == EXTMCMC_KERNEL_RW_GAUSS || upd->kernel == EXTMCMC_KERNEL_RW_GAUSS_MIX;
+    if (upd->kernel != EXTMCMC_KERNEL_RW_UNIFORM && !gauss)
         return fail(h, EXTMCMC_EUNSUPPORTED, "transition kernel not implemented on the GPU path");
     if (upd->prior < EXTMCMC_PRIOR_IMPROPER || upd->prior > EXTMCMC_PRIOR_UNIFORM)
         return fail(h, EXTMCMC_EUNSUPPORTED, "prior not implemented on the GPU path");
-    if (upd->adapt.kind != EXTMCMC_ADAPT_NONE && upd->adapt.kind != EXTMCMC_ADAPT_UNIF_RW)
-        return fail(h, EXTMCMC_EUNSUPPORTED, "adaptation not implemented on the GPU path");
-    if (upd->n_coords < 1 || upd->n_coords > kMaxCoords)
-        return fail(h, EXTMCMC_EUNSUPPORTED, "1 <= n_coords <= 16 for random-walk updates");
+    // readjust! exists only for (UniformRandomWalk, AdaptationUnifRW) and
+    // (GaussianRandomWalkMix, HaarioTypeAdaptation): adaptation.jl:273,422
+    if (!(upd->adapt.kind == EXTMCMC_ADAPT_NONE ||
+          (upd->adapt.kind == EXTMCMC_ADAPT_UNIF_RW && upd->kernel == EXTMCMC_KERNEL_RW_UNIFORM) ||
+          (upd->adapt.kind == EXTMCMC_ADAPT_HAARIO && upd->kernel == EXTMCMC_KERNEL_RW_GAUSS_MIX)))
+        return fail(h, EXTMCMC_EUNSUPPORTED, "adaptation not implemented for this transition kernel");
+    if (upd->n_coords < 1 || upd->n_coords > (gauss ? kMaxGaussCoords : kMaxCoords))
+        return fail(h, EXTMCMC_EUNSUPPORTED, gauss ? "1 <= n_coords <= 8 for Gaussian random walks on the GPU path"
+                                                    : "1 <= n_coords <= 16 for random-walk updates");
     if (!upd->coords || !upd->step) return fail(h, EXTMCMC_EINVAL, "coords/step missing");
     if (upd->n_prior_params > kMaxPriorParams || (upd->n_prior_params > 0 && !upd->prior_params))
         return fail(h, EXTMCMC_EINVAL, "bad prior parameters");
     if ((upd->prior == EXTMCMC_PRIOR_NORMAL || upd->prior == EXTMCMC_PRIOR_GAMMA ||
          upd->prior == EXTMCMC_PRIOR_UNIFORM) && upd->n_prior_params < 2)
         return fail(h, EXTMCMC_EINVAL, "prior needs two parameters");
-    if (upd->adapt.kind == EXTMCMC_ADAPT_UNIF_RW && upd->adapt.adapt_every_k_steps < 1)
+    if (upd->adapt.kind != EXTMCMC_ADAPT_NONE && upd->adapt.adapt_every_k_steps < 1)
         return fail(h, EXTMCMC_EINVAL, "adapt_every_k_steps must be >= 1");
     CK(h, cudaSetDevice(h->cfg.device));
     const int64_t C = h->d.C;
@@ -583,7 +595,7 @@ int32_t extmcmc_set_update(extmcmc_t h, int32_t u, const extmcmc_update_t *upd) 
     for (int i = 0; i < upd->n_coords; ++i) {
         if (upd->coords[i] < 0 || upd->coords[i] >= h->cfg.n_params)
             return fail(h, EXTMCMC_EINVAL, "coordinate out of range");
-        if (!(upd->step[i] > 0.0))  // UniformRandomWalk: @assert all(eps .> 0.0), random_walk.jl:50
+        if (!gauss && !(upd->step[i] > 0.0))  // UniformRandomWalk: @assert all(eps .> 0.0), random_walk.jl:50
             return fail(h, EXTMCMC_EINVAL, "eps must be > 0");
         t.coords[i] = upd->coords[i];
         t.pos[i] = upd->pos ? upd->pos[i] : 0;
@@ -594,18 +606,43 @@ int32_t extmcmc_set_update(extmcmc_t h, int32_t u, const extmcmc_update_t *upd) 
     t.target = upd->adapt.target_accpt_rate; t.scale = upd->adapt.scale;
     t.vmin = upd->adapt.min; t.vmax = upd->adapt.max; t.offset = upd->adapt.offset;
     int32_t rc = 0;
+    const int nc = upd->n_coords, nn = nc * nc;
+    const bool mix = upd->kernel == EXTMCMC_KERNEL_RW_GAUSS_MIX;
+    const bool haario = upd->adapt.kind == EXTMCMC_ADAPT_HAARIO;
+    if (mix && !(upd->step[2 * nn] >= 0.0 && upd->step[2 * nn] <= 1.0))   // @assert 0 <= lambda <= 1, random_walk.jl:199
+        return fail(h, EXTMCMC_EINVAL, "lambda must be in [0, 1]");
     if (fresh) {
-        if ((rc = dev_alloc(h, &t.eps, (size_t)upd->n_coords * C)) ||
+        if ((rc = dev_alloc(h, &t.eps, (size_t)nc * C)) ||
             (rc = dev_alloc(h, &t.adapt_prop, (size_t)C)) || (rc = dev_alloc(h, &t.adapt_acc, (size_t)C)) ||
             (rc = dev_alloc(h, &t.tot_prop, (size_t)C)) || (rc = dev_alloc(h, &t.tot_acc, (size_t)C)) ||
             (rc = dev_alloc(h, &t.ra_val, (size_t)C)) || (rc = dev_alloc(h, &t.acc_ring, (size_t)W * C)))
             return rc;
+        if (gauss && (rc = dev_alloc(h, &t.sigA, (size_t)nn))) return rc;
+        if (mix && (rc = dev_alloc(h, &t.sigB, (size_t)nn * C))) return rc;
+        if (haario && ((rc = dev_alloc(h, &t.hmean, (size_t)nc * C)) || (rc = dev_alloc(h, &t.hcov, (size_t)nn * C)))) return rc;
+    } else if ((mix && !t.sigB) || (gauss && !t.sigA) || (haario && !t.hmean)) {
+        return fail(h, EXTMCMC_EINVAL, "cannot change the kernel family of an update");
     }
-    // broadcast the initial step size to every chain, zero the counters
-    std::vector<double> eps0((size_t)upd->n_coords * C);
-    for (int i = 0; i < upd->n_coords; ++i) std::fill_n(eps0.begin() + (size_t)i * C, C, upd->step[i]);
     CK(h, cudaStreamSynchronize(h->stream));
-    CK(h, cudaMemcpy(t.eps, eps0.data(), eps0.size() * sizeof(double), cudaMemcpyHostToDevice));
+    if (!gauss) {
+        // broadcast the initial step size to every chain
+        std::vector<double> eps0((size_t)nc * C);
+        for (int i = 0; i < nc; ++i) std::fill_n(eps0.begin() + (size_t)i * C, C, upd->step[i]);
+        CK(h, cudaMemcpy(t.eps, eps0.data(), eps0.size() * sizeof(double), cudaMemcpyHostToDevice));
+    } else {
+        CK(h, cudaMemcpy(t.sigA, upd->step, sizeof(double) * nn, cudaMemcpyHostToDevice));
+        if (mix) {
+            std::vector<double> sb((size_t)nn * C);
+            for (int k = 0; k < nn; ++k) std::fill_n(sb.begin() + (size_t)k * C, C, upd->step[nn + k]);
+            CK(h, cudaMemcpy(t.sigB, sb.data(), sb.size() * sizeof(double), cudaMemcpyHostToDevice));
+            t.lambda = upd->step[2 * nn];
+        }
+        if (haario) {
+            CK(h, cudaMemset(t.hmean, 0, sizeof(double) * nc * C));
+            CK(h, cudaMemset(t.hcov, 0, sizeof(double) * nn * C));
+        }
+    }
+    h->haario_M[u] = 0;
     CK(h, cudaMemset(t.adapt_prop, 0, sizeof(int32_t) * C));
     CK(h, cudaMemset(t.adapt_acc, 0, sizeof(int32_t) * C));
     CK(h, cudaMemset(t.tot_prop, 0, sizeof(int64_t) * C));
@@ -614,6 +651,10 @@ int32_t extmcmc_set_update(extmcmc_t h, int32_t u, const extmcmc_update_t *upd) 
     CK(h, cudaMemset(t.acc_ring, 0, (size_t)W * C));
     h->upd_set[u] = true;
     h->upd_dirty = true;
+    int nh = 0;
+    for (int v = 0; v < h->cfg.n_updates; ++v)
+        if (h->upd_set[v] && h->upd_host[v].adapt_kind == EXTMCMC_ADAPT_HAARIO) ++nh;
+    if (nh != h->d.n_haario) { h->d.n_haario = nh; invalidate_graphs(h); }
     return EXTMCMC_OK;
 }
 
@@ -639,7 +680,12 @@ int32_t extmcmc_set_state(extmcmc_t h, const double *theta) {
         CK(h, cudaMemset(t.tot_acc, 0, sizeof(int64_t) * C));
         CK(h, cudaMemset(t.ra_val, 0, sizeof(double) * C));
         CK(h, cudaMemset(t.acc_ring, 0, (size_t)d.W * C));
+        if (t.hmean) {
+            CK(h, cudaMemset(t.hmean, 0, sizeof(double) * t.n_coords * C));
+            CK(h, cudaMemset(t.hcov, 0, sizeof(double) * t.n_coords * t.n_coords * C));
+        }
     }
+    std::fill(h->haario_M.begin(), h->haario_M.end(), 0);
     h->seq_next = 0;
     if (h->fetch_active) { cudaEventSynchronize(h->fetch_done); h->fetch_active = false; }
     std::fill(h->ra_iter.begin(), h->ra_iter.end(), 0);
@@ -827,7 +873,24 @@ int32_t extmcmc_get_eps(extmcmc_t h, int32_t u, double *eps) {
     CK(h, cudaSetDevice(h->cfg.device));
     CK(h, cudaStreamSynchronize(h->stream));
     const DevUpdate &t = h->upd_host[u];
-    CK(h, cudaMemcpy(eps, t.eps, sizeof(double) * t.n_coords * h->d.C, cudaMemcpyDeviceToHost));
+    if (t.kernel == EXTMCMC_KERNEL_RW_UNIFORM)
+        CK(h, cudaMemcpy(eps, t.eps, sizeof(double) * t.n_coords * h->d.C, cudaMemcpyDeviceToHost));
+    else if (t.kernel == EXTMCMC_KERNEL_RW_GAUSS_MIX)
+        CK(h, cudaMemcpy(eps, t.sigB, sizeof(double) * t.n_coords * t.n_coords * h->d.C, cudaMemcpyDeviceToHost));
+    else
+        return fail(h, EXTMCMC_EINVAL, "this transition kernel has no per-chain step-size state");
+    return EXTMCMC_OK;
+}
+
+int32_t extmcmc_get_adapt_state(extmcmc_t h, int32_t u, double *mean, double *cov) {
+    if (!h) return EXTMCMC_EINVAL;
+    if (u < 0 || u >= h->cfg.n_updates || !h->upd_set[u]) return fail(h, EXTMCMC_EINVAL, "update not set");
+    const DevUpdate &t = h->upd_host[u];
+    if (t.adapt_kind != EXTMCMC_ADAPT_HAARIO) return fail(h, EXTMCMC_EINVAL, "update has no Haario adaptation");
+    CK(h, cudaSetDevice(h->cfg.device));
+    CK(h, cudaStreamSynchronize(h->stream));
+    if (mean) CK(h, cudaMemcpy(mean, t.hmean, sizeof(double) * t.n_coords * h->d.C, cudaMemcpyDeviceToHost));
+    if (cov) CK(h, cudaMemcpy(cov, t.hcov, sizeof(double) * t.n_coords * t.n_coords * h->d.C, cudaMemcpyDeviceToHost));
     return EXTMCMC_OK;
 }
 

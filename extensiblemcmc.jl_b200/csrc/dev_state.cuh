@@ -15,6 +15,7 @@
 namespace extmcmc {
 
 constexpr int kMaxCoords = 16;      // p_u limit of the scalar per-chain step kernels
+constexpr int kMaxGaussCoords = 8; // p_u limit of the Gaussian random walks on the device
 constexpr int kMaxPriorParams = 4;
 constexpr int kMaxObsDim = 8;       // general-d Gaussian law on the device: d <= 8
 
@@ -33,6 +34,12 @@ struct DevUpdate {
     int64_t *tot_acc;     // [C]
     double  *ra_val;      // [C] latest rolling acceptance rate of this update
     uint8_t *acc_ring;    // [W][C] acceptance bits of the last W iterations
+    // Gaussian random walks (random_walk.jl:123-232)
+    double *sigA;         // [n*n] column-major, shared by all chains (GaussianRandomWalk.Sigma / gsn_A)
+    double *sigB;         // [n*n][C] per chain (gsn_B.Sigma, rewritten by the Haario adaptation)
+    double  lambda;       // GaussianRandomWalkMix.lambda
+    double *hmean;        // [n][C]   HaarioTypeAdaptation.mean
+    double *hcov;         // [n*n][C] HaarioTypeAdaptation.cov
 };
 
 // One schedule element (src/schedule.jl:56-66) plus what the host planner knows.
@@ -45,7 +52,7 @@ struct StepDesc {
     int32_t ra_prev_valid;  // rolling_ar[max(1, iter-1)][pidx] was written (else 0.0)
     int32_t acc_out_valid;  // acceptance_history[iter - W] of this update was written
     int32_t replay_row;     // row of this step in the replay buffers
-    int32_t pad_;
+    int32_t haario_ready;   // this step brings the update's own-turn counter M to k (adaptation.jl:416-420)
 };
 
 struct DevState {
@@ -54,6 +61,7 @@ struct DevState {
     int64_t n_obs_total;    // N over all ranks (enters the log-likelihood constant)
     int32_t p, NU, W, H;    // params, updates, rolling window, history ring length
     int32_t law, stats_mode, rng_mode, p_u_max;
+    int32_t n_haario;       // updates with HaarioTypeAdaptation (they register on every step)
     int32_t obs_dim, lawc_k;  // observation dimension; per-chain law constants in lawc
     uint64_t seed;
     // current state

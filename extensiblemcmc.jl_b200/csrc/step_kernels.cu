@@ -67,6 +67,69 @@ __device__ __forceinline__ double log_q_unif(const DevUpdate &u, const double *e
     return s;
 }
 
+// ---- Gaussian random walks (random_walk.jl:123-232), n <= kMaxGaussCoords -------------------
+constexpr double kTwoPi = 6.283185307179586476925286766559;
+
+// Lower Cholesky factor of Symmetric(S) (upper triangle of the column-major n x n S).
+__device__ __forceinline__ bool chol_lower_sym_upper(const double *S, int n, double *L) {
+    for (int j = 0; j < n; ++j) {
+        double s = S[j + j * n];
+        for (int k = 0; k < j; ++k) s -= L[j + k * n] * L[j + k * n];
+        if (!(s > 0.0) || isinf(s)) return false;
+        const double ljj = sqrt(s);
+        L[j + j * n] = ljj;
+        for (int i = j + 1; i < n; ++i) {
+            double a = S[j + i * n];
+            for (int k = 0; k < j; ++k) a -= L[i + k * n] * L[j + k * n];
+            L[i + j * n] = a / ljj;
+        }
+    }
+    return true;
+}
+
+__device__ __forceinline__ double mvn_logpdf_chol(const double *L, int n, const double *mu, const double *x) {
+    double z[kMaxGaussCoords], sq = 0.0, logdet = 0.0;
+    for (int r = 0; r < n; ++r) {
+        double a = x[r] - mu[r];
+        for (int k = 0; k < r; ++k) a -= L[r + k * n] * z[k];
+        z[r] = a / L[r + r * n];
+        sq += z[r] * z[r];
+        logdet += log(L[r + r * n]);
+    }
+    return -((double)n * kLog2Pi + 2.0 * logdet) / 2.0 - sq / 2.0;
+}
+
+// Sigma of a Gaussian walk as a dense local matrix: shared sigA, or this chain's sigB
+__device__ __forceinline__ void load_sigma(const DevUpdate &u, bool useB, int64_t C, int64_t c, double *S) {
+    const int nn = u.n_coords * u.n_coords;
+    if (useB) for (int k = 0; k < nn; ++k) S[k] = u.sigB[(int64_t)k * C + c];
+    else      for (int k = 0; k < nn; ++k) S[k] = u.sigA[k];
+}
+
+// logpdf(rw::GaussianRandomWalk, from, to) random_walk.jl:163-171, on transformed copies
+__device__ __forceinline__ double log_q_gauss(const DevUpdate &u, const double *L, const double *from,
+                                              const double *to) {
+    const int n = u.n_coords;
+    double tf[kMaxGaussCoords], tt[kMaxGaussCoords], s = 0.0;
+    for (int i = 0; i < n; ++i) if (u.pos[i]) s += log(to[i]);
+    const double logJ = -s;
+    for (int i = 0; i < n; ++i) {
+        tf[i] = u.pos[i] ? log(from[i]) : from[i];
+        tt[i] = u.pos[i] ? log(to[i]) : to[i];
+    }
+    return mvn_logpdf_chol(L, n, tf, tt) + logJ;
+}
+
+// q(from -> to) - both directions share the factorisations LA / LB computed once per step
+__device__ __forceinline__ double log_q_any(const DevUpdate &u, const double *eps, const double *LA,
+                                            const double *LB, const double *from, const double *to) {
+    if (u.kernel == EXTMCMC_KERNEL_RW_UNIFORM) return log_q_unif(u, eps, to);
+    if (u.kernel == EXTMCMC_KERNEL_RW_GAUSS) return log_q_gauss(u, LA, from, to);
+    // GaussianRandomWalkMix random_walk.jl:229-232 (no log-sum-exp guard, as in the reference)
+    const double lpA = log_q_gauss(u, LA, from, to), lpB = log_q_gauss(u, LB, from, to);
+    return log((1.0 - u.lambda) * exp(lpA) + u.lambda * exp(lpB));
+}
+
 // Per-chain law constants of a parameter vector.
 //   GSN_IID_1D: lawc = { mu, c0 = -(log 2pi + 2 log sqrt(var))/2, 1/(2 var) },
 //               ll = N c0 - S/(2 var),  S = sum (x - mu)^2     (gsn_target.jl:15-29, d = 1)
@@ -171,12 +234,40 @@ __device__ __forceinline__ void propose_chain(const DevState &d, const StepDesc 
     } else {
         ChainStepStream rng(d.seed, (uint64_t)(d.chain_offset + c), sd.mcmciter, sd.pidx);
         for (;;) {
-            for (int i = 0; i < n; ++i) {
-                const double r = rng.next();
-                const double e = u.eps[(int64_t)i * d.C + c];
-                const double a = -e, b = e;
-                const double U = a + (b - a) * r;  // rand(Uniform(-eps, eps))
-                prop[i] = u.pos[i] ? th[i] * exp(U) : th[i] + U;  // random_walk.jl:72
+            if (u.kernel == EXTMCMC_KERNEL_RW_UNIFORM) {
+                for (int i = 0; i < n; ++i) {
+                    const double r = rng.next();
+                    const double e = u.eps[(int64_t)i * d.C + c];
+                    const double a = -e, b = e;
+                    const double U = a + (b - a) * r;  // rand(Uniform(-eps, eps))
+                    prop[i] = u.pos[i] ? th[i] * exp(U) : th[i] + U;  // random_walk.jl:72
+                }
+            } else {
+                // rand(rw::GaussianRandomWalk[Mix]) random_walk.jl:145-151,213-227
+                bool useB = false;
+                if (u.kernel == EXTMCMC_KERNEL_RW_GAUSS_MIX) useB = rng.next() <= u.lambda;  // Bernoulli(lambda)
+                double Sg[kMaxGaussCoords * kMaxGaussCoords], L[kMaxGaussCoords * kMaxGaussCoords], z[kMaxGaussCoords];
+                load_sigma(u, useB, d.C, c, Sg);
+                for (int q = 0; q < n; q += 2) {  // randn via Box-Muller on the uniform stream
+                    const double u1 = rng.next(), u2 = rng.next();
+                    const double rad = sqrt(-2.0 * log(u1));
+                    double sn, cs;
+                    sincospi(2.0 * u2, &sn, &cs);
+                    z[q] = rad * cs;
+                    if (q + 1 < n) z[q + 1] = rad * sn;
+                }
+                if (!chol_lower_sym_upper(Sg, n, L)) {
+                    *d.err_flag = 1;  // reference: PosDefException from MvNormal(theta, Sigma)
+                    for (int i = 0; i < n; ++i) prop[i] = NAN;
+                    break;
+                }
+                for (int i = 0; i < n; ++i) {
+                    double t = u.pos[i] ? log(th[i]) : th[i];
+                    double a = 0.0;
+                    for (int k = 0; k <= i; ++k) a += L[i + k * n] * z[k];
+                    t = a + t;
+                    prop[i] = u.pos[i] ? exp(t) : t;
+                }
             }
             // whole-vector redraw while the prior is exactly -Inf (updates.jl:193-195)
             if (!(log_prior(u, prop) == -INFINITY)) break;
@@ -298,12 +389,30 @@ accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fuse_ne
     for (int i = 0; i < n; ++i) {
         th[i] = d.theta[(int64_t)u.coords[i] * C + c];
         prop[i] = d.prop_loc[(int64_t)i * C + c];
-        eps[i] = u.eps[(int64_t)i * C + c];
+        eps[i] = u.kernel == EXTMCMC_KERNEL_RW_UNIFORM ? u.eps[(int64_t)i * C + c] : 0.0;
     }
     // llr, strictly left to right (run.jl:271-277)
     double llr = ll_prop - ll_cur;
-    llr = llr + log_q_unif(u, eps, th);    // theta° -> theta
-    llr = llr - log_q_unif(u, eps, prop);  // theta -> theta°
+    if (u.kernel == EXTMCMC_KERNEL_RW_UNIFORM) {
+        llr = llr + log_q_unif(u, eps, th);    // theta° -> theta
+        llr = llr - log_q_unif(u, eps, prop);  // theta -> theta°
+    } else {
+        double Sg[kMaxGaussCoords * kMaxGaussCoords], LA[kMaxGaussCoords * kMaxGaussCoords],
+            LB[kMaxGaussCoords * kMaxGaussCoords];
+        load_sigma(u, false, C, c, Sg);
+        bool ok = chol_lower_sym_upper(Sg, n, LA);
+        if (u.kernel == EXTMCMC_KERNEL_RW_GAUSS_MIX) {
+            load_sigma(u, true, C, c, Sg);
+            ok = chol_lower_sym_upper(Sg, n, LB) && ok;
+        }
+        if (!ok) {
+            *d.err_flag = 1;
+            llr = NAN;
+        } else {
+            llr = llr + log_q_any(u, eps, LA, LB, prop, th);   // theta° -> theta
+            llr = llr - log_q_any(u, eps, LA, LB, th, prop);   // theta -> theta°
+        }
+    }
     llr = llr + log_prior(u, prop);
     llr = llr - log_prior(u, th);
 
@@ -402,6 +511,39 @@ accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fuse_ne
         }
         u.adapt_prop[c] = prop_n;
         u.adapt_acc[c] = acc_n;
+    }
+    // HaarioTypeAdaptation registers on EVERY update step of ANY update (adaptation.jl:399-414),
+    // on that update's view of the (already committed) global state, log-transformed copy.
+    if (d.n_haario > 0) {
+        for (int v = 0; v < d.NU; ++v) {
+            const DevUpdate &w = (v == sd.pidx) ? u : d.upd[v];
+            if (w.adapt_kind != EXTMCMC_ADAPT_HAARIO) continue;
+            const int m = w.n_coords;
+            double t[kMaxGaussCoords], om[kMaxGaussCoords], nm[kMaxGaussCoords];
+            for (int i = 0; i < m; ++i) {
+                const double x = d.theta[(int64_t)w.coords[i] * C + c];
+                t[i] = w.pos[i] ? log(x) : x;
+                om[i] = w.hmean[(int64_t)i * C + c];
+            }
+            const int64_t hn = sd.stat_n;  // adpt.N: starts at 1, +1 per registration = per executed step
+            const double f_old = (double)(hn - 1) / (double)hn, f_mean = (double)hn / (double)(hn + 1);
+            const double f_new = (double)(hn + 1) / (double)hn;
+            for (int i = 0; i < m; ++i) {
+                nm[i] = om[i] * f_mean + t[i] / (double)(hn + 1);
+                w.hmean[(int64_t)i * C + c] = nm[i];
+            }
+            const bool ready = (v == sd.pidx) && sd.haario_ready;
+            for (int b = 0; b < m; ++b)
+                for (int a = 0; a < m; ++a) {
+                    const int64_t idx = (int64_t)(a + b * m) * C + c;
+                    const double old_sum_sq = f_old * w.hcov[idx] + om[a] * om[b];
+                    const double new_sum_sq = old_sum_sq + (t[a] * t[b]) / (double)hn;
+                    const double cv = new_sum_sq - f_new * (nm[a] * nm[b]);
+                    w.hcov[idx] = cv;
+                    // readjust!(rw::GaussianRandomWalkMix, ...) adaptation.jl:422-426
+                    if (ready) w.sigB[idx] = (2.38 * 2.38) / (double)m * cv;
+                }
+        }
     }
     // proposal of the NEXT schedule element of this block, fused here: the chain's thread
     // already holds its freshly committed state, and one launch per update step is saved

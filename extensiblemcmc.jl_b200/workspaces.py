@@ -134,11 +134,13 @@ class CUDAGlobalWorkspace(GlobalWorkspace):
                 ida = np.frombuffer(bytes(backend.comm_id), dtype=np.uint8).copy()
                 self._ck(lib.extmcmc_comm_init(self.handle, ida.ctypes.data_as(_abi.c_uint8_p)))
             self._keep = []
+            self._kernels = []
             for i, updt in enumerate(updates):
                 if not hasattr(updt, "to_abi"):
                     raise NotImplementedError(f"update {type(updt).__name__} is not implemented on the GPU path")
                 u, keep = updt.to_abi(self.p)
                 self._keep.append(keep)
+                self._kernels.append(u.kernel)
                 self._ck(lib.extmcmc_set_update(self.handle, i, C.byref(u)))
             if isinstance(obs, DeviceGeneratedObs):
                 self._ck(lib.extmcmc_generate_obs_normal(self.handle, obs.first, obs.n, obs.mean, obs.sd, obs.seed))
@@ -211,11 +213,20 @@ class CUDAGlobalWorkspace(GlobalWorkspace):
         return dict(mean=mean, cov=cov, rolling_ar=ra, n_accept=na, n_prop=npr)
 
     def eps(self, u):
-        """Current per-chain step sizes of update u (1-based): [p_u, C]."""
+        """Current per-chain step-size state of update u (1-based): eps [p_u, C] for a uniform
+        walk, Sigma_B [p_u^2, C] (column-major) for a Gaussian mixture walk."""
         n = len(self._keep[u - 1][0])
-        out = np.empty((n, self.C))
+        rows = n * n if self._kernels[u - 1] == _abi.KERNEL_RW_GAUSS_MIX else n
+        out = np.empty((rows, self.C))
         self._ck(self.lib.extmcmc_get_eps(self.handle, u - 1, _abi.dptr(out)))
         return out
+
+    def adapt_state(self, u):
+        """HaarioTypeAdaptation mean [p_u, C] and cov [p_u^2, C] of update u (1-based)."""
+        n = len(self._keep[u - 1][0])
+        mean, cov = np.empty((n, self.C)), np.empty((n * n, self.C))
+        self._ck(self.lib.extmcmc_get_adapt_state(self.handle, u - 1, _abi.dptr(mean), _abi.dptr(cov)))
+        return mean, cov
 
     def eval_loglik(self):
         out = np.empty(self.C)

@@ -256,8 +256,11 @@ int32_t extmcmc_history_fetch_end(extmcmc_t h, double *theta, double *theta_prop
 int32_t extmcmc_get_stats(extmcmc_t h, double *mean, double *cov,
                           double *rolling_ar, int64_t *n_accept, int64_t *n_prop);
 /* Current step-size state of update u per chain: eps[p_u][C] (RW_UNIFORM),
- * tau[1][C] (MALA). */
+ * Sigma_B[p_u*p_u][C] column-major (RW_GAUSS_MIX: gsn_B.Sigma after readjust!,
+ * adaptation.jl:422-426), tau[1][C] (MALA). */
 int32_t extmcmc_get_eps(extmcmc_t h, int32_t u, double *eps);
+/* HaarioTypeAdaptation.mean [p_u][C] and .cov [p_u*p_u][C] (adaptation.jl:372-379). */
+int32_t extmcmc_get_adapt_state(extmcmc_t h, int32_t u, double *mean, double *cov);
 /* Evaluate the full-data log-likelihood of the current state of every chain
  * (one sweep, nothing else); ll_out[C].  Used by parity tests. */
 int32_t extmcmc_eval_loglik(extmcmc_t h, double *ll_out);

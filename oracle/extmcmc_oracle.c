@@ -80,6 +80,9 @@ typedef struct {
     extmcmc_adapt_t adapt;
     int32_t step_len; /* doubles of step-size state per chain */
     double *step0;    /* initial step-size state [step_len] */
+    double *hmean;    /* HaarioTypeAdaptation.mean [C][n]   (adaptation.jl:373) */
+    double *hcov;     /* HaarioTypeAdaptation.cov  [C][n*n] column-major (:374) */
+    int64_t *hM;      /* HaarioTypeAdaptation.M    [C]      (:378) */
 } orc_update_t;
 
 struct oracle_handle {
@@ -150,8 +153,18 @@ int32_t oracle_create(const extmcmc_config_t *cfg, const extmcmc_update_t *updat
     for (int u = 0; u < NU; ++u) {
         const extmcmc_update_t *s = &updates[u];
         orc_update_t *t = &h->upd[u];
-        if (s->kernel != EXTMCMC_KERNEL_RW_UNIFORM) {
+        if (s->kernel != EXTMCMC_KERNEL_RW_UNIFORM && s->kernel != EXTMCMC_KERNEL_RW_GAUSS &&
+            s->kernel != EXTMCMC_KERNEL_RW_GAUSS_MIX) {
             set_err("oracle: transition kernel not implemented");
+            oracle_destroy(h);
+            return EXTMCMC_EUNSUPPORTED;
+        }
+        if ((s->adapt.kind == EXTMCMC_ADAPT_UNIF_RW && s->kernel != EXTMCMC_KERNEL_RW_UNIFORM) ||
+            (s->adapt.kind == EXTMCMC_ADAPT_HAARIO && s->kernel != EXTMCMC_KERNEL_RW_GAUSS_MIX) ||
+            s->adapt.kind > EXTMCMC_ADAPT_HAARIO) {
+            /* readjust!(rw, adpt, iter) exists only for (UniformRandomWalk, AdaptationUnifRW) and
+             * (GaussianRandomWalkMix, HaarioTypeAdaptation): adaptation.jl:273,422 */
+            set_err("oracle: adaptation does not match the transition kernel");
             oracle_destroy(h);
             return EXTMCMC_EUNSUPPORTED;
         }
@@ -170,10 +183,20 @@ int32_t oracle_create(const extmcmc_config_t *cfg, const extmcmc_update_t *updat
             t->pos[i] = s->pos ? s->pos[i] : 0;
             if (s->coords[i] < 0 || s->coords[i] >= p) { set_err("coord out of range"); oracle_destroy(h); return EXTMCMC_EINVAL; }
             /* UniformRandomWalk asserts all(eps .> 0), random_walk.jl:50 */
-            if (!(s->step[i] > 0.0)) { set_err("eps must be > 0"); oracle_destroy(h); return EXTMCMC_EINVAL; }
+            if (s->kernel == EXTMCMC_KERNEL_RW_UNIFORM && !(s->step[i] > 0.0)) { set_err("eps must be > 0"); oracle_destroy(h); return EXTMCMC_EINVAL; }
         }
         for (int i = 0; i < s->n_prior_params && i < 8; ++i) t->prior_params[i] = s->prior_params[i];
-        t->step_len = s->n_coords;
+        {
+            const int nn = s->n_coords * s->n_coords;
+            t->step_len = s->kernel == EXTMCMC_KERNEL_RW_UNIFORM ? s->n_coords
+                        : s->kernel == EXTMCMC_KERNEL_RW_GAUSS ? nn : 2 * nn + 1;
+            if (s->kernel != EXTMCMC_KERNEL_RW_UNIFORM && s->n_coords > 16) { set_err("oracle: Gaussian walks need n_coords <= 16"); oracle_destroy(h); return EXTMCMC_EINVAL; }
+            if (s->adapt.kind == EXTMCMC_ADAPT_HAARIO) {
+                t->hmean = xcalloc((size_t)C * s->n_coords, sizeof(double));   /* zero(state), adaptation.jl:388 */
+                t->hcov = xcalloc((size_t)C * nn, sizeof(double));
+                t->hM = xcalloc((size_t)C, sizeof(int64_t));
+            }
+        }
         t->step0 = xcalloc(t->step_len, sizeof(double));
         memcpy(t->step0, s->step, t->step_len * sizeof(double));
         h->step[u] = xcalloc((size_t)C * t->step_len, sizeof(double));
@@ -203,7 +226,8 @@ int32_t oracle_create(const extmcmc_config_t *cfg, const extmcmc_update_t *updat
 
 void oracle_destroy(oracle_t h) {
     if (!h) return;
-    if (h->upd) for (int u = 0; u < h->NU; ++u) { free(h->upd[u].coords); free(h->upd[u].pos); free(h->upd[u].step0); }
+    if (h->upd) for (int u = 0; u < h->NU; ++u) { free(h->upd[u].coords); free(h->upd[u].pos); free(h->upd[u].step0);
+                                                  free(h->upd[u].hmean); free(h->upd[u].hcov); free(h->upd[u].hM); }
     if (h->step) for (int u = 0; u < h->NU; ++u) free(h->step[u]);
     free(h->upd); free(h->step); free(h->obs); free(h->y); free(h->theta); free(h->ll);
     free(h->mean); free(h->cov); free(h->statN); free(h->proposed); free(h->accepted);
@@ -332,6 +356,80 @@ static double log_q_unif(const orc_update_t *u, const double *eps, const double 
 }
 
 /* ------------------------------------------------------------------------- */
+/* Gaussian random walks (src/transition_kernels/random_walk.jl:123-232)     */
+/* ------------------------------------------------------------------------- */
+/* Lower Cholesky factor of Symmetric(S) (upper triangle of the column-major n x n S;
+ * GaussianRandomWalk stores Symmetric(Sigma), random_walk.jl:132).  Returns 0 if S is not
+ * positive definite (MvNormal(theta, Sigma) throws PosDefException in the reference). */
+static int chol_lower_sym_upper(const double *S, int n, double *L) {
+    for (int j = 0; j < n; ++j) {
+        double s = S[j + j * n];
+        for (int k = 0; k < j; ++k) s -= L[j + k * n] * L[j + k * n];
+        if (!(s > 0.0) || !isfinite(s)) return 0;
+        double ljj = sqrt(s);
+        L[j + j * n] = ljj;
+        for (int i = j + 1; i < n; ++i) {
+            double a = S[j + i * n];
+            for (int k = 0; k < j; ++k) a -= L[i + k * n] * L[j + k * n];
+            L[i + j * n] = a / ljj;
+        }
+    }
+    return 1;
+}
+
+/* logpdf(MvNormal(mu, L L'), x) = -(n log 2pi + 2 sum log L_ii)/2 - |L \ (x - mu)|^2 / 2 */
+static double mvn_logpdf_chol(const double *L, int n, const double *mu, const double *x) {
+    double z[16], sq = 0.0, logdet = 0.0;
+    for (int r = 0; r < n; ++r) {
+        double a = x[r] - mu[r];
+        for (int k = 0; k < r; ++k) a -= L[r + k * n] * z[k];
+        z[r] = a / L[r + r * n];
+        sq += z[r] * z[r];
+        logdet += log(L[r + r * n]);
+    }
+    return -((double)n * LOG2PI + 2.0 * logdet) / 2.0 - sq / 2.0;
+}
+
+/* logpdf(rw::GaussianRandomWalk, from, to) random_walk.jl:163-171 on transformed COPIES
+ * (the reference log/exp-transforms in place and perturbs the state by ulps). */
+static double log_q_gauss(const uint8_t *pos, int n, const double *Sigma, const double *from,
+                          const double *to, int *bad) {
+    double L[256], tf[16], tt[16], logJ = 0.0;
+    if (!chol_lower_sym_upper(Sigma, n, L)) { *bad = 1; return NAN; }
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) if (pos[i]) s += log(to[i]);     /* _logjacobian: -sum(log.(to[pos])) */
+    logJ = -s;
+    for (int i = 0; i < n; ++i) { tf[i] = pos[i] ? log(from[i]) : from[i]; tt[i] = pos[i] ? log(to[i]) : to[i]; }
+    return mvn_logpdf_chol(L, n, tf, tt) + logJ;
+}
+
+/* log transition density of an update's kernel, from -> to */
+static double log_q(const orc_update_t *u, const double *step, const double *from, const double *to, int *bad) {
+    const int n = u->n_coords;
+    if (u->kernel == EXTMCMC_KERNEL_RW_UNIFORM) return log_q_unif(u, step, to);
+    if (u->kernel == EXTMCMC_KERNEL_RW_GAUSS) return log_q_gauss(u->pos, n, step, from, to, bad);
+    /* GaussianRandomWalkMix, random_walk.jl:229-232 (no log-sum-exp guard, as in the reference) */
+    const double lam = step[2 * n * n];
+    const double lpA = log_q_gauss(u->pos, n, step, from, to, bad);
+    const double lpB = log_q_gauss(u->pos, n, step + n * n, from, to, bad);
+    return log((1.0 - lam) * exp(lpA) + lam * exp(lpB));
+}
+
+/* rand(rw::GaussianRandomWalk, theta) random_walk.jl:145-151: theta° = exp-back(log-transform(theta) + L z) */
+static void gauss_propose(const uint8_t *pos, int n, const double *Sigma, const double *th,
+                          const double *z, double *out, int *bad) {
+    double L[256];
+    if (!chol_lower_sym_upper(Sigma, n, L)) { *bad = 1; for (int i = 0; i < n; ++i) out[i] = NAN; return; }
+    for (int i = 0; i < n; ++i) {
+        double t = pos[i] ? log(th[i]) : th[i];
+        double a = 0.0;
+        for (int k = 0; k <= i; ++k) a += L[i + k * n] * z[k];   /* unwhiten: L * z */
+        t = a + t;                                               /* + mu */
+        out[i] = pos[i] ? exp(t) : t;
+    }
+}
+
+/* ------------------------------------------------------------------------- */
 /* One schedule element for one chain: the body of __run! src/run.jl:70-82   */
 /* ------------------------------------------------------------------------- */
 typedef struct {
@@ -367,13 +465,33 @@ static void chain_step(struct oracle_handle *h, int64_t c, const extmcmc_step_t 
             th_prop[i] = io->rec_prop[((int64_t)s_idx * io->p_u_max + i) * C + c];
     } else {
         for (;;) {
-            for (int i = 0; i < n; ++i) {
-                double r = oracle_uniform(h->cfg.seed, gchain, st->mcmciter, u_idx, j++);
-                /* rand(Uniform(a, b)) = a + (b - a) * rand() with a = -eps, b = eps */
-                double a = -eps[i], b = eps[i];
-                double U = a + (b - a) * r;
-                /* theta .* (exp.(U).*pos .+ 1.0.*.!pos) .+ U.*.!pos, random_walk.jl:72 */
-                th_prop[i] = u->pos[i] ? th_loc[i] * exp(U) : th_loc[i] + U;
+            if (u->kernel == EXTMCMC_KERNEL_RW_UNIFORM) {
+                for (int i = 0; i < n; ++i) {
+                    double r = oracle_uniform(h->cfg.seed, gchain, st->mcmciter, u_idx, j++);
+                    /* rand(Uniform(a, b)) = a + (b - a) * rand() with a = -eps, b = eps */
+                    double a = -eps[i], b = eps[i];
+                    double U = a + (b - a) * r;
+                    /* theta .* (exp.(U).*pos .+ 1.0.*.!pos) .+ U.*.!pos, random_walk.jl:72 */
+                    th_prop[i] = u->pos[i] ? th_loc[i] * exp(U) : th_loc[i] + U;
+                }
+            } else {
+                /* Mix: pick_kernel, rand(Bernoulli(lambda)) = rand() <= lambda, random_walk.jl:225-227 */
+                const double *Sig = eps;
+                if (u->kernel == EXTMCMC_KERNEL_RW_GAUSS_MIX) {
+                    double r = oracle_uniform(h->cfg.seed, gchain, st->mcmciter, u_idx, j++);
+                    if (r <= eps[2 * n * n]) Sig = eps + n * n;
+                }
+                double z[16];
+                for (int q = 0; q < n; q += 2) {          /* randn via Box-Muller on the uniform stream */
+                    double u1 = oracle_uniform(h->cfg.seed, gchain, st->mcmciter, u_idx, j++);
+                    double u2 = oracle_uniform(h->cfg.seed, gchain, st->mcmciter, u_idx, j++);
+                    double rad = sqrt(-2.0 * log(u1));
+                    z[q] = rad * cos(6.283185307179586476925286766559 * u2);
+                    if (q + 1 < n) z[q + 1] = rad * sin(6.283185307179586476925286766559 * u2);
+                }
+                int badp = 0;
+                gauss_propose(u->pos, n, Sig, th_loc, z, th_prop, &badp);
+                if (badp) { h->domain_err = 1; break; }
             }
             /* redraw the whole vector while the prior is exactly -Inf, updates.jl:193-195 */
             if (!(log_prior(u, th_prop) == -INFINITY)) break;
@@ -397,8 +515,12 @@ static void chain_step(struct oracle_handle *h, int64_t c, const extmcmc_step_t 
 
     /* accept_reject! src/run.jl:268-281; strict left-to-right association */
     double llr = ll_prop - ll_cur;
-    llr = llr + log_q_unif(u, eps, th_loc);   /* ltd(Proposal): theta° -> theta, run.jl:360-367 */
-    llr = llr - log_q_unif(u, eps, th_prop);  /* ltd(Previous): theta -> theta°, run.jl:344-351 */
+    {
+        int badq = 0;
+        llr = llr + log_q(u, eps, th_prop, th_loc, &badq);   /* ltd(Proposal): theta° -> theta, run.jl:360-367 */
+        llr = llr - log_q(u, eps, th_loc, th_prop, &badq);   /* ltd(Previous): theta -> theta°, run.jl:344-351 */
+        if (badq) h->domain_err = 1;
+    }
     llr = llr + log_prior(u, th_prop);
     llr = llr - log_prior(u, th_loc);
     double E;
@@ -479,6 +601,35 @@ static void chain_step(struct oracle_handle *h, int64_t c, const extmcmc_step_t 
                 e = e > u->adapt.min ? e : u->adapt.min;    /* max(., min) */
                 eps[i] = e;
             }
+        }
+    }
+    /* HaarioTypeAdaptation registers on EVERY update step of ANY update
+     * (register_only_on_my_turn(::Val{false}, ::Haario) = false, adaptation.jl:399-404), on the
+     * update's view of the global state, log-transformed (here: a transformed copy). */
+    for (int v = 0; v < NU; ++v) {
+        const orc_update_t *w = &h->upd[v];
+        if (w->adapt.kind != EXTMCMC_ADAPT_HAARIO) continue;
+        const int m = w->n_coords;
+        double *hm = w->hmean + c * m, *hc = w->hcov + c * m * m;
+        if (v == u_idx) w->hM[c] += 1;                           /* my turn: M += 1, :401-404 */
+        double t[16], old_m[16];
+        for (int i = 0; i < m; ++i) { double x = theta[w->coords[i]]; t[i] = w->pos[i] ? log(x) : x; }
+        const int64_t N = h->statN[c] - 1;                       /* adpt.N: starts at 1, +1 per register */
+        const double f_old = (double)(N - 1) / (double)N, f_mean = (double)N / (double)(N + 1);
+        const double f_new = (double)(N + 1) / (double)N;
+        for (int i = 0; i < m; ++i) old_m[i] = hm[i];
+        for (int i = 0; i < m; ++i) hm[i] = old_m[i] * f_mean + t[i] / (double)(N + 1);     /* :409 */
+        for (int b = 0; b < m; ++b)
+            for (int a = 0; a < m; ++a) {
+                double old_sum_sq = f_old * hc[a + b * m] + old_m[a] * old_m[b];          /* :408 */
+                double new_sum_sq = old_sum_sq + (t[a] * t[b]) / (double)N;                /* :410 */
+                hc[a + b * m] = new_sum_sq - f_new * (hm[a] * hm[b]);                      /* :411 */
+            }
+        if (v == u_idx && w->hM[c] >= w->adapt.adapt_every_k_steps) {   /* time_to_update :416-420 */
+            w->hM[c] = 0;
+            double *SigB = h->step[v] + c * w->step_len + m * m;
+            for (int k = 0; k < m * m; ++k) SigB[k] = (2.38 * 2.38) / (double)m * hc[k];   /* 2.38^2/length(rw)*cov :423 */
+            /* lambda = f_lambda(lambda, N, iter): the default closure returns lambda unchanged (:385) */
         }
     }
 }
@@ -587,6 +738,16 @@ int32_t oracle_get_eps(oracle_t h, int32_t u, double *eps) {
     int L = h->upd[u].step_len;
     for (int64_t c = 0; c < h->C; ++c)
         for (int i = 0; i < L; ++i) eps[(int64_t)i * h->C + c] = h->step[u][c * L + i];
+    return EXTMCMC_OK;
+}
+
+int32_t oracle_get_adapt_state(oracle_t h, int32_t u, double *mean, double *cov) {
+    if (u < 0 || u >= h->NU || h->upd[u].adapt.kind != EXTMCMC_ADAPT_HAARIO) return EXTMCMC_EINVAL;
+    const int m = h->upd[u].n_coords;
+    for (int64_t c = 0; c < h->C; ++c) {
+        if (mean) for (int i = 0; i < m; ++i) mean[(int64_t)i * h->C + c] = h->upd[u].hmean[c * m + i];
+        if (cov) for (int k = 0; k < m * m; ++k) cov[(int64_t)k * h->C + c] = h->upd[u].hcov[c * m * m + k];
+    }
     return EXTMCMC_OK;
 }
 

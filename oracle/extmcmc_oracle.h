@@ -63,7 +63,10 @@ int32_t oracle_run_block(oracle_t h, const extmcmc_step_t *steps, int32_t n_step
 int32_t oracle_get_state(oracle_t h, double *theta, double *ll);
 int32_t oracle_get_stats(oracle_t h, double *mean, double *cov, double *rolling_ar,
                          int64_t *n_accept, int64_t *n_prop);
+/* Per-chain step-size state of update u, [len][C]: eps (RW_UNIFORM, len = p_u), Sigma (RW_GAUSS,
+ * len = p_u^2), [Sigma_A, Sigma_B, lambda] (RW_GAUSS_MIX, len = 2 p_u^2 + 1). */
 int32_t oracle_get_eps(oracle_t h, int32_t u, double *eps);
+int32_t oracle_get_adapt_state(oracle_t h, int32_t u, double *mean, double *cov);
 /* Full-data log-likelihood of arbitrary parameter vectors theta[p][C]
  * (the reference's loglikelihood(P, obs), src/example/gsn_target.jl:23-29). */
 int32_t oracle_loglik(oracle_t h, const double *theta, int64_t n_chains_eval,

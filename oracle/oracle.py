@@ -46,6 +46,8 @@ def load():
     lib.oracle_get_stats.argtypes = [H, dp, dp, dp, i64p, i64p]
     lib.oracle_get_eps.restype = C.c_int32
     lib.oracle_get_eps.argtypes = [H, C.c_int32, dp]
+    lib.oracle_get_adapt_state.restype = C.c_int32
+    lib.oracle_get_adapt_state.argtypes = [H, C.c_int32, dp, dp]
     lib.oracle_loglik.restype = C.c_int32
     lib.oracle_loglik.argtypes = [H, dp, C.c_int64, dp, C.c_int32]
     lib.oracle_philox4x32_10.restype = None
@@ -99,6 +101,7 @@ class Oracle:
             arr[i] = a
             self._keep.append(keep)
             self.p_u.append(len(u.coords))
+            self.kernels = getattr(self, "kernels", []) + [a.kernel]
         self.p_u_max = max(self.p_u)
         obs = np.ascontiguousarray(np.asarray(obs, dtype=np.float64))
         if obs.ndim == 1:
@@ -164,9 +167,19 @@ class Oracle:
                     n_accept=na, n_prop=npr)
 
     def eps(self, u):
-        out = np.empty((self.p_u[u - 1], self.C))
+        """eps [p_u, C] (uniform walk) or Sigma_B [p_u^2, C] (Gaussian mixture walk)."""
+        n, k = self.p_u[u - 1], self.kernels[u - 1]
+        ln = n if k == _abi.KERNEL_RW_UNIFORM else (n * n if k == _abi.KERNEL_RW_GAUSS else 2 * n * n + 1)
+        out = np.empty((ln, self.C))
         self.lib.oracle_get_eps(self.h, u - 1, _abi.dptr(out))
-        return out
+        return out[n * n:2 * n * n] if k == _abi.KERNEL_RW_GAUSS_MIX else out
+
+    def adapt_state(self, u):
+        n = self.p_u[u - 1]
+        mean, cov = np.empty((n, self.C)), np.empty((n * n, self.C))
+        rc = self.lib.oracle_get_adapt_state(self.h, u - 1, _abi.dptr(mean), _abi.dptr(cov))
+        assert rc == 0
+        return mean, cov
 
     def loglik(self, theta, n_threads=1):
         theta = np.ascontiguousarray(theta, dtype=np.float64)

@@ -55,10 +55,12 @@ class GpuSession:
             raise _abi.ExtMCMCError(rc, self.lib.extmcmc_last_error(None).decode())
         self._keep = []
         self.p_u = []
+        self.kernels = []
         for i, u in enumerate(updates):
             a, keep = u.to_abi(self.p)
             self._keep.append(keep)
             self.p_u.append(len(u.coords))
+            self.kernels.append(a.kernel)
             self.ck(self.lib.extmcmc_set_update(self.h, i, C.byref(a)))
         obs = np.ascontiguousarray(obs, dtype=np.float64)
         self.ck(self.lib.extmcmc_upload_obs(self.h, _abi.dptr(obs), obs.shape[0], law.obs_dim, None))
@@ -125,9 +127,17 @@ class GpuSession:
                     n_accept=na, n_prop=npr)
 
     def eps(self, u):
-        out = np.empty((self.p_u[u - 1], self.C))
+        n = self.p_u[u - 1]
+        rows = n * n if self.kernels[u - 1] == _abi.KERNEL_RW_GAUSS_MIX else n
+        out = np.empty((rows, self.C))
         self.ck(self.lib.extmcmc_get_eps(self.h, u - 1, _abi.dptr(out)))
         return out
+
+    def adapt_state(self, u):
+        n = self.p_u[u - 1]
+        mean, cov = np.empty((n, self.C)), np.empty((n * n, self.C))
+        self.ck(self.lib.extmcmc_get_adapt_state(self.h, u - 1, _abi.dptr(mean), _abi.dptr(cov)))
+        return mean, cov
 
     def eval_loglik(self):
         out = np.empty(self.C)
@@ -188,7 +198,10 @@ def replay_compare(x, n_chains, n_iters, seed=1, updates=None, theta_init=None, 
     rep["variant"] = g.variant()
     if check_state and rep["chains_diverged"] == 0:
         so, sg = o.stats(), g.stats()
-        rep["eps_bitexact"] = all(np.array_equal(o.eps(u), g.eps(u)) for u in range(1, len(updates) + 1))
+        with_state = [u for u in range(1, len(updates) + 1) if g.kernels[u - 1] != _abi.KERNEL_RW_GAUSS]
+        rep["eps_bitexact"] = all(np.array_equal(o.eps(u), g.eps(u)) for u in with_state)
+        rep["eps_max_rel"] = max([float(np.max(np.abs(o.eps(u) - g.eps(u)) / np.maximum(np.abs(o.eps(u)), 1e-300)))
+                                  for u in with_state] or [0.0])
         rep["mean_bitexact"] = bool(np.array_equal(so["mean"], sg["mean"]))
         rep["cov_bitexact"] = bool(np.array_equal(so["cov"], sg["cov"]))
         rep["rolling_ar_bitexact"] = bool(np.array_equal(so["rolling_ar"], sg["rolling_ar"]))
