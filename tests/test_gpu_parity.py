@@ -231,7 +231,9 @@ def test_unsupported_requests_raise():
     assert lib.extmcmc_create(C.byref(cfg), C.byref(h)) == _abi.EUNSUPPORTED
     x = _data(50)
     with pytest.raises(_abi.ExtMCMCError) as ei:
-        GpuSession(em.GsnTargetLaw([0.0]), [em.RandomWalkUpdate(em.GaussianRandomWalk([[1.0]]), [1])], x, [0.0, 1.0], 4)
+        big = em.GsnTargetLaw(np.zeros(3))      # 12 parameters: a 9-coordinate Gaussian walk exceeds the device limit
+        GpuSession(big, [em.RandomWalkUpdate(em.GaussianRandomWalk(np.eye(9)), list(range(1, 10)))],
+                   np.zeros((5, 3)), big.theta, 4)
     assert ei.value.code == _abi.EUNSUPPORTED
 
 
