@@ -8,11 +8,13 @@ from .types import (MCMCUpdate, MCMCParamUpdate, MCMCGradientBasedUpdate, MCMCBa
                     PreMCMCStep, PostMCMCStep)
 from .schedule import MCMCSchedule, Step, reschedule_
 from .random_walk import UniformRandomWalk, GaussianRandomWalk, GaussianRandomWalkMix
-from .adaptation import NoAdaptation, AdaptationUnifRW, HaarioTypeAdaptation, isequal_except
+from .adaptation import (NoAdaptation, AdaptationUnifRW, HaarioTypeAdaptation, AdaptationMALA,
+                         isequal_except)
 from .priors import (Prior, ImproperPrior, ImproperPosPrior, StandardPrior, ProductPrior,
                      Normal, Gamma, Uniform)
 from .updates import RandomWalkUpdate, MALAUpdate, HamiltonianMCUpdate
 from .gsn_target import GsnTargetLaw
+from .hier_normal import HierNormalLaw
 from .workspaces import (CUDAMCMCBackend, CUDAGlobalWorkspace, CUDALocalWorkspace,
                          DeviceGeneratedObs, init_global_workspace, create_workspace,
                          create_workspaces, state, state_prop, ll, ll_prop, accepted, llr,

@@ -118,6 +118,7 @@ SIGNATURES = {
     "extmcmc_get_eps": (C.c_int32, [Handle, C.c_int32, c_double_p]),
     "extmcmc_get_adapt_state": (C.c_int32, [Handle, C.c_int32, c_double_p, c_double_p]),
     "extmcmc_eval_loglik": (C.c_int32, [Handle, c_double_p]),
+    "extmcmc_eval_grad": (C.c_int32, [Handle, c_double_p, c_double_p]),
     "extmcmc_timer_start": (C.c_int32, [Handle]),
     "extmcmc_timer_stop": (C.c_int32, [Handle, C.POINTER(C.c_float)]),
     "extmcmc_event_record": (C.c_int32, [Handle, C.c_int32]),

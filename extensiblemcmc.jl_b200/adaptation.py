@@ -110,3 +110,18 @@ class HaarioTypeAdaptation(Adaptation):
                 "only the default f = (x, y, z) -> x (constant lambda) is implemented on the GPU path")
         # NB the reference's readjust! ignores `scale` and uses 2.38^2 / length(rw) (adaptation.jl:423)
         return _abi.Adapt(_abi.ADAPT_HAARIO, self.adapt_every_k_steps, 0.0, self.scale, 0.0, 0.0, 0.0)
+
+
+class AdaptationMALA(AdaptationUnifRW):
+    """Acceptance-rate targeting of the MALA step size tau with the reference's +-delta rule
+    (compute_delta / compute_eps, adaptation.jl:312-329); default target 0.574.  The reference
+    only has a TODO for adaptive MALA (adaptation.jl:8-10)."""
+
+    def __init__(self, **kwargs):
+        kwargs.setdefault("target_accpt_rate", 0.574)
+        super().__init__([0.0], **kwargs)
+
+    def to_abi(self):
+        a = super().to_abi()
+        a.kind = _abi.ADAPT_MALA
+        return a

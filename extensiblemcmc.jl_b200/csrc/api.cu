@@ -75,12 +75,17 @@ struct extmcmc_handle {
     bool upd_dirty = true;
     double *obs_dev = nullptr;
     int64_t n_obs_local = 0;
+    int64_t n_obs_largest = 0;           // observations of the largest group
+    int64_t *goff_dev = nullptr, *glen_dev = nullptr;  // [G] padded group offsets / true lengths
+    bool grad_valid = false;             // grad_cur holds d ll/d theta of the CURRENT state
+    bool any_mala = false;
     bool state_set = false;
     SweepPlan plan{};
     bool plan_valid = false;
     Slot slot[2];
     int next_slot = 0;
     std::map<long long, cudaGraphExec_t> graphs;
+    std::map<long long, int64_t> graph_launches;   // kernels per cached graph
     // schedule bookkeeping for the rolling acceptance rate (chain_statistics.jl:53-64)
     int64_t seq_next = 0;
     std::vector<int64_t> ra_iter;   // [NU] mcmciter at which the update last ran (0 = never)
@@ -155,18 +160,20 @@ int32_t dev_alloc(extmcmc_t h, T **out, size_t n) {
 void invalidate_graphs(extmcmc_t h) {
     for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second);
     h->graphs.clear();
+    h->graph_launches.clear();
 }
 
 int32_t ensure_plan(extmcmc_t h) {
     if (h->plan_valid) return EXTMCMC_OK;
-    if (h->cfg.law == EXTMCMC_LAW_GSN_IID_1D)
-        h->plan = plan_sweep_gsn1d(h->d.C, h->n_obs_local, h->cfg.sweep_variant, h->num_sms);
+    if (h->cfg.law == EXTMCMC_LAW_GSN_IID_1D || h->cfg.law == EXTMCMC_LAW_HIER_NORMAL)
+        h->plan = plan_sweep_gsn1d(h->d.C, h->n_obs_largest, h->cfg.sweep_variant, h->num_sms, h->d.G);
     else if (h->cfg.law == EXTMCMC_LAW_GSN_MV)
         h->plan = plan_sweep_gsnmv(h->cfg.obs_dim, h->d.C, h->n_obs_local, h->cfg.sweep_variant, h->num_sms);
     else
         return fail(h, EXTMCMC_EUNSUPPORTED, "law not implemented on the GPU path");
     h->d.S = h->plan.S;
-    int32_t rc = dev_alloc(h, &h->d.partial, (size_t)h->plan.S * h->d.C);
+    // two quantities (second- and first-order sums) x G groups x S segments
+    int32_t rc = dev_alloc(h, &h->d.partial, (size_t)2 * h->d.G * h->plan.S * h->d.C);
     if (rc) return rc;
     h->plan_valid = true;
     invalidate_graphs(h);
@@ -204,18 +211,21 @@ bool obs_sharded(extmcmc_t h) {
     return h->cfg.shard_mode == EXTMCMC_SHARD_OBS && h->cfg.world_size > 1;
 }
 
-// One likelihood sweep of lawc[0] (+ cross-rank reduction when observations are sharded).
-int32_t enqueue_sweep(extmcmc_t h, bool instrument) {
+// One likelihood sweep over the law constants in lawc (+ cross-rank reduction when the
+// observations are sharded).  grad: also accumulate the first-order sums.
+int32_t enqueue_sweep(extmcmc_t h, bool instrument, bool grad = false) {
     std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
     if (instrument) {
         if (!h->ev_free.empty()) { ev = h->ev_free.back(); h->ev_free.pop_back(); }
         else { CK(h, cudaEventCreate(&ev.first)); CK(h, cudaEventCreate(&ev.second)); }
         CK(h, cudaEventRecord(ev.first, h->stream));
     }
-    if (h->cfg.law == EXTMCMC_LAW_GSN_IID_1D)
-        launch_sweep_gsn1d(h->plan, h->obs_dev, h->n_obs_local, h->d.lawc, h->d.C, h->d.partial, h->stream);
-    else
+    if (h->cfg.law == EXTMCMC_LAW_GSN_IID_1D || h->cfg.law == EXTMCMC_LAW_HIER_NORMAL) {
+        Gsn1dArgs a{h->obs_dev, h->goff_dev, h->glen_dev, h->d.G, h->d.lawc, h->d.C, h->d.partial, h->plan.S};
+        launch_sweep_gsn1d(h->plan, a, grad, h->stream);
+    } else {
         launch_sweep_gsnmv(h->plan, h->obs_dev, h->n_obs_local, h->d.lawc, h->d.C, h->d.partial, h->stream);
+    }
     h->launches += h->plan.launches;
     if (instrument) {
         CK(h, cudaEventRecord(ev.second, h->stream));
@@ -230,15 +240,38 @@ int32_t enqueue_sweep(extmcmc_t h, bool instrument) {
     return EXTMCMC_OK;
 }
 
-int32_t enqueue_steps(extmcmc_t h, const StepDesc *d_descs, int n_steps, bool instrument) {
-    // propose(0); then per element: sweep, accept(k) [+ propose(k+1) fused in the same kernel]
-    launch_propose(h->d, d_descs, 0, h->stream);
-    h->launches += 1;
+// Kernel sequence of one block.  kinds[k] = transition kernel of schedule element k (host copy
+// of the descriptors).  Random-walk element: [propose] sweep accept(+ next RW proposal fused).
+// MALA element: [current-state gradient sweep if grad_cur is stale] propose, gradient sweep,
+// finalize, accept.  grad_valid is threaded through so that a captured graph and the eager
+// path make identical decisions.
+int32_t enqueue_steps(extmcmc_t h, const StepDesc *d_descs, const int *kinds, int n_steps,
+                      bool instrument, bool &grad_valid) {
+    bool fused = false;  // the proposal of element k was already issued by accept(k-1)
     for (int k = 0; k < n_steps; ++k) {
-        int32_t rc = enqueue_sweep(h, instrument);
-        if (rc) return rc;
-        launch_accept(h->d, d_descs, k, k + 1 < n_steps ? 1 : 0, h->stream);
-        h->launches += 1;
+        int32_t rc;
+        if (kinds[k] == EXTMCMC_KERNEL_MALA) {
+            if (!grad_valid) {
+                launch_prepare_current(h->d, h->stream);
+                if ((rc = enqueue_sweep(h, instrument, true))) return rc;
+                launch_grad_finalize(h->d, h->d.theta, h->scratch_ll, h->d.grad_cur, h->stream);
+                h->launches += 2;
+            }
+            launch_mala_propose(h->d, d_descs, k, h->stream);
+            if ((rc = enqueue_sweep(h, instrument, true))) return rc;
+            launch_grad_finalize(h->d, h->d.prop_full, h->d.ll_prop, h->d.grad_prop, h->stream);
+            launch_mala_accept(h->d, d_descs, k, h->stream);
+            h->launches += 3;
+            grad_valid = true;
+            fused = false;
+        } else {
+            if (!fused) { launch_propose(h->d, d_descs, k, h->stream); h->launches += 1; }
+            if ((rc = enqueue_sweep(h, instrument, false))) return rc;
+            fused = k + 1 < n_steps && kinds[k + 1] != EXTMCMC_KERNEL_MALA;
+            launch_accept(h->d, d_descs, k, fused ? 1 : 0, h->stream);
+            h->launches += 1;
+            grad_valid = false;
+        }
     }
     CK(h, cudaGetLastError());
     return EXTMCMC_OK;
@@ -267,6 +300,8 @@ int32_t run_block_impl(extmcmc_t h, const extmcmc_step_t *steps, int32_t n_steps
         if (!h->upd_set[u]) return fail(h, EXTMCMC_EINVAL, "update " + std::to_string(u) + " not set");
     if (n_steps > h->cfg.history_window)
         return fail(h, EXTMCMC_EINVAL, "block longer than history_window");
+    if (h->any_mala && obs_sharded(h))
+        return fail(h, EXTMCMC_EUNSUPPORTED, "MALA updates with sharded observations are not implemented");
     for (int s = 0; s < n_steps; ++s)
         if (steps[s].pidx < 0 || steps[s].pidx >= h->cfg.n_updates || steps[s].mcmciter < 1)
             return fail(h, EXTMCMC_EINVAL, "step out of range");
@@ -343,23 +378,35 @@ int32_t run_block_impl(extmcmc_t h, const extmcmc_step_t *steps, int32_t n_steps
         (void)NU;
     }
 
+    std::vector<int> kinds(n_steps);
+    unsigned long long hash = 1469598103934665603ull;  // FNV-1a over the kernel-kind sequence
+    for (int s = 0; s < n_steps; ++s) {
+        kinds[s] = h->upd_host[steps[s].pidx].kernel;
+        hash = (hash ^ (unsigned long long)kinds[s]) * 1099511628211ull;
+    }
+    hash = (hash ^ (unsigned long long)(h->grad_valid ? 7 : 3)) * 1099511628211ull;
+    hash = (hash ^ (unsigned long long)n_steps) * 1099511628211ull;
     const bool instrument = h->cfg.instrument != 0;
     const bool use_graph = h->cfg.use_graphs && !instrument && rng_mode == EXTMCMC_RNG_PHILOX;
     if (!use_graph) {
         CK(h, cudaMemcpyAsync(sl.d_descs, sl.h_descs, sizeof(StepDesc) * n_steps,
                               cudaMemcpyHostToDevice, h->stream));
-        if ((rc = enqueue_steps(h, sl.d_descs, n_steps, instrument))) return rc;
+        if ((rc = enqueue_steps(h, sl.d_descs, kinds.data(), n_steps, instrument, h->grad_valid))) return rc;
     } else {
-        const long long key = ((long long)n_steps << 1) | si;
+        // the kernel sequence depends on the kinds of the block's updates (and on whether the
+        // current-state gradient is fresh), not on which update each element names
+        const long long key = (long long)((hash << 1) | (unsigned long long)si);
         auto it = h->graphs.find(key);
         if (it == h->graphs.end()) {
             const int64_t launches_before = h->launches;
+            bool gv = h->grad_valid;
             cudaGraph_t g = nullptr;
             CK(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
             cudaError_t e1 = cudaMemcpyAsync(sl.d_descs, sl.h_descs, sizeof(StepDesc) * n_steps,
                                              cudaMemcpyHostToDevice, h->stream);
-            int32_t rc2 = e1 == cudaSuccess ? enqueue_steps(h, sl.d_descs, n_steps, false) : EXTMCMC_ECUDA;
+            int32_t rc2 = e1 == cudaSuccess ? enqueue_steps(h, sl.d_descs, kinds.data(), n_steps, false, gv) : EXTMCMC_ECUDA;
             cudaError_t e2 = cudaStreamEndCapture(h->stream, &g);
+            h->graph_launches[key] = h->launches - launches_before;
             h->launches = launches_before;
             if (rc2 || e2 != cudaSuccess || !g) {
                 if (g) cudaGraphDestroy(g);
@@ -373,7 +420,8 @@ int32_t run_block_impl(extmcmc_t h, const extmcmc_step_t *steps, int32_t n_steps
             it = h->graphs.emplace(key, ge).first;
         }
         CK(h, cudaGraphLaunch(it->second, h->stream));
-        h->launches += 1 + (int64_t)n_steps * (1 + h->plan.launches + (obs_sharded(h) ? 1 : 0));
+        h->launches += h->graph_launches[key];
+        h->grad_valid = kinds[n_steps - 1] == EXTMCMC_KERNEL_MALA;
     }
     CK(h, cudaEventRecord(sl.done, h->stream));
     sl.in_flight = true;
@@ -407,6 +455,12 @@ int32_t extmcmc_create(const extmcmc_config_t *cfg, extmcmc_t *out) {
             return fail(nullptr, EXTMCMC_EUNSUPPORTED, "GSN_MV on the GPU path needs 2 <= obs_dim <= 8 (d = 1: GSN_IID_1D)");
         if (cfg->n_params != cfg->obs_dim * (cfg->obs_dim + 1))
             return fail(nullptr, EXTMCMC_EINVAL, "GSN_MV needs n_params = d (d + 1)");
+        break;
+    case EXTMCMC_LAW_HIER_NORMAL:
+        if (cfg->obs_dim != 1 || cfg->n_params < 3)
+            return fail(nullptr, EXTMCMC_EINVAL, "HIER_NORMAL needs obs_dim = 1 and n_params = G + 2 >= 3");
+        if (cfg->shard_mode == EXTMCMC_SHARD_OBS && cfg->world_size > 1)
+            return fail(nullptr, EXTMCMC_EUNSUPPORTED, "HIER_NORMAL with sharded observations is not implemented");
         break;
     default:
         // the reference's convention for a missing method: error("... not implemented")
@@ -458,7 +512,10 @@ int32_t extmcmc_create(const extmcmc_config_t *cfg, extmcmc_t *out) {
     d.law = cfg->law; d.stats_mode = cfg->stats_mode; d.rng_mode = EXTMCMC_RNG_PHILOX;
     d.p_u_max = 1; d.seed = cfg->seed;
     d.obs_dim = cfg->obs_dim;
-    d.lawc_k = cfg->law == EXTMCMC_LAW_GSN_IID_1D ? 3 : cfg->obs_dim + cfg->obs_dim * (cfg->obs_dim + 1) / 2 + 1;
+    d.G = cfg->law == EXTMCMC_LAW_HIER_NORMAL ? cfg->n_params - 2 : 1;
+    d.lawc_k = cfg->law == EXTMCMC_LAW_GSN_IID_1D ? 3
+             : cfg->law == EXTMCMC_LAW_HIER_NORMAL ? d.G
+             : cfg->obs_dim + cfg->obs_dim * (cfg->obs_dim + 1) / 2 + 1;
     d.use_ssum = (cfg->shard_mode == EXTMCMC_SHARD_OBS && cfg->world_size > 1) ? 1 : 0;
     int32_t rc = 0;
     const size_t covn = cfg->stats_mode == 0 ? (size_t)p * p : (cfg->stats_mode == 1 ? (size_t)p : 0);
@@ -467,6 +524,9 @@ int32_t extmcmc_create(const extmcmc_config_t *cfg, extmcmc_t *out) {
         (rc = dev_alloc(h, &d.prop_full, (size_t)p * C)) ||
         (rc = dev_alloc(h, &d.lawc, (size_t)d.lawc_k * C)) ||
         (rc = dev_alloc(h, &d.n_used, (size_t)C)) || (rc = dev_alloc(h, &d.ssum, (size_t)C)) ||
+        (rc = dev_alloc(h, &d.ll_prop, (size_t)C)) || (rc = dev_alloc(h, &d.grad_cur, (size_t)p * C)) ||
+        (rc = dev_alloc(h, &d.grad_prop, (size_t)p * C)) ||
+        (rc = dev_alloc(h, &h->goff_dev, (size_t)d.G)) || (rc = dev_alloc(h, &h->glen_dev, (size_t)d.G)) ||
         (rc = dev_alloc(h, &d.mean, (size_t)p * C)) || (rc = dev_alloc(h, &d.cov, covn * C)) ||
         (rc = dev_alloc(h, &d.h_theta, (size_t)d.H * p * C)) ||
         (rc = dev_alloc(h, &d.h_prop, (size_t)d.H * p * C)) ||
@@ -516,15 +576,29 @@ int32_t extmcmc_destroy(extmcmc_t h) {
     return EXTMCMC_OK;
 }
 
-static int32_t install_obs(extmcmc_t h, int64_t n_obs) {
-    // padded to an even count of doubles (+ one spare pair): the sweep's bulk copies move 16 B units
+// Device layout of the observations: group g occupies [goff[g], goff[g] + glen[g]) doubles with
+// goff even (16-byte units of the sweep's bulk copies) and one spare pair at the end.
+static int32_t install_obs(extmcmc_t h, int64_t n_obs, const std::vector<int64_t> &glen) {
     if (h->obs_dev) { cudaFree(h->obs_dev); h->obs_dev = nullptr; }
-    const size_t padded = ((size_t)n_obs * (size_t)h->cfg.obs_dim + 3) & ~(size_t)1;
+    const int G = (int)glen.size();
+    std::vector<int64_t> goff(G);
+    int64_t tot = 0, largest = 0;
+    for (int g = 0; g < G; ++g) {
+        goff[g] = tot;
+        tot += (glen[g] * h->cfg.obs_dim + 1) & ~(int64_t)1;
+        largest = std::max(largest, glen[g]);
+    }
+    const size_t padded = (size_t)tot + 2;
     CK(h, cudaMalloc(&h->obs_dev, padded * sizeof(double)));
     CK(h, cudaMemsetAsync(h->obs_dev, 0, padded * sizeof(double), h->stream));
+    CK(h, cudaMemcpyAsync(h->goff_dev, goff.data(), sizeof(int64_t) * G, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(h->glen_dev, glen.data(), sizeof(int64_t) * G, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
     h->n_obs_local = n_obs;
+    h->n_obs_largest = largest;
     h->plan_valid = false;
     h->n_total_known = false;
+    h->grad_valid = false;
     return EXTMCMC_OK;
 }
 
@@ -533,12 +607,32 @@ int32_t extmcmc_upload_obs(extmcmc_t h, const double *obs, int64_t n_obs, int32_
     if (!h) return EXTMCMC_EINVAL;
     if (!obs || n_obs < 1) return fail(h, EXTMCMC_EINVAL, "need at least one observation");
     if (obs_dim != h->cfg.obs_dim) return fail(h, EXTMCMC_EINVAL, "obs_dim differs from the configuration");
-    (void)y;
     CK(h, cudaSetDevice(h->cfg.device));
     CK(h, cudaStreamSynchronize(h->stream));
-    int32_t rc = install_obs(h, n_obs);
+    std::vector<int64_t> glen(h->d.G, 0);
+    if (h->cfg.law == EXTMCMC_LAW_HIER_NORMAL) {
+        // y[i] = group index of observation i (0-based), non-decreasing
+        if (!y) return fail(h, EXTMCMC_EINVAL, "HIER_NORMAL needs the group index of every observation in y");
+        int64_t prev = 0;
+        for (int64_t i = 0; i < n_obs; ++i) {
+            const int64_t g = (int64_t)y[i];
+            if (g < prev || g >= h->d.G || (double)g != y[i])
+                return fail(h, EXTMCMC_EINVAL, "group indices must be integers in [0, G), sorted ascending");
+            prev = g;
+            ++glen[g];
+        }
+    } else {
+        glen[0] = n_obs;
+    }
+    int32_t rc = install_obs(h, n_obs, glen);
     if (rc) return rc;
-    CK(h, cudaMemcpyAsync(h->obs_dev, obs, (size_t)n_obs * obs_dim * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    int64_t src = 0, dst = 0;
+    for (int g = 0; g < h->d.G; ++g) {
+        const int64_t nd = glen[g] * obs_dim;
+        if (nd) CK(h, cudaMemcpyAsync(h->obs_dev + dst, obs + src, (size_t)nd * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        src += nd;
+        dst += (nd + 1) & ~(int64_t)1;
+    }
     CK(h, cudaStreamSynchronize(h->stream));
     return EXTMCMC_OK;
 }
@@ -547,10 +641,10 @@ int32_t extmcmc_generate_obs_normal(extmcmc_t h, int64_t first, int64_t n_obs, d
                                     uint64_t seed) {
     if (!h) return EXTMCMC_EINVAL;
     if (n_obs < 1 || first < 0 || !(sd > 0.0)) return fail(h, EXTMCMC_EINVAL, "bad generate_obs arguments");
-    if (h->cfg.obs_dim != 1) return fail(h, EXTMCMC_EUNSUPPORTED, "generate_obs_normal needs obs_dim = 1");
+    if (h->cfg.law != EXTMCMC_LAW_GSN_IID_1D) return fail(h, EXTMCMC_EUNSUPPORTED, "generate_obs_normal needs the GSN_IID_1D law");
     CK(h, cudaSetDevice(h->cfg.device));
     CK(h, cudaStreamSynchronize(h->stream));
-    int32_t rc = install_obs(h, n_obs);
+    int32_t rc = install_obs(h, n_obs, std::vector<int64_t>{n_obs});
     if (rc) return rc;
     launch_generate_obs_normal(h->obs_dev, first, n_obs, mean, sd, seed, h->num_sms, h->stream);
     h->launches += 1;
@@ -563,17 +657,28 @@ int32_t extmcmc_set_update(extmcmc_t h, int32_t u, const extmcmc_update_t *upd) 
     if (!h || !upd) return EXTMCMC_EINVAL;
     if (u < 0 || u >= h->cfg.n_updates) return fail(h, EXTMCMC_EINVAL, "update index out of range");
     const bool gauss = upd->kernel == EXTMCMC_KERNEL_RW_GAUSS || upd->kernel == EXTMCMC_KERNEL_RW_GAUSS_MIX;
-    if (upd->kernel != EXTMCMC_KERNEL_RW_UNIFORM && !gauss)
+    const bool mala = upd->kernel == EXTMCMC_KERNEL_MALA;
+    if (upd->kernel != EXTMCMC_KERNEL_RW_UNIFORM && !gauss && !mala)
         return fail(h, EXTMCMC_EUNSUPPORTED, "transition kernel not implemented on the GPU path");
+    if (mala) {
+        if (h->cfg.law != EXTMCMC_LAW_GSN_IID_1D && h->cfg.law != EXTMCMC_LAW_HIER_NORMAL)
+            return fail(h, EXTMCMC_EUNSUPPORTED, "MALA needs a law with a device gradient (GSN_IID_1D, HIER_NORMAL)");
+        if (upd->prior != EXTMCMC_PRIOR_IMPROPER && upd->prior != EXTMCMC_PRIOR_NORMAL)
+            return fail(h, EXTMCMC_EUNSUPPORTED, "MALA supports ImproperPrior and Normal priors only");
+        if (upd->pos)
+            for (int i = 0; i < upd->n_coords; ++i)
+                if (upd->pos[i]) return fail(h, EXTMCMC_EUNSUPPORTED, "MALA on positivity-constrained coordinates is not implemented");
+    }
     if (upd->prior < EXTMCMC_PRIOR_IMPROPER || upd->prior > EXTMCMC_PRIOR_UNIFORM)
         return fail(h, EXTMCMC_EUNSUPPORTED, "prior not implemented on the GPU path");
     // readjust! exists only for (UniformRandomWalk, AdaptationUnifRW) and
     // (GaussianRandomWalkMix, HaarioTypeAdaptation): adaptation.jl:273,422
     if (!(upd->adapt.kind == EXTMCMC_ADAPT_NONE ||
+          (upd->adapt.kind == EXTMCMC_ADAPT_MALA && mala) ||
           (upd->adapt.kind == EXTMCMC_ADAPT_UNIF_RW && upd->kernel == EXTMCMC_KERNEL_RW_UNIFORM) ||
           (upd->adapt.kind == EXTMCMC_ADAPT_HAARIO && upd->kernel == EXTMCMC_KERNEL_RW_GAUSS_MIX)))
         return fail(h, EXTMCMC_EUNSUPPORTED, "adaptation not implemented for this transition kernel");
-    if (upd->n_coords < 1 || upd->n_coords > (gauss ? kMaxGaussCoords : kMaxCoords))
+    if (upd->n_coords < 1 || upd->n_coords > (mala ? h->cfg.n_params : gauss ? kMaxGaussCoords : kMaxCoords))
         return fail(h, EXTMCMC_EUNSUPPORTED, gauss ? "1 <= n_coords <= 8 for Gaussian random walks on the GPU path"
                                                     : "1 <= n_coords <= 16 for random-walk updates");
     if (!upd->coords || !upd->step) return fail(h, EXTMCMC_EINVAL, "coords/step missing");
@@ -595,10 +700,12 @@ int32_t extmcmc_set_update(extmcmc_t h, int32_t u, const extmcmc_update_t *upd) 
     for (int i = 0; i < upd->n_coords; ++i) {
         if (upd->coords[i] < 0 || upd->coords[i] >= h->cfg.n_params)
             return fail(h, EXTMCMC_EINVAL, "coordinate out of range");
-        if (!gauss && !(upd->step[i] > 0.0))  // UniformRandomWalk: @assert all(eps .> 0.0), random_walk.jl:50
+        if (!gauss && !mala && !(upd->step[i] > 0.0))  // UniformRandomWalk: @assert all(eps .> 0.0), random_walk.jl:50
             return fail(h, EXTMCMC_EINVAL, "eps must be > 0");
-        t.coords[i] = upd->coords[i];
-        t.pos[i] = upd->pos ? upd->pos[i] : 0;
+        if (i < kMaxCoords) {
+            t.coords[i] = upd->coords[i];
+            t.pos[i] = upd->pos ? upd->pos[i] : 0;
+        }
     }
     for (int i = 0; i < kMaxPriorParams; ++i)
         t.prior_params[i] = i < upd->n_prior_params ? upd->prior_params[i] : 0.0;
@@ -611,8 +718,10 @@ int32_t extmcmc_set_update(extmcmc_t h, int32_t u, const extmcmc_update_t *upd) 
     const bool haario = upd->adapt.kind == EXTMCMC_ADAPT_HAARIO;
     if (mix && !(upd->step[2 * nn] >= 0.0 && upd->step[2 * nn] <= 1.0))   // @assert 0 <= lambda <= 1, random_walk.jl:199
         return fail(h, EXTMCMC_EINVAL, "lambda must be in [0, 1]");
+    if (mala && !(upd->step[0] > 0.0)) return fail(h, EXTMCMC_EINVAL, "MALA step tau must be > 0");
     if (fresh) {
-        if ((rc = dev_alloc(h, &t.eps, (size_t)nc * C)) ||
+        if ((rc = dev_alloc(h, &t.coords_dev, (size_t)nc)) ||
+            (rc = dev_alloc(h, &t.eps, (size_t)nc * C)) ||
             (rc = dev_alloc(h, &t.adapt_prop, (size_t)C)) || (rc = dev_alloc(h, &t.adapt_acc, (size_t)C)) ||
             (rc = dev_alloc(h, &t.tot_prop, (size_t)C)) || (rc = dev_alloc(h, &t.tot_acc, (size_t)C)) ||
             (rc = dev_alloc(h, &t.ra_val, (size_t)C)) || (rc = dev_alloc(h, &t.acc_ring, (size_t)W * C)))
@@ -624,7 +733,11 @@ int32_t extmcmc_set_update(extmcmc_t h, int32_t u, const extmcmc_update_t *upd) 
         return fail(h, EXTMCMC_EINVAL, "cannot change the kernel family of an update");
     }
     CK(h, cudaStreamSynchronize(h->stream));
-    if (!gauss) {
+    CK(h, cudaMemcpy(t.coords_dev, upd->coords, sizeof(int32_t) * nc, cudaMemcpyHostToDevice));
+    if (mala) {
+        std::vector<double> tau0((size_t)C, upd->step[0]);   // one step size tau per chain
+        CK(h, cudaMemcpy(t.eps, tau0.data(), tau0.size() * sizeof(double), cudaMemcpyHostToDevice));
+    } else if (!gauss) {
         // broadcast the initial step size to every chain
         std::vector<double> eps0((size_t)nc * C);
         for (int i = 0; i < nc; ++i) std::fill_n(eps0.begin() + (size_t)i * C, C, upd->step[i]);
@@ -652,8 +765,11 @@ int32_t extmcmc_set_update(extmcmc_t h, int32_t u, const extmcmc_update_t *upd) 
     h->upd_set[u] = true;
     h->upd_dirty = true;
     int nh = 0;
-    for (int v = 0; v < h->cfg.n_updates; ++v)
+    h->any_mala = false;
+    for (int v = 0; v < h->cfg.n_updates; ++v) {
+        if (h->upd_set[v] && h->upd_host[v].kernel == EXTMCMC_KERNEL_MALA) h->any_mala = true;
         if (h->upd_set[v] && h->upd_host[v].adapt_kind == EXTMCMC_ADAPT_HAARIO) ++nh;
+    }
     if (nh != h->d.n_haario) { h->d.n_haario = nh; invalidate_graphs(h); }
     return EXTMCMC_OK;
 }
@@ -687,6 +803,7 @@ int32_t extmcmc_set_state(extmcmc_t h, const double *theta) {
     }
     std::fill(h->haario_M.begin(), h->haario_M.end(), 0);
     h->seq_next = 0;
+    h->grad_valid = false;
     if (h->fetch_active) { cudaEventSynchronize(h->fetch_done); h->fetch_active = false; }
     std::fill(h->ra_iter.begin(), h->ra_iter.end(), 0);
     std::fill(h->acc_tag.begin(), h->acc_tag.end(), 0);
@@ -875,6 +992,8 @@ int32_t extmcmc_get_eps(extmcmc_t h, int32_t u, double *eps) {
     const DevUpdate &t = h->upd_host[u];
     if (t.kernel == EXTMCMC_KERNEL_RW_UNIFORM)
         CK(h, cudaMemcpy(eps, t.eps, sizeof(double) * t.n_coords * h->d.C, cudaMemcpyDeviceToHost));
+    else if (t.kernel == EXTMCMC_KERNEL_MALA)
+        CK(h, cudaMemcpy(eps, t.eps, sizeof(double) * h->d.C, cudaMemcpyDeviceToHost));
     else if (t.kernel == EXTMCMC_KERNEL_RW_GAUSS_MIX)
         CK(h, cudaMemcpy(eps, t.sigB, sizeof(double) * t.n_coords * t.n_coords * h->d.C, cudaMemcpyDeviceToHost));
     else
@@ -908,6 +1027,28 @@ int32_t extmcmc_eval_loglik(extmcmc_t h, double *ll_out) {
     h->launches += 2;
     CK(h, cudaGetLastError());
     CK(h, cudaMemcpyAsync(ll_out, h->scratch_ll, sizeof(double) * h->d.C, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return EXTMCMC_OK;
+}
+
+int32_t extmcmc_eval_grad(extmcmc_t h, double *ll_out, double *grad_out) {
+    if (!h || !grad_out) return EXTMCMC_EINVAL;
+    if (!h->obs_dev || !h->state_set) return fail(h, EXTMCMC_EINVAL, "observations and state required");
+    if (h->cfg.law != EXTMCMC_LAW_GSN_IID_1D && h->cfg.law != EXTMCMC_LAW_HIER_NORMAL)
+        return fail(h, EXTMCMC_EUNSUPPORTED, "this law has no device gradient");
+    if (obs_sharded(h)) return fail(h, EXTMCMC_EUNSUPPORTED, "gradients with sharded observations are not implemented");
+    CK(h, cudaSetDevice(h->cfg.device));
+    int32_t rc;
+    if ((rc = ensure_plan(h))) return rc;
+    if ((rc = ensure_total_obs(h))) return rc;
+    launch_prepare_current(h->d, h->stream);
+    if ((rc = enqueue_sweep(h, h->cfg.instrument != 0, true))) return rc;
+    launch_grad_finalize(h->d, h->d.theta, h->scratch_ll, h->d.grad_cur, h->stream);
+    h->launches += 2;
+    h->grad_valid = true;
+    CK(h, cudaGetLastError());
+    if (ll_out) CK(h, cudaMemcpyAsync(ll_out, h->scratch_ll, sizeof(double) * h->d.C, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaMemcpyAsync(grad_out, h->d.grad_cur, sizeof(double) * h->d.p * h->d.C, cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
     return EXTMCMC_OK;
 }

@@ -40,6 +40,7 @@ struct DevUpdate {
     double  lambda;       // GaussianRandomWalkMix.lambda
     double *hmean;        // [n][C]   HaarioTypeAdaptation.mean
     double *hcov;         // [n*n][C] HaarioTypeAdaptation.cov
+    int32_t *coords_dev;  // [n_coords] device copy of coords (MALA: n_coords may exceed kMaxCoords)
 };
 
 // One schedule element (src/schedule.jl:56-66) plus what the host planner knows.
@@ -63,6 +64,10 @@ struct DevState {
     int32_t law, stats_mode, rng_mode, p_u_max;
     int32_t n_haario;       // updates with HaarioTypeAdaptation (they register on every step)
     int32_t obs_dim, lawc_k;  // observation dimension; per-chain law constants in lawc
+    int32_t G;              // observation groups (HIER_NORMAL; 1 otherwise)
+    double *ll_prop;        // [C] finalized proposal log-likelihood (gradient path)
+    double *grad_cur;       // [p][C] d ll / d theta at the current state
+    double *grad_prop;      // [p][C] ... at the proposal
     uint64_t seed;
     // current state
     double *theta;          // [p][C]
@@ -73,7 +78,7 @@ struct DevState {
     double *lawc;           // [lawc_k][C] per-chain law constants of the proposal
     uint32_t *n_used;       // [C] uniforms consumed by the proposal (next index = Exp draw)
     // sweep output
-    double *partial;        // [S][C] per-segment partial sums
+    double *partial;        // [2][G*S][C] per-segment partial sums: q = 0 second-order, q = 1 first-order
     int32_t S;
     double *ssum;           // [C] reduced (and, under obs sharding, all-reduced) sums
     int32_t use_ssum;       // accept kernel reads ssum instead of partial

@@ -151,6 +151,10 @@ __device__ __forceinline__ void law_prepare(const DevState &d, int64_t c, const 
         d.lawc[c] = mu;
         d.lawc[d.C + c] = c0;
         d.lawc[2 * d.C + c] = inv2;
+    } else if (d.law == EXTMCMC_LAW_HIER_NORMAL) {
+        for (int g = 0; g < d.G; ++g) d.lawc[(int64_t)g * d.C + c] = full[(int64_t)g * stride];
+        const double tau = full[(int64_t)(d.G + 1) * stride];
+        if (!(tau > 0.0) || isinf(tau)) *d.err_flag = 1;
     } else if (d.law == EXTMCMC_LAW_GSN_MV) {
         const int n = d.obs_dim;
         double L[kMaxObsDim * kMaxObsDim], W[kMaxObsDim * kMaxObsDim];
@@ -191,9 +195,20 @@ __device__ __forceinline__ void law_prepare(const DevState &d, int64_t c, const 
     }
 }
 
-__device__ __forceinline__ double law_finalize(const DevState &d, int64_t c, double S) {
+// th: this chain's parameter vector the sums were computed for (stride C)
+__device__ __forceinline__ double law_finalize(const DevState &d, int64_t c, double S, const double *th) {
     if (d.law == EXTMCMC_LAW_GSN_IID_1D)  // N*c0 - S/(2 var)
         return (double)d.n_obs_total * d.lawc[d.C + c] - S * d.lawc[2 * d.C + c];
+    if (d.law == EXTMCMC_LAW_HIER_NORMAL) {
+        // sum_gj logN(y_gj; th_g, 1) + sum_g logN(th_g; mu, tau^2)
+        const int G = d.G;
+        const double mu = th[(int64_t)G * d.C], tau = th[(int64_t)(G + 1) * d.C];
+        if (!(tau > 0.0) || isinf(tau)) return NAN;
+        double dev2 = 0.0;
+        for (int g = 0; g < G; ++g) { const double dv = th[(int64_t)g * d.C] - mu; dev2 += dv * dv; }
+        return -0.5 * (double)d.n_obs_total * kLog2Pi - S / 2.0 +
+               (double)G * (-0.5 * kLog2Pi - log(tau)) - dev2 / (2.0 * tau * tau);
+    }
     return (double)d.n_obs_total * d.lawc[(int64_t)(d.lawc_k - 1) * d.C + c] - S / 2.0;
 }
 }  // namespace
@@ -317,15 +332,16 @@ __device__ __forceinline__ double reduce_segments(const DevState &d, double *sh 
     double s = 0.0;
     if (c < d.C) {
         const double *p = d.partial + c;
+        const int nrows = d.S * d.G;   // all segments of all observation groups
         int i = slice;
-        for (; i + 3 * kRedSlices < d.S; i += 4 * kRedSlices) {
+        for (; i + 3 * kRedSlices < nrows; i += 4 * kRedSlices) {
             const double a0 = p[(int64_t)i * d.C];
             const double a1 = p[(int64_t)(i + kRedSlices) * d.C];
             const double a2 = p[(int64_t)(i + 2 * kRedSlices) * d.C];
             const double a3 = p[(int64_t)(i + 3 * kRedSlices) * d.C];
             s += a0; s += a1; s += a2; s += a3;
         }
-        for (; i < d.S; i += kRedSlices) s += p[(int64_t)i * d.C];
+        for (; i < nrows; i += kRedSlices) s += p[(int64_t)i * d.C];
     }
     if (kRedSlices == 1) return s;
     sh[slice * kRedChains + lane_c] = s;
@@ -350,86 +366,21 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(DevState d) {
 __global__ void __launch_bounds__(256) finalize_loglik_kernel(DevState d, double *ll_out) {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= d.C) return;
-    ll_out[c] = law_finalize(d, c, d.ssum[c]);
+    ll_out[c] = law_finalize(d, c, d.ssum[c], d.theta + c);
 }
 
 // ---------------------------------------------------------------------------------
-// K3: accept_reject! (src/run.jl:268-281) + register_accept_reject_results!
-//     (:299-335) + set_chain_param! (:312-320) + update_stats!
-//     (src/chain_statistics.jl:41-66) + update_adaptation! (src/run.jl:136-173,
-//     src/transition_kernels/adaptation.jl:273-329).
+// What follows an accept/reject decision, shared by the random-walk and MALA paths:
+// register_accept_reject_results! (src/run.jl:299-335) + set_chain_param! (:312-320, the
+// caller has already committed theta) + update_stats! (src/chain_statistics.jl:41-66) +
+// update_adaptation! (src/run.jl:136-173, src/transition_kernels/adaptation.jl:273-329).
+// n_eps = entries of the update's step-size vector (p_u for the uniform walk, 1 for MALA).
 // ---------------------------------------------------------------------------------
-template <int SL>
-__global__ void __launch_bounds__(256)
-accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fuse_next) {
-    // 256 threads = (256/SL) chains x SL reduction slices; slice 0 carries on with the chain
-    constexpr int kRedChains = kRedThreads / SL;
-    __shared__ double sh[kRedThreads];
-    __shared__ StepCtx ctx, ctx_next;
-    load_step_ctx(&ctx, d, descs, k);
-    if (fuse_next) load_step_ctx(&ctx_next, d, descs, k + 1);
-    const int64_t c = (int64_t)blockIdx.x * kRedChains + (threadIdx.x % kRedChains);
-    double S;
-    if (d.use_ssum) {
-        S = c < d.C ? d.ssum[c] : 0.0;
-    } else {
-        S = reduce_segments<SL>(d, sh);
-    }
-    if ((threadIdx.x / kRedChains) != 0 || c >= d.C) return;
-    const StepDesc &sd = ctx.sd;
-    const DevUpdate &u = ctx.u;
-    const int n = u.n_coords;
+__device__ __forceinline__ void post_decision(const DevState &d, const StepDesc &sd, const DevUpdate &u,
+                                              int64_t c, bool accepted, double ll_new, double ll_prop,
+                                              int n_eps) {
     const int64_t C = d.C;
-    const double ll_prop = law_finalize(d, c, S);
-    // update_workspaces! (run.jl:101-112): ll of the previously executed update; on the
-    // very first element it is still the initial -Inf (workspaces.jl:425)
-    const double ll_cur = sd.first ? -INFINITY : d.ll[c];
-
-    double th[kMaxCoords], prop[kMaxCoords], eps[kMaxCoords];
-    for (int i = 0; i < n; ++i) {
-        th[i] = d.theta[(int64_t)u.coords[i] * C + c];
-        prop[i] = d.prop_loc[(int64_t)i * C + c];
-        eps[i] = u.kernel == EXTMCMC_KERNEL_RW_UNIFORM ? u.eps[(int64_t)i * C + c] : 0.0;
-    }
-    // llr, strictly left to right (run.jl:271-277)
-    double llr = ll_prop - ll_cur;
-    if (u.kernel == EXTMCMC_KERNEL_RW_UNIFORM) {
-        llr = llr + log_q_unif(u, eps, th);    // theta° -> theta
-        llr = llr - log_q_unif(u, eps, prop);  // theta -> theta°
-    } else {
-        double Sg[kMaxGaussCoords * kMaxGaussCoords], LA[kMaxGaussCoords * kMaxGaussCoords],
-            LB[kMaxGaussCoords * kMaxGaussCoords];
-        load_sigma(u, false, C, c, Sg);
-        bool ok = chol_lower_sym_upper(Sg, n, LA);
-        if (u.kernel == EXTMCMC_KERNEL_RW_GAUSS_MIX) {
-            load_sigma(u, true, C, c, Sg);
-            ok = chol_lower_sym_upper(Sg, n, LB) && ok;
-        }
-        if (!ok) {
-            *d.err_flag = 1;
-            llr = NAN;
-        } else {
-            llr = llr + log_q_any(u, eps, LA, LB, prop, th);   // theta° -> theta
-            llr = llr - log_q_any(u, eps, LA, LB, th, prop);   // theta -> theta°
-        }
-    }
-    llr = llr + log_prior(u, prop);
-    llr = llr - log_prior(u, th);
-
-    double E;
-    if (d.rng_mode == EXTMCMC_RNG_REPLAY) {
-        E = d.rp_exp[(int64_t)sd.replay_row * C + c];
-    } else {
-        ChainStepStream rng(d.seed, (uint64_t)(d.chain_offset + c), sd.mcmciter, sd.pidx, d.n_used[c]);
-        E = -log(rng.next());  // rand(Exponential(1.0)), run.jl:278
-    }
-    const bool accepted = E > -llr;  // NaN compares false -> reject
-
-    const double ll_new = accepted ? ll_prop : ll_cur;
-    if (accepted)
-        for (int i = 0; i < n; ++i) d.theta[(int64_t)u.coords[i] * C + c] = prop[i];
     d.ll[c] = ll_new;
-
     // history row (state_history / state_proposal_history / ll_history / acceptance_history)
     const int64_t slot = sd.seq % d.H;
     for (int j = 0; j < d.p; ++j) {
@@ -493,7 +444,7 @@ accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fuse_ne
     // update_adaptation! -- only the update whose turn it is registers (run.jl:176-177)
     u.tot_prop[c] += 1;
     u.tot_acc[c] += accepted ? 1 : 0;
-    if (u.adapt_kind == EXTMCMC_ADAPT_UNIF_RW) {
+    if (u.adapt_kind == EXTMCMC_ADAPT_UNIF_RW || u.adapt_kind == EXTMCMC_ADAPT_MALA) {
         int32_t prop_n = u.adapt_prop[c] + 1;                      // register! :292-295
         int32_t acc_n = u.adapt_acc[c] + (accepted ? 1 : 0);
         if (prop_n >= u.adapt_every_k) {                           // time_to_update :302-304
@@ -502,8 +453,8 @@ accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fuse_ne
             const double a_r = (double)acc_n / (double)prop_n;       // acceptance_rate :242-244
             prop_n = 0; acc_n = 0;                                   // reset! :263-266
             const double sgn = (a_r > u.target) ? 1.0 : -1.0;
-            for (int i = 0; i < n; ++i) {                            // compute_eps :326-329
-                double e = eps[i] + sgn * delta;
+            for (int i = 0; i < n_eps; ++i) {                        // compute_eps :326-329
+                double e = u.eps[(int64_t)i * C + c] + sgn * delta;
                 e = e < u.vmax ? e : u.vmax;
                 e = e > u.vmin ? e : u.vmin;
                 u.eps[(int64_t)i * C + c] = e;
@@ -545,9 +496,233 @@ accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fuse_ne
                 }
         }
     }
+}
+
+__device__ __forceinline__ double draw_exp(const DevState &d, const StepDesc &sd, int64_t c) {
+    if (d.rng_mode == EXTMCMC_RNG_REPLAY) return d.rp_exp[(int64_t)sd.replay_row * d.C + c];
+    ChainStepStream rng(d.seed, (uint64_t)(d.chain_offset + c), sd.mcmciter, sd.pidx, d.n_used[c]);
+    return -log(rng.next());  // rand(Exponential(1.0)), run.jl:278
+}
+
+// ---------------------------------------------------------------------------------
+// K3: accept_reject! (src/run.jl:268-281) for the random-walk updates.
+// ---------------------------------------------------------------------------------
+template <int SL>
+__global__ void __launch_bounds__(256)
+accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fuse_next) {
+    // 256 threads = (256/SL) chains x SL reduction slices; slice 0 carries on with the chain
+    constexpr int kRedChains = kRedThreads / SL;
+    __shared__ double sh[kRedThreads];
+    __shared__ StepCtx ctx, ctx_next;
+    load_step_ctx(&ctx, d, descs, k);
+    if (fuse_next) load_step_ctx(&ctx_next, d, descs, k + 1);
+    const int64_t c = (int64_t)blockIdx.x * kRedChains + (threadIdx.x % kRedChains);
+    double S;
+    if (d.use_ssum) {
+        S = c < d.C ? d.ssum[c] : 0.0;
+    } else {
+        S = reduce_segments<SL>(d, sh);
+    }
+    if ((threadIdx.x / kRedChains) != 0 || c >= d.C) return;
+    const StepDesc &sd = ctx.sd;
+    const DevUpdate &u = ctx.u;
+    const int n = u.n_coords;
+    const int64_t C = d.C;
+    const double ll_prop = law_finalize(d, c, S, d.prop_full + c);
+    // update_workspaces! (run.jl:101-112): ll of the previously executed update; on the
+    // very first element it is still the initial -Inf (workspaces.jl:425)
+    const double ll_cur = sd.first ? -INFINITY : d.ll[c];
+
+    double th[kMaxCoords], prop[kMaxCoords], eps[kMaxCoords];
+    for (int i = 0; i < n; ++i) {
+        th[i] = d.theta[(int64_t)u.coords[i] * C + c];
+        prop[i] = d.prop_loc[(int64_t)i * C + c];
+        eps[i] = u.kernel == EXTMCMC_KERNEL_RW_UNIFORM ? u.eps[(int64_t)i * C + c] : 0.0;
+    }
+    // llr, strictly left to right (run.jl:271-277)
+    double llr = ll_prop - ll_cur;
+    if (u.kernel == EXTMCMC_KERNEL_RW_UNIFORM) {
+        llr = llr + log_q_unif(u, eps, th);    // theta° -> theta
+        llr = llr - log_q_unif(u, eps, prop);  // theta -> theta°
+    } else {
+        double Sg[kMaxGaussCoords * kMaxGaussCoords], LA[kMaxGaussCoords * kMaxGaussCoords],
+            LB[kMaxGaussCoords * kMaxGaussCoords];
+        load_sigma(u, false, C, c, Sg);
+        bool ok = chol_lower_sym_upper(Sg, n, LA);
+        if (u.kernel == EXTMCMC_KERNEL_RW_GAUSS_MIX) {
+            load_sigma(u, true, C, c, Sg);
+            ok = chol_lower_sym_upper(Sg, n, LB) && ok;
+        }
+        if (!ok) {
+            *d.err_flag = 1;
+            llr = NAN;
+        } else {
+            llr = llr + log_q_any(u, eps, LA, LB, prop, th);   // theta° -> theta
+            llr = llr - log_q_any(u, eps, LA, LB, th, prop);   // theta -> theta°
+        }
+    }
+    llr = llr + log_prior(u, prop);
+    llr = llr - log_prior(u, th);
+
+    const double E = draw_exp(d, sd, c);
+    const bool accepted = E > -llr;  // NaN compares false -> reject
+    const double ll_new = accepted ? ll_prop : ll_cur;
+    if (accepted)
+        for (int i = 0; i < n; ++i) d.theta[(int64_t)u.coords[i] * C + c] = prop[i];
+    post_decision(d, sd, u, c, accepted, ll_new, ll_prop, u.kernel == EXTMCMC_KERNEL_RW_UNIFORM ? n : 0);
     // proposal of the NEXT schedule element of this block, fused here: the chain's thread
     // already holds its freshly committed state, and one launch per update step is saved
     if (fuse_next) propose_chain(d, ctx_next.sd, ctx_next.u, c);
+}
+
+// ---------------------------------------------------------------------------------
+// Gradient path (MALAUpdate; the reference only has the hooks: MCMCGradientBasedUpdate
+// src/types.jl:24, compute_gradients_and_momenta! src/updates.jl:129-133 called at
+// src/run.jl:110,259, the `∇ll` buffer src/workspaces.jl:417).
+//
+// grad_finalize_kernel: fixed-order reduction of the sweep's partial sums per chain (and
+// per observation group), then ll and d ll / d theta for ALL p parameters.
+//   GSN_IID_1D : d/dmu = T/var, d/dvar = -N/(2 var) + S/(2 var^2)
+//   HIER_NORMAL: theta = [th_1..th_G, mu, tau], y_gj ~ N(th_g, 1), th_g ~ N(mu, tau^2) (the
+//                hierarchical term lives in the law because priors only see their own
+//                coordinates, src/run.jl:374-385):
+//                d/dth_g = T_g - (th_g - mu)/tau^2, d/dmu = sum_g (th_g - mu)/tau^2,
+//                d/dtau = -G/tau + sum_g (th_g - mu)^2 / tau^3
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+grad_finalize_kernel(DevState d, const double *__restrict__ src, double *__restrict__ ll_out,
+                     double *__restrict__ grad_out) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= d.C) return;
+    const int64_t C = d.C;
+    const int G = d.G, S = d.S;
+    const int64_t rows = (int64_t)G * S;
+    if (d.law == EXTMCMC_LAW_GSN_IID_1D) {
+        double s2 = 0.0, s1 = 0.0;
+        for (int i = 0; i < S; ++i) { s2 += d.partial[(int64_t)i * C + c]; s1 += d.partial[(rows + i) * C + c]; }
+        const double var = src[C + c];
+        ll_out[c] = law_finalize(d, c, s2, src + c);
+        grad_out[c] = s1 / var;
+        grad_out[C + c] = -(double)d.n_obs_total / (2.0 * var) + s2 / (2.0 * var * var);
+    } else if (d.law == EXTMCMC_LAW_HIER_NORMAL) {
+        const double mu = src[(int64_t)G * C + c], tau = src[(int64_t)(G + 1) * C + c];
+        const double it2 = 1.0 / (tau * tau);
+        double s2_tot = 0.0, dmu = 0.0, dev2 = 0.0;
+        for (int g = 0; g < G; ++g) {
+            double s2 = 0.0, s1 = 0.0;
+            for (int i = 0; i < S; ++i) {
+                s2 += d.partial[((int64_t)g * S + i) * C + c];
+                s1 += d.partial[(rows + (int64_t)g * S + i) * C + c];
+            }
+            s2_tot += s2;
+            const double dv = src[(int64_t)g * C + c] - mu;
+            grad_out[(int64_t)g * C + c] = s1 - dv * it2;
+            dmu += dv * it2;
+            dev2 += dv * dv;
+        }
+        grad_out[(int64_t)G * C + c] = dmu;
+        grad_out[(int64_t)(G + 1) * C + c] = -(double)G / tau + dev2 * it2 / tau;
+        ll_out[c] = law_finalize(d, c, s2_tot, src + c);
+    }
+}
+
+// d log prior / d theta_i for the priors that have one on the device
+__device__ __forceinline__ double prior_grad(const DevUpdate &u, double th) {
+    if (u.prior == EXTMCMC_PRIOR_NORMAL) return -(th - u.prior_params[0]) / (u.prior_params[1] * u.prior_params[1]);
+    return 0.0;  // ImproperPrior
+}
+__device__ __forceinline__ double prior_logpdf1(const DevUpdate &u, double th) {
+    if (u.prior == EXTMCMC_PRIOR_NORMAL) {
+        const double z = (th - u.prior_params[0]) / u.prior_params[1];
+        return -(z * z + kLog2Pi) / 2.0 - log(u.prior_params[1]);
+    }
+    return 0.0;
+}
+
+// K5a: MALA proposal  theta° = theta + (tau^2/2) g(theta) + tau z,  g = grad(ll + log prior)
+__global__ void __launch_bounds__(128)
+mala_propose_kernel(DevState d, const StepDesc *__restrict__ descs, int k) {
+    __shared__ StepCtx ctx;
+    load_step_ctx(&ctx, d, descs, k);
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= d.C) return;
+    const StepDesc &sd = ctx.sd;
+    const DevUpdate &u = ctx.u;
+    const int64_t C = d.C;
+    const int n = u.n_coords;
+    const double tau = u.eps[c], h2 = tau * tau / 2.0;
+    for (int j = 0; j < d.p; ++j) d.prop_full[(int64_t)j * C + c] = d.theta[(int64_t)j * C + c];
+    if (d.rng_mode == EXTMCMC_RNG_REPLAY) {
+        for (int i = 0; i < n; ++i)
+            d.prop_full[(int64_t)u.coords_dev[i] * C + c] = d.rp_prop[((int64_t)sd.replay_row * d.p_u_max + i) * C + c];
+        d.n_used[c] = 0;
+    } else {
+        ChainStepStream rng(d.seed, (uint64_t)(d.chain_offset + c), sd.mcmciter, sd.pidx);
+        for (int i = 0; i < n; i += 2) {
+            const double u1 = rng.next(), u2 = rng.next();
+            const double rad = sqrt(-2.0 * log(u1));
+            double sn, cs;
+            sincospi(2.0 * u2, &sn, &cs);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                if (i + q >= n) break;
+                const int64_t j = u.coords_dev[i + q];
+                const double th = d.theta[j * C + c];
+                const double g = d.grad_cur[j * C + c] + prior_grad(u, th);
+                d.prop_full[j * C + c] = th + h2 * g + tau * (rad * (q ? sn : cs));
+            }
+        }
+        d.n_used[c] = rng.j;
+    }
+    law_prepare(d, c, d.prop_full + c, C);
+}
+
+// K5b: MALA accept/reject.  log q(a -> b) = -|b - a - (tau^2/2) g(a)|^2 / (2 tau^2) (the
+// normalising constant is the same in both directions and is left out).
+__global__ void __launch_bounds__(128)
+mala_accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k) {
+    __shared__ StepCtx ctx;
+    load_step_ctx(&ctx, d, descs, k);
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= d.C) return;
+    const StepDesc &sd = ctx.sd;
+    const DevUpdate &u = ctx.u;
+    const int64_t C = d.C;
+    const int n = u.n_coords;
+    const double tau = u.eps[c], h2 = tau * tau / 2.0;
+    double qf = 0.0, qb = 0.0, lp_prop = 0.0, lp_cur = 0.0;
+    for (int i = 0; i < n; ++i) {
+        const int64_t j = u.coords_dev[i];
+        const double a = d.theta[j * C + c], b = d.prop_full[j * C + c];
+        const double ga = d.grad_cur[j * C + c] + prior_grad(u, a);
+        const double gb = d.grad_prop[j * C + c] + prior_grad(u, b);
+        const double rf = b - a - h2 * ga, rb = a - b - h2 * gb;
+        qf += rf * rf;
+        qb += rb * rb;
+        lp_prop += prior_logpdf1(u, b);
+        lp_cur += prior_logpdf1(u, a);
+    }
+    const double inv = 1.0 / (2.0 * tau * tau);
+    qf = -qf * inv;  // theta -> theta°
+    qb = -qb * inv;  // theta° -> theta
+    const double ll_prop = d.ll_prop[c];
+    const double ll_cur = sd.first ? -INFINITY : d.ll[c];
+    double llr = ll_prop - ll_cur;  // same association as run.jl:271-277
+    llr = llr + qb;
+    llr = llr - qf;
+    llr = llr + lp_prop;
+    llr = llr - lp_cur;
+    const double E = draw_exp(d, sd, c);
+    const bool accepted = E > -llr;
+    const double ll_new = accepted ? ll_prop : ll_cur;
+    if (accepted) {
+        for (int i = 0; i < n; ++i) {
+            const int64_t j = u.coords_dev[i];
+            d.theta[j * C + c] = d.prop_full[j * C + c];
+        }
+        for (int j = 0; j < d.p; ++j) d.grad_cur[(int64_t)j * C + c] = d.grad_prop[(int64_t)j * C + c];
+    }
+    post_decision(d, sd, u, c, accepted, ll_new, ll_prop, 1);
 }
 
 // ---------------------------------------------------------------------------------
@@ -607,18 +782,28 @@ static inline int red_blocks_for(int64_t C, int sl) {
     const int ch = kRedThreads / sl;
     return (int)((C + ch - 1) / ch);
 }
-static inline int slices_for(const DevState &d) { return (!d.use_ssum && d.S > 16) ? 8 : 1; }
+static inline int slices_for(const DevState &d) { return (!d.use_ssum && d.S * d.G > 16) ? 8 : 1; }
 void launch_accept(const DevState &d, const StepDesc *descs, int k, int fuse_next, cudaStream_t st) {
     if (slices_for(d) == 8)
         accept_kernel<8><<<red_blocks_for(d.C, 8), 256, 0, st>>>(d, descs, k, fuse_next);
     else
         accept_kernel<1><<<red_blocks_for(d.C, 1), 256, 0, st>>>(d, descs, k, fuse_next);
 }
+void launch_grad_finalize(const DevState &d, const double *src, double *ll_out, double *grad_out,
+                          cudaStream_t st) {
+    grad_finalize_kernel<<<(int)((d.C + 127) / 128), 128, 0, st>>>(d, src, ll_out, grad_out);
+}
+void launch_mala_propose(const DevState &d, const StepDesc *descs, int k, cudaStream_t st) {
+    mala_propose_kernel<<<(int)((d.C + 127) / 128), 128, 0, st>>>(d, descs, k);
+}
+void launch_mala_accept(const DevState &d, const StepDesc *descs, int k, cudaStream_t st) {
+    mala_accept_kernel<<<(int)((d.C + 127) / 128), 128, 0, st>>>(d, descs, k);
+}
 void launch_prepare_current(const DevState &d, cudaStream_t st) {
     prepare_current_kernel<<<blocks_for(d.C), 256, 0, st>>>(d);
 }
 void launch_reduce_partials(const DevState &d, cudaStream_t st) {
-    if (d.S > 16)
+    if (d.S * d.G > 16)
         reduce_partials_kernel<8><<<red_blocks_for(d.C, 8), 256, 0, st>>>(d);
     else
         reduce_partials_kernel<1><<<red_blocks_for(d.C, 1), 256, 0, st>>>(d);

@@ -14,15 +14,28 @@ struct SweepPlan {
     int S;             // observation segments = rows of partial[S][C]
     int launches;      // kernel launches per sweep
     int D;             // observation dimension (general-d Gaussian law)
+    int G;             // observation groups (hierarchical law; 1 otherwise)
     const char *name;
 };
 
-SweepPlan plan_sweep_gsn1d(int64_t C, int64_t n_obs, int force_variant, int num_sms);
+// Arguments of the 1-D Gaussian sweeps.  Observations of group g occupy
+// obs[goff[g] .. goff[g] + glen[g]) (goff even, buffer readable up to the next even index);
+// mu[g][C] are the per-chain means; partial[q][G*S][C] receives q = 0: sum (x - mu)^2 and,
+// with grad, q = 1: sum (x - mu).
+struct Gsn1dArgs {
+    const double *obs;
+    const int64_t *goff;
+    const int64_t *glen;
+    int G;
+    const double *mu;
+    int64_t C;
+    double *partial;
+    int S;
+};
+
+SweepPlan plan_sweep_gsn1d(int64_t C, int64_t n_obs_largest_group, int force_variant, int num_sms, int G);
 cudaError_t sweep_gsn1d_init();
-// partial[S][C] <- per-segment sums of (x - mu_c)^2.  obs must be 16-byte aligned and
-// readable up to the next even observation index (the library pads its copy).
-void launch_sweep_gsn1d(const SweepPlan &pl, const double *obs, int64_t n_obs, const double *mu,
-                        int64_t C, double *partial, cudaStream_t st);
+void launch_sweep_gsn1d(const SweepPlan &pl, const Gsn1dArgs &a, bool grad, cudaStream_t st);
 
 // General-d GsnTargetLaw: lawc = [mu(d), W = inv(chol(Sigma)) lower-tri row-major, c0],
 // obs row-major [n_obs][d], readable up to the next 16-byte boundary.

@@ -22,6 +22,10 @@
 //       chains' accumulators in registers; a fixed-order shuffle + shared-memory
 //       block reduction ends each CTA.  HBM-bound: 8 bytes per observation per sweep.
 // Both are deterministic: fixed tiling, fixed reduction order, no atomics.
+//
+// The same kernels serve the hierarchical-normal law (BASELINE cfg 4): observations come in G
+// groups, group g has its own per-chain mean mu[g][C] (gridDim.z = G), and with GRAD = true the
+// first-order sum  T = sum_i (x_i - mu)  is accumulated next to S for gradient-based updates.
 #include <cstdint>
 #include <cuda_runtime.h>
 #include "sweep.h"
@@ -29,8 +33,8 @@
 
 namespace extmcmc {
 
-// Segment s of S over n_obs observations, boundaries on even indices so that every
-// bulk copy starts 16-byte aligned.
+// Segment s of S over the n observations of one group, boundaries on even indices so that
+// every bulk copy starts 16-byte aligned (group starts are even in the padded device layout).
 __device__ __forceinline__ void segment_bounds(int64_t n_obs, int s, int S, int64_t &lo, int64_t &hi) {
     const int64_t n_pairs = (n_obs + 1) >> 1;
     lo = 2 * ((int64_t)s * n_pairs / S);
@@ -41,28 +45,31 @@ __device__ __forceinline__ void segment_bounds(int64_t n_obs, int s, int S, int6
 // ---------------------------------------------------------------------------------
 // "chains" mapping
 // ---------------------------------------------------------------------------------
-template <int R, int NT, int TILE, int STAGES>
+template <int R, int NT, int TILE, int STAGES, bool GRAD>
 __global__ void __launch_bounds__(NT)
-sweep_gsn1d_chains_kernel(const double *__restrict__ obs, int64_t n_obs,
-                          const double *__restrict__ mu, int64_t C,
-                          double *__restrict__ partial, int S) {
+sweep_gsn1d_chains_kernel(Gsn1dArgs a) {
     __shared__ __align__(128) double tile[STAGES][TILE];
     __shared__ __align__(8) uint64_t bar[STAGES];
     const int tid = threadIdx.x;
-    const int seg = blockIdx.x;
+    const int seg = blockIdx.x, g = blockIdx.z;
+    const int S = a.S;
+    const int64_t C = a.C;
     const int64_t cbase = (int64_t)blockIdx.y * (NT * R);
+    const double *__restrict__ obs = a.obs + a.goff[g];
+    const double *__restrict__ mu = a.mu + (int64_t)g * C;
 
     int64_t lo, hi;
-    segment_bounds(n_obs, seg, S, lo, hi);
+    segment_bounds(a.glen[g], seg, S, lo, hi);
     const int64_t len = hi - lo;
     const int n_tiles = (int)((len + TILE - 1) / TILE);
 
-    double m[R], acc[R];
+    double m[R], acc[R], accT[GRAD ? R : 1];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const int64_t c = cbase + (int64_t)r * NT + tid;
         m[r] = c < C ? mu[c] : 0.0;
         acc[r] = 0.0;
+        if (GRAD) accT[r] = 0.0;
     }
     if (tid == 0) {
 #pragma unroll
@@ -96,11 +103,13 @@ sweep_gsn1d_chains_kernel(const double *__restrict__ obs, int64_t n_obs,
             for (int r = 0; r < R; ++r) {
                 const double d0 = x.x - m[r];
                 acc[r] = fma(d0, d0, acc[r]);
+                if (GRAD) accT[r] += d0;
             }
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const double d1 = x.y - m[r];
                 acc[r] = fma(d1, d1, acc[r]);
+                if (GRAD) accT[r] += d1;
             }
         }
         if (cnt & 1) {
@@ -109,43 +118,51 @@ sweep_gsn1d_chains_kernel(const double *__restrict__ obs, int64_t n_obs,
             for (int r = 0; r < R; ++r) {
                 const double d0 = x - m[r];
                 acc[r] = fma(d0, d0, acc[r]);
+                if (GRAD) accT[r] += d0;
             }
         }
         __syncthreads();  // everyone is done with this stage before it is refilled
         if (tid == 0 && t + STAGES < n_tiles) issue(t + STAGES);
     }
+    const int64_t row = (int64_t)g * S + seg, rows = (int64_t)gridDim.z * S;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const int64_t c = cbase + (int64_t)r * NT + tid;
-        if (c < C) partial[(int64_t)seg * C + c] = acc[r];
+        if (c < C) {
+            a.partial[row * C + c] = acc[r];
+            if (GRAD) a.partial[(rows + row) * C + c] = accT[r];
+        }
     }
 }
 
 // ---------------------------------------------------------------------------------
 // "obs" mapping
 // ---------------------------------------------------------------------------------
-template <int CB, int NT, int TILE, int STAGES>
+template <int CB, int NT, int TILE, int STAGES, bool GRAD>
 __global__ void __launch_bounds__(NT)
-sweep_gsn1d_obs_kernel(const double *__restrict__ obs, int64_t n_obs,
-                       const double *__restrict__ mu, int64_t C, int64_t c_first,
-                       double *__restrict__ partial, int S) {
+sweep_gsn1d_obs_kernel(Gsn1dArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *tile = reinterpret_cast<double *>(smem_raw);                    // [STAGES][TILE]
     uint64_t *bar = reinterpret_cast<uint64_t *>(tile + STAGES * TILE);     // [STAGES]
-    double *red = reinterpret_cast<double *>(bar + STAGES);                 // [NT/32][CB]
+    double *red = reinterpret_cast<double *>(bar + STAGES);                 // [2][NT/32][CB]
     const int tid = threadIdx.x;
-    const int seg = blockIdx.x;
+    const int seg = blockIdx.x, g = blockIdx.z;
+    const int S = a.S;
+    const int64_t C = a.C;
+    const double *__restrict__ obs = a.obs + a.goff[g];
+    const double *__restrict__ mu = a.mu + (int64_t)g * C;
 
     int64_t lo, hi;
-    segment_bounds(n_obs, seg, S, lo, hi);
+    segment_bounds(a.glen[g], seg, S, lo, hi);
     const int64_t len = hi - lo;
     const int n_tiles = (int)((len + TILE - 1) / TILE);
 
-    double m[CB], acc[CB];
+    double m[CB], acc[CB], accT[GRAD ? CB : 1];
 #pragma unroll
     for (int c = 0; c < CB; ++c) {
-        m[c] = (c_first + c) < C ? mu[c_first + c] : 0.0;
+        m[c] = c < C ? mu[c] : 0.0;
         acc[c] = 0.0;
+        if (GRAD) accT[c] = 0.0;
     }
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) mbar_init(&bar[s], 1);
@@ -164,6 +181,16 @@ sweep_gsn1d_obs_kernel(const double *__restrict__ obs, int64_t n_obs,
     if (tid == 0)
         for (int t = 0; t < STAGES && t < n_tiles; ++t) issue(t);
 
+    auto eat = [&](const double2 x) {
+#pragma unroll
+        for (int c = 0; c < CB; ++c) {
+            const double d0 = x.x - m[c];
+            acc[c] = fma(d0, d0, acc[c]);
+            const double d1 = x.y - m[c];
+            acc[c] = fma(d1, d1, acc[c]);
+            if (GRAD) { accT[c] += d0; accT[c] += d1; }
+        }
+    };
     for (int t = 0; t < n_tiles; ++t) {
         const int st = t % STAGES;
         mbar_wait(&bar[st], (uint32_t)(t / STAGES) & 1u);
@@ -172,34 +199,17 @@ sweep_gsn1d_obs_kernel(const double *__restrict__ obs, int64_t n_obs,
         const double2 *xs = reinterpret_cast<const double2 *>(tile + st * TILE);
         if (cnt == TILE) {
 #pragma unroll
-            for (int k = 0; k < TILE / 2 / NT; ++k) {
-                const double2 x = xs[k * NT + tid];  // consecutive threads, consecutive 16 B
-#pragma unroll
-                for (int c = 0; c < CB; ++c) {
-                    const double d0 = x.x - m[c];
-                    acc[c] = fma(d0, d0, acc[c]);
-                    const double d1 = x.y - m[c];
-                    acc[c] = fma(d1, d1, acc[c]);
-                }
-            }
+            for (int k = 0; k < TILE / 2 / NT; ++k) eat(xs[k * NT + tid]);  // consecutive threads, consecutive 16 B
         } else {
             const int np = cnt >> 1;
-            for (int i = tid; i < np; i += NT) {
-                const double2 x = xs[i];
-#pragma unroll
-                for (int c = 0; c < CB; ++c) {
-                    const double d0 = x.x - m[c];
-                    acc[c] = fma(d0, d0, acc[c]);
-                    const double d1 = x.y - m[c];
-                    acc[c] = fma(d1, d1, acc[c]);
-                }
-            }
+            for (int i = tid; i < np; i += NT) eat(xs[i]);
             if ((cnt & 1) && tid == 0) {
                 const double x = tile[st * TILE + cnt - 1];
 #pragma unroll
                 for (int c = 0; c < CB; ++c) {
                     const double d0 = x - m[c];
                     acc[c] = fma(d0, d0, acc[c]);
+                    if (GRAD) accT[c] += d0;
                 }
             }
         }
@@ -208,18 +218,31 @@ sweep_gsn1d_obs_kernel(const double *__restrict__ obs, int64_t n_obs,
     }
 
     // fixed-order block reduction: xor-shuffle tree inside each warp, then warp 0..W-1
+    constexpr int NW = NT / 32;
 #pragma unroll
     for (int c = 0; c < CB; ++c) {
         double v = acc[c];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         if ((tid & 31) == 0) red[(tid >> 5) * CB + c] = v;
+        if (GRAD) {
+            double w = accT[c];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+            if ((tid & 31) == 0) red[(NW + (tid >> 5)) * CB + c] = w;
+        }
     }
     __syncthreads();
-    if (tid < CB && (c_first + tid) < C) {
+    const int64_t row = (int64_t)g * S + seg, rows = (int64_t)gridDim.z * S;
+    if (tid < CB && tid < C) {
         double v = 0.0;
-        for (int w = 0; w < NT / 32; ++w) v += red[w * CB + tid];
-        partial[(int64_t)seg * C + c_first + tid] = v;
+        for (int w = 0; w < NW; ++w) v += red[w * CB + tid];
+        a.partial[row * C + tid] = v;
+        if (GRAD) {
+            double t2 = 0.0;
+            for (int w = 0; w < NW; ++w) t2 += red[(NW + w) * CB + tid];
+            a.partial[(rows + row) * C + tid] = t2;
+        }
     }
 }
 
@@ -230,38 +253,45 @@ namespace {
 constexpr int kChainsNT = 128, kChainsTile = 1024, kChainsStages = 2;
 constexpr int kObsNT = 256, kObsTile = 2048, kObsStages = 4;
 constexpr size_t kObsSmem(int cb) {
-    return (size_t)kObsStages * kObsTile * 8 + kObsStages * 8 + (size_t)(kObsNT / 32) * cb * 8;
+    return (size_t)kObsStages * kObsTile * 8 + kObsStages * 8 + (size_t)2 * (kObsNT / 32) * cb * 8;
 }
 
 template <int R>
-void launch_chains(const SweepPlan &pl, const double *obs, int64_t n_obs, const double *mu,
-                   int64_t C, double *partial, cudaStream_t st) {
-    dim3 grid(pl.S, pl.groups);
-    sweep_gsn1d_chains_kernel<R, kChainsNT, kChainsTile, kChainsStages>
-        <<<grid, kChainsNT, 0, st>>>(obs, n_obs, mu, C, partial, pl.S);
+void launch_chains(const SweepPlan &pl, const Gsn1dArgs &a, bool grad, cudaStream_t st) {
+    dim3 grid(pl.S, pl.groups, a.G);
+    if (grad)
+        sweep_gsn1d_chains_kernel<R, kChainsNT, kChainsTile, kChainsStages, true><<<grid, kChainsNT, 0, st>>>(a);
+    else
+        sweep_gsn1d_chains_kernel<R, kChainsNT, kChainsTile, kChainsStages, false><<<grid, kChainsNT, 0, st>>>(a);
 }
 template <int CB>
 cudaError_t prep_obs() {
-    return cudaFuncSetAttribute(sweep_gsn1d_obs_kernel<CB, kObsNT, kObsTile, kObsStages>,
+    cudaError_t e = cudaFuncSetAttribute(sweep_gsn1d_obs_kernel<CB, kObsNT, kObsTile, kObsStages, false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kObsSmem(CB));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(sweep_gsn1d_obs_kernel<CB, kObsNT, kObsTile, kObsStages, true>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kObsSmem(CB));
 }
 template <int CB>
-void launch_obs(const SweepPlan &pl, const double *obs, int64_t n_obs, const double *mu, int64_t C,
-                double *partial, cudaStream_t st) {
-    for (int g = 0; g < pl.groups; ++g)
-        sweep_gsn1d_obs_kernel<CB, kObsNT, kObsTile, kObsStages>
-            <<<pl.S, kObsNT, kObsSmem(CB), st>>>(obs, n_obs, mu, C, (int64_t)g * CB, partial, pl.S);
+void launch_obs(const SweepPlan &pl, const Gsn1dArgs &a, bool grad, cudaStream_t st) {
+    dim3 grid(pl.S, 1, a.G);
+    if (grad)
+        sweep_gsn1d_obs_kernel<CB, kObsNT, kObsTile, kObsStages, true><<<grid, kObsNT, kObsSmem(CB), st>>>(a);
+    else
+        sweep_gsn1d_obs_kernel<CB, kObsNT, kObsTile, kObsStages, false><<<grid, kObsNT, kObsSmem(CB), st>>>(a);
 }
 }  // namespace
 
-SweepPlan plan_sweep_gsn1d(int64_t C, int64_t n_obs, int force_variant, int num_sms) {
+// n_obs: observations of the LARGEST group (all of them when G = 1)
+SweepPlan plan_sweep_gsn1d(int64_t C, int64_t n_obs, int force_variant, int num_sms, int G) {
     SweepPlan pl{};
+    pl.G = G;
     const int64_t n_pairs = (n_obs + 1) / 2;
     bool chains = C > 32;
     int force_R = 0;  // force_variant 11, 12, 14, 18: "chains" mapping with R = 1, 2, 4, 8 (tests)
     if (force_variant > 10) { force_R = force_variant - 10; force_variant = SWEEP_VARIANT_CHAINS; }
     if (force_variant == SWEEP_VARIANT_CHAINS) chains = true;
-    if (force_variant == SWEEP_VARIANT_OBS) chains = false;
+    if (force_variant == SWEEP_VARIANT_OBS && C <= 32) chains = false;
     if (chains) {
         // chains per thread: the largest R in {8,4,2,1} that still yields >= 2 CTAs per SM
         // (small N limits the number of segments, so small problems trade registers for CTAs)
@@ -269,11 +299,11 @@ SweepPlan plan_sweep_gsn1d(int64_t C, int64_t n_obs, int force_variant, int num_
         int R = 8, S = 1, groups = 1;
         for (;; R >>= 1) {
             groups = (int)((C + (int64_t)kChainsNT * R - 1) / ((int64_t)kChainsNT * R));
-            S = (num_sms * 4 + groups - 1) / groups;
+            S = (num_sms * 4 + groups * G - 1) / (groups * G);
             if (S > max_S) S = (int)max_S;
             if (S < 1) S = 1;
             const bool fits = C >= (int64_t)kChainsNT * R;      // no mostly-empty thread tiles
-            if (force_R ? R == force_R : (R == 1 || (fits && (int64_t)groups * S >= 2 * num_sms))) break;
+            if (force_R ? R == force_R : (R == 1 || (fits && (int64_t)groups * S * G >= 2 * num_sms))) break;
             if (R == 1) break;
         }
         pl.variant = SWEEP_VARIANT_CHAINS;
@@ -289,13 +319,13 @@ SweepPlan plan_sweep_gsn1d(int64_t C, int64_t n_obs, int force_variant, int num_
         while (CB < C && CB < 32) CB <<= 1;
         pl.variant = SWEEP_VARIANT_OBS;
         pl.R = CB;
-        pl.groups = (int)((C + CB - 1) / CB);
-        int S = num_sms * 3;  // 3 CTAs x 64 KB of staging per SM
+        pl.groups = 1;
+        int S = (num_sms * 3 + G - 1) / G;  // 3 CTAs x 64 KB of staging per SM
         const int64_t max_S = (n_pairs + 1023) / 1024;  // >= one 2048-observation tile
         if (S > max_S) S = (int)max_S;
         if (S < 1) S = 1;
         pl.S = S;
-        pl.launches = pl.groups;
+        pl.launches = 1;
         pl.name = CB == 1 ? "gsn1d_obs_C1" : CB == 2 ? "gsn1d_obs_C2" : CB == 4 ? "gsn1d_obs_C4"
                 : CB == 8 ? "gsn1d_obs_C8" : CB == 16 ? "gsn1d_obs_C16" : "gsn1d_obs_C32";
     }
@@ -313,23 +343,22 @@ cudaError_t sweep_gsn1d_init() {
     return cudaSuccess;
 }
 
-void launch_sweep_gsn1d(const SweepPlan &pl, const double *obs, int64_t n_obs, const double *mu,
-                        int64_t C, double *partial, cudaStream_t st) {
+void launch_sweep_gsn1d(const SweepPlan &pl, const Gsn1dArgs &a, bool grad, cudaStream_t st) {
     if (pl.variant == SWEEP_VARIANT_CHAINS) {
         switch (pl.R) {
-        case 1: launch_chains<1>(pl, obs, n_obs, mu, C, partial, st); break;
-        case 2: launch_chains<2>(pl, obs, n_obs, mu, C, partial, st); break;
-        case 4: launch_chains<4>(pl, obs, n_obs, mu, C, partial, st); break;
-        default: launch_chains<8>(pl, obs, n_obs, mu, C, partial, st); break;
+        case 1: launch_chains<1>(pl, a, grad, st); break;
+        case 2: launch_chains<2>(pl, a, grad, st); break;
+        case 4: launch_chains<4>(pl, a, grad, st); break;
+        default: launch_chains<8>(pl, a, grad, st); break;
         }
     } else {
         switch (pl.R) {
-        case 1: launch_obs<1>(pl, obs, n_obs, mu, C, partial, st); break;
-        case 2: launch_obs<2>(pl, obs, n_obs, mu, C, partial, st); break;
-        case 4: launch_obs<4>(pl, obs, n_obs, mu, C, partial, st); break;
-        case 8: launch_obs<8>(pl, obs, n_obs, mu, C, partial, st); break;
-        case 16: launch_obs<16>(pl, obs, n_obs, mu, C, partial, st); break;
-        default: launch_obs<32>(pl, obs, n_obs, mu, C, partial, st); break;
+        case 1: launch_obs<1>(pl, a, grad, st); break;
+        case 2: launch_obs<2>(pl, a, grad, st); break;
+        case 4: launch_obs<4>(pl, a, grad, st); break;
+        case 8: launch_obs<8>(pl, a, grad, st); break;
+        case 16: launch_obs<16>(pl, a, grad, st); break;
+        default: launch_obs<32>(pl, a, grad, st); break;
         }
     }
 }

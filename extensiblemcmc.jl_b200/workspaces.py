@@ -39,12 +39,13 @@ class CUDAMCMCBackend(MCMCBackend):
     history        "full": every (iteration, update) row is copied back (reference
                    behaviour); "none": histories stay on the device ring only
     stats_mode     0 mean + covariance (reference), 1 mean + variances, 2 off
+                   (default: 0 for p <= 16 parameters, 1 above)
     shard_mode     "chains" (default) or "obs" (observations sharded over ranks, NCCL)
     rank/world_size/chain_offset  one process per GPU; see parallel.py
     """
 
     def __init__(self, n_chains=1, device=0, seed=0, block_len=128, history="full",
-                 stats_mode=0, use_graphs=True, instrument=False, sweep_variant=0,
+                 stats_mode=None, use_graphs=True, instrument=False, sweep_variant=0,
                  shard_mode="chains", rank=0, world_size=1, chain_offset=0, roll_window=100,
                  comm_id=None):
         assert history in ("full", "none")
@@ -54,7 +55,7 @@ class CUDAMCMCBackend(MCMCBackend):
         self.seed = int(seed)
         self.block_len = int(block_len)
         self.history = history
-        self.stats_mode = int(stats_mode)
+        self.stats_mode = None if stats_mode is None else int(stats_mode)   # None: 0 if p <= 16 else 1
         self.use_graphs = bool(use_graphs)
         self.instrument = bool(instrument)
         self.sweep_variant = int(sweep_variant)
@@ -122,7 +123,8 @@ class CUDAGlobalWorkspace(GlobalWorkspace):
         cfg.use_graphs = 1 if backend.use_graphs else 0
         cfg.instrument = 1 if backend.instrument else 0
         cfg.sweep_variant = backend.sweep_variant
-        cfg.stats_mode = backend.stats_mode
+        cfg.stats_mode = backend.stats_mode if backend.stats_mode is not None else (0 if self.p <= 16 else 1)
+        backend.stats_mode = cfg.stats_mode
         self.cfg = cfg
         self.handle = _abi.Handle()
         rc = lib.extmcmc_create(C.byref(cfg), C.byref(self.handle))
@@ -152,7 +154,10 @@ class CUDAGlobalWorkspace(GlobalWorkspace):
                 if obs.shape[1] != law.obs_dim:
                     raise ValueError("observations must have shape (n_obs, obs_dim)")
                 self.n_obs = obs.shape[0]
-                self._ck(lib.extmcmc_upload_obs(self.handle, _abi.dptr(obs), self.n_obs, law.obs_dim, None))
+                y = law.abi_y(data) if hasattr(law, "abi_y") else None
+                if y is not None and y.shape[0] != self.n_obs:
+                    raise ValueError("one group index / response per observation is required")
+                self._ck(lib.extmcmc_upload_obs(self.handle, _abi.dptr(obs), self.n_obs, law.obs_dim, _abi.dptr(y)))
             self._ck(lib.extmcmc_set_state(self.handle, _abi.dptr(self.theta_init)))
         except Exception:
             lib.extmcmc_destroy(self.handle)
@@ -216,7 +221,8 @@ class CUDAGlobalWorkspace(GlobalWorkspace):
         """Current per-chain step-size state of update u (1-based): eps [p_u, C] for a uniform
         walk, Sigma_B [p_u^2, C] (column-major) for a Gaussian mixture walk."""
         n = len(self._keep[u - 1][0])
-        rows = n * n if self._kernels[u - 1] == _abi.KERNEL_RW_GAUSS_MIX else n
+        k = self._kernels[u - 1]
+        rows = n * n if k == _abi.KERNEL_RW_GAUSS_MIX else (1 if k == _abi.KERNEL_MALA else n)
         out = np.empty((rows, self.C))
         self._ck(self.lib.extmcmc_get_eps(self.handle, u - 1, _abi.dptr(out)))
         return out
@@ -232,6 +238,12 @@ class CUDAGlobalWorkspace(GlobalWorkspace):
         out = np.empty(self.C)
         self._ck(self.lib.extmcmc_eval_loglik(self.handle, _abi.dptr(out)))
         return out
+
+    def eval_grad(self):
+        """(ll [C], d ll / d theta [p, C]) at the current state (laws with a device gradient)."""
+        ll, g = np.empty(self.C), np.empty((self.p, self.C))
+        self._ck(self.lib.extmcmc_eval_grad(self.handle, _abi.dptr(ll), _abi.dptr(g)))
+        return ll, g
 
 
 class DeviceGeneratedObs:

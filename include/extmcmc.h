@@ -69,7 +69,9 @@ enum {
     EXTMCMC_KERNEL_RW_UNIFORM   = 1, /* UniformRandomWalk, random_walk.jl:45-94  */
     EXTMCMC_KERNEL_RW_GAUSS     = 2, /* GaussianRandomWalk, :123-171             */
     EXTMCMC_KERNEL_RW_GAUSS_MIX = 3, /* GaussianRandomWalkMix, :193-232          */
-    EXTMCMC_KERNEL_MALA         = 4  /* MALAUpdate (stub in reference, updates.jl:216-218) */
+    EXTMCMC_KERNEL_MALA         = 4  /* MALAUpdate (stub in reference, updates.jl:216-218):
+                                        th° = th + tau^2/2 grad(ll + log prior)(th) + tau z;
+                                        step = tau[1]; priors: IMPROPER, NORMAL            */
 };
 
 /* ---- priors (src/priors.jl) ---------------------------------------------- */
@@ -192,8 +194,9 @@ int32_t extmcmc_abi_version(void);
 
 /* ---- model, data, updates ------------------------------------------------- */
 /* Replaces the user's law object + its observations: data = (P = law, obs = ...)
- * (src/workspaces.jl:229-237).  Row-major obs[n_obs][obs_dim]; y (responses,
- * LOGISTIC / group index for HIER_NORMAL) may be NULL.  The library copies.
+ * (src/workspaces.jl:229-237).  Row-major obs[n_obs][obs_dim]; y = responses (LOGISTIC)
+ * or the 0-based group index of every observation, sorted ascending (HIER_NORMAL);
+ * NULL otherwise.  The library copies.
  * Under EXTMCMC_SHARD_OBS each rank uploads only its own slice. */
 int32_t extmcmc_upload_obs(extmcmc_t h, const double *obs, int64_t n_obs,
                            int32_t obs_dim, const double *y);
@@ -264,6 +267,10 @@ int32_t extmcmc_get_adapt_state(extmcmc_t h, int32_t u, double *mean, double *co
 /* Evaluate the full-data log-likelihood of the current state of every chain
  * (one sweep, nothing else); ll_out[C].  Used by parity tests. */
 int32_t extmcmc_eval_loglik(extmcmc_t h, double *ll_out);
+/* Same plus the gradient d ll / d theta of all p parameters, grad_out[p][C] (laws with a
+ * device gradient only).  The reference has only the hook for this:
+ * compute_gradients_and_momenta! src/updates.jl:129-133, `grad ll` src/workspaces.jl:417. */
+int32_t extmcmc_eval_grad(extmcmc_t h, double *ll_out, double *grad_out);
 
 /* ---- measurement ---------------------------------------------------------- */
 /* CUDA-event stopwatch on the handle's stream. */

@@ -120,7 +120,8 @@ int32_t oracle_create(const extmcmc_config_t *cfg, const extmcmc_update_t *updat
                       const double *obs, int64_t n_obs, const double *y,
                       const double *theta_init, oracle_t *out) {
     if (!cfg || !updates || !out || !theta_init) { set_err("null argument"); return EXTMCMC_EINVAL; }
-    if (cfg->law != EXTMCMC_LAW_GSN_IID_1D && cfg->law != EXTMCMC_LAW_GSN_MV) {
+    if (cfg->law != EXTMCMC_LAW_GSN_IID_1D && cfg->law != EXTMCMC_LAW_GSN_MV &&
+        cfg->law != EXTMCMC_LAW_HIER_NORMAL) {
         set_err("oracle: law not implemented");
         return EXTMCMC_EUNSUPPORTED;
     }
@@ -138,7 +139,11 @@ int32_t oracle_create(const extmcmc_config_t *cfg, const extmcmc_update_t *updat
         return EXTMCMC_EINVAL;
     }
     for (int u = 0; u < cfg->n_updates; ++u)
-        if (updates[u].n_coords < 1 || updates[u].n_coords > 64) { set_err("oracle: 1 <= n_coords <= 64"); return EXTMCMC_EINVAL; }
+        if (updates[u].n_coords < 1 || updates[u].n_coords > 256) { set_err("oracle: 1 <= n_coords <= 256"); return EXTMCMC_EINVAL; }
+    if (cfg->law == EXTMCMC_LAW_HIER_NORMAL && (d != 1 || cfg->n_params < 3 || !y)) {
+        set_err("HIER_NORMAL needs obs_dim = 1, n_params = G + 2 and group indices in y");
+        return EXTMCMC_EINVAL;
+    }
     struct oracle_handle *h = xcalloc(1, sizeof *h);
     h->cfg = *cfg;
     h->C = cfg->n_chains; h->p = cfg->n_params; h->NU = cfg->n_updates;
@@ -154,14 +159,15 @@ int32_t oracle_create(const extmcmc_config_t *cfg, const extmcmc_update_t *updat
         const extmcmc_update_t *s = &updates[u];
         orc_update_t *t = &h->upd[u];
         if (s->kernel != EXTMCMC_KERNEL_RW_UNIFORM && s->kernel != EXTMCMC_KERNEL_RW_GAUSS &&
-            s->kernel != EXTMCMC_KERNEL_RW_GAUSS_MIX) {
+            s->kernel != EXTMCMC_KERNEL_RW_GAUSS_MIX && s->kernel != EXTMCMC_KERNEL_MALA) {
             set_err("oracle: transition kernel not implemented");
             oracle_destroy(h);
             return EXTMCMC_EUNSUPPORTED;
         }
         if ((s->adapt.kind == EXTMCMC_ADAPT_UNIF_RW && s->kernel != EXTMCMC_KERNEL_RW_UNIFORM) ||
             (s->adapt.kind == EXTMCMC_ADAPT_HAARIO && s->kernel != EXTMCMC_KERNEL_RW_GAUSS_MIX) ||
-            s->adapt.kind > EXTMCMC_ADAPT_HAARIO) {
+            (s->adapt.kind == EXTMCMC_ADAPT_MALA && s->kernel != EXTMCMC_KERNEL_MALA) ||
+            s->adapt.kind > EXTMCMC_ADAPT_MALA) {
             /* readjust!(rw, adpt, iter) exists only for (UniformRandomWalk, AdaptationUnifRW) and
              * (GaussianRandomWalkMix, HaarioTypeAdaptation): adaptation.jl:273,422 */
             set_err("oracle: adaptation does not match the transition kernel");
@@ -189,8 +195,9 @@ int32_t oracle_create(const extmcmc_config_t *cfg, const extmcmc_update_t *updat
         {
             const int nn = s->n_coords * s->n_coords;
             t->step_len = s->kernel == EXTMCMC_KERNEL_RW_UNIFORM ? s->n_coords
+                        : s->kernel == EXTMCMC_KERNEL_MALA ? 1
                         : s->kernel == EXTMCMC_KERNEL_RW_GAUSS ? nn : 2 * nn + 1;
-            if (s->kernel != EXTMCMC_KERNEL_RW_UNIFORM && s->n_coords > 16) { set_err("oracle: Gaussian walks need n_coords <= 16"); oracle_destroy(h); return EXTMCMC_EINVAL; }
+            if ((s->kernel == EXTMCMC_KERNEL_RW_GAUSS || s->kernel == EXTMCMC_KERNEL_RW_GAUSS_MIX) && s->n_coords > 16) { set_err("oracle: Gaussian walks need n_coords <= 16"); oracle_destroy(h); return EXTMCMC_EINVAL; }
             if (s->adapt.kind == EXTMCMC_ADAPT_HAARIO) {
                 t->hmean = xcalloc((size_t)C * s->n_coords, sizeof(double));   /* zero(state), adaptation.jl:388 */
                 t->hcov = xcalloc((size_t)C * nn, sizeof(double));
@@ -299,10 +306,60 @@ static double loglik_gsn_mv(const double *x, int64_t n, int d, const double *the
     return ll;
 }
 
+/* Hierarchical normal law (BASELINE cfg 4; no reference law, build-defined):
+ * theta = [th_1..th_G, mu, tau];  y_gj ~ N(th_g, 1),  th_g ~ N(mu, tau^2).  The hierarchical
+ * term is part of the law because the reference's priors only see the update's own coordinates
+ * (src/run.jl:374-385).  One sequential sum over the observations, like gsn_target.jl:23-29. */
+static double loglik_hier(const struct oracle_handle *h, const double *th, double *grad, int *bad) {
+    const int G = h->p - 2;
+    const double mu = th[G], tau = th[G + 1];
+    if (grad) for (int k = 0; k < h->p; ++k) grad[k] = 0.0;
+    if (!(tau > 0.0) || !isfinite(tau)) { *bad = 1; return NAN; }
+    double ll = 0.0;
+    for (int64_t i = 0; i < h->n_obs; ++i) {
+        const int g = (int)h->y[i];
+        const double r = h->obs[i] - th[g];
+        ll += -0.5 * LOG2PI - (r * r) / 2.0;
+        if (grad) grad[g] += r;
+    }
+    for (int g = 0; g < G; ++g) {
+        const double dv = th[g] - mu;
+        ll += -0.5 * LOG2PI - log(tau) - (dv * dv) / (2.0 * tau * tau);
+        if (grad) {
+            grad[g] += -dv / (tau * tau);
+            grad[G] += dv / (tau * tau);
+            grad[G + 1] += -1.0 / tau + (dv * dv) / (tau * tau * tau);
+        }
+    }
+    return ll;
+}
+
+/* d/dmu and d/dvar of the 1-D Gaussian log-likelihood, sequential per-observation sums */
+static void grad_gsn_1d(const double *x, int64_t n, double mu, double var, double *grad) {
+    double gm = 0.0, gv = 0.0;
+    for (int64_t i = 0; i < n; ++i) {
+        const double r = x[i] - mu;
+        gm += r / var;
+        gv += -1.0 / (2.0 * var) + (r * r) / (2.0 * var * var);
+    }
+    grad[0] = gm; grad[1] = gv;
+}
+
 static double law_loglik(const struct oracle_handle *h, const double *theta, int *bad) {
     if (h->cfg.law == EXTMCMC_LAW_GSN_IID_1D)
         return loglik_gsn_1d(h->obs, h->n_obs, theta[0], theta[1], bad);
+    if (h->cfg.law == EXTMCMC_LAW_HIER_NORMAL)
+        return loglik_hier(h, theta, NULL, bad);
     return loglik_gsn_mv(h->obs, h->n_obs, h->cfg.obs_dim, theta, bad);
+}
+
+/* log-likelihood and its gradient w.r.t. all p parameters (laws with a gradient only) */
+static double law_loglik_grad(const struct oracle_handle *h, const double *theta, double *grad, int *bad) {
+    if (h->cfg.law == EXTMCMC_LAW_HIER_NORMAL) return loglik_hier(h, theta, grad, bad);
+    double ll = loglik_gsn_1d(h->obs, h->n_obs, theta[0], theta[1], bad);
+    if (*bad) { grad[0] = grad[1] = NAN; return ll; }
+    grad_gsn_1d(h->obs, h->n_obs, theta[0], theta[1], grad);
+    return ll;
 }
 
 /* ------------------------------------------------------------------------- */
@@ -432,6 +489,18 @@ static void gauss_propose(const uint8_t *pos, int n, const double *Sigma, const 
 /* ------------------------------------------------------------------------- */
 /* One schedule element for one chain: the body of __run! src/run.jl:70-82   */
 /* ------------------------------------------------------------------------- */
+static double mala_prior_grad(const orc_update_t *u, double th) {
+    if (u->prior == EXTMCMC_PRIOR_NORMAL) return -(th - u->prior_params[0]) / (u->prior_params[1] * u->prior_params[1]);
+    return 0.0;
+}
+static double mala_prior_logpdf1(const orc_update_t *u, double th) {
+    if (u->prior == EXTMCMC_PRIOR_NORMAL) {
+        const double z = (th - u->prior_params[0]) / u->prior_params[1];
+        return -(z * z + LOG2PI) / 2.0 - log(u->prior_params[1]);
+    }
+    return 0.0;
+}
+
 typedef struct {
     double *rec_prop, *rec_exp;
     double *theta_hist, *prop_hist, *ll_hist, *llp_hist, *llr_hist;
@@ -453,10 +522,19 @@ static void chain_step(struct oracle_handle *h, int64_t c, const extmcmc_step_t 
     /* update_workspaces! src/run.jl:101-112: local state <- global state[coords];
      * local ll <- ll_history of the previously executed update (here: the carried
      * ll); on the very first element prev is `nothing` and ll stays -Inf. */
-    double th_loc[64], th_prop[64];
+    double th_loc[256], th_prop[256];
+    double g_cur[256], g_prop[256];
     for (int i = 0; i < n; ++i) th_loc[i] = theta[u->coords[i]];
     double ll_cur = (st->prev_pidx < 0) ? -INFINITY : h->ll[c];
     if (st->prev_pidx < 0) h->ll[c] = -INFINITY;
+
+    /* compute_gradients_and_momenta!(updt, ws, Previous) -- the reference's hook for
+     * gradient-based updates, called on every step (src/run.jl:110, src/updates.jl:129-133) */
+    if (u->kernel == EXTMCMC_KERNEL_MALA) {
+        int badg = 0;
+        law_loglik_grad(h, theta, g_cur, &badg);
+        if (badg) h->domain_err = 1;
+    }
 
     /* proposal! src/updates.jl:191-196 + rand(::UniformRandomWalk) random_walk.jl:65-73 */
     uint32_t j = 0; /* index into this chain-step's uniform substream */
@@ -465,7 +543,23 @@ static void chain_step(struct oracle_handle *h, int64_t c, const extmcmc_step_t 
             th_prop[i] = io->rec_prop[((int64_t)s_idx * io->p_u_max + i) * C + c];
     } else {
         for (;;) {
-            if (u->kernel == EXTMCMC_KERNEL_RW_UNIFORM) {
+            if (u->kernel == EXTMCMC_KERNEL_MALA) {
+                /* theta° = theta + (tau^2/2) grad(ll + log prior)(theta) + tau z */
+                const double tau = eps[0], h2 = tau * tau / 2.0;
+                for (int q = 0; q < n; q += 2) {
+                    double u1 = oracle_uniform(h->cfg.seed, gchain, st->mcmciter, u_idx, j++);
+                    double u2 = oracle_uniform(h->cfg.seed, gchain, st->mcmciter, u_idx, j++);
+                    double rad = sqrt(-2.0 * log(u1));
+                    double zz[2] = {rad * cos(6.283185307179586476925286766559 * u2),
+                                    rad * sin(6.283185307179586476925286766559 * u2)};
+                    for (int w = 0; w < 2 && q + w < n; ++w) {
+                        const int i = q + w;
+                        const double g = g_cur[u->coords[i]] + mala_prior_grad(u, th_loc[i]);
+                        th_prop[i] = th_loc[i] + h2 * g + tau * zz[w];
+                    }
+                }
+                break;   /* no prior-support redraw: MALA priors have full support */
+            } else if (u->kernel == EXTMCMC_KERNEL_RW_UNIFORM) {
                 for (int i = 0; i < n; ++i) {
                     double r = oracle_uniform(h->cfg.seed, gchain, st->mcmciter, u_idx, j++);
                     /* rand(Uniform(a, b)) = a + (b - a) * rand() with a = -eps, b = eps */
@@ -510,19 +604,39 @@ static void chain_step(struct oracle_handle *h, int64_t c, const extmcmc_step_t 
 
     /* compute_ll! src/run.jl:251-260 -> loglikelihood(P°, obs) */
     int bad = 0;
-    double ll_prop = law_loglik(h, full_prop, &bad);
+    /* compute_ll! + compute_gradients_and_momenta!(updt, ws, Proposal), src/run.jl:257-259 */
+    double ll_prop = (u->kernel == EXTMCMC_KERNEL_MALA) ? law_loglik_grad(h, full_prop, g_prop, &bad)
+                                                         : law_loglik(h, full_prop, &bad);
     if (bad) h->domain_err = 1;
 
     /* accept_reject! src/run.jl:268-281; strict left-to-right association */
     double llr = ll_prop - ll_cur;
-    {
+    if (u->kernel == EXTMCMC_KERNEL_MALA) {
+        /* log q(a -> b) = -|b - a - (tau^2/2) g(a)|^2 / (2 tau^2); constant omitted (same both ways) */
+        const double tau = eps[0], h2 = tau * tau / 2.0;
+        double qf = 0.0, qb = 0.0, lpp = 0.0, lpc = 0.0;
+        for (int i = 0; i < n; ++i) {
+            const double a = th_loc[i], b = th_prop[i];
+            const double ga = g_cur[u->coords[i]] + mala_prior_grad(u, a);
+            const double gb = g_prop[u->coords[i]] + mala_prior_grad(u, b);
+            const double rf = b - a - h2 * ga, rb = a - b - h2 * gb;
+            qf += rf * rf; qb += rb * rb;
+            lpp += mala_prior_logpdf1(u, b); lpc += mala_prior_logpdf1(u, a);
+        }
+        const double inv = 1.0 / (2.0 * tau * tau);
+        qf = -qf * inv; qb = -qb * inv;
+        llr = llr + qb;
+        llr = llr - qf;
+        llr = llr + lpp;
+        llr = llr - lpc;
+    } else {
         int badq = 0;
         llr = llr + log_q(u, eps, th_prop, th_loc, &badq);   /* ltd(Proposal): theta° -> theta, run.jl:360-367 */
         llr = llr - log_q(u, eps, th_loc, th_prop, &badq);   /* ltd(Previous): theta -> theta°, run.jl:344-351 */
         if (badq) h->domain_err = 1;
+        llr = llr + log_prior(u, th_prop);
+        llr = llr - log_prior(u, th_loc);
     }
-    llr = llr + log_prior(u, th_prop);
-    llr = llr - log_prior(u, th_loc);
     double E;
     if (io->rng_mode == EXTMCMC_RNG_REPLAY) {
         E = io->rec_exp[(int64_t)s_idx * C + c];
@@ -585,7 +699,8 @@ static void chain_step(struct oracle_handle *h, int64_t c, const extmcmc_step_t 
      * src/transition_kernels/adaptation.jl:273-329 */
     h->tot_prop[c * NU + u_idx] += 1;
     h->tot_acc[c * NU + u_idx] += accepted;
-    if (u->adapt.kind == EXTMCMC_ADAPT_UNIF_RW) {
+    if (u->adapt.kind == EXTMCMC_ADAPT_UNIF_RW || u->adapt.kind == EXTMCMC_ADAPT_MALA) {
+        const int n_eps = u->kernel == EXTMCMC_KERNEL_MALA ? 1 : n;
         int64_t *prop = &h->proposed[c * NU + u_idx], *acc = &h->accepted[c * NU + u_idx];
         *acc += accepted; *prop += 1;                       /* register! :292-295 */
         if (*prop >= u->adapt.adapt_every_k_steps) {        /* time_to_update :302-304 */
@@ -595,7 +710,7 @@ static void chain_step(struct oracle_handle *h, int64_t c, const extmcmc_step_t 
             double a_r = (*prop == 0) ? 0.0 : (double)*acc / (double)*prop; /* :242-244 */
             *prop = 0; *acc = 0;                            /* reset! :263-266 */
             double sgn = (a_r > u->adapt.target_accpt_rate) ? 1.0 : -1.0;
-            for (int i = 0; i < n; ++i) {                   /* compute_eps :326-329 */
+            for (int i = 0; i < n_eps; ++i) {               /* compute_eps :326-329 */
                 double e = eps[i] + sgn * delta;
                 e = e < u->adapt.max ? e : u->adapt.max;    /* min(e, max) */
                 e = e > u->adapt.min ? e : u->adapt.min;    /* max(., min) */
@@ -738,6 +853,18 @@ int32_t oracle_get_eps(oracle_t h, int32_t u, double *eps) {
     int L = h->upd[u].step_len;
     for (int64_t c = 0; c < h->C; ++c)
         for (int i = 0; i < L; ++i) eps[(int64_t)i * h->C + c] = h->step[u][c * L + i];
+    return EXTMCMC_OK;
+}
+
+int32_t oracle_loglik_grad(oracle_t h, const double *theta, int64_t n_eval, double *ll_out, double *grad_out) {
+    if (h->cfg.law != EXTMCMC_LAW_GSN_IID_1D && h->cfg.law != EXTMCMC_LAW_HIER_NORMAL) return EXTMCMC_EUNSUPPORTED;
+    for (int64_t c = 0; c < n_eval; ++c) {
+        double th[256], g[256];
+        int bad = 0;
+        for (int k = 0; k < h->p; ++k) th[k] = theta[(int64_t)k * n_eval + c];
+        ll_out[c] = law_loglik_grad(h, th, g, &bad);
+        for (int k = 0; k < h->p; ++k) grad_out[(int64_t)k * n_eval + c] = g[k];
+    }
     return EXTMCMC_OK;
 }
 

@@ -72,6 +72,10 @@ int32_t oracle_get_adapt_state(oracle_t h, int32_t u, double *mean, double *cov)
 int32_t oracle_loglik(oracle_t h, const double *theta, int64_t n_chains_eval,
                       double *ll_out, int32_t n_threads);
 
+/* ll and d ll / d theta (all p parameters) for laws with a gradient: grad_out[p][n]. */
+int32_t oracle_loglik_grad(oracle_t h, const double *theta, int64_t n_chains_eval, double *ll_out,
+                           double *grad_out);
+
 /* Philox4x32-10 block function, exposed for known-answer tests. */
 void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 /* j-th uniform in (0,1) of the (chain, mcmciter, pidx) substream. */

@@ -50,6 +50,8 @@ def load():
     lib.oracle_get_adapt_state.argtypes = [H, C.c_int32, dp, dp]
     lib.oracle_loglik.restype = C.c_int32
     lib.oracle_loglik.argtypes = [H, dp, C.c_int64, dp, C.c_int32]
+    lib.oracle_loglik_grad.restype = C.c_int32
+    lib.oracle_loglik_grad.argtypes = [H, dp, C.c_int64, dp, dp]
     lib.oracle_philox4x32_10.restype = None
     lib.oracle_philox4x32_10.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     lib.oracle_uniform.restype = C.c_double
@@ -80,7 +82,7 @@ class Oracle:
     """CPU restatement of the reference sampler for C independent chains."""
 
     def __init__(self, law, updates, obs, theta_init, n_chains, seed=0, chain_offset=0,
-                 roll_window=100):
+                 roll_window=100, y=None):
         lib = load()
         self.lib = lib
         self.C, self.p, self.NU = int(n_chains), law.n_params, len(updates)
@@ -112,7 +114,8 @@ class Oracle:
         theta_init = np.ascontiguousarray(theta_init)
         assert theta_init.shape == (self.p, self.C)
         self.h = C.c_void_p()
-        rc = lib.oracle_create(C.byref(cfg), arr, _abi.dptr(obs), obs.shape[0], None,
+        y = None if y is None else np.ascontiguousarray(y, dtype=np.float64)
+        rc = lib.oracle_create(C.byref(cfg), arr, _abi.dptr(obs), obs.shape[0], _abi.dptr(y),
                                _abi.dptr(theta_init), C.byref(self.h))
         if rc != 0:
             raise OracleError(rc, lib.oracle_last_error().decode())
@@ -169,7 +172,8 @@ class Oracle:
     def eps(self, u):
         """eps [p_u, C] (uniform walk) or Sigma_B [p_u^2, C] (Gaussian mixture walk)."""
         n, k = self.p_u[u - 1], self.kernels[u - 1]
-        ln = n if k == _abi.KERNEL_RW_UNIFORM else (n * n if k == _abi.KERNEL_RW_GAUSS else 2 * n * n + 1)
+        ln = (n if k == _abi.KERNEL_RW_UNIFORM else 1 if k == _abi.KERNEL_MALA
+              else (n * n if k == _abi.KERNEL_RW_GAUSS else 2 * n * n + 1))
         out = np.empty((ln, self.C))
         self.lib.oracle_get_eps(self.h, u - 1, _abi.dptr(out))
         return out[n * n:2 * n * n] if k == _abi.KERNEL_RW_GAUSS_MIX else out
@@ -187,6 +191,18 @@ class Oracle:
         out = np.empty(n)
         self.lib.oracle_loglik(self.h, _abi.dptr(theta), n, _abi.dptr(out), n_threads)
         return out
+
+
+def _loglik_grad(self, theta):
+    theta = np.ascontiguousarray(theta, dtype=np.float64)
+    n = theta.shape[1]
+    ll, g = np.empty(n), np.empty((self.p, n))
+    rc = self.lib.oracle_loglik_grad(self.h, _abi.dptr(theta), n, _abi.dptr(ll), _abi.dptr(g))
+    assert rc == 0
+    return ll, g
+
+
+Oracle.loglik_grad = _loglik_grad
 
 
 def philox(ctr, key):

@@ -37,7 +37,7 @@ class GpuSession:
     """Thin driver of the C ABI for tests (replay mode lives below the Python mirror)."""
 
     def __init__(self, law, updates, obs, theta_init, n_chains, seed=0, history_window=None,
-                 n_steps_hint=64, **cfg_kw):
+                 n_steps_hint=64, y=None, **cfg_kw):
         self.lib = _abi.load()
         self.C, self.p, self.NU = n_chains, law.n_params, len(updates)
         cfg = _abi.Config()
@@ -63,7 +63,8 @@ class GpuSession:
             self.kernels.append(a.kernel)
             self.ck(self.lib.extmcmc_set_update(self.h, i, C.byref(a)))
         obs = np.ascontiguousarray(obs, dtype=np.float64)
-        self.ck(self.lib.extmcmc_upload_obs(self.h, _abi.dptr(obs), obs.shape[0], law.obs_dim, None))
+        y = None if y is None else np.ascontiguousarray(y, dtype=np.float64)
+        self.ck(self.lib.extmcmc_upload_obs(self.h, _abi.dptr(obs), obs.shape[0], law.obs_dim, _abi.dptr(y)))
         th = np.asarray(theta_init, dtype=np.float64)
         if th.ndim == 1:
             th = np.repeat(th[:, None], n_chains, axis=1)
@@ -128,10 +129,16 @@ class GpuSession:
 
     def eps(self, u):
         n = self.p_u[u - 1]
-        rows = n * n if self.kernels[u - 1] == _abi.KERNEL_RW_GAUSS_MIX else n
+        k = self.kernels[u - 1]
+        rows = n * n if k == _abi.KERNEL_RW_GAUSS_MIX else (1 if k == _abi.KERNEL_MALA else n)
         out = np.empty((rows, self.C))
         self.ck(self.lib.extmcmc_get_eps(self.h, u - 1, _abi.dptr(out)))
         return out
+
+    def eval_grad(self):
+        ll, g = np.empty(self.C), np.empty((self.p, self.C))
+        self.ck(self.lib.extmcmc_eval_grad(self.h, _abi.dptr(ll), _abi.dptr(g)))
+        return ll, g
 
     def adapt_state(self, u):
         n = self.p_u[u - 1]
@@ -178,16 +185,16 @@ def compare_histories(o, g, tie_tol=1e-12):
 
 
 def replay_compare(x, n_chains, n_iters, seed=1, updates=None, theta_init=None, exclude=(),
-                   block=None, check_state=True, law=None, **cfg_kw):
+                   block=None, check_state=True, law=None, y=None, **cfg_kw):
     """Oracle (own Philox stream, recording) vs GPU (replaying) on the same inputs."""
     law = law if law is not None else em.GsnTargetLaw([0.0], [[1.0]])
     updates = updates if updates is not None else cfg2_updates(eps0=0.05, scale=5e-3, k=10, offset=2.0)
     theta_init = theta_init if theta_init is not None else theta_init_for(x, n_chains)
     steps = list(em.MCMCSchedule(n_iters, len(updates), exclude))
     o = orc.Oracle(law, updates, x, theta_init, n_chains, seed=seed,
-                   roll_window=cfg_kw.get("roll_window", 100))
+                   roll_window=cfg_kw.get("roll_window", 100), y=y)
     ro = o.run(steps, n_threads=8)
-    g = GpuSession(law, updates, x, theta_init, n_chains, seed=seed, n_steps_hint=len(steps), **cfg_kw)
+    g = GpuSession(law, updates, x, theta_init, n_chains, seed=seed, n_steps_hint=len(steps), y=y, **cfg_kw)
     block = block or len(steps)
     parts = []
     for b in range(0, len(steps), block):

@@ -1,0 +1,182 @@
+"""MALAUpdate (a #TODO stub in the reference, src/updates.jl:216-218; build-defined semantics),
+device gradients and the hierarchical-normal law of BASELINE cfg 4, against the oracle.
+No reference oracle exists for these: pinned by finite differences, by the
+acceptance-rate -> 1 limit as tau -> 0 (detailed balance of the proposal/Hastings pair) and by
+posterior agreement with an independent long oracle run."""
+import math
+
+import numpy as np
+import pytest
+
+import extensiblemcmc_jl_b200 as em
+from extensiblemcmc_jl_b200 import _abi
+from oracle import oracle as orc
+from tests.parity import GpuSession, replay_compare, theta_init_for
+
+pytestmark = pytest.mark.gpu
+
+
+def _hier_data(G=8, ng=400, seed=5, ragged=False):
+    rng = np.random.default_rng(seed)
+    tg = rng.standard_normal(G)
+    sizes = [ng + (3 * g + 1 if ragged else 0) for g in range(G)]
+    y = np.concatenate([tg[g] + rng.standard_normal(sizes[g]) for g in range(G)])
+    grp = np.concatenate([np.full(sizes[g], g) for g in range(G)])
+    return y, grp, tg
+
+
+def _hier_updates(G, tau=0.1):
+    return [em.MALAUpdate(tau, list(range(1, G + 1)),
+                          adpt=em.AdaptationMALA(adapt_every_k_steps=6, scale=0.004, offset=1.0)),
+            em.RandomWalkUpdate(em.UniformRandomWalk([0.4]), [G + 1],
+                                adpt=em.AdaptationUnifRW([0.0], adapt_every_k_steps=5, scale=0.02, offset=1.0)),
+            em.RandomWalkUpdate(em.UniformRandomWalk([0.4], [True]), [G + 2], prior=em.ImproperPosPrior())]
+
+
+def _hier_theta0(G, n_chains, seed=2):
+    rng = np.random.default_rng(seed)
+    th = np.zeros((G + 2, n_chains))
+    th[:G] = 0.3 * rng.standard_normal((G, n_chains))
+    th[G] = 0.1 * rng.standard_normal(n_chains)
+    th[G + 1] = np.exp(0.2 * rng.standard_normal(n_chains))
+    return th
+
+
+def _clean(rep):
+    assert rep["accept_mismatch"] == 0 and rep["near_ties"] == 0, rep
+    assert rep["theta_bitexact"] and rep["ll_rel_err"] < 1e-10, rep
+    assert rep["eps_bitexact"] and rep["mean_bitexact"] and rep["cov_bitexact"] and rep["counts_equal"], rep
+    assert rep["rolling_ar_bitexact"] and rep["final_state_bitexact"], rep
+    assert 0.02 < rep["accept_rate"] < 0.98, rep
+
+
+@pytest.mark.parametrize("n_chains", [70, 5])
+def test_gradient_gsn1d_against_oracle_and_finite_differences(n_chains):
+    x = 1.5 + 2.0 * np.random.default_rng(1).standard_normal(3001)
+    law = em.GsnTargetLaw([0.0])
+    th0 = theta_init_for(x, n_chains)
+    ups = [em.MALAUpdate(0.01, [1])]
+    g = GpuSession(law, ups, x, th0, n_chains)
+    ll, gr = g.eval_grad()
+    o = orc.Oracle(law, ups, x, th0, n_chains)
+    llo, gro = o.loglik_grad(th0)
+    assert np.allclose(ll, llo, rtol=1e-10, atol=0) and np.allclose(gr, gro, rtol=1e-9, atol=1e-9)
+    h = 1e-6
+    for k in range(2):
+        e = np.zeros_like(th0); e[k] = h
+        fd = (o.loglik(th0 + e) - o.loglik(th0 - e)) / (2 * h)
+        assert np.allclose(gr[k], fd, rtol=1e-5, atol=1e-4)
+    g.close()
+
+
+@pytest.mark.parametrize("n_chains,ragged", [(300, False), (6, True)])
+def test_gradient_hier_against_oracle_and_finite_differences(n_chains, ragged):
+    G = 8
+    y, grp, _ = _hier_data(G, 333, ragged=ragged)
+    law = em.HierNormalLaw(G)
+    th0 = _hier_theta0(G, n_chains)
+    ups = _hier_updates(G)
+    g = GpuSession(law, ups, y, th0, n_chains, y=grp)
+    ll, gr = g.eval_grad()
+    o = orc.Oracle(law, ups, y, th0, n_chains, y=grp)
+    llo, gro = o.loglik_grad(th0)
+    assert np.allclose(ll, llo, rtol=1e-10, atol=0)
+    assert np.allclose(gr, gro, rtol=1e-9, atol=1e-9)
+    assert np.allclose(g.eval_loglik(), llo, rtol=1e-10, atol=0)
+    h = 1e-6
+    for k in (0, G - 1, G, G + 1):
+        e = np.zeros_like(th0); e[k] = h
+        fd = (o.loglik(th0 + e) - o.loglik(th0 - e)) / (2 * h)
+        assert np.allclose(gr[k], fd, rtol=1e-5, atol=1e-4)
+    g.close()
+
+
+def test_mala_replay_parity_gsn1d():
+    x = 1.5 + 2.0 * np.random.default_rng(3).standard_normal(2500)
+    ups = [em.MALAUpdate(0.05, [1], prior=em.StandardPrior(em.Normal(0.0, 10.0)),
+                         adpt=em.AdaptationMALA(adapt_every_k_steps=5, scale=0.003, offset=1.0)),
+           em.RandomWalkUpdate(em.UniformRandomWalk([0.05], [True]), [2], prior=em.ImproperPosPrior())]
+    rep = replay_compare(x, 90, 50, seed=6, updates=ups, block=17, history_window=32)
+    _clean(rep)
+
+
+def test_mala_replay_parity_joint_update():
+    x = 1.5 + 2.0 * np.random.default_rng(4).standard_normal(1800)
+    ups = [em.MALAUpdate(0.04, [1, 2], adpt=em.AdaptationMALA(adapt_every_k_steps=7, scale=0.002, offset=1.0))]
+    rep = replay_compare(x, 64, 60, seed=9, updates=ups)
+    _clean(rep)
+
+
+@pytest.mark.parametrize("n_chains,ragged", [(200, False), (7, True)])
+def test_cfg4_schedule_replay_parity(n_chains, ragged):
+    # BASELINE cfg 4: MALA on theta_1..8, uniform walk on mu, multiplicative walk on tau
+    G = 8
+    y, grp, _ = _hier_data(G, 256, ragged=ragged)
+    rep = replay_compare(y, n_chains, 30, seed=12, updates=_hier_updates(G), law=em.HierNormalLaw(G), y=grp,
+                         theta_init=_hier_theta0(G, n_chains), exclude=[(2, range(5, 9))], block=31,
+                         history_window=40)
+    _clean(rep)
+
+
+def test_mala_accepts_everything_as_tau_goes_to_zero():
+    G = 4
+    y, grp, _ = _hier_data(G, 100, seed=8)
+    law = em.HierNormalLaw(G)
+    th0 = _hier_theta0(G, 64)
+    rates = []
+    for tau in (0.3, 1e-3):
+        g = GpuSession(law, [em.MALAUpdate(tau, [1, 2, 3, 4])], y, th0, 64, seed=4, y=grp, n_steps_hint=40)
+        r = g.run(list(em.MCMCSchedule(40, 1)))
+        rates.append(r["accepted"][1:].mean())
+        g.close()
+    assert rates[1] > 0.995 and rates[0] < rates[1]
+
+
+def test_cfg4_posterior_matches_oracle_and_graphs_and_sharding_are_exact():
+    G = 8
+    y, grp, _ = _hier_data(G, 400, seed=11)
+    law = em.HierNormalLaw(G)
+    data = dict(P=law, obs=y, groups=grp)
+    th0 = np.concatenate([np.zeros(G), [0.0, 1.0]])
+    mk = lambda: [em.MALAUpdate(0.1, list(range(1, G + 1)),
+                                adpt=em.AdaptationMALA(adapt_every_k_steps=25, scale=0.01, offset=2.0)),
+                  em.RandomWalkUpdate(em.UniformRandomWalk([0.5]), [G + 1]),
+                  em.RandomWalkUpdate(em.UniformRandomWalk([0.5], [True]), [G + 2], prior=em.ImproperPosPrior())]
+    Cn, M = 256, 1500
+    mcmc = em.MCMC(mk(), backend=em.CUDAMCMCBackend(n_chains=Cn, seed=31, block_len=96))
+    ws, lws = em.run_(mcmc, M, data, th0)
+    tr = ws.sub_ws.state_history[500:, 2]                     # [iters, p, C]
+    o = orc.Oracle(law, mk(), y, th0, 32, seed=77, y=grp)
+    ro = o.run(list(em.MCMCSchedule(M, 3)), n_threads=8, record=False)
+    tro = ro["theta"].reshape(M, 3, G + 2, 32)[500:, 2]
+    ess, esso = em.ess_geyer(tr), em.ess_geyer(tro)
+    for k in range(G + 2):
+        se = math.sqrt(tr[:, k].var() / ess[k].sum() + tro[:, k].var() / esso[k].sum())
+        assert abs(tr[:, k].mean() - tro[:, k].mean()) < 3 * se, k
+    acc = ws.stats()["n_accept"].sum(axis=1) / ws.stats()["n_prop"].sum(axis=1)
+    assert 0.35 < acc[0] < 0.8                                 # MALA step adapted towards 0.574
+    full = ws.sub_ws.state_history[:60].copy()
+    tau = ws.eps(1).copy()
+    ws.close()
+    # eager launches and a 2-way chain split reproduce the graph run bit-for-bit
+    outs = []
+    for off, cnt, graphs in ((0, Cn, False), (0, 100, True), (100, Cn - 100, True)):
+        m2 = em.MCMC(mk(), backend=em.CUDAMCMCBackend(n_chains=cnt, chain_offset=off, seed=31, block_len=50,
+                                                      use_graphs=graphs))
+        w2, _ = em.run_(m2, 60, data, th0)
+        outs.append(w2.sub_ws.state_history.copy())
+        w2.close()
+    assert np.array_equal(outs[0], full)
+    assert np.array_equal(np.concatenate(outs[1:], axis=-1), full)
+    assert tau.shape == (1, Cn)
+
+
+def test_mala_unsupported_combinations():
+    x = np.zeros(10)
+    with pytest.raises(_abi.ExtMCMCError) as ei:       # no device gradient for the general-d law
+        GpuSession(em.GsnTargetLaw(np.zeros(2)), [em.MALAUpdate(0.1, [1])], np.zeros((10, 2)),
+                   em.GsnTargetLaw(np.zeros(2)).theta, 4)
+    assert ei.value.code == _abi.EUNSUPPORTED
+    with pytest.raises(_abi.ExtMCMCError) as ei:
+        GpuSession(em.GsnTargetLaw([0.0]), [em.MALAUpdate(0.1, [1], prior=em.ImproperPosPrior())], x, [0.0, 1.0], 4)
+    assert ei.value.code == _abi.EUNSUPPORTED
