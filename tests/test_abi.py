@@ -75,4 +75,8 @@ def test_unsupported_configurations_raise():
     with pytest.raises(NotImplementedError):
         em.StandardPrior(object()).to_abi()
     with pytest.raises(NotImplementedError):
-        em.MALAUpdate().to_abi(2)
+        em.HamiltonianMCUpdate().to_abi(2)
+    u, _keep = em.MALAUpdate(0.1, [1, 2]).to_abi(2)
+    assert (u.kernel, u.n_coords) == (_abi.KERNEL_MALA, 2)
+    assert em.AdaptationMALA().to_abi().kind == _abi.ADAPT_MALA
+    assert em.AdaptationMALA().target_accpt_rate == 0.574
