@@ -15,6 +15,7 @@ from .priors import (Prior, ImproperPrior, ImproperPosPrior, StandardPrior, Prod
 from .updates import RandomWalkUpdate, MALAUpdate, HamiltonianMCUpdate
 from .gsn_target import GsnTargetLaw
 from .hier_normal import HierNormalLaw
+from .logistic import LogisticLaw
 from .workspaces import (CUDAMCMCBackend, CUDAGlobalWorkspace, CUDALocalWorkspace,
                          DeviceGeneratedObs, init_global_workspace, create_workspace,
                          create_workspaces, state, state_prop, ll, ll_prop, accepted, llr,

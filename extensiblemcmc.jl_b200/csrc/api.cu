@@ -77,6 +77,8 @@ struct extmcmc_handle {
     int64_t n_obs_local = 0;
     int64_t n_obs_largest = 0;           // observations of the largest group
     int64_t *goff_dev = nullptr, *glen_dev = nullptr;  // [G] padded group offsets / true lengths
+    double *y_dev = nullptr;             // LOGISTIC: responses, padded like the rows of X
+    int logi_D = 0;                      // LOGISTIC: padded feature dimension
     bool grad_valid = false;             // grad_cur holds d ll/d theta of the CURRENT state
     bool any_mala = false;
     bool state_set = false;
@@ -169,11 +171,16 @@ int32_t ensure_plan(extmcmc_t h) {
         h->plan = plan_sweep_gsn1d(h->d.C, h->n_obs_largest, h->cfg.sweep_variant, h->num_sms, h->d.G);
     else if (h->cfg.law == EXTMCMC_LAW_GSN_MV)
         h->plan = plan_sweep_gsnmv(h->cfg.obs_dim, h->d.C, h->n_obs_local, h->cfg.sweep_variant, h->num_sms);
+    else if (h->cfg.law == EXTMCMC_LAW_LOGISTIC)
+        h->plan = plan_sweep_logistic(h->cfg.obs_dim, h->d.C, h->n_obs_local, h->num_sms);
     else
         return fail(h, EXTMCMC_EUNSUPPORTED, "law not implemented on the GPU path");
     h->d.S = h->plan.S;
-    // two quantities (second- and first-order sums) x G groups x S segments
-    int32_t rc = dev_alloc(h, &h->d.partial, (size_t)2 * h->d.G * h->plan.S * h->d.C);
+    // Gaussian laws: two quantities (second- and first-order sums) x G groups x S segments;
+    // logistic: ll_part[S][C] followed by g_part[S][d][C]
+    const size_t part_rows = h->cfg.law == EXTMCMC_LAW_LOGISTIC ? (size_t)h->plan.S * (h->cfg.obs_dim + 1)
+                                                                : (size_t)2 * h->d.G * h->plan.S;
+    int32_t rc = dev_alloc(h, &h->d.partial, part_rows * h->d.C);
     if (rc) return rc;
     h->plan_valid = true;
     invalidate_graphs(h);
@@ -211,9 +218,12 @@ bool obs_sharded(extmcmc_t h) {
     return h->cfg.shard_mode == EXTMCMC_SHARD_OBS && h->cfg.world_size > 1;
 }
 
-// One likelihood sweep over the law constants in lawc (+ cross-rank reduction when the
-// observations are sharded).  grad: also accumulate the first-order sums.
-int32_t enqueue_sweep(extmcmc_t h, bool instrument, bool grad = false) {
+// One likelihood sweep (+ cross-rank reduction when the observations are sharded).  Gaussian
+// laws read the law constants the proposal kernel left in lawc and leave per-segment sums in
+// `partial` (grad: also the first-order sums).  The logistic law reads the parameters from
+// `src` ([p][C]) and finishes ll (-> ll_dst) and the gradient (-> grad_dst, may be NULL) itself.
+int32_t enqueue_sweep(extmcmc_t h, bool instrument, bool grad = false, const double *src = nullptr,
+                      double *ll_dst = nullptr, double *grad_dst = nullptr) {
     std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
     if (instrument) {
         if (!h->ev_free.empty()) { ev = h->ev_free.back(); h->ev_free.pop_back(); }
@@ -223,6 +233,10 @@ int32_t enqueue_sweep(extmcmc_t h, bool instrument, bool grad = false) {
     if (h->cfg.law == EXTMCMC_LAW_GSN_IID_1D || h->cfg.law == EXTMCMC_LAW_HIER_NORMAL) {
         Gsn1dArgs a{h->obs_dev, h->goff_dev, h->glen_dev, h->d.G, h->d.lawc, h->d.C, h->d.partial, h->plan.S};
         launch_sweep_gsn1d(h->plan, a, grad, h->stream);
+    } else if (h->cfg.law == EXTMCMC_LAW_LOGISTIC) {
+        LogisticArgs a{h->obs_dev, h->y_dev, h->n_obs_local, src, h->cfg.obs_dim, h->d.C, h->d.partial,
+                       h->d.partial + (size_t)h->plan.S * h->d.C, h->plan.S};
+        launch_sweep_logistic(h->plan, a, ll_dst, grad_dst, h->stream);
     } else {
         launch_sweep_gsnmv(h->plan, h->obs_dev, h->n_obs_local, h->d.lawc, h->d.C, h->d.partial, h->stream);
     }
@@ -251,22 +265,32 @@ int32_t enqueue_steps(extmcmc_t h, const StepDesc *d_descs, const int *kinds, in
     for (int k = 0; k < n_steps; ++k) {
         int32_t rc;
         if (kinds[k] == EXTMCMC_KERNEL_MALA) {
+            const bool logi = h->cfg.law == EXTMCMC_LAW_LOGISTIC;
             if (!grad_valid) {
-                launch_prepare_current(h->d, h->stream);
-                if ((rc = enqueue_sweep(h, instrument, true))) return rc;
-                launch_grad_finalize(h->d, h->d.theta, h->scratch_ll, h->d.grad_cur, h->stream);
-                h->launches += 2;
+                if (logi) {
+                    if ((rc = enqueue_sweep(h, instrument, true, h->d.theta, h->scratch_ll, h->d.grad_cur))) return rc;
+                } else {
+                    launch_prepare_current(h->d, h->stream);
+                    if ((rc = enqueue_sweep(h, instrument, true))) return rc;
+                    launch_grad_finalize(h->d, h->d.theta, h->scratch_ll, h->d.grad_cur, h->stream);
+                    h->launches += 2;
+                }
             }
             launch_mala_propose(h->d, d_descs, k, h->stream);
-            if ((rc = enqueue_sweep(h, instrument, true))) return rc;
-            launch_grad_finalize(h->d, h->d.prop_full, h->d.ll_prop, h->d.grad_prop, h->stream);
+            if (logi) {
+                if ((rc = enqueue_sweep(h, instrument, true, h->d.prop_full, h->d.ll_prop, h->d.grad_prop))) return rc;
+            } else {
+                if ((rc = enqueue_sweep(h, instrument, true))) return rc;
+                launch_grad_finalize(h->d, h->d.prop_full, h->d.ll_prop, h->d.grad_prop, h->stream);
+                h->launches += 1;
+            }
             launch_mala_accept(h->d, d_descs, k, h->stream);
-            h->launches += 3;
+            h->launches += 2;
             grad_valid = true;
             fused = false;
         } else {
             if (!fused) { launch_propose(h->d, d_descs, k, h->stream); h->launches += 1; }
-            if ((rc = enqueue_sweep(h, instrument, false))) return rc;
+            if ((rc = enqueue_sweep(h, instrument, false, h->d.prop_full, h->d.ssum, nullptr))) return rc;
             fused = k + 1 < n_steps && kinds[k + 1] != EXTMCMC_KERNEL_MALA;
             launch_accept(h->d, d_descs, k, fused ? 1 : 0, h->stream);
             h->launches += 1;
@@ -456,6 +480,12 @@ int32_t extmcmc_create(const extmcmc_config_t *cfg, extmcmc_t *out) {
         if (cfg->n_params != cfg->obs_dim * (cfg->obs_dim + 1))
             return fail(nullptr, EXTMCMC_EINVAL, "GSN_MV needs n_params = d (d + 1)");
         break;
+    case EXTMCMC_LAW_LOGISTIC:
+        if (cfg->obs_dim != cfg->n_params || cfg->obs_dim < 1 || logistic_padded_dim(cfg->obs_dim) == 0)
+            return fail(nullptr, EXTMCMC_EUNSUPPORTED, "LOGISTIC needs obs_dim = n_params = d with 1 <= d <= 256");
+        if (cfg->shard_mode == EXTMCMC_SHARD_OBS && cfg->world_size > 1)
+            return fail(nullptr, EXTMCMC_EUNSUPPORTED, "LOGISTIC with sharded observations is not implemented");
+        break;
     case EXTMCMC_LAW_HIER_NORMAL:
         if (cfg->obs_dim != 1 || cfg->n_params < 3)
             return fail(nullptr, EXTMCMC_EINVAL, "HIER_NORMAL needs obs_dim = 1 and n_params = G + 2 >= 3");
@@ -502,6 +532,8 @@ int32_t extmcmc_create(const extmcmc_config_t *cfg, extmcmc_t *out) {
     CKC(cudaEventCreate(&h->t1));
     for (auto &sl : h->slot) CKC(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
     CKC(sweep_gsn1d_init());
+    CKC(sweep_logistic_init());
+    h->logi_D = cfg->law == EXTMCMC_LAW_LOGISTIC ? logistic_padded_dim(cfg->obs_dim) : 0;
 
     DevState &d = h->d;
     const int64_t C = cfg->n_chains;
@@ -514,9 +546,13 @@ int32_t extmcmc_create(const extmcmc_config_t *cfg, extmcmc_t *out) {
     d.obs_dim = cfg->obs_dim;
     d.G = cfg->law == EXTMCMC_LAW_HIER_NORMAL ? cfg->n_params - 2 : 1;
     d.lawc_k = cfg->law == EXTMCMC_LAW_GSN_IID_1D ? 3
+             : cfg->law == EXTMCMC_LAW_LOGISTIC ? 1
              : cfg->law == EXTMCMC_LAW_HIER_NORMAL ? d.G
              : cfg->obs_dim + cfg->obs_dim * (cfg->obs_dim + 1) / 2 + 1;
-    d.use_ssum = (cfg->shard_mode == EXTMCMC_SHARD_OBS && cfg->world_size > 1) ? 1 : 0;
+    // the accept kernel reads the finished sum from ssum when another kernel produced it:
+    // the NCCL all-reduce under observation sharding, or the logistic sweep's own finalize
+    d.use_ssum = ((cfg->shard_mode == EXTMCMC_SHARD_OBS && cfg->world_size > 1) ||
+                  cfg->law == EXTMCMC_LAW_LOGISTIC) ? 1 : 0;
     int32_t rc = 0;
     const size_t covn = cfg->stats_mode == 0 ? (size_t)p * p : (cfg->stats_mode == 1 ? (size_t)p : 0);
     if ((rc = dev_alloc(h, &d.theta, (size_t)p * C)) || (rc = dev_alloc(h, &d.ll, (size_t)C)) ||
@@ -554,6 +590,7 @@ int32_t extmcmc_destroy(extmcmc_t h) {
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     for (void *p : h->allocs) cudaFree(p);
     if (h->obs_dev) cudaFree(h->obs_dev);
+    if (h->y_dev) cudaFree(h->y_dev);
     if (h->rp_prop) cudaFree(h->rp_prop);
     if (h->rp_exp) cudaFree(h->rp_exp);
     if (h->flush_buf) cudaFree(h->flush_buf);
@@ -609,6 +646,28 @@ int32_t extmcmc_upload_obs(extmcmc_t h, const double *obs, int64_t n_obs, int32_
     if (obs_dim != h->cfg.obs_dim) return fail(h, EXTMCMC_EINVAL, "obs_dim differs from the configuration");
     CK(h, cudaSetDevice(h->cfg.device));
     CK(h, cudaStreamSynchronize(h->stream));
+    if (h->cfg.law == EXTMCMC_LAW_LOGISTIC) {
+        // X -> [n_pad][D] (zero rows up to a multiple of 16, zero columns up to D), y -> [n_pad]
+        if (!y) return fail(h, EXTMCMC_EINVAL, "LOGISTIC needs the responses y");
+        const int D = h->logi_D;
+        const size_t n_pad = ((size_t)n_obs + 15) & ~(size_t)15;
+        if (h->obs_dev) { cudaFree(h->obs_dev); h->obs_dev = nullptr; }
+        if (h->y_dev) { cudaFree(h->y_dev); h->y_dev = nullptr; }
+        CK(h, cudaMalloc(&h->obs_dev, n_pad * D * sizeof(double)));
+        CK(h, cudaMalloc(&h->y_dev, n_pad * sizeof(double)));
+        CK(h, cudaMemsetAsync(h->obs_dev, 0, n_pad * D * sizeof(double), h->stream));
+        CK(h, cudaMemsetAsync(h->y_dev, 0, n_pad * sizeof(double), h->stream));
+        CK(h, cudaMemcpy2DAsync(h->obs_dev, (size_t)D * 8, obs, (size_t)obs_dim * 8, (size_t)obs_dim * 8,
+                                (size_t)n_obs, cudaMemcpyHostToDevice, h->stream));
+        CK(h, cudaMemcpyAsync(h->y_dev, y, (size_t)n_obs * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CK(h, cudaStreamSynchronize(h->stream));
+        h->n_obs_local = n_obs;
+        h->n_obs_largest = n_obs;
+        h->plan_valid = false;
+        h->n_total_known = false;
+        h->grad_valid = false;
+        return EXTMCMC_OK;
+    }
     std::vector<int64_t> glen(h->d.G, 0);
     if (h->cfg.law == EXTMCMC_LAW_HIER_NORMAL) {
         // y[i] = group index of observation i (0-based), non-decreasing
@@ -661,8 +720,9 @@ int32_t extmcmc_set_update(extmcmc_t h, int32_t u, const extmcmc_update_t *upd) 
     if (upd->kernel != EXTMCMC_KERNEL_RW_UNIFORM && !gauss && !mala)
         return fail(h, EXTMCMC_EUNSUPPORTED, "transition kernel not implemented on the GPU path");
     if (mala) {
-        if (h->cfg.law != EXTMCMC_LAW_GSN_IID_1D && h->cfg.law != EXTMCMC_LAW_HIER_NORMAL)
-            return fail(h, EXTMCMC_EUNSUPPORTED, "MALA needs a law with a device gradient (GSN_IID_1D, HIER_NORMAL)");
+        if (h->cfg.law != EXTMCMC_LAW_GSN_IID_1D && h->cfg.law != EXTMCMC_LAW_HIER_NORMAL &&
+            h->cfg.law != EXTMCMC_LAW_LOGISTIC)
+            return fail(h, EXTMCMC_EUNSUPPORTED, "MALA needs a law with a device gradient (GSN_IID_1D, HIER_NORMAL, LOGISTIC)");
         if (upd->prior != EXTMCMC_PRIOR_IMPROPER && upd->prior != EXTMCMC_PRIOR_NORMAL)
             return fail(h, EXTMCMC_EUNSUPPORTED, "MALA supports ImproperPrior and Normal priors only");
         if (upd->pos)
@@ -1020,11 +1080,15 @@ int32_t extmcmc_eval_loglik(extmcmc_t h, double *ll_out) {
     int32_t rc;
     if ((rc = ensure_plan(h))) return rc;
     if ((rc = ensure_total_obs(h))) return rc;
-    launch_prepare_current(h->d, h->stream);
-    if ((rc = enqueue_sweep(h, h->cfg.instrument != 0))) return rc;
-    if (!obs_sharded(h)) { launch_reduce_partials(h->d, h->stream); h->launches += 1; }
-    launch_finalize_loglik(h->d, h->scratch_ll, h->stream);
-    h->launches += 2;
+    if (h->cfg.law == EXTMCMC_LAW_LOGISTIC) {
+        if ((rc = enqueue_sweep(h, h->cfg.instrument != 0, false, h->d.theta, h->scratch_ll, nullptr))) return rc;
+    } else {
+        launch_prepare_current(h->d, h->stream);
+        if ((rc = enqueue_sweep(h, h->cfg.instrument != 0))) return rc;
+        if (!obs_sharded(h)) { launch_reduce_partials(h->d, h->stream); h->launches += 1; }
+        launch_finalize_loglik(h->d, h->scratch_ll, h->stream);
+        h->launches += 2;
+    }
     CK(h, cudaGetLastError());
     CK(h, cudaMemcpyAsync(ll_out, h->scratch_ll, sizeof(double) * h->d.C, cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
@@ -1034,17 +1098,22 @@ int32_t extmcmc_eval_loglik(extmcmc_t h, double *ll_out) {
 int32_t extmcmc_eval_grad(extmcmc_t h, double *ll_out, double *grad_out) {
     if (!h || !grad_out) return EXTMCMC_EINVAL;
     if (!h->obs_dev || !h->state_set) return fail(h, EXTMCMC_EINVAL, "observations and state required");
-    if (h->cfg.law != EXTMCMC_LAW_GSN_IID_1D && h->cfg.law != EXTMCMC_LAW_HIER_NORMAL)
+    if (h->cfg.law != EXTMCMC_LAW_GSN_IID_1D && h->cfg.law != EXTMCMC_LAW_HIER_NORMAL &&
+        h->cfg.law != EXTMCMC_LAW_LOGISTIC)
         return fail(h, EXTMCMC_EUNSUPPORTED, "this law has no device gradient");
     if (obs_sharded(h)) return fail(h, EXTMCMC_EUNSUPPORTED, "gradients with sharded observations are not implemented");
     CK(h, cudaSetDevice(h->cfg.device));
     int32_t rc;
     if ((rc = ensure_plan(h))) return rc;
     if ((rc = ensure_total_obs(h))) return rc;
-    launch_prepare_current(h->d, h->stream);
-    if ((rc = enqueue_sweep(h, h->cfg.instrument != 0, true))) return rc;
-    launch_grad_finalize(h->d, h->d.theta, h->scratch_ll, h->d.grad_cur, h->stream);
-    h->launches += 2;
+    if (h->cfg.law == EXTMCMC_LAW_LOGISTIC) {
+        if ((rc = enqueue_sweep(h, h->cfg.instrument != 0, true, h->d.theta, h->scratch_ll, h->d.grad_cur))) return rc;
+    } else {
+        launch_prepare_current(h->d, h->stream);
+        if ((rc = enqueue_sweep(h, h->cfg.instrument != 0, true))) return rc;
+        launch_grad_finalize(h->d, h->d.theta, h->scratch_ll, h->d.grad_cur, h->stream);
+        h->launches += 2;
+    }
     h->grad_valid = true;
     CK(h, cudaGetLastError());
     if (ll_out) CK(h, cudaMemcpyAsync(ll_out, h->scratch_ll, sizeof(double) * h->d.C, cudaMemcpyDeviceToHost, h->stream));

@@ -197,6 +197,7 @@ __device__ __forceinline__ void law_prepare(const DevState &d, int64_t c, const 
 
 // th: this chain's parameter vector the sums were computed for (stride C)
 __device__ __forceinline__ double law_finalize(const DevState &d, int64_t c, double S, const double *th) {
+    if (d.law == EXTMCMC_LAW_LOGISTIC) return S;  // the logistic sweep finishes ll itself
     if (d.law == EXTMCMC_LAW_GSN_IID_1D)  // N*c0 - S/(2 var)
         return (double)d.n_obs_total * d.lawc[d.C + c] - S * d.lawc[2 * d.C + c];
     if (d.law == EXTMCMC_LAW_HIER_NORMAL) {

@@ -43,4 +43,25 @@ SweepPlan plan_sweep_gsnmv(int d, int64_t C, int64_t n_obs, int force_variant, i
 void launch_sweep_gsnmv(const SweepPlan &pl, const double *obs, int64_t n_obs, const double *lawc,
                         int64_t C, double *partial, cudaStream_t st);
 
+// Logistic regression.  X: row-major [n_pad][D] with D = logistic_padded_dim(d) and n_pad a
+// multiple of 16 (zero rows / columns beyond n_obs / d); y: [n_pad]; theta: SoA [d][C];
+// ll_part [S][C], g_part [S][d][C].
+struct LogisticArgs {
+    const double *X;
+    const double *y;
+    int64_t n_obs;
+    const double *theta;
+    int d;
+    int64_t C;
+    double *ll_part;
+    double *g_part;
+    int S;
+};
+int logistic_padded_dim(int d);
+cudaError_t sweep_logistic_init();
+SweepPlan plan_sweep_logistic(int d, int64_t C, int64_t n_obs, int num_sms);
+// sweep + fixed-order finalize: ll_out[C], grad_out[d][C] (grad_out may be NULL)
+void launch_sweep_logistic(const SweepPlan &pl, const LogisticArgs &a, double *ll_out, double *grad_out,
+                           cudaStream_t st);
+
 }  // namespace extmcmc

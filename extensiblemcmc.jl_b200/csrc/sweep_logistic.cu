@@ -1,0 +1,252 @@
+// K4 -- Bayesian logistic regression (BASELINE cfg 3): log-likelihood AND its gradient for all
+// chains in one pass over the design matrix, on the FP64 tensor-core path.
+//
+//   z_ic = x_i . theta_c,   ll_c = sum_i [ y_i z_ic - log(1 + e^{z_ic}) ],
+//   grad_c = sum_i (y_i - sigmoid(z_ic)) x_i.
+//
+// No reference equivalent exists (the reference ships only GsnTargetLaw and an empty MALAUpdate
+// stub, src/updates.jl:216-218); the gradient feeds the hook compute_gradients_and_momenta!
+// (src/updates.jl:129-133).
+//
+// Both contractions are GEMM-shaped and run as FP64 DMMA (mma.sync.m8n8k4.f64 -- tcgen05 has no
+// FP64 kind, so this legacy path IS Blackwell's FP64 tensor pipe):
+//   phase 1  Z[16 obs x 64 chains]  = X_tile[16 x D] . Theta_blk^T[D x 64]
+//   epilogue r = y - sigmoid(z), ll += y z - softplus(z)   (registers -> shared R tile)
+//   phase 2  G[64 chains x D]      += R^T[64 x 16] . X_tile[16 x D]      (accumulators in registers)
+// A CTA owns 64 chains and a contiguous range of 16-observation tiles; the X tile is TMA
+// bulk-copied (UBLKCP, one 1-D copy per row into a padded, bank-conflict-free layout) into a
+// 2-stage ring and is used by BOTH phases, so X is read from L2/HBM once per (chain block,
+// sweep).  Theta_blk stays resident in shared memory for the whole kernel.  Partial ll / G per
+// (segment, chain) are reduced in fixed order by logistic_finalize_kernel: deterministic.
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "sweep.h"
+#include "tma.cuh"
+
+namespace extmcmc {
+
+namespace {
+constexpr int kBM = 16;    // observations per tile (2 x 16 x (D+4) + 64 x (D+4) doubles fit 227 KB at D = 256)
+constexpr int kBN = 64;    // chains per CTA
+constexpr int kNT = 256;   // 8 warps; warp w owns chains 8w..8w+7 in both phases
+constexpr int kPad = 4;    // row padding (doubles) of the shared tiles
+constexpr int kRPad = 68;  // row stride of the R tile
+
+__device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+template <int D>
+constexpr size_t logistic_smem() {
+    return (size_t)(kBN + 2 * kBM) * (D + kPad) * 8 + (size_t)kBM * kRPad * 8 + 2 * kBM * 8 + 2 * 8;
+}
+}  // namespace
+
+template <int D>
+__global__ void __launch_bounds__(kNT, 1) sweep_logistic_kernel(LogisticArgs a) {
+    constexpr int LD = D + kPad;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *Th = reinterpret_cast<double *>(smem_raw);   // [kBN][LD]   Theta block, row = chain
+    double *Xs = Th + kBN * LD;                           // [2][kBM][LD] observation tiles
+    double *Rs = Xs + 2 * kBM * LD;                       // [kBM][kRPad] residuals y - sigmoid(z)
+    double *ys = Rs + kBM * kRPad;                        // [2][kBM]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(ys + 2 * kBM);  // [2]
+
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int gq = lane >> 2, tq = lane & 3;  // mma fragment coordinates: group id, thread in group
+    const int seg = blockIdx.x;
+    const int64_t C = a.C;
+    const int64_t cbase = (int64_t)blockIdx.y * kBN;
+
+    // tiles of this segment
+    const int64_t n_tiles_all = (a.n_obs + kBM - 1) / kBM;
+    const int64_t t0 = (int64_t)seg * n_tiles_all / a.S, t1 = (int64_t)(seg + 1) * n_tiles_all / a.S;
+    const int n_tiles = (int)(t1 - t0);
+
+    // Theta block -> shared (coalesced over chains), zero beyond d or beyond C
+    for (int idx = tid; idx < kBN * D; idx += kNT) {
+        const int k = idx / kBN, c = idx % kBN;
+        const int64_t gc = cbase + c;
+        Th[c * LD + k] = (k < a.d && gc < C) ? a.theta[(int64_t)k * C + gc] : 0.0;
+    }
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    // producer: warp 0, one bulk copy per observation row (+ one for the y slice)
+    auto issue = [&](int t) {
+        const int st = t & 1;
+        const int64_t row0 = (t0 + t) * kBM;
+        if (lane == 0) mbar_expect_tx(&bar[st], (uint32_t)(kBM * D * 8 + kBM * 8));
+        __syncwarp();
+        if (lane < kBM)
+            bulk_g2s(Xs + (st * kBM + lane) * LD, a.X + (row0 + lane) * D, (uint32_t)(D * 8), &bar[st]);
+        if (lane == 0) bulk_g2s(ys + st * kBM, a.y + row0, (uint32_t)(kBM * 8), &bar[st]);
+    };
+    if (w == 0)
+        for (int t = 0; t < 2 && t < n_tiles; ++t) issue(t);
+
+    double G[D / 8][2];
+#pragma unroll
+    for (int nb = 0; nb < D / 8; ++nb) G[nb][0] = G[nb][1] = 0.0;
+    double ll0 = 0.0, ll1 = 0.0;  // chains cbase + 8w + 2 tq + {0, 1}, rows gq, gq + 8, ...
+
+    for (int t = 0; t < n_tiles; ++t) {
+        const int st = t & 1;
+        mbar_wait(&bar[st], (uint32_t)(t >> 1) & 1u);
+        const double *X = Xs + st * kBM * LD;
+        const int64_t row0 = (t0 + t) * kBM;
+
+        // ---- phase 1: Z[16 x 8(w)] = X[16 x D] . Th[8w.., :]^T  -------------------------------
+        constexpr int MB = kBM / 8;
+        double z[MB][2];
+#pragma unroll
+        for (int m = 0; m < MB; ++m) z[m][0] = z[m][1] = 0.0;
+        const double *Bp = Th + (8 * w + gq) * LD + tq;
+        const double *Ap = X + gq * LD + tq;
+#pragma unroll 4
+        for (int k0 = 0; k0 < D; k0 += 4) {
+            const double b = Bp[k0];
+#pragma unroll
+            for (int m = 0; m < MB; ++m) dmma(z[m][0], z[m][1], Ap[(8 * m) * LD + k0], b);
+        }
+        // ---- epilogue: residuals and log-likelihood ------------------------------------------
+#pragma unroll
+        for (int m = 0; m < MB; ++m) {
+            const int r = 8 * m + gq;
+            const bool live = row0 + r < a.n_obs;   // zero-padded rows must not contribute
+            const double yv = ys[st * kBM + r];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const double zz = z[m][j];
+                const double e = exp(-fabs(zz));
+                const double sp = fmax(zz, 0.0) + log1p(e);          // softplus(z)
+                const double sg = (zz >= 0.0 ? 1.0 : e) / (1.0 + e);  // sigmoid(z)
+                const double res = live ? yv - sg : 0.0;
+                const double lli = live ? yv * zz - sp : 0.0;
+                if (j == 0) ll0 += lli; else ll1 += lli;
+                Rs[r * kRPad + 8 * w + 2 * tq + j] = res;
+            }
+        }
+        __syncwarp();  // the R columns 8w..8w+7 are produced and consumed by this warp only
+
+        // ---- phase 2: G[8(w) x D] += R[:, 8w..]^T . X[16 x D]  ---------------------------------
+#pragma unroll
+        for (int i0 = 0; i0 < kBM; i0 += 4) {
+            const double af = Rs[(i0 + tq) * kRPad + 8 * w + gq];
+            const double *Xr = X + (i0 + tq) * LD + gq;
+#pragma unroll
+            for (int nb = 0; nb < D / 8; ++nb) dmma(G[nb][0], G[nb][1], af, Xr[8 * nb]);
+        }
+        __syncthreads();  // everyone is done with this X stage before it is refilled
+        if (w == 0 && t + 2 < n_tiles) issue(t + 2);
+    }
+
+    // ---- write the partials of this (segment, chain block) -----------------------------------
+    // ll: rows are spread over gq (lane bits 2..4): xor-shuffle tree, fixed order
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {
+        ll0 += __shfl_xor_sync(0xffffffffu, ll0, o);
+        ll1 += __shfl_xor_sync(0xffffffffu, ll1, o);
+    }
+    if (gq == 0) {
+        const int64_t c = cbase + 8 * w + 2 * tq;
+        if (c < C) a.ll_part[(int64_t)seg * C + c] = ll0;
+        if (c + 1 < C) a.ll_part[(int64_t)seg * C + c + 1] = ll1;
+    }
+    const int64_t c = cbase + 8 * w + gq;
+    if (c < C) {
+#pragma unroll
+        for (int nb = 0; nb < D / 8; ++nb) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int k = 8 * nb + 2 * tq + j;
+                if (k < a.d) a.g_part[((int64_t)seg * a.d + k) * C + c] = G[nb][j];
+            }
+        }
+    }
+}
+
+// ll[c] = sum_s ll_part[s][c];  grad[k][c] = sum_s g_part[s][k][c]  (fixed order)
+__global__ void __launch_bounds__(256)
+logistic_finalize_kernel(LogisticArgs a, double *__restrict__ ll_out, double *__restrict__ grad_out) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t C = a.C;
+    if (idx >= (int64_t)(a.d + 1) * C) return;
+    const int64_t row = idx / C, c = idx % C;
+    double s = 0.0;
+    if (row == a.d) {
+        for (int i = 0; i < a.S; ++i) s += a.ll_part[(int64_t)i * C + c];
+        ll_out[c] = s;
+    } else {
+        for (int i = 0; i < a.S; ++i) s += a.g_part[((int64_t)i * a.d + row) * C + c];
+        if (grad_out) grad_out[row * C + c] = s;
+    }
+}
+
+namespace {
+template <int D>
+cudaError_t prep() {
+    return cudaFuncSetAttribute(sweep_logistic_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)logistic_smem<D>());
+}
+template <int D>
+void launch(const SweepPlan &pl, const LogisticArgs &a, cudaStream_t st) {
+    dim3 grid(pl.S, pl.groups);
+    sweep_logistic_kernel<D><<<grid, kNT, logistic_smem<D>(), st>>>(a);
+}
+}  // namespace
+
+int logistic_padded_dim(int d) {
+    for (int D : {8, 16, 32, 64, 128, 256})
+        if (d <= D) return D;
+    return 0;
+}
+
+cudaError_t sweep_logistic_init() {
+    cudaError_t e;
+    if ((e = prep<8>()) != cudaSuccess) return e;
+    if ((e = prep<16>()) != cudaSuccess) return e;
+    if ((e = prep<32>()) != cudaSuccess) return e;
+    if ((e = prep<64>()) != cudaSuccess) return e;
+    if ((e = prep<128>()) != cudaSuccess) return e;
+    if ((e = prep<256>()) != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
+SweepPlan plan_sweep_logistic(int d, int64_t C, int64_t n_obs, int num_sms) {
+    SweepPlan pl{};
+    pl.D = logistic_padded_dim(d);
+    pl.variant = SWEEP_VARIANT_CHAINS;
+    pl.R = kBN;
+    pl.groups = (int)((C + kBN - 1) / kBN);
+    const int64_t n_tiles = (n_obs + kBM - 1) / kBM;
+    int S = num_sms / pl.groups;  // one CTA per SM (the tiles take ~215 KB of shared memory)
+    if (S < 1) S = 1;
+    if (S > n_tiles) S = (int)n_tiles;
+    pl.S = S;
+    pl.launches = 2;  // sweep + finalize
+    pl.name = "logistic_dmma";
+    return pl;
+}
+
+void launch_sweep_logistic(const SweepPlan &pl, const LogisticArgs &a, double *ll_out, double *grad_out,
+                           cudaStream_t st) {
+    switch (pl.D) {
+    case 8: launch<8>(pl, a, st); break;
+    case 16: launch<16>(pl, a, st); break;
+    case 32: launch<32>(pl, a, st); break;
+    case 64: launch<64>(pl, a, st); break;
+    case 128: launch<128>(pl, a, st); break;
+    default: launch<256>(pl, a, st); break;
+    }
+    const int64_t n = (int64_t)(a.d + 1) * a.C;
+    logistic_finalize_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(a, ll_out, grad_out);
+}
+
+}  // namespace extmcmc

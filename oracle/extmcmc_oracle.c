@@ -121,7 +121,7 @@ int32_t oracle_create(const extmcmc_config_t *cfg, const extmcmc_update_t *updat
                       const double *theta_init, oracle_t *out) {
     if (!cfg || !updates || !out || !theta_init) { set_err("null argument"); return EXTMCMC_EINVAL; }
     if (cfg->law != EXTMCMC_LAW_GSN_IID_1D && cfg->law != EXTMCMC_LAW_GSN_MV &&
-        cfg->law != EXTMCMC_LAW_HIER_NORMAL) {
+        cfg->law != EXTMCMC_LAW_HIER_NORMAL && cfg->law != EXTMCMC_LAW_LOGISTIC) {
         set_err("oracle: law not implemented");
         return EXTMCMC_EUNSUPPORTED;
     }
@@ -140,6 +140,10 @@ int32_t oracle_create(const extmcmc_config_t *cfg, const extmcmc_update_t *updat
     }
     for (int u = 0; u < cfg->n_updates; ++u)
         if (updates[u].n_coords < 1 || updates[u].n_coords > 256) { set_err("oracle: 1 <= n_coords <= 256"); return EXTMCMC_EINVAL; }
+    if (cfg->law == EXTMCMC_LAW_LOGISTIC && (d != cfg->n_params || d < 1 || d > 256 || !y)) {
+        set_err("LOGISTIC needs obs_dim = n_params = d <= 256 and responses in y");
+        return EXTMCMC_EINVAL;
+    }
     if (cfg->law == EXTMCMC_LAW_HIER_NORMAL && (d != 1 || cfg->n_params < 3 || !y)) {
         set_err("HIER_NORMAL needs obs_dim = 1, n_params = G + 2 and group indices in y");
         return EXTMCMC_EINVAL;
@@ -334,6 +338,26 @@ static double loglik_hier(const struct oracle_handle *h, const double *th, doubl
     return ll;
 }
 
+/* Bayesian logistic regression (BASELINE cfg 3; no reference law, build-defined):
+ * theta = beta[d];  y_i ~ Bernoulli(sigmoid(x_i . beta)).
+ * ll = sum_i [ y_i z_i - softplus(z_i) ],  grad = sum_i (y_i - sigmoid(z_i)) x_i, sequential sums. */
+static double loglik_logistic(const struct oracle_handle *h, const double *th, double *grad) {
+    const int d = h->p;
+    if (grad) for (int k = 0; k < d; ++k) grad[k] = 0.0;
+    double ll = 0.0;
+    for (int64_t i = 0; i < h->n_obs; ++i) {
+        const double *x = h->obs + i * d;
+        double z = 0.0;
+        for (int k = 0; k < d; ++k) z += x[k] * th[k];
+        const double e = exp(-fabs(z));
+        const double sp = (z > 0.0 ? z : 0.0) + log1p(e);
+        const double sg = (z >= 0.0 ? 1.0 : e) / (1.0 + e);
+        ll += h->y[i] * z - sp;
+        if (grad) { const double r = h->y[i] - sg; for (int k = 0; k < d; ++k) grad[k] += r * x[k]; }
+    }
+    return ll;
+}
+
 /* d/dmu and d/dvar of the 1-D Gaussian log-likelihood, sequential per-observation sums */
 static void grad_gsn_1d(const double *x, int64_t n, double mu, double var, double *grad) {
     double gm = 0.0, gv = 0.0;
@@ -350,12 +374,15 @@ static double law_loglik(const struct oracle_handle *h, const double *theta, int
         return loglik_gsn_1d(h->obs, h->n_obs, theta[0], theta[1], bad);
     if (h->cfg.law == EXTMCMC_LAW_HIER_NORMAL)
         return loglik_hier(h, theta, NULL, bad);
+    if (h->cfg.law == EXTMCMC_LAW_LOGISTIC)
+        return loglik_logistic(h, theta, NULL);
     return loglik_gsn_mv(h->obs, h->n_obs, h->cfg.obs_dim, theta, bad);
 }
 
 /* log-likelihood and its gradient w.r.t. all p parameters (laws with a gradient only) */
 static double law_loglik_grad(const struct oracle_handle *h, const double *theta, double *grad, int *bad) {
     if (h->cfg.law == EXTMCMC_LAW_HIER_NORMAL) return loglik_hier(h, theta, grad, bad);
+    if (h->cfg.law == EXTMCMC_LAW_LOGISTIC) return loglik_logistic(h, theta, grad);
     double ll = loglik_gsn_1d(h->obs, h->n_obs, theta[0], theta[1], bad);
     if (*bad) { grad[0] = grad[1] = NAN; return ll; }
     grad_gsn_1d(h->obs, h->n_obs, theta[0], theta[1], grad);
@@ -857,7 +884,7 @@ int32_t oracle_get_eps(oracle_t h, int32_t u, double *eps) {
 }
 
 int32_t oracle_loglik_grad(oracle_t h, const double *theta, int64_t n_eval, double *ll_out, double *grad_out) {
-    if (h->cfg.law != EXTMCMC_LAW_GSN_IID_1D && h->cfg.law != EXTMCMC_LAW_HIER_NORMAL) return EXTMCMC_EUNSUPPORTED;
+    if (h->cfg.law == EXTMCMC_LAW_GSN_MV) return EXTMCMC_EUNSUPPORTED;
     for (int64_t c = 0; c < n_eval; ++c) {
         double th[256], g[256];
         int bad = 0;
