@@ -408,6 +408,139 @@ def run_cfg5(args):
         "gpu_launches": launches, "clocks": clocks}))
 
 
+def _generic_timed(ws, _abi, n_updates, K, W):
+    """W warm-up + K timed MCMC iterations of an n_updates-element schedule (one graph block per
+    iteration, one CUDA event pair per iteration)."""
+    import ctypes
+    lib, h = ws.lib, ws.handle
+
+    def block(it):
+        arr = (_abi.Step * n_updates)()
+        for pj in range(n_updates):
+            first = it == 1 and pj == 0
+            arr[pj].mcmciter, arr[pj].pidx = it, pj
+            arr[pj].prev_pidx = -1 if first else (pj - 1 if pj else n_updates - 1)
+            arr[pj].prev_mcmciter = 0 if first else (it if pj else it - 1)
+        return arr
+    it = 1
+    for _ in range(W):
+        ws._ck(lib.extmcmc_run_block(h, block(it), n_updates)); it += 1
+    ws.sync()
+    for k in range(K):
+        ws._ck(lib.extmcmc_event_record(h, 2 * k))
+        ws._ck(lib.extmcmc_run_block(h, block(it), n_updates)); it += 1
+        ws._ck(lib.extmcmc_event_record(h, 2 * k + 1))
+    ws.sync()
+    ms, total = ctypes.c_float(), 0.0
+    for k in range(K):
+        ws._ck(lib.extmcmc_event_elapsed(h, 2 * k, 2 * k + 1, ctypes.byref(ms)))
+        total += ms.value
+    return total
+
+
+def run_cfg34(args):
+    """Secondary workloads: BASELINE cfg 3 (logistic regression, d=256, N=1e6, 1024 chains, MALA,
+    FP64 tensor-core GEMMs) and cfg 4 (hierarchical normal, 8 groups x 4096 obs, MALA + 2 RW
+    updates, 8192 chains per GPU).  Chains shard over the ranks; no collective."""
+    import ctypes
+    import torch
+    import extensiblemcmc_jl_b200 as em
+    from extensiblemcmc_jl_b200 import _abi, parallel as par
+    from extensiblemcmc_jl_b200.mcmc import init_
+    rank, world, local = par.env_rank_world()
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rng = np.random.default_rng(4 if args.workload == "cfg3" else 5)
+    if args.workload == "cfg3":
+        C, d, N = 1024, 256, args.n_obs if args.n_obs != 1_000_000_000 else 1_000_000
+        X = rng.standard_normal((N, d)) / np.sqrt(d)
+        beta = rng.standard_normal(d)
+        y = (rng.random(N) < 1.0 / (1.0 + np.exp(-X @ beta))).astype(np.float64)
+        law, data = em.LogisticLaw(d), None
+        data = dict(P=law, obs=X, y=y)
+        ups = [em.MALAUpdate(0.02, list(range(1, d + 1)), prior=em.StandardPrior(em.Normal(0.0, 10.0)),
+                             adpt=em.AdaptationMALA(adapt_every_k_steps=20, scale=1e-3, min=1e-5, offset=2.0))]
+        th0 = 0.01 * np.random.default_rng(40 + rank).standard_normal((d, C))
+        n_obs, flops_per_sweep = N, 4.0 * d * C * N
+        desc = f"BASELINE cfg3: logistic regression d={d}, N={N:.3g}, {C} chains/GPU, MALAUpdate on all coordinates"
+    else:
+        C, G, ng = 8192, 8, 4096
+        tg = rng.standard_normal(G)
+        yv = np.concatenate([tg[g] + rng.standard_normal(ng) for g in range(G)])
+        law = em.HierNormalLaw(G)
+        data = dict(P=law, obs=yv, groups=np.repeat(np.arange(G), ng))
+        ups = [em.MALAUpdate(0.02, list(range(1, G + 1)), adpt=em.AdaptationMALA(adapt_every_k_steps=50, scale=1e-3, min=1e-5)),
+               em.RandomWalkUpdate(em.UniformRandomWalk([0.3]), [G + 1], adpt=em.AdaptationUnifRW([0.0], adapt_every_k_steps=50, scale=0.02)),
+               em.RandomWalkUpdate(em.UniformRandomWalk([0.3], [True]), [G + 2], prior=em.ImproperPosPrior(),
+                                   adpt=em.AdaptationUnifRW([0.0], adapt_every_k_steps=50, scale=0.02))]
+        th0 = np.concatenate([np.zeros(G), [0.0, 1.0]])
+        n_obs, flops_per_sweep = G * ng, 4.0 * C * G * ng
+        desc = (f"BASELINE cfg4: hierarchical normal, {G} groups x {ng} obs, {C} chains/GPU, "
+                "schedule MALA(theta_1..8) + RW(mu) + RW-pos(tau)")
+    NUc = len(ups)
+
+    def make(instrument):
+        mcmc = em.MCMC(ups, backend=em.CUDAMCMCBackend(n_chains=C, chain_offset=rank * C, device=local, seed=7,
+                                                       history="none", block_len=NUc, use_graphs=not instrument,
+                                                       instrument=instrument, stats_mode=1))
+        init_(mcmc, 1, data, th0)
+        return mcmc.workspace
+    K, Wm = args.steps, max(args.warmup, 3)
+    ws = make(False)
+    sampler = ClockSampler(local)
+    _generic_timed(ws, _abi, NUc, 0, Wm)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    l0 = ws.lib.extmcmc_launch_count(ws.handle)
+    ms_total = _generic_timed(ws, _abi, NUc, K, 0)
+    launches = int(ws.lib.extmcmc_launch_count(ws.handle) - l0)
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    variant = ws.lib.extmcmc_sweep_variant_name(ws.handle).decode()
+    pk64, pkmma = ctypes.c_double(), ctypes.c_double()
+    ws._ck(ws.lib.extmcmc_measure_fp64_peak(ws.handle, ctypes.byref(pk64)))
+    ws._ck(ws.lib.extmcmc_measure_dmma_peak(ws.handle, ctypes.byref(pkmma)))
+    acc = ws.stats()["n_accept"].sum(axis=1) / np.maximum(ws.stats()["n_prop"].sum(axis=1), 1)
+    ws.close()
+    wi = make(True)
+    _generic_timed(wi, _abi, NUc, 0, Wm)
+    msw, nl = ctypes.c_float(), ctypes.c_int64()
+    wi._ck(wi.lib.extmcmc_get_sweep_time(wi.handle, ctypes.byref(msw), ctypes.byref(nl)))
+    step_ms = _generic_timed(wi, _abi, NUc, min(K, 20), 0)
+    wi._ck(wi.lib.extmcmc_get_sweep_time(wi.handle, ctypes.byref(msw), ctypes.byref(nl)))
+    sweep_ms = msw.value / max(nl.value, 1)
+    wi.close()
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.barrier()
+        dist.destroy_process_group()
+    ms_total = float(t.item())
+    if rank != 0:
+        return
+    peak = pkmma.value if args.workload == "cfg3" else pk64.value
+    ach = flops_per_sweep / (sweep_ms * 1e-3) / 1e12
+    print(json.dumps({
+        "metric": "chain-steps x obs/sec", "value": float(world) * C * K * NUc * n_obs / (ms_total * 1e-3),
+        "unit": "chain-step*obs/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms_total / K,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "l2": "no flush: the design matrix (2 GB) exceeds L2" if args.workload == "cfg3"
+                   else "no flush: 256 KB of observations are L2/shared-memory resident by design"},
+        "roofline": {"kernel": variant, "bound": "tensor" if args.workload == "cfg3" else "fp64",
+                     "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None,
+                     "peak_source": ("FP64 DMMA (mma.sync m8n8k4) micro-benchmark in this process" if args.workload == "cfg3"
+                                     else "FP64 FMA micro-benchmark in this process"),
+                     "fp64_fma_peak": pk64.value, "fp64_dmma_peak": pkmma.value, "avg_launch_ms": sweep_ms,
+                     "launches_timed": int(nl.value), "share_of_step": msw.value / step_ms if step_ms else None,
+                     "algorithmic_flops_per_launch": flops_per_sweep, "traffic": None},
+        "accept_rate_per_update": [float(a) for a in acc], "gpu_launches": launches, "clocks": clocks}))
+
+
 def cpu_oracle_rate(x, n_chains, n_iters, n_threads):
     import extensiblemcmc_jl_b200 as em
     from oracle import oracle as orc
@@ -466,13 +599,15 @@ def main():
     ap.add_argument("--cpu-iters", type=int, default=150)
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-hbm", action="store_true")
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg5"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--n-obs", type=int, default=1_000_000_000, help="cfg5 only: total observations")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "cfg5":
         run_cfg5(args)
+    elif args.workload in ("cfg3", "cfg4"):
+        run_cfg34(args)
     else:
         run_ours(args)
 

@@ -127,6 +127,7 @@ SIGNATURES = {
     "extmcmc_launch_count": (C.c_int64, [Handle]),
     "extmcmc_flush_l2": (C.c_int32, [Handle]),
     "extmcmc_measure_fp64_peak": (C.c_int32, [Handle, c_double_p]),
+    "extmcmc_measure_dmma_peak": (C.c_int32, [Handle, c_double_p]),
     "extmcmc_sweep_variant_name": (C.c_char_p, [Handle]),
 }
 

@@ -1200,6 +1200,26 @@ int32_t extmcmc_measure_fp64_peak(extmcmc_t h, double *tflops_out) {
     return EXTMCMC_OK;
 }
 
+int32_t extmcmc_measure_dmma_peak(extmcmc_t h, double *tflops_out) {
+    if (!h || !tflops_out) return EXTMCMC_EINVAL;
+    CK(h, cudaSetDevice(h->cfg.device));
+    const int iters = 4000;
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        CK(h, cudaEventRecord(h->t0, h->stream));
+        launch_dmma_peak(h->scratch_ll, iters, h->num_sms, h->stream);
+        CK(h, cudaEventRecord(h->t1, h->stream));
+        CK(h, cudaEventSynchronize(h->t1));
+        float ms = 0.f;
+        CK(h, cudaEventElapsedTime(&ms, h->t0, h->t1));
+        // warps x 8 independent MMAs x 512 flop (8 x 8 x 4 x 2)
+        const double flops = (double)h->num_sms * 8 * 8 /*warps per CTA*/ * 8.0 * iters * 512.0;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    *tflops_out = best;
+    return EXTMCMC_OK;
+}
+
 const char *extmcmc_sweep_variant_name(extmcmc_t h) {
     if (!h) return "";
     if (!h->plan_valid && h->obs_dev) ensure_plan(h);

@@ -771,6 +771,25 @@ __global__ void fp64_peak_kernel(double *out, int iters, double a, double b) {
     if (s == 123.456) out[0] = s;
 }
 
+// Independent FP64 tensor-core MMA chains (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4): 8 accumulator
+// pairs per warp, 512 flop per instruction.
+__global__ void dmma_peak_kernel(double *out, int iters, double a, double b) {
+    double c[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { c[i][0] = (double)threadIdx.x; c[i][1] = (double)i; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[i][0]), "+d"(c[i][1])
+                         : "d"(a), "d"(b));
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+    if (s == 123.456) out[0] = s;
+}
+
 // ---------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------
@@ -818,6 +837,9 @@ void launch_generate_obs_normal(double *obs, int64_t first, int64_t n, double me
 }
 void launch_flush_l2(double *buf, int64_t n, int num_sms, cudaStream_t st) {
     flush_l2_kernel<<<num_sms * 8, 256, 0, st>>>(buf, n, 1.0);
+}
+void launch_dmma_peak(double *out, int iters, int num_sms, cudaStream_t st) {
+    dmma_peak_kernel<<<num_sms * 8, 256, 0, st>>>(out, iters, 1.0000001, 1e-9);
 }
 void launch_fp64_peak(double *out, int iters, int num_sms, cudaStream_t st) {
     fp64_peak_kernel<<<num_sms * 8, 256, 0, st>>>(out, iters, 1.0000001, 1e-9);

@@ -17,4 +17,5 @@ void launch_generate_obs_normal(double *obs, int64_t first, int64_t n, double me
                                 uint64_t seed, int num_sms, cudaStream_t st);
 void launch_flush_l2(double *buf, int64_t n, int num_sms, cudaStream_t st);
 void launch_fp64_peak(double *out, int iters, int num_sms, cudaStream_t st);
+void launch_dmma_peak(double *out, int iters, int num_sms, cudaStream_t st);
 }  // namespace extmcmc

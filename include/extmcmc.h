@@ -290,6 +290,8 @@ int64_t extmcmc_launch_count(extmcmc_t h);
 int32_t extmcmc_flush_l2(extmcmc_t h);
 /* FP64 FMA micro-benchmark on the handle's device: TFLOP/s (2 flop per FMA). */
 int32_t extmcmc_measure_fp64_peak(extmcmc_t h, double *tflops_out);
+/* FP64 tensor-core (DMMA m8n8k4) micro-benchmark: TFLOP/s. */
+int32_t extmcmc_measure_dmma_peak(extmcmc_t h, double *tflops_out);
 /* Name of the sweep kernel variant selected for the current shapes. */
 const char *extmcmc_sweep_variant_name(extmcmc_t h);
 
