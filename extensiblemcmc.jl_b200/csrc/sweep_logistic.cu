@@ -28,8 +28,11 @@ namespace extmcmc {
 namespace {
 constexpr int kBM = 16;    // observations per tile (2 x 16 x (D+4) + 64 x (D+4) doubles fit 227 KB at D = 256)
 constexpr int kBN = 64;    // chains per CTA
-constexpr int kNT = 256;   // 8 warps; warp w owns chains 8w..8w+7 in both phases
-constexpr int kPad = 4;    // row padding (doubles) of the shared tiles
+constexpr int kNC = 256;   // 8 consumer warps; warp w owns chains 8w..8w+7 in both phases
+constexpr int kNT = kNC + 32;  // + 1 producer warp (TMA)
+constexpr int kPad = 4;    // row padding (doubles) of the X tiles: 128-bit loads indexed (row tq, col 2 gq)
+                           // and (row rho(gq), col 2 tq) are both bank-conflict free with stride D + 4
+constexpr int kPadT = 8;   // row padding of the Theta tile: 128-bit loads indexed (row gq, col 2 tq)
 constexpr int kRPad = 68;  // row stride of the R tile
 
 __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b) {
@@ -40,19 +43,21 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
 
 template <int D>
 constexpr size_t logistic_smem() {
-    return (size_t)(kBN + 2 * kBM) * (D + kPad) * 8 + (size_t)kBM * kRPad * 8 + 2 * kBM * 8 + 2 * 8;
+    return (size_t)kBN * (D + kPadT) * 8 + (size_t)2 * kBM * (D + kPad) * 8 + (size_t)kBM * kRPad * 8 +
+           2 * kBM * 8 + 4 * 8;
 }
 }  // namespace
 
 template <int D>
 __global__ void __launch_bounds__(kNT, 1) sweep_logistic_kernel(LogisticArgs a) {
-    constexpr int LD = D + kPad;
+    constexpr int LD = D + kPad, LDT = D + kPadT;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *Th = reinterpret_cast<double *>(smem_raw);   // [kBN][LD]   Theta block, row = chain
-    double *Xs = Th + kBN * LD;                           // [2][kBM][LD] observation tiles
+    double *Th = reinterpret_cast<double *>(smem_raw);   // [kBN][LDT]  Theta block, row = chain
+    double *Xs = Th + kBN * LDT;                          // [2][kBM][LD] observation tiles
     double *Rs = Xs + 2 * kBM * LD;                       // [kBM][kRPad] residuals y - sigmoid(z)
     double *ys = Rs + kBM * kRPad;                        // [2][kBM]
-    uint64_t *bar = reinterpret_cast<uint64_t *>(ys + 2 * kBM);  // [2]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(ys + 2 * kBM);  // [2] full (TMA landed)
+    uint64_t *empty = bar + 2;                                   // [2] empty (all 8 consumer warps done)
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int gq = lane >> 2, tq = lane & 3;  // mma fragment coordinates: group id, thread in group
@@ -69,16 +74,22 @@ __global__ void __launch_bounds__(kNT, 1) sweep_logistic_kernel(LogisticArgs a) 
     for (int idx = tid; idx < kBN * D; idx += kNT) {
         const int k = idx / kBN, c = idx % kBN;
         const int64_t gc = cbase + c;
-        Th[c * LD + k] = (k < a.d && gc < C) ? a.theta[(int64_t)k * C + gc] : 0.0;
+        Th[c * LDT + k] = (k < a.d && gc < C) ? a.theta[(int64_t)k * C + gc] : 0.0;
     }
     if (tid == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
+        mbar_init(&empty[0], kNC / 32);
+        mbar_init(&empty[1], kNC / 32);
         mbar_fence_init();
     }
     __syncthreads();
 
-    // producer: warp 0, one bulk copy per observation row (+ one for the y slice)
+    // Producer warp: one bulk copy per observation row (+ one for the y slice) into a 2-stage
+    // ring; a stage is refilled as soon as all 8 consumer warps released it.  There is no
+    // CTA-wide barrier in the main loop, so the consumer warps are free to drift: the two warps
+    // that share an SM sub-partition run half a tile apart (see the skew below) and one of them
+    // keeps the tensor pipe busy while the other is in its FP64 epilogue.
     auto issue = [&](int t) {
         const int st = t & 1;
         const int64_t row0 = (t0 + t) * kBM;
@@ -88,8 +99,14 @@ __global__ void __launch_bounds__(kNT, 1) sweep_logistic_kernel(LogisticArgs a) 
             bulk_g2s(Xs + (st * kBM + lane) * LD, a.X + (row0 + lane) * D, (uint32_t)(D * 8), &bar[st]);
         if (lane == 0) bulk_g2s(ys + st * kBM, a.y + row0, (uint32_t)(kBM * 8), &bar[st]);
     };
-    if (w == 0)
-        for (int t = 0; t < 2 && t < n_tiles; ++t) issue(t);
+    if (w == kNC / 32) {
+        for (int t = 0; t < n_tiles; ++t) {
+            if (t >= 2) mbar_wait(&empty[t & 1], (uint32_t)((t >> 1) + 1) & 1u);
+            issue(t);
+        }
+        return;
+    }
+    if (w >= 4) __nanosleep(2500);  // one-off skew of the second warp of every sub-partition
 
     double G[D / 8][2];
 #pragma unroll
@@ -103,22 +120,35 @@ __global__ void __launch_bounds__(kNT, 1) sweep_logistic_kernel(LogisticArgs a) 
         const int64_t row0 = (t0 + t) * kBM;
 
         // ---- phase 1: Z[16 x 8(w)] = X[16 x D] . Th[8w.., :]^T  -------------------------------
+        // The k index of the MMA fragments is a relabelling of the real feature index: fragment
+        // slot tq of MMA e (e = 0, 1) of pair s stands for feature 8s + 2 tq + e, so that one
+        // LDS.128 per operand feeds two MMAs, and the two MMAs go to independent accumulators.
         constexpr int MB = kBM / 8;
+        double za[MB][2], zb[MB][2];
+#pragma unroll
+        for (int m = 0; m < MB; ++m) za[m][0] = za[m][1] = zb[m][0] = zb[m][1] = 0.0;
+        // fragment row gq stands for observation rho(gq) of the 8-block (bits 0 and 1 swapped):
+        // the two rows a quarter-warp touches are then 2 apart, which the D + 4 stride separates
+        const int rq = (gq & 4) | ((gq & 1) << 1) | ((gq >> 1) & 1);
+        const double *Bp = Th + (8 * w + gq) * LDT + 2 * tq;
+        const double *Ap = X + rq * LD + 2 * tq;
+#pragma unroll 4
+        for (int k0 = 0; k0 < D; k0 += 8) {
+            const double2 b = *reinterpret_cast<const double2 *>(Bp + k0);
+#pragma unroll
+            for (int m = 0; m < MB; ++m) {
+                const double2 av = *reinterpret_cast<const double2 *>(Ap + (8 * m) * LD + k0);
+                dmma(za[m][0], za[m][1], av.x, b.x);
+                dmma(zb[m][0], zb[m][1], av.y, b.y);
+            }
+        }
         double z[MB][2];
 #pragma unroll
-        for (int m = 0; m < MB; ++m) z[m][0] = z[m][1] = 0.0;
-        const double *Bp = Th + (8 * w + gq) * LD + tq;
-        const double *Ap = X + gq * LD + tq;
-#pragma unroll 4
-        for (int k0 = 0; k0 < D; k0 += 4) {
-            const double b = Bp[k0];
-#pragma unroll
-            for (int m = 0; m < MB; ++m) dmma(z[m][0], z[m][1], Ap[(8 * m) * LD + k0], b);
-        }
+        for (int m = 0; m < MB; ++m) { z[m][0] = za[m][0] + zb[m][0]; z[m][1] = za[m][1] + zb[m][1]; }
         // ---- epilogue: residuals and log-likelihood ------------------------------------------
 #pragma unroll
         for (int m = 0; m < MB; ++m) {
-            const int r = 8 * m + gq;
+            const int r = 8 * m + rq;
             const bool live = row0 + r < a.n_obs;   // zero-padded rows must not contribute
             const double yv = ys[st * kBM + r];
 #pragma unroll
@@ -136,15 +166,21 @@ __global__ void __launch_bounds__(kNT, 1) sweep_logistic_kernel(LogisticArgs a) 
         __syncwarp();  // the R columns 8w..8w+7 are produced and consumed by this warp only
 
         // ---- phase 2: G[8(w) x D] += R[:, 8w..]^T . X[16 x D]  ---------------------------------
+        // Column relabelling: column gq of MMA e of pair P stands for feature 16 P + 2 gq + e
+        // (one LDS.128 of X feeds two MMAs); undone when the partials are written.
 #pragma unroll
         for (int i0 = 0; i0 < kBM; i0 += 4) {
             const double af = Rs[(i0 + tq) * kRPad + 8 * w + gq];
-            const double *Xr = X + (i0 + tq) * LD + gq;
+            const double *Xr = X + (i0 + tq) * LD + 2 * gq;
 #pragma unroll
-            for (int nb = 0; nb < D / 8; ++nb) dmma(G[nb][0], G[nb][1], af, Xr[8 * nb]);
+            for (int P = 0; P < D / 16; ++P) {
+                const double2 xv = *reinterpret_cast<const double2 *>(Xr + 16 * P);
+                dmma(G[2 * P][0], G[2 * P][1], af, xv.x);
+                dmma(G[2 * P + 1][0], G[2 * P + 1][1], af, xv.y);
+            }
         }
-        __syncthreads();  // everyone is done with this X stage before it is refilled
-        if (w == 0 && t + 2 < n_tiles) issue(t + 2);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[st]);  // this warp is done with the X stage
     }
 
     // ---- write the partials of this (segment, chain block) -----------------------------------
@@ -165,7 +201,8 @@ __global__ void __launch_bounds__(kNT, 1) sweep_logistic_kernel(LogisticArgs a) 
         for (int nb = 0; nb < D / 8; ++nb) {
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                const int k = 8 * nb + 2 * tq + j;
+                // accumulator (P = nb / 2, e = nb & 1), fragment column 2 tq + j -> feature index
+                const int k = 16 * (nb >> 1) + 2 * (2 * tq + j) + (nb & 1);
                 if (k < a.d) a.g_part[((int64_t)seg * a.d + k) * C + c] = G[nb][j];
             }
         }
@@ -203,14 +240,13 @@ void launch(const SweepPlan &pl, const LogisticArgs &a, cudaStream_t st) {
 }  // namespace
 
 int logistic_padded_dim(int d) {
-    for (int D : {8, 16, 32, 64, 128, 256})
+    for (int D : {16, 32, 64, 128, 256})
         if (d <= D) return D;
     return 0;
 }
 
 cudaError_t sweep_logistic_init() {
     cudaError_t e;
-    if ((e = prep<8>()) != cudaSuccess) return e;
     if ((e = prep<16>()) != cudaSuccess) return e;
     if ((e = prep<32>()) != cudaSuccess) return e;
     if ((e = prep<64>()) != cudaSuccess) return e;
@@ -238,7 +274,6 @@ SweepPlan plan_sweep_logistic(int d, int64_t C, int64_t n_obs, int num_sms) {
 void launch_sweep_logistic(const SweepPlan &pl, const LogisticArgs &a, double *ll_out, double *grad_out,
                            cudaStream_t st) {
     switch (pl.D) {
-    case 8: launch<8>(pl, a, st); break;
     case 16: launch<16>(pl, a, st); break;
     case 32: launch<32>(pl, a, st); break;
     case 64: launch<64>(pl, a, st); break;
