@@ -36,9 +36,51 @@ constexpr int kPadT = 8;   // row padding of the Theta tile: 128-bit loads index
 constexpr int kRPad = 68;  // row stride of the R tile
 
 __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(c0), "+d"(c1)
-                 : "d"(a), "d"(b));
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c0), "+d"(c1)
+        : "d"(a), "d"(b));
+}
+
+// softplus(z) = log(1 + e^z) and sigmoid(z) in one go, ~60 FP64 instructions (the libm route
+// exp + log1p + divide costs ~4x more and made the epilogue, not the tensor pipe, the critical
+// path of a warp).  e = exp(-|z|) by 2^k * Taylor-13 on |r| <= ln2/2; log(1 + e) = 2 atanh(s),
+// s = e/(2 + e) <= 1/3, odd series to s^35; one shared reciprocal.  Max relative error vs
+// long-double libm over z in [-60, 60] and the tails: softplus 4.8e-16, sigmoid 3.7e-16.
+__device__ __forceinline__ void softplus_sigmoid(double z, double &sp, double &sg) {
+    const double x = -fabs(z);
+    double kf = rint(x * 1.4426950408889634074);
+    kf = fmax(kf, -1000.0);
+    double r = fma(-kf, 6.93147180369123816490e-01, x);
+    r = fma(-kf, 1.90821492927058770002e-10, r);
+    double p = 1.0 / 6227020800.0;
+    p = fma(p, r, 1.0 / 479001600.0);
+    p = fma(p, r, 1.0 / 39916800.0);
+    p = fma(p, r, 1.0 / 3628800.0);
+    p = fma(p, r, 1.0 / 362880.0);
+    p = fma(p, r, 1.0 / 40320.0);
+    p = fma(p, r, 1.0 / 5040.0);
+    p = fma(p, r, 1.0 / 720.0);
+    p = fma(p, r, 1.0 / 120.0);
+    p = fma(p, r, 1.0 / 24.0);
+    p = fma(p, r, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    double e = __longlong_as_double(__double_as_longlong(p) + ((long long)kf << 52));
+    if (x < -700.0) e = 0.0;
+    const double t1 = 1.0 + e, t2 = 2.0 + e;
+    const double rc = 1.0 / (t1 * t2);
+    const double inv = t2 * rc;            // 1 / (1 + e)
+    sg = z >= 0.0 ? inv : e * inv;
+    const double s = e * (t1 * rc), s2 = s * s;   // e / (2 + e)
+    double q = 1.0 / 35.0;
+    q = fma(q, s2, 1.0 / 33.0); q = fma(q, s2, 1.0 / 31.0); q = fma(q, s2, 1.0 / 29.0);
+    q = fma(q, s2, 1.0 / 27.0); q = fma(q, s2, 1.0 / 25.0); q = fma(q, s2, 1.0 / 23.0);
+    q = fma(q, s2, 1.0 / 21.0); q = fma(q, s2, 1.0 / 19.0); q = fma(q, s2, 1.0 / 17.0);
+    q = fma(q, s2, 1.0 / 15.0); q = fma(q, s2, 1.0 / 13.0); q = fma(q, s2, 1.0 / 11.0);
+    q = fma(q, s2, 1.0 / 9.0);  q = fma(q, s2, 1.0 / 7.0);  q = fma(q, s2, 1.0 / 5.0);
+    q = fma(q, s2, 1.0 / 3.0);  q = fma(q, s2, 1.0);
+    sp = fmax(z, 0.0) + 2.0 * s * q;
 }
 
 template <int D>
@@ -49,7 +91,7 @@ constexpr size_t logistic_smem() {
 }  // namespace
 
 template <int D>
-__global__ void __launch_bounds__(kNT, 1) sweep_logistic_kernel(LogisticArgs a) {
+__global__ void __maxnreg__(224) sweep_logistic_kernel(LogisticArgs a) {
     constexpr int LD = D + kPad, LDT = D + kPadT;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *Th = reinterpret_cast<double *>(smem_raw);   // [kBN][LDT]  Theta block, row = chain
@@ -106,7 +148,7 @@ __global__ void __launch_bounds__(kNT, 1) sweep_logistic_kernel(LogisticArgs a) 
         }
         return;
     }
-    if (w >= 4) __nanosleep(2500);  // one-off skew of the second warp of every sub-partition
+    // (a one-off skew of half the warps was tried and measured slower: they re-align through the ring)
 
     double G[D / 8][2];
 #pragma unroll
@@ -132,15 +174,27 @@ __global__ void __launch_bounds__(kNT, 1) sweep_logistic_kernel(LogisticArgs a) 
         const int rq = (gq & 4) | ((gq & 1) << 1) | ((gq >> 1) & 1);
         const double *Bp = Th + (8 * w + gq) * LDT + 2 * tq;
         const double *Ap = X + rq * LD + 2 * tq;
-#pragma unroll 4
+        // fragments are fetched one k-pair ahead into their own registers (software pipeline):
+        // the MMAs of step k never wait for the shared-memory loads of step k
+        double2 b_cur = *reinterpret_cast<const double2 *>(Bp);
+        double2 a_cur[MB];
+#pragma unroll
+        for (int m = 0; m < MB; ++m) a_cur[m] = *reinterpret_cast<const double2 *>(Ap + (8 * m) * LD);
+#pragma unroll 8
         for (int k0 = 0; k0 < D; k0 += 8) {
-            const double2 b = *reinterpret_cast<const double2 *>(Bp + k0);
+            const int kn = k0 + 8 < D ? k0 + 8 : k0;
+            const double2 b_nxt = *reinterpret_cast<const double2 *>(Bp + kn);
+            double2 a_nxt[MB];
+#pragma unroll
+            for (int m = 0; m < MB; ++m) a_nxt[m] = *reinterpret_cast<const double2 *>(Ap + (8 * m) * LD + kn);
 #pragma unroll
             for (int m = 0; m < MB; ++m) {
-                const double2 av = *reinterpret_cast<const double2 *>(Ap + (8 * m) * LD + k0);
-                dmma(za[m][0], za[m][1], av.x, b.x);
-                dmma(zb[m][0], zb[m][1], av.y, b.y);
+                dmma(za[m][0], za[m][1], a_cur[m].x, b_cur.x);
+                dmma(zb[m][0], zb[m][1], a_cur[m].y, b_cur.y);
             }
+            b_cur = b_nxt;
+#pragma unroll
+            for (int m = 0; m < MB; ++m) a_cur[m] = a_nxt[m];
         }
         double z[MB][2];
 #pragma unroll
@@ -154,9 +208,8 @@ __global__ void __launch_bounds__(kNT, 1) sweep_logistic_kernel(LogisticArgs a) 
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 const double zz = z[m][j];
-                const double e = exp(-fabs(zz));
-                const double sp = fmax(zz, 0.0) + log1p(e);          // softplus(z)
-                const double sg = (zz >= 0.0 ? 1.0 : e) / (1.0 + e);  // sigmoid(z)
+                double sp, sg;
+                softplus_sigmoid(zz, sp, sg);
                 const double res = live ? yv - sg : 0.0;
                 const double lli = live ? yv * zz - sp : 0.0;
                 if (j == 0) ll0 += lli; else ll1 += lli;
@@ -172,9 +225,15 @@ __global__ void __launch_bounds__(kNT, 1) sweep_logistic_kernel(LogisticArgs a) 
         for (int i0 = 0; i0 < kBM; i0 += 4) {
             const double af = Rs[(i0 + tq) * kRPad + 8 * w + gq];
             const double *Xr = X + (i0 + tq) * LD + 2 * gq;
+            // X fragments fetched four pairs ahead of the MMAs that use them
+            constexpr int NP = D / 16, AH = NP < 4 ? NP : 4;
+            double2 xq[AH];
 #pragma unroll
-            for (int P = 0; P < D / 16; ++P) {
-                const double2 xv = *reinterpret_cast<const double2 *>(Xr + 16 * P);
+            for (int P = 0; P < AH; ++P) xq[P] = *reinterpret_cast<const double2 *>(Xr + 16 * P);
+#pragma unroll
+            for (int P = 0; P < NP; ++P) {
+                const double2 xv = xq[P % AH];
+                if (P + AH < NP) xq[P % AH] = *reinterpret_cast<const double2 *>(Xr + 16 * (P + AH));
                 dmma(G[2 * P][0], G[2 * P][1], af, xv.x);
                 dmma(G[2 * P + 1][0], G[2 * P + 1][1], af, xv.y);
             }
