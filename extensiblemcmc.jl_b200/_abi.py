@@ -107,6 +107,8 @@ SIGNATURES = {
     "extmcmc_set_state": (C.c_int32, [Handle, c_double_p]),
     "extmcmc_comm_unique_id": (C.c_int32, [c_uint8_p]),
     "extmcmc_comm_init": (C.c_int32, [Handle, c_uint8_p]),
+    "extmcmc_p2p_export": (C.c_int32, [Handle, c_uint8_p]),
+    "extmcmc_p2p_import": (C.c_int32, [Handle, c_uint8_p]),
     "extmcmc_run_block": (C.c_int32, [Handle, C.POINTER(Step), C.c_int32]),
     "extmcmc_run_block_replay": (C.c_int32, [Handle, C.POINTER(Step), C.c_int32, C.c_int32, c_double_p, c_double_p]),
     "extmcmc_sync": (C.c_int32, [Handle]),

@@ -113,6 +113,9 @@ struct extmcmc_handle {
     size_t stage_cap = 0;
     int64_t fetch_lo = 0, fetch_hi = 0;
     bool fetch_active = false;
+    // fused peer exchange
+    void *p2p_region = nullptr;                 // rx[2][W][C] doubles followed by flag[2][W] u64
+    std::vector<void *> p2p_opened;             // peer mappings to close
     // multi-rank
     ncclComm_t comm = nullptr;
     int64_t *n_obs_dev = nullptr;
@@ -223,7 +226,8 @@ bool obs_sharded(extmcmc_t h) {
 // `partial` (grad: also the first-order sums).  The logistic law reads the parameters from
 // `src` ([p][C]) and finishes ll (-> ll_dst) and the gradient (-> grad_dst, may be NULL) itself.
 int32_t enqueue_sweep(extmcmc_t h, bool instrument, bool grad = false, const double *src = nullptr,
-                      double *ll_dst = nullptr, double *grad_dst = nullptr) {
+                      double *ll_dst = nullptr, double *grad_dst = nullptr,
+                      const StepDesc *d_descs = nullptr, int k = 0) {
     std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
     if (instrument) {
         if (!h->ev_free.empty()) { ev = h->ev_free.back(); h->ev_free.pop_back(); }
@@ -246,10 +250,16 @@ int32_t enqueue_sweep(extmcmc_t h, bool instrument, bool grad = false, const dou
         h->ev_pending.push_back(ev);
     }
     if (obs_sharded(h)) {
-        launch_reduce_partials(h->d, h->stream);
-        h->launches += 1;
-        NK(h, g_nccl.AllReduce(h->d.ssum, h->d.ssum, (size_t)h->d.C, ncclFloat64, ncclSum, h->comm,
-                               h->stream));
+        if (h->d.p2p && d_descs) {
+            // our own exchange: peer stores + flags here, wait + ordered sum inside accept_kernel
+            launch_reduce_push(h->d, d_descs, k, h->stream);
+            h->launches += 1;
+        } else {
+            launch_reduce_partials(h->d, h->stream);
+            h->launches += 1;
+            NK(h, g_nccl.AllReduce(h->d.ssum, h->d.ssum, (size_t)h->d.C, ncclFloat64, ncclSum, h->comm,
+                                   h->stream));
+        }
     }
     return EXTMCMC_OK;
 }
@@ -290,7 +300,7 @@ int32_t enqueue_steps(extmcmc_t h, const StepDesc *d_descs, const int *kinds, in
             fused = false;
         } else {
             if (!fused) { launch_propose(h->d, d_descs, k, h->stream); h->launches += 1; }
-            if ((rc = enqueue_sweep(h, instrument, false, h->d.prop_full, h->d.ssum, nullptr))) return rc;
+            if ((rc = enqueue_sweep(h, instrument, false, h->d.prop_full, h->d.ssum, nullptr, d_descs, k))) return rc;
             fused = k + 1 < n_steps && kinds[k + 1] != EXTMCMC_KERNEL_MALA;
             launch_accept(h->d, d_descs, k, fused ? 1 : 0, h->stream);
             h->launches += 1;
@@ -588,6 +598,8 @@ int32_t extmcmc_destroy(extmcmc_t h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     invalidate_graphs(h);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    for (void *p : h->p2p_opened) cudaIpcCloseMemHandle(p);
+    if (h->p2p_region) cudaFree(h->p2p_region);
     for (void *p : h->allocs) cudaFree(p);
     if (h->obs_dev) cudaFree(h->obs_dev);
     if (h->y_dev) cudaFree(h->y_dev);
@@ -863,6 +875,8 @@ int32_t extmcmc_set_state(extmcmc_t h, const double *theta) {
     }
     std::fill(h->haario_M.begin(), h->haario_M.end(), 0);
     h->seq_next = 0;
+    h->d.epoch += 1;
+    invalidate_graphs(h);   // the epoch is baked into the kernel arguments
     h->grad_valid = false;
     if (h->fetch_active) { cudaEventSynchronize(h->fetch_done); h->fetch_active = false; }
     std::fill(h->ra_iter.begin(), h->ra_iter.end(), 0);
@@ -894,6 +908,63 @@ int32_t extmcmc_comm_init(extmcmc_t h, const uint8_t id_in[128]) {
     return EXTMCMC_OK;
 }
 
+static size_t p2p_region_bytes(extmcmc_t h) {
+    const size_t W = (size_t)h->cfg.world_size;
+    return 2 * W * (size_t)h->d.C * sizeof(double) + 2 * W * sizeof(unsigned long long);
+}
+
+int32_t extmcmc_p2p_export(extmcmc_t h, uint8_t handle_out[64]) {
+    if (!h || !handle_out) return EXTMCMC_EINVAL;
+    if (!obs_sharded(h)) return fail(h, EXTMCMC_EINVAL, "peer exchange is for EXTMCMC_SHARD_OBS with world_size > 1");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    CK(h, cudaSetDevice(h->cfg.device));
+    if (!h->p2p_region) {
+        CK(h, cudaMalloc(&h->p2p_region, p2p_region_bytes(h)));
+        CK(h, cudaMemset(h->p2p_region, 0, p2p_region_bytes(h)));
+    }
+    cudaIpcMemHandle_t hd;
+    CK(h, cudaIpcGetMemHandle(&hd, h->p2p_region));
+    std::memcpy(handle_out, &hd, 64);
+    return EXTMCMC_OK;
+}
+
+int32_t extmcmc_p2p_import(extmcmc_t h, const uint8_t *handles) {
+    if (!h || !handles) return EXTMCMC_EINVAL;
+    if (!h->p2p_region) return fail(h, EXTMCMC_EINVAL, "call extmcmc_p2p_export first");
+    CK(h, cudaSetDevice(h->cfg.device));
+    const int W = h->cfg.world_size;
+    const size_t rx_bytes = 2 * (size_t)W * h->d.C * sizeof(double);
+    std::vector<double *> rx(W);
+    std::vector<unsigned long long *> fl(W);
+    for (int q = 0; q < W; ++q) {
+        void *base = nullptr;
+        if (q == h->cfg.rank) {
+            base = h->p2p_region;
+        } else {
+            cudaIpcMemHandle_t hd;
+            std::memcpy(&hd, handles + 64 * (size_t)q, 64);
+            CK(h, cudaIpcOpenMemHandle(&base, hd, cudaIpcMemLazyEnablePeerAccess));
+            h->p2p_opened.push_back(base);
+        }
+        rx[q] = (double *)base;
+        fl[q] = (unsigned long long *)((char *)base + rx_bytes);
+    }
+    int32_t rc;
+    if ((rc = dev_alloc(h, &h->d.peer_rx, (size_t)W)) || (rc = dev_alloc(h, &h->d.peer_flag, (size_t)W)) ||
+        (rc = dev_alloc(h, &h->d.push_counter, 1)))
+        return rc;
+    CK(h, cudaMemcpy(h->d.peer_rx, rx.data(), sizeof(double *) * W, cudaMemcpyHostToDevice));
+    CK(h, cudaMemcpy(h->d.peer_flag, fl.data(), sizeof(unsigned long long *) * W, cudaMemcpyHostToDevice));
+    CK(h, cudaMemset(h->d.push_counter, 0, sizeof(unsigned int)));
+    h->d.my_rx = rx[h->cfg.rank];
+    h->d.my_flag = fl[h->cfg.rank];
+    h->d.rank = h->cfg.rank;
+    h->d.world = W;
+    h->d.p2p = 1;
+    invalidate_graphs(h);
+    return EXTMCMC_OK;
+}
+
 int32_t extmcmc_run_block(extmcmc_t h, const extmcmc_step_t *steps, int32_t n_steps) {
     return run_block_impl(h, steps, n_steps, EXTMCMC_RNG_PHILOX, 0, nullptr, nullptr);
 }
@@ -911,6 +982,10 @@ int32_t extmcmc_sync(extmcmc_t h) {
     if (rc) return rc;
     int32_t flag = 0;
     CK(h, cudaMemcpy(&flag, h->d.err_flag, sizeof flag, cudaMemcpyDeviceToHost));
+    if (flag == 2) {
+        CK(h, cudaMemset(h->d.err_flag, 0, sizeof flag));
+        return fail(h, EXTMCMC_ENCCL, "peer exchange timed out: a rank did not deliver its partial sums");
+    }
     if (flag) {
         CK(h, cudaMemset(h->d.err_flag, 0, sizeof flag));
         return fail(h, EXTMCMC_EDOMAIN,

@@ -94,7 +94,18 @@ struct DevState {
     // replay buffers (EXTMCMC_RNG_REPLAY)
     const double *rp_prop;  // [rows][p_u_max][C]
     const double *rp_exp;   // [rows][C]
-    int32_t *err_flag;      // sticky: a chain left the law's domain
+    // fused cross-GPU exchange of the per-chain sums under observation sharding (no NCCL on the
+    // hot path): every rank pushes its sums into slot [parity][rank] of every peer's rx buffer
+    // over NVLink peer mappings and raises a sequence flag; the accept kernel waits for all
+    // flags and adds the slots in rank order (identical totals on every rank).
+    int32_t p2p, rank, world;
+    uint64_t epoch;                     // bumped by set_state so stale flags never match
+    double **peer_rx;                   // [world] -> rx[2][world][C] of each rank
+    unsigned long long **peer_flag;     // [world] -> flag[2][world] of each rank
+    double *my_rx;
+    unsigned long long *my_flag;
+    unsigned int *push_counter;
+    int32_t *err_flag;      // sticky: 1 = a chain left the law's domain, 2 = peer exchange timed out
     DevUpdate *upd;         // [NU]
 };
 

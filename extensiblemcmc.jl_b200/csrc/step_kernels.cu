@@ -364,6 +364,63 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(DevState d) {
     if ((threadIdx.x / kRedChains) == 0 && c < d.C) d.ssum[c] = tot;
 }
 
+__device__ __forceinline__ unsigned long long exchange_tag(const DevState &d, const StepDesc &sd) {
+    return (d.epoch << 40) | (unsigned long long)(sd.seq + 1);
+}
+
+// Reduce this rank's partial sums and push them to every rank (itself included) through peer
+// pointers; the last CTA to finish raises this rank's flag on every peer (threadfence pattern).
+template <int SL>
+__global__ void __launch_bounds__(256)
+reduce_push_kernel(DevState d, const StepDesc *__restrict__ descs, int k) {
+    __shared__ double sh[kRedThreads];
+    __shared__ bool last;
+    constexpr int kRedChains = kRedThreads / SL;
+    const StepDesc sd = descs[k];
+    const int parity = (int)(sd.seq & 1);
+    const double tot = reduce_segments<SL>(d, sh);
+    const int64_t c = (int64_t)blockIdx.x * kRedChains + (threadIdx.x % kRedChains);
+    if ((threadIdx.x / kRedChains) == 0 && c < d.C) {
+        const int64_t slot = ((int64_t)parity * d.world + d.rank) * d.C + c;
+        for (int q = 0; q < d.world; ++q) d.peer_rx[q][slot] = tot;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(d.push_counter, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        *d.push_counter = 0;
+        __threadfence_system();
+        const unsigned long long tag = exchange_tag(d, sd);
+        for (int q = 0; q < d.world; ++q) {
+            unsigned long long *f = d.peer_flag[q] + (parity * d.world + d.rank);
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(tag) : "memory");
+        }
+    }
+}
+
+// Wait until every rank's sums of this step have landed, then add them in rank order.
+__device__ __forceinline__ double wait_and_combine(const DevState &d, const StepDesc &sd, int64_t c) {
+    const int parity = (int)(sd.seq & 1);
+    if (threadIdx.x == 0) {
+        const unsigned long long tag = exchange_tag(d, sd);
+        const long long t0 = clock64();
+        for (int r = 0; r < d.world; ++r) {
+            const unsigned long long *f = d.my_flag + (parity * d.world + r);
+            unsigned long long v;
+            do {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+                if (v < tag && clock64() - t0 > 6000000000ll) { *d.err_flag = 2; v = tag; }  // ~3 s
+            } while (v < tag);
+        }
+    }
+    __syncthreads();
+    double s = 0.0;
+    if (c < d.C)
+        for (int r = 0; r < d.world; ++r) s += __ldcg(d.my_rx + ((int64_t)parity * d.world + r) * d.C + c);
+    return s;
+}
+
 __global__ void __launch_bounds__(256) finalize_loglik_kernel(DevState d, double *ll_out) {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= d.C) return;
@@ -519,7 +576,9 @@ accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fuse_ne
     if (fuse_next) load_step_ctx(&ctx_next, d, descs, k + 1);
     const int64_t c = (int64_t)blockIdx.x * kRedChains + (threadIdx.x % kRedChains);
     double S;
-    if (d.use_ssum) {
+    if (d.p2p) {
+        S = wait_and_combine(d, ctx.sd, c);
+    } else if (d.use_ssum) {
         S = c < d.C ? d.ssum[c] : 0.0;
     } else {
         S = reduce_segments<SL>(d, sh);
@@ -827,6 +886,12 @@ void launch_reduce_partials(const DevState &d, cudaStream_t st) {
         reduce_partials_kernel<8><<<red_blocks_for(d.C, 8), 256, 0, st>>>(d);
     else
         reduce_partials_kernel<1><<<red_blocks_for(d.C, 1), 256, 0, st>>>(d);
+}
+void launch_reduce_push(const DevState &d, const StepDesc *descs, int k, cudaStream_t st) {
+    if (d.S * d.G > 16)
+        reduce_push_kernel<8><<<red_blocks_for(d.C, 8), 256, 0, st>>>(d, descs, k);
+    else
+        reduce_push_kernel<1><<<red_blocks_for(d.C, 1), 256, 0, st>>>(d, descs, k);
 }
 void launch_finalize_loglik(const DevState &d, double *ll_out, cudaStream_t st) {
     finalize_loglik_kernel<<<blocks_for(d.C), 256, 0, st>>>(d, ll_out);
