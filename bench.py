@@ -361,7 +361,8 @@ def run_cfg5(args):
     ups = [em.RandomWalkUpdate(em.UniformRandomWalk([5e-3 / 30]), [1], adpt=mk()),
            em.RandomWalkUpdate(em.UniformRandomWalk([5e-3 / 30], [True]), [2], prior=em.ImproperPosPrior(), adpt=mk())]
     bk = par.backend_for_rank(rank, world, local, C, shard="obs" if world > 1 else "chains", comm_id=cid,
-                              seed=6, history="none", block_len=NU, use_graphs=True)
+                              seed=6, history="none", block_len=NU, use_graphs=True,
+                              **({"p2p_allgather": par.p2p_allgather_fn(dist)} if (world > 1 and args.p2p) else {}))
     if world == 1:
         bk = em.CUDAMCMCBackend(n_chains=C, device=local, seed=6, history="none", block_len=NU, use_graphs=True)
     mcmc = em.MCMC(ups, backend=bk)
@@ -600,6 +601,7 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-hbm", action="store_true")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--p2p", action="store_true", help="cfg5: the library's NVLink peer exchange instead of ncclAllReduce")
     ap.add_argument("--n-obs", type=int, default=1_000_000_000, help="cfg5 only: total observations")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -52,6 +52,15 @@ def exchange_comm_id(dist, make_id=nccl_unique_id):
     return ids[0]
 
 
+def p2p_allgather_fn(dist):
+    """bytes -> list of every rank's bytes (rank order), for CUDAMCMCBackend(p2p_allgather=...)."""
+    def gather(b):
+        out = [None] * dist.get_world_size()
+        dist.all_gather_object(out, b)
+        return out
+    return gather
+
+
 def backend_for_rank(rank, world, local_rank, n_chains_total, shard="chains", comm_id=None, **kw):
     """CUDAMCMCBackend of this rank.  shard='chains': n_chains_total is split; shard='obs':
     every rank runs all n_chains_total chains on its slice of the observations."""

@@ -47,7 +47,7 @@ class CUDAMCMCBackend(MCMCBackend):
     def __init__(self, n_chains=1, device=0, seed=0, block_len=128, history="full",
                  stats_mode=None, use_graphs=True, instrument=False, sweep_variant=0,
                  shard_mode="chains", rank=0, world_size=1, chain_offset=0, roll_window=100,
-                 comm_id=None):
+                 comm_id=None, p2p_allgather=None):
         assert history in ("full", "none")
         assert shard_mode in ("chains", "obs")
         self.n_chains = int(n_chains)
@@ -63,6 +63,9 @@ class CUDAMCMCBackend(MCMCBackend):
         self.rank, self.world_size, self.chain_offset = int(rank), int(world_size), int(chain_offset)
         self.roll_window = int(roll_window)
         self.comm_id = comm_id
+        # callable bytes -> [bytes of every rank, rank order]; enables the library's own NVLink
+        # peer exchange of the per-chain sums instead of ncclAllReduce (shard_mode="obs")
+        self.p2p_allgather = p2p_allgather
 
 
 class _GlobalSub:
@@ -135,6 +138,13 @@ class CUDAGlobalWorkspace(GlobalWorkspace):
             if backend.comm_id is not None:
                 ida = np.frombuffer(bytes(backend.comm_id), dtype=np.uint8).copy()
                 self._ck(lib.extmcmc_comm_init(self.handle, ida.ctypes.data_as(_abi.c_uint8_p)))
+            if backend.p2p_allgather is not None:
+                mine = (C.c_uint8 * 64)()
+                self._ck(lib.extmcmc_p2p_export(self.handle, mine))
+                allh = backend.p2p_allgather(bytes(mine))
+                buf = np.frombuffer(b"".join(allh), dtype=np.uint8).copy()
+                assert buf.size == 64 * backend.world_size
+                self._ck(lib.extmcmc_p2p_import(self.handle, buf.ctypes.data_as(_abi.c_uint8_p)))
             self._keep = []
             self._kernels = []
             for i, updt in enumerate(updates):

@@ -62,13 +62,21 @@ def main():
     same_dec = np.array_equal(sh["acc"], single["acc"])
     rel = np.abs(sh["ll"][fin] - single["ll"][fin]) / np.abs(single["ll"][fin])
     flips = int((sh["acc"] != single["acc"]).any(axis=(0, 1)).sum())
+    # 2b. the same with the library's own NVLink peer exchange instead of ncclAllReduce
+    bp = par.backend_for_rank(rank, world, local, Cn, shard="obs", comm_id=par.exchange_comm_id(dist), seed=9,
+                              block_len=16, p2p_allgather=par.p2p_allgather_fn(dist))
+    shp = run(bp, x[first:first + cnt], th0, M)
+    p2p_same = bool(np.array_equal(shp["acc"], sh["acc"]) and np.array_equal(shp["theta"], sh["theta"]))
+    fin_p = np.isfinite(sh["ll"])
+    p2p_rel = float((np.abs(shp["ll"][fin_p] - sh["ll"][fin_p]) / np.abs(sh["ll"][fin_p])).max())
     gathered = par.gather_chain_axis(dist, sh["theta"][..., :4])
     if rank == 0:
         report.update(obs_ll_rel_err=float(rel.max()) if same_dec else None, obs_decisions_equal=bool(same_dec),
                       obs_chains_with_flips=flips,
                       obs_ranks_identical=bool(all(np.array_equal(gathered[..., :4], gathered[..., 4 * r:4 * r + 4])
                                                    for r in range(world))))
-        ok &= same_dec and rel.max() < 1e-10 and report["obs_ranks_identical"]
+        report.update(p2p_matches_nccl=p2p_same, p2p_ll_rel_vs_nccl=p2p_rel)
+        ok &= same_dec and rel.max() < 1e-10 and report["obs_ranks_identical"] and p2p_same and p2p_rel < 1e-12
         report["world"] = world
         print(json.dumps(report))
     dist.barrier()
