@@ -400,8 +400,9 @@ def run_cfg5(args):
         "unit": "chain-step*obs/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms_total / K,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"BASELINE cfg5: N={n_total:.3g} Gaussian observations generated on device, sharded "
-                               f"by observations over {world} GPU(s), C=8 replicated chains, NCCL all-reduce of "
-                               "partial sums per update step", "l2": "inputs larger than L2, no flush"},
+                               f"by observations over {world} GPU(s), C=8 replicated chains, "
+                               + ("fused NVLink peer exchange" if args.p2p else "NCCL all-reduce") +
+                               " of partial sums per update step", "l2": "inputs larger than L2, no flush"},
         "roofline": {"kernel": variant, "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": gbs / peaks["hbm_gbs"], "peak_source": peak_src,
                      "note": "per-GPU bytes of one update step / whole update-step time (sweep + reduce + all-reduce + accept)",
