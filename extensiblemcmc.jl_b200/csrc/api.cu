@@ -741,8 +741,23 @@ int32_t extmcmc_set_update(extmcmc_t h, int32_t u, const extmcmc_update_t *upd) 
             for (int i = 0; i < upd->n_coords; ++i)
                 if (upd->pos[i]) return fail(h, EXTMCMC_EUNSUPPORTED, "MALA on positivity-constrained coordinates is not implemented");
     }
-    if (upd->prior < EXTMCMC_PRIOR_IMPROPER || upd->prior > EXTMCMC_PRIOR_UNIFORM)
+    if (upd->prior < EXTMCMC_PRIOR_IMPROPER || upd->prior > EXTMCMC_PRIOR_PRODUCT)
         return fail(h, EXTMCMC_EUNSUPPORTED, "prior not implemented on the GPU path");
+    if (upd->prior == EXTMCMC_PRIOR_PRODUCT) {
+        // {K, then per factor: kind, dim, p0, p1}; the dims must tile the update's coordinates
+        if (upd->n_prior_params < 1 || !upd->prior_params) return fail(h, EXTMCMC_EINVAL, "ProductPrior parameters missing");
+        const int K = (int)upd->prior_params[0];
+        if (K < 1 || K > kMaxPriorFactors || upd->n_prior_params != 1 + 4 * K)
+            return fail(h, EXTMCMC_EUNSUPPORTED, "ProductPrior: 1 <= factors <= 8");
+        int tot = 0;
+        for (int k = 0; k < K; ++k) {
+            const int kind = (int)upd->prior_params[1 + 4 * k], dim = (int)upd->prior_params[2 + 4 * k];
+            if (kind < EXTMCMC_PRIOR_IMPROPER || kind > EXTMCMC_PRIOR_UNIFORM || dim < 1)
+                return fail(h, EXTMCMC_EUNSUPPORTED, "ProductPrior factor not implemented on the GPU path");
+            tot += dim;
+        }
+        if (tot != upd->n_coords) return fail(h, EXTMCMC_EINVAL, "ProductPrior dims must add up to length(coords)");
+    }
     // readjust! exists only for (UniformRandomWalk, AdaptationUnifRW) and
     // (GaussianRandomWalkMix, HaarioTypeAdaptation): adaptation.jl:273,422
     if (!(upd->adapt.kind == EXTMCMC_ADAPT_NONE ||

@@ -16,7 +16,8 @@ namespace extmcmc {
 
 constexpr int kMaxCoords = 16;      // p_u limit of the scalar per-chain step kernels
 constexpr int kMaxGaussCoords = 8; // p_u limit of the Gaussian random walks on the device
-constexpr int kMaxPriorParams = 4;
+constexpr int kMaxPriorFactors = 8;  // ProductPrior factors
+constexpr int kMaxPriorParams = 1 + 4 * kMaxPriorFactors;
 constexpr int kMaxObsDim = 8;       // general-d Gaussian law on the device: d <= 8
 
 // One update as the kernels see it (constant per run; lives in a device table).

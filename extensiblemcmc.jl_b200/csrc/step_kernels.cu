@@ -16,9 +16,8 @@ constexpr double kLog2Pi = 1.8378770664093454835606594728112;
 
 // logpdf(prior, theta_loc) on the update's own coordinates (src/updates.jl:104,
 // src/priors.jl:18-39).
-__device__ __forceinline__ double log_prior(const DevUpdate &u, const double *th) {
-    const int n = u.n_coords;
-    switch (u.prior) {
+__device__ __forceinline__ double log_prior_family(int kind, const double *pp, const double *th, int n) {
+    switch (kind) {
     case EXTMCMC_PRIOR_IMPROPER: return 0.0;  // priors.jl:19
     case EXTMCMC_PRIOR_IMPROPER_POS: {        // -sum(log.(th)), priors.jl:26
         double s = 0.0;
@@ -26,7 +25,7 @@ __device__ __forceinline__ double log_prior(const DevUpdate &u, const double *th
         return -s;
     }
     case EXTMCMC_PRIOR_NORMAL: {
-        const double m = u.prior_params[0], sd = u.prior_params[1];
+        const double m = pp[0], sd = pp[1];
         double s = 0.0;
         for (int i = 0; i < n; ++i) {
             const double z = (th[i] - m) / sd;
@@ -35,7 +34,7 @@ __device__ __forceinline__ double log_prior(const DevUpdate &u, const double *th
         return s;
     }
     case EXTMCMC_PRIOR_GAMMA: {
-        const double k = u.prior_params[0], sc = u.prior_params[1];
+        const double k = pp[0], sc = pp[1];
         double s = 0.0;
         for (int i = 0; i < n; ++i) {
             if (!(th[i] > 0.0)) return -INFINITY;
@@ -44,7 +43,7 @@ __device__ __forceinline__ double log_prior(const DevUpdate &u, const double *th
         return s;
     }
     case EXTMCMC_PRIOR_UNIFORM: {
-        const double a = u.prior_params[0], b = u.prior_params[1];
+        const double a = pp[0], b = pp[1];
         double s = 0.0;
         for (int i = 0; i < n; ++i) {
             if (!(th[i] >= a && th[i] <= b)) return -INFINITY;
@@ -54,6 +53,21 @@ __device__ __forceinline__ double log_prior(const DevUpdate &u, const double *th
     }
     }
     return NAN;
+}
+
+__device__ __forceinline__ double log_prior(const DevUpdate &u, const double *th) {
+    if (u.prior != EXTMCMC_PRIOR_PRODUCT) return log_prior_family(u.prior, u.prior_params, th, u.n_coords);
+    // ProductPrior (priors.jl:82-88): lp = 0.0; lp += logpdf(dist_k, th[idx_k])
+    const int K = (int)u.prior_params[0];
+    double lp = 0.0;
+    int off = 0;
+    for (int k = 0; k < K; ++k) {
+        const double *f = u.prior_params + 1 + 4 * k;
+        const int dim = (int)f[1];
+        lp += log_prior_family((int)f[0], f + 2, th + off, dim);
+        off += dim;
+    }
+    return lp;
 }
 
 // logpdf(rw::UniformRandomWalk, from, to) (random_walk.jl:88-94): only positive-

@@ -60,6 +60,21 @@ class StandardPrior(Prior):                           # priors.jl:35-39
 
 
 class ProductPrior(Prior):                            # priors.jl:60-88
+    """ProductPrior(dists, dims): factor k applies to the next dims[k] coordinates of the update
+    (consecutive index groups, priors.jl:66-78).  Each factor is an ImproperPrior /
+    ImproperPosPrior or one of the Normal / Gamma / Uniform stand-ins (iid within its group)."""
+
     def __init__(self, dists, dims):
-        self.dists, self.dims = tuple(dists), tuple(dims)
-    # to_abi: inherited -> raises (device path: next round)
+        self.dists, self.dims = tuple(dists), tuple(int(d) for d in dims)
+        assert len(self.dists) == len(self.dims)
+
+    def to_abi(self):
+        out = [float(len(self.dists))]
+        for dist, dim in zip(self.dists, self.dims):
+            pr = dist if isinstance(dist, Prior) else StandardPrior(dist)
+            kind, pp = pr.to_abi()
+            if kind == _abi.PRIOR_PRODUCT:
+                raise NotImplementedError("nested ProductPrior is not implemented on the GPU path")
+            pp = list(pp) + [0.0, 0.0]
+            out += [float(kind), float(dim), pp[0], pp[1]]
+        return _abi.PRIOR_PRODUCT, np.array(out)

@@ -82,8 +82,11 @@ enum {
                                        (iid product), params = {m, s}  priors.jl:35-39 */
     EXTMCMC_PRIOR_GAMMA        = 3, /* StandardPrior(Gamma(shape, scale)) iid product,
                                        params = {shape, scale}; -Inf for th <= 0      */
-    EXTMCMC_PRIOR_UNIFORM      = 4  /* StandardPrior(Uniform(a, b)) iid product,
+    EXTMCMC_PRIOR_UNIFORM      = 4, /* StandardPrior(Uniform(a, b)) iid product,
                                        params = {a, b}; -Inf outside [a, b]           */
+    EXTMCMC_PRIOR_PRODUCT      = 5  /* ProductPrior(dists, dims), priors.jl:60-88: factors over
+                                       consecutive coordinate groups; params = {K, then per
+                                       factor: kind (one of the above), dim, p0, p1}, K <= 8 */
 };
 
 /* ---- adaptation schemes (src/transition_kernels/adaptation.jl) ----------- */

@@ -76,7 +76,7 @@ typedef struct {
     int32_t kernel, n_coords, prior, n_prior_params;
     int32_t *coords;
     uint8_t *pos;
-    double prior_params[8];
+    double prior_params[40];
     extmcmc_adapt_t adapt;
     int32_t step_len; /* doubles of step-size state per chain */
     double *step0;    /* initial step-size state [step_len] */
@@ -178,7 +178,7 @@ int32_t oracle_create(const extmcmc_config_t *cfg, const extmcmc_update_t *updat
             oracle_destroy(h);
             return EXTMCMC_EUNSUPPORTED;
         }
-        if (s->prior < EXTMCMC_PRIOR_IMPROPER || s->prior > EXTMCMC_PRIOR_UNIFORM) {
+        if (s->prior < EXTMCMC_PRIOR_IMPROPER || s->prior > EXTMCMC_PRIOR_PRODUCT) {
             /* reference: error("logpdf not implemented for prior ...") src/priors.jl:11-13 */
             set_err("oracle: prior not implemented");
             oracle_destroy(h);
@@ -195,7 +195,7 @@ int32_t oracle_create(const extmcmc_config_t *cfg, const extmcmc_update_t *updat
             /* UniformRandomWalk asserts all(eps .> 0), random_walk.jl:50 */
             if (s->kernel == EXTMCMC_KERNEL_RW_UNIFORM && !(s->step[i] > 0.0)) { set_err("eps must be > 0"); oracle_destroy(h); return EXTMCMC_EINVAL; }
         }
-        for (int i = 0; i < s->n_prior_params && i < 8; ++i) t->prior_params[i] = s->prior_params[i];
+        for (int i = 0; i < s->n_prior_params && i < 40; ++i) t->prior_params[i] = s->prior_params[i];
         {
             const int nn = s->n_coords * s->n_coords;
             t->step_len = s->kernel == EXTMCMC_KERNEL_RW_UNIFORM ? s->n_coords
@@ -393,9 +393,8 @@ static double law_loglik_grad(const struct oracle_handle *h, const double *theta
 /* Priors: logpdf(prior, theta_loc) on the update's own coordinates only     */
 /*   src/updates.jl:104, src/run.jl:374-385, src/priors.jl:18-39             */
 /* ------------------------------------------------------------------------- */
-static double log_prior(const orc_update_t *u, const double *th) {
-    int n = u->n_coords;
-    switch (u->prior) {
+static double log_prior_family(int kind, const double *pp, const double *th, int n) {
+    switch (kind) {
     case EXTMCMC_PRIOR_IMPROPER: /* logpdf(::ImproperPrior, th) = 0.0, priors.jl:19 */
         return 0.0;
     case EXTMCMC_PRIOR_IMPROPER_POS: { /* -sum(log.(th)), priors.jl:26 */
@@ -404,12 +403,12 @@ static double log_prior(const orc_update_t *u, const double *th) {
         return -s;
     }
     case EXTMCMC_PRIOR_NORMAL: { /* StandardPrior(dist), priors.jl:35-39; Normal: -(z^2 + log2pi)/2 - log(s) */
-        double m = u->prior_params[0], sd = u->prior_params[1], s = 0.0;
+        double m = pp[0], sd = pp[1], s = 0.0;
         for (int i = 0; i < n; ++i) { double z = (th[i] - m) / sd; s += -(z * z + LOG2PI) / 2.0 - log(sd); }
         return s;
     }
     case EXTMCMC_PRIOR_GAMMA: { /* Gamma(k, scale): -lgamma(k) - k log(scale) + (k-1) log x - x/scale */
-        double k = u->prior_params[0], sc = u->prior_params[1], s = 0.0;
+        double k = pp[0], sc = pp[1], s = 0.0;
         for (int i = 0; i < n; ++i) {
             if (!(th[i] > 0.0)) return -INFINITY;
             s += -lgamma(k) - k * log(sc) + (k - 1.0) * log(th[i]) - th[i] / sc;
@@ -417,7 +416,7 @@ static double log_prior(const orc_update_t *u, const double *th) {
         return s;
     }
     case EXTMCMC_PRIOR_UNIFORM: { /* Uniform(a, b): -log(b - a) inside, -Inf outside */
-        double a = u->prior_params[0], b = u->prior_params[1], s = 0.0;
+        double a = pp[0], b = pp[1], s = 0.0;
         for (int i = 0; i < n; ++i) {
             if (!(th[i] >= a && th[i] <= b)) return -INFINITY;
             s += -log(b - a);
@@ -426,6 +425,21 @@ static double log_prior(const orc_update_t *u, const double *th) {
     }
     }
     return NAN;
+}
+
+static double log_prior(const orc_update_t *u, const double *th) {
+    if (u->prior != EXTMCMC_PRIOR_PRODUCT) return log_prior_family(u->prior, u->prior_params, th, u->n_coords);
+    /* logpdf(prior::ProductPrior, th): lp = 0.0; lp += logpdf(dist_k, th[idx_k]), priors.jl:82-88 */
+    const int K = (int)u->prior_params[0];
+    double lp = 0.0;
+    int off = 0;
+    for (int k = 0; k < K; ++k) {
+        const double *f = u->prior_params + 1 + 4 * k;
+        const int dim = (int)f[1];
+        lp += log_prior_family((int)f[0], f + 2, th + off, dim);
+        off += dim;
+    }
+    return lp;
 }
 
 /* logpdf(rw::UniformRandomWalk, a, b): sum over i of pos[i] ? -log(2 eps_i) - log(b_i) : 0.0

@@ -85,6 +85,23 @@ def test_replay_no_adaptation_and_priors():
     _assert_clean(rep)
 
 
+def test_product_prior_and_support_redraw():
+    # ProductPrior over a joint update (priors.jl:60-88); the Uniform factor has bounded support, so
+    # the oracle's own stream exercises the whole-vector redraw of proposal! (updates.jl:193-195)
+    x = _data(2500, seed=8, mean=0.4, sd=1.0)
+    pr = em.ProductPrior([em.Uniform(0.2, 0.6), em.Gamma(2.0, 1.5)], [1, 1])
+    ups = [em.RandomWalkUpdate(em.UniformRandomWalk([0.3, 0.08], [False, True]), [1, 2], prior=pr)]
+    th0 = np.repeat(np.array([[0.4], [1.0]]), 72, axis=1)
+    rep = replay_compare(x, 72, 50, seed=6, updates=ups, theta_init=th0)
+    _assert_clean(rep)
+    # own Philox stream on the GPU: every proposal and every state stays inside the support
+    s = GpuSession(em.GsnTargetLaw([0.0]), ups, x, th0, 72, seed=3, n_steps_hint=50)
+    r = s.run(list(em.MCMCSchedule(50, 1)))
+    assert (r["theta_prop"][:, 0] >= 0.2).all() and (r["theta_prop"][:, 0] <= 0.6).all()
+    assert (r["theta"][:, 0] >= 0.2).all() and (r["theta"][:, 0] <= 0.6).all()
+    s.close()
+
+
 def test_joint_update_of_both_coordinates():
     x = _data(3000, seed=7)
     ups = [em.RandomWalkUpdate(em.UniformRandomWalk([0.03, 0.04], [False, True]), [1, 2],

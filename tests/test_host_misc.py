@@ -1,0 +1,64 @@
+"""Host-side pieces that need no GPU: ESS estimator, Julia-style float printing of the CSV
+writer, ProductPrior translation, oracle priors against scipy."""
+import math
+
+import numpy as np
+from scipy import stats
+
+import extensiblemcmc_jl_b200 as em
+from extensiblemcmc_jl_b200 import _abi
+from extensiblemcmc_jl_b200.callbacks import _jl
+from oracle import oracle as orc
+
+
+def test_ess_geyer_on_ar1():
+    rng = np.random.default_rng(0)
+    n, rho = 20000, 0.9
+    x = np.empty((n, 3))
+    x[0] = rng.standard_normal(3)
+    for t in range(1, n):
+        x[t] = rho * x[t - 1] + math.sqrt(1 - rho * rho) * rng.standard_normal(3)
+    ess = em.ess_geyer(x)
+    want = n * (1 - rho) / (1 + rho)
+    assert ess.shape == (3,) and np.all(np.abs(ess - want) < 0.25 * want)
+    iid = em.ess_geyer(rng.standard_normal((5000, 2)))
+    assert np.all(iid > 3500)
+    assert em.ess_geyer(np.ones((100, 2))).shape == (2,)
+
+
+def test_julia_style_float_printing():
+    assert _jl(1.0) == "1.0" and _jl(-0.5) == "-0.5" and _jl(1e-7) == "1.0e-7" and _jl(1.5e22) == "1.5e22"
+    assert _jl(float("inf")) == "Inf" and _jl(float("-inf")) == "-Inf" and _jl(float("nan")) == "NaN"
+    assert float(_jl(0.1 + 0.2)) == 0.1 + 0.2
+
+
+def test_product_prior_translation():
+    kind, pp = em.ProductPrior([em.Normal(1.0, 2.0), em.ImproperPosPrior(), em.Uniform(0.0, 3.0)], [2, 1, 1]).to_abi()
+    assert kind == _abi.PRIOR_PRODUCT
+    assert list(pp) == [3.0, _abi.PRIOR_NORMAL, 2.0, 1.0, 2.0, _abi.PRIOR_IMPROPER_POS, 1.0, 0.0, 0.0,
+                        _abi.PRIOR_UNIFORM, 1.0, 0.0, 3.0]
+
+
+def test_oracle_priors_against_scipy():
+    # one step, first element: llr = +Inf regardless of the prior, so probe the priors through a
+    # second step from a known state with a replayed proposal and read back llr
+    x = np.array([0.3, -0.2, 0.9])
+    law = em.GsnTargetLaw([0.0])
+    cases = [
+        (em.StandardPrior(em.Normal(0.5, 2.0)), lambda t: stats.norm.logpdf(t, 0.5, 2.0).sum()),
+        (em.StandardPrior(em.Gamma(2.5, 1.5)), lambda t: stats.gamma.logpdf(t, 2.5, scale=1.5).sum()),
+        (em.StandardPrior(em.Uniform(0.0, 4.0)), lambda t: stats.uniform.logpdf(t, 0.0, 4.0).sum()),
+        (em.ImproperPosPrior(), lambda t: -np.log(t).sum()),
+        (em.ProductPrior([em.Normal(0.0, 1.0), em.Gamma(2.0, 2.0)], [1, 1]),
+         lambda t: stats.norm.logpdf(t[0]) + stats.gamma.logpdf(t[1], 2.0, scale=2.0)),
+    ]
+    for prior, ref in cases:
+        ups = [em.RandomWalkUpdate(em.UniformRandomWalk([0.1, 0.1]), [1, 2], prior=prior)]
+        o = orc.Oracle(law, ups, x, [1.0, 2.0], n_chains=1)
+        steps = list(em.MCMCSchedule(2, 1))
+        props = np.array([[[1.0], [2.0]], [[1.3], [2.4]]])          # step 1 re-proposes the start
+        exps = np.array([[1.0], [1e9]])
+        r = o.run(steps, replay=(props, exps))
+        ll0, ll1 = r["ll"][0, 0], r["ll_prop"][1, 0]
+        want = (ll1 - ll0) + ref(np.array([1.3, 2.4])) - ref(np.array([1.0, 2.0]))
+        assert abs(r["llr"][1, 0] - want) < 1e-12 * max(1.0, abs(want)), type(prior.dist if hasattr(prior, "dist") else prior)
