@@ -28,8 +28,8 @@ namespace extmcmc {
 namespace {
 constexpr int kBM = 16;    // observations per tile (2 x 16 x (D+4) + 64 x (D+4) doubles fit 227 KB at D = 256)
 constexpr int kBN = 64;    // chains per CTA
-constexpr int kNC = 256;   // 8 consumer warps; warp w owns chains 8w..8w+7 in both phases
-constexpr int kNT = kNC + 32;  // + 1 producer warp (TMA)
+constexpr int kNC = 256;   // 8 warps; warp w owns chains 8w..8w+7 in both phases
+constexpr int kNT = kNC;   // (a 9th producer warp would round up to 12 warps of register allocation)
 constexpr int kPad = 4;    // row padding (doubles) of the X tiles: 128-bit loads indexed (row tq, col 2 gq)
                            // and (row rho(gq), col 2 tq) are both bank-conflict free with stride D + 4
 constexpr int kPadT = 8;   // row padding of the Theta tile: 128-bit loads indexed (row gq, col 2 tq)
@@ -91,7 +91,7 @@ constexpr size_t logistic_smem() {
 }  // namespace
 
 template <int D>
-__global__ void __maxnreg__(224) sweep_logistic_kernel(LogisticArgs a) {
+__global__ void __launch_bounds__(kNT, 1) sweep_logistic_kernel(LogisticArgs a) {
     constexpr int LD = D + kPad, LDT = D + kPadT;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *Th = reinterpret_cast<double *>(smem_raw);   // [kBN][LDT]  Theta block, row = chain
@@ -99,7 +99,7 @@ __global__ void __maxnreg__(224) sweep_logistic_kernel(LogisticArgs a) {
     double *Rs = Xs + 2 * kBM * LD;                       // [kBM][kRPad] residuals y - sigmoid(z)
     double *ys = Rs + kBM * kRPad;                        // [2][kBM]
     uint64_t *bar = reinterpret_cast<uint64_t *>(ys + 2 * kBM);  // [2] full (TMA landed)
-    uint64_t *empty = bar + 2;                                   // [2] empty (all 8 consumer warps done)
+    unsigned int *done = reinterpret_cast<unsigned int *>(bar + 2);  // [2] warps done with a stage
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int gq = lane >> 2, tq = lane & 3;  // mma fragment coordinates: group id, thread in group
@@ -121,17 +121,15 @@ __global__ void __maxnreg__(224) sweep_logistic_kernel(LogisticArgs a) {
     if (tid == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
-        mbar_init(&empty[0], kNC / 32);
-        mbar_init(&empty[1], kNC / 32);
+        done[0] = done[1] = 0u;
         mbar_fence_init();
     }
     __syncthreads();
 
-    // Producer warp: one bulk copy per observation row (+ one for the y slice) into a 2-stage
-    // ring; a stage is refilled as soon as all 8 consumer warps released it.  There is no
-    // CTA-wide barrier in the main loop, so the consumer warps are free to drift: the two warps
-    // that share an SM sub-partition run half a tile apart (see the skew below) and one of them
-    // keeps the tensor pipe busy while the other is in its FP64 epilogue.
+    // One bulk copy per observation row (+ one for the y slice) into a 2-stage ring.  There is no
+    // CTA-wide barrier in the main loop: each warp counts itself out of a stage when it is done
+    // with it, and the warp that completes the count (the last one) refills the stage, so nobody
+    // ever waits for a slower warp.
     auto issue = [&](int t) {
         const int st = t & 1;
         const int64_t row0 = (t0 + t) * kBM;
@@ -141,14 +139,8 @@ __global__ void __maxnreg__(224) sweep_logistic_kernel(LogisticArgs a) {
             bulk_g2s(Xs + (st * kBM + lane) * LD, a.X + (row0 + lane) * D, (uint32_t)(D * 8), &bar[st]);
         if (lane == 0) bulk_g2s(ys + st * kBM, a.y + row0, (uint32_t)(kBM * 8), &bar[st]);
     };
-    if (w == kNC / 32) {
-        for (int t = 0; t < n_tiles; ++t) {
-            if (t >= 2) mbar_wait(&empty[t & 1], (uint32_t)((t >> 1) + 1) & 1u);
-            issue(t);
-        }
-        return;
-    }
-    // (a one-off skew of half the warps was tried and measured slower: they re-align through the ring)
+    if (w == 0)
+        for (int t = 0; t < 2 && t < n_tiles; ++t) issue(t);
 
     double G[D / 8][2];
 #pragma unroll
@@ -239,7 +231,14 @@ __global__ void __maxnreg__(224) sweep_logistic_kernel(LogisticArgs a) {
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[st]);  // this warp is done with the X stage
+        unsigned int prev = 0u;
+        if (lane == 0) prev = atomicAdd(&done[st], 1u);
+        prev = __shfl_sync(0xffffffffu, prev, 0);
+        if (prev == kNC / 32 - 1) {          // last warp out of this stage: refill it
+            if (lane == 0) done[st] = 0u;
+            __syncwarp();
+            if (t + 2 < n_tiles) issue(t + 2);
+        }
     }
 
     // ---- write the partials of this (segment, chain block) -----------------------------------
