@@ -27,6 +27,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: keep NCCL's version banner out of it
+os.environ["NCCL_DEBUG"] = os.environ.get("EXTMCMC_NCCL_DEBUG", "WARN")
 
 N_OBS = 1_000_000
 CHAINS_PER_GPU = 4096
