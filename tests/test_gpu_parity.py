@@ -266,3 +266,31 @@ def test_history_ring_staleness():
     with pytest.raises(_abi.ExtMCMCError):
         s.run(list(em.MCMCSchedule(7, 1)))          # block longer than the ring
     s.close()
+
+
+def test_full_size_cfg2_replay_parity():
+    """BASELINE cfg 2 at full size (C = 4096, N = 1e6) for 3 iterations.  The oracle runs chains
+    0..511 (one chain costs 6e6 logpdf evaluations per iteration); the GPU runs all 4096, chains
+    c and c mod 512 being replicas (same start, same replayed randomness), so every chain is
+    checked: the first 512 against the oracle, the rest against their replica, bit for bit."""
+    n, Cn, sub, M = 1_000_000, 4096, 512, 3
+    x = _data(n, seed=2)
+    ups = cfg2_updates()                                       # eps0 = 5e-3, k = 50, scale = 5e-4, ...
+    th_sub = theta_init_for(x, sub)
+    steps = list(em.MCMCSchedule(M, 2))
+    o = orc.Oracle(em.GsnTargetLaw([0.0]), ups, x, th_sub, sub, seed=3)
+    ro = o.run(steps, n_threads=8)
+    reps = Cn // sub
+    g = GpuSession(em.GsnTargetLaw([0.0]), ups, x, np.tile(th_sub, (1, reps)), Cn, seed=3, n_steps_hint=len(steps))
+    assert g.variant() == "gsn1d_chains_R8"
+    rg = g.run(steps, replay=(np.tile(ro["proposals"], (1, 1, reps)), np.tile(ro["exp_draws"], (1, reps))))
+    first = {k: v[..., :sub] for k, v in rg.items() if hasattr(v, "shape")}
+    rep = compare_histories(ro, first)
+    assert rep["accept_mismatch"] == 0 and rep["theta_bitexact"], rep
+    assert rep["ll_rel_err"] < LL_RTOL, rep                     # observed ~1e-15
+    if rep["near_ties"] == 0:
+        for k in ("theta", "theta_prop", "ll", "ll_prop", "accepted"):
+            full = rg[k].reshape(rg[k].shape[:-1] + (reps, sub))
+            assert np.array_equal(full, np.broadcast_to(full[..., :1, :], full.shape)), k
+        assert np.array_equal(g.eps(1)[:, :sub], o.eps(1)) and np.array_equal(g.eps(2)[:, :sub], o.eps(2))
+    g.close()
