@@ -390,6 +390,24 @@ def run_cfg5(args):
     ms_total = float(t.item())
     variant = ws.lib.extmcmc_sweep_variant_name(ws.handle).decode()
     ws.close()
+    # the sweep kernel alone (every launch bracketed by events; single rank only: the instrumented
+    # handle cannot replay graphs)
+    sweep_only_ms = None
+    if world == 1:
+        import ctypes
+        bki = em.CUDAMCMCBackend(n_chains=C, device=local, seed=6, history="none", block_len=NU,
+                                 use_graphs=False, instrument=True)
+        mi = em.MCMC(ups, backend=bki)
+        init_(mi, 1, dict(P=em.GsnTargetLaw([0.0]), obs=em.DeviceGeneratedObs(cnt, 1.5, 2.0, 6, first)),
+              np.repeat(np.array([[1.5], [4.0]]), C, axis=1))
+        wi = mi.workspace
+        msw, nl = ctypes.c_float(), ctypes.c_int64()
+        timed_steps(wi, _abi, C, 0, 3, flush=False)
+        wi._ck(wi.lib.extmcmc_get_sweep_time(wi.handle, ctypes.byref(msw), ctypes.byref(nl)))
+        timed_steps(wi, _abi, C, 10, 0, flush=False)
+        wi._ck(wi.lib.extmcmc_get_sweep_time(wi.handle, ctypes.byref(msw), ctypes.byref(nl)))
+        sweep_only_ms = msw.value / max(nl.value, 1)
+        wi.close()
     if dist is not None:
         dist.destroy_process_group()
     if rank != 0:
@@ -408,6 +426,8 @@ def run_cfg5(args):
         "roofline": {"kernel": variant, "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": gbs / peaks["hbm_gbs"], "peak_source": peak_src,
                      "note": "per-GPU bytes of one update step / whole update-step time (sweep + reduce + all-reduce + accept)",
+                     "sweep_kernel_ms": sweep_only_ms,
+                     "sweep_kernel_frac": (8.0 * cnt / (sweep_only_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]) if sweep_only_ms else None,
                      "traffic": None},
         "gpu_launches": launches, "clocks": clocks}))
 

@@ -8,6 +8,8 @@
 #include "dev_state.cuh"
 #include "philox.cuh"
 #include "step_kernels.h"
+#include "tma.cuh"
+#include "sweep.h"
 
 namespace extmcmc {
 
@@ -251,11 +253,15 @@ __device__ __forceinline__ void load_step_ctx(StepCtx *ctx, const DevState &d, c
 //     + set_proposal! (src/run.jl:221-240): writes the full proposal and the law
 //     constants the sweep consumes.
 // ---------------------------------------------------------------------------------
+// state_regs / eps_regs: optional register copies (current full state, this update's eps) that a
+// caller already holds; they spare the dependent global loads on the accept kernel's critical path.
 __device__ __forceinline__ void propose_chain(const DevState &d, const StepDesc &sd, const DevUpdate &u,
-                                              int64_t c) {
+                                              int64_t c, const double *state_regs = nullptr,
+                                              const double *eps_regs = nullptr) {
     const int n = u.n_coords;
     double th[kMaxCoords], prop[kMaxCoords];
-    for (int i = 0; i < n; ++i) th[i] = d.theta[(int64_t)u.coords[i] * d.C + c];
+    for (int i = 0; i < n; ++i)
+        th[i] = state_regs ? state_regs[u.coords[i]] : d.theta[(int64_t)u.coords[i] * d.C + c];
 
     uint32_t used = 0;
     if (d.rng_mode == EXTMCMC_RNG_REPLAY) {
@@ -267,7 +273,7 @@ __device__ __forceinline__ void propose_chain(const DevState &d, const StepDesc 
             if (u.kernel == EXTMCMC_KERNEL_RW_UNIFORM) {
                 for (int i = 0; i < n; ++i) {
                     const double r = rng.next();
-                    const double e = u.eps[(int64_t)i * d.C + c];
+                    const double e = eps_regs ? eps_regs[i] : u.eps[(int64_t)i * d.C + c];
                     const double a = -e, b = e;
                     const double U = a + (b - a) * r;  // rand(Uniform(-eps, eps))
                     prop[i] = u.pos[i] ? th[i] * exp(U) : th[i] + U;  // random_walk.jl:72
@@ -308,7 +314,8 @@ __device__ __forceinline__ void propose_chain(const DevState &d, const StepDesc 
     d.n_used[c] = used;
     for (int i = 0; i < n; ++i) d.prop_loc[(int64_t)i * d.C + c] = prop[i];
     // full proposal = current state with the update's coordinates replaced (run.jl:237-239)
-    for (int j = 0; j < d.p; ++j) d.prop_full[(int64_t)j * d.C + c] = d.theta[(int64_t)j * d.C + c];
+    for (int j = 0; j < d.p; ++j)
+        d.prop_full[(int64_t)j * d.C + c] = state_regs ? state_regs[j] : d.theta[(int64_t)j * d.C + c];
     for (int i = 0; i < n; ++i) d.prop_full[(int64_t)u.coords[i] * d.C + c] = prop[i];
     law_prepare(d, c, d.prop_full + c, d.C);
 }
@@ -448,13 +455,115 @@ __global__ void __launch_bounds__(256) finalize_loglik_kernel(DevState d, double
 // update_adaptation! (src/run.jl:136-173, src/transition_kernels/adaptation.jl:273-329).
 // n_eps = entries of the update's step-size vector (p_u for the uniform walk, 1 for MALA).
 // ---------------------------------------------------------------------------------
+// Everything the post-decision code reads, fetched into registers BEFORE the decision is known
+// (small parameter vectors only): under PDL these loads are issued while the sweep is still
+// running, so that after the sweep only the partial sums remain on the critical path.
+constexpr int kPreP = 4;
+struct Prefetch {
+    double state[kPreP];        // current full state theta
+    double prop[kPreP];         // full proposal
+    double mean[kPreP];
+    double cov[kPreP * kPreP];
+    double ra_prev;
+    int acc_out;
+    int32_t adapt_prop, adapt_acc;
+    int64_t tot_prop, tot_acc;
+    double eps[kMaxCoords];     // this update's step sizes
+    double new_state[kPreP];    // out: state after the decision
+};
+
+__device__ __forceinline__ void prefetch_chain(const DevState &d, const StepDesc &sd, const DevUpdate &u,
+                                               int64_t c, Prefetch &pf) {
+    const int64_t C = d.C;
+    const int p = d.p;
+    for (int j = 0; j < p; ++j) {
+        pf.state[j] = d.theta[(int64_t)j * C + c];
+        pf.prop[j] = d.prop_full[(int64_t)j * C + c];
+    }
+    if (d.stats_mode != 2) {
+        for (int j = 0; j < p; ++j) pf.mean[j] = d.mean[(int64_t)j * C + c];
+        const int nc = d.stats_mode == 0 ? p * p : p;
+        for (int j = 0; j < nc; ++j) pf.cov[j] = d.cov[(int64_t)j * C + c];
+    }
+    pf.ra_prev = sd.ra_prev_valid ? u.ra_val[c] : 0.0;
+    pf.acc_out = sd.acc_out_valid ? (int)u.acc_ring[(sd.mcmciter % d.W) * C + c] : 0;
+    pf.adapt_prop = u.adapt_prop[c];
+    pf.adapt_acc = u.adapt_acc[c];
+    pf.tot_prop = u.tot_prop[c];
+    pf.tot_acc = u.tot_acc[c];
+}
+
 __device__ __forceinline__ void post_decision(const DevState &d, const StepDesc &sd, const DevUpdate &u,
                                               int64_t c, bool accepted, double ll_new, double ll_prop,
-                                              int n_eps) {
+                                              int n_eps, Prefetch *pf = nullptr) {
     const int64_t C = d.C;
     d.ll[c] = ll_new;
     // history row (state_history / state_proposal_history / ll_history / acceptance_history)
     const int64_t slot = sd.seq % d.H;
+    if (pf) {
+        // register path: identical arithmetic, no loads
+        const int p = d.p;
+        for (int j = 0; j < p; ++j) {
+            pf->new_state[j] = accepted ? pf->prop[j] : pf->state[j];
+            d.h_theta[(slot * p + j) * C + c] = pf->new_state[j];
+            d.h_prop[(slot * p + j) * C + c] = pf->prop[j];
+        }
+        d.h_ll[slot * C + c] = ll_new;
+        d.h_llp[slot * C + c] = ll_prop;
+        d.h_acc[slot * C + c] = accepted ? 1 : 0;
+        const int64_t N = sd.stat_n;
+        if (d.stats_mode != 2) {
+            const double f_old = (double)(N - 1) / (double)N;
+            const double f_mean = (double)N / (double)(N + 1);
+            const double f_new = (double)(N + 1) / (double)N;
+            double nm[kPreP];
+            for (int a = 0; a < p; ++a) nm[a] = pf->mean[a] * f_mean + pf->new_state[a] / (double)(N + 1);
+            if (d.stats_mode == 0) {
+                for (int b = 0; b < p; ++b)
+                    for (int a = 0; a < p; ++a) {
+                        const double old_sum_sq = f_old * pf->cov[a + b * p] + pf->mean[a] * pf->mean[b];
+                        const double new_sum_sq = old_sum_sq + (pf->new_state[a] * pf->new_state[b]) / (double)N;
+                        d.cov[(int64_t)(a + b * p) * C + c] = new_sum_sq - f_new * (nm[a] * nm[b]);
+                    }
+            } else {
+                for (int a = 0; a < p; ++a) {
+                    const double old_sum_sq = f_old * pf->cov[a] + pf->mean[a] * pf->mean[a];
+                    const double new_sum_sq = old_sum_sq + (pf->new_state[a] * pf->new_state[a]) / (double)N;
+                    d.cov[(int64_t)a * C + c] = new_sum_sq - f_new * (nm[a] * nm[a]);
+                }
+            }
+            for (int a = 0; a < p; ++a) d.mean[(int64_t)a * C + c] = nm[a];
+        }
+        {
+            const int W = d.W;
+            const int64_t mn = (int64_t)W < N ? (int64_t)W : N;
+            u.ra_val[c] = (pf->ra_prev * (double)W + (double)((int)accepted - pf->acc_out)) / (double)mn;
+            u.acc_ring[(sd.mcmciter % W) * C + c] = accepted ? 1 : 0;
+        }
+        u.tot_prop[c] = pf->tot_prop + 1;
+        u.tot_acc[c] = pf->tot_acc + (accepted ? 1 : 0);
+        if (u.adapt_kind == EXTMCMC_ADAPT_UNIF_RW || u.adapt_kind == EXTMCMC_ADAPT_MALA) {
+            int32_t prop_n = pf->adapt_prop + 1;
+            int32_t acc_n = pf->adapt_acc + (accepted ? 1 : 0);
+            if (prop_n >= u.adapt_every_k) {
+                const double r = (double)sd.mcmciter / (double)u.adapt_every_k - u.offset;
+                const double delta = u.scale / sqrt(r > 1.0 ? r : 1.0);
+                const double a_r = (double)acc_n / (double)prop_n;
+                prop_n = 0; acc_n = 0;
+                const double sgn = (a_r > u.target) ? 1.0 : -1.0;
+                for (int i = 0; i < n_eps; ++i) {
+                    double e = pf->eps[i] + sgn * delta;
+                    e = e < u.vmax ? e : u.vmax;
+                    e = e > u.vmin ? e : u.vmin;
+                    pf->eps[i] = e;
+                    u.eps[(int64_t)i * C + c] = e;
+                }
+            }
+            u.adapt_prop[c] = prop_n;
+            u.adapt_acc[c] = acc_n;
+        }
+        return;
+    }
     for (int j = 0; j < d.p; ++j) {
         d.h_theta[(slot * d.p + j) * C + c] = d.theta[(int64_t)j * C + c];
         d.h_prop[(slot * d.p + j) * C + c] = d.prop_full[(int64_t)j * C + c];
@@ -586,9 +695,72 @@ accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fuse_ne
     constexpr int kRedChains = kRedThreads / SL;
     __shared__ double sh[kRedThreads];
     __shared__ StepCtx ctx, ctx_next;
+    // PDL: this kernel may have been scheduled while the likelihood sweep is still running.
+    // Everything up to griddep_wait() only READS state that was final before the sweep started
+    // (chain state, proposal, step sizes, law constants, RNG counters) -- the transition-density
+    // and prior terms and the Exp(1) draw are computed here, hidden behind the sweep.
+    griddep_launch_dependents();
     load_step_ctx(&ctx, d, descs, k);
     if (fuse_next) load_step_ctx(&ctx_next, d, descs, k + 1);
     const int64_t c = (int64_t)blockIdx.x * kRedChains + (threadIdx.x % kRedChains);
+    const bool worker = (threadIdx.x / kRedChains) == 0 && c < d.C;
+    const StepDesc &sd = ctx.sd;
+    const DevUpdate &u = ctx.u;
+    const int n = u.n_coords;
+    const int64_t C = d.C;
+    double th[kMaxCoords], prop[kMaxCoords], eps[kMaxCoords];
+    double q_back = 0.0, q_fwd = 0.0, lp_prop = 0.0, lp_cur = 0.0, E = 0.0, ll_cur = 0.0;
+    if (worker) {
+        // update_workspaces! (run.jl:101-112): ll of the previously executed update; on the
+        // very first element it is still the initial -Inf (workspaces.jl:425)
+        ll_cur = sd.first ? -INFINITY : d.ll[c];
+        for (int i = 0; i < n; ++i) {
+            th[i] = d.theta[(int64_t)u.coords[i] * C + c];
+            prop[i] = d.prop_loc[(int64_t)i * C + c];
+            eps[i] = u.kernel == EXTMCMC_KERNEL_RW_UNIFORM ? u.eps[(int64_t)i * C + c] : 0.0;
+        }
+        if (u.kernel == EXTMCMC_KERNEL_RW_UNIFORM) {
+            q_back = log_q_unif(u, eps, th);    // theta° -> theta
+            q_fwd = log_q_unif(u, eps, prop);   // theta -> theta°
+        } else {
+            double Sg[kMaxGaussCoords * kMaxGaussCoords], LA[kMaxGaussCoords * kMaxGaussCoords],
+                LB[kMaxGaussCoords * kMaxGaussCoords];
+            load_sigma(u, false, C, c, Sg);
+            bool ok = chol_lower_sym_upper(Sg, n, LA);
+            if (u.kernel == EXTMCMC_KERNEL_RW_GAUSS_MIX) {
+                load_sigma(u, true, C, c, Sg);
+                ok = chol_lower_sym_upper(Sg, n, LB) && ok;
+            }
+            if (!ok) {
+                *d.err_flag = 1;
+                q_back = NAN;
+            } else {
+                q_back = log_q_any(u, eps, LA, LB, prop, th);   // theta° -> theta
+                q_fwd = log_q_any(u, eps, LA, LB, th, prop);    // theta -> theta°
+            }
+        }
+        lp_prop = log_prior(u, prop);
+        lp_cur = log_prior(u, th);
+        E = draw_exp(d, sd, c);
+    }
+    // register path for small models without Haario adaptation (cfg 1, 2, 5)
+    const bool use_pf = d.p <= kPreP && d.n_haario == 0;
+    Prefetch pf;
+    double law0 = 0.0, law1 = 0.0, eps_next[kMaxCoords];
+    bool next_eps_ok = false;
+    if (worker && use_pf) {
+        prefetch_chain(d, sd, u, c, pf);
+        for (int i = 0; i < n; ++i) pf.eps[i] = eps[i];
+        if (d.law == EXTMCMC_LAW_GSN_IID_1D) { law0 = d.lawc[C + c]; law1 = d.lawc[2 * C + c]; }
+        // step sizes of the NEXT element's update (fused proposal); not when it is this very update,
+        // whose eps the adaptation below may still change
+        if (fuse_next && ctx_next.sd.pidx != sd.pidx && ctx_next.u.kernel == EXTMCMC_KERNEL_RW_UNIFORM) {
+            for (int i = 0; i < ctx_next.u.n_coords; ++i) eps_next[i] = ctx_next.u.eps[(int64_t)i * C + c];
+            next_eps_ok = true;
+        }
+    }
+
+    griddep_wait();   // the sweep (and, under sharding, the exchange) has finished
     double S;
     if (d.p2p) {
         S = wait_and_combine(d, ctx.sd, c);
@@ -597,56 +769,35 @@ accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fuse_ne
     } else {
         S = reduce_segments<SL>(d, sh);
     }
-    if ((threadIdx.x / kRedChains) != 0 || c >= d.C) return;
-    const StepDesc &sd = ctx.sd;
-    const DevUpdate &u = ctx.u;
-    const int n = u.n_coords;
-    const int64_t C = d.C;
-    const double ll_prop = law_finalize(d, c, S, d.prop_full + c);
-    // update_workspaces! (run.jl:101-112): ll of the previously executed update; on the
-    // very first element it is still the initial -Inf (workspaces.jl:425)
-    const double ll_cur = sd.first ? -INFINITY : d.ll[c];
-
-    double th[kMaxCoords], prop[kMaxCoords], eps[kMaxCoords];
-    for (int i = 0; i < n; ++i) {
-        th[i] = d.theta[(int64_t)u.coords[i] * C + c];
-        prop[i] = d.prop_loc[(int64_t)i * C + c];
-        eps[i] = u.kernel == EXTMCMC_KERNEL_RW_UNIFORM ? u.eps[(int64_t)i * C + c] : 0.0;
-    }
+    if (!worker) return;
+    const double ll_prop = (use_pf && d.law == EXTMCMC_LAW_GSN_IID_1D)
+                               ? (double)d.n_obs_total * law0 - S * law1   // = law_finalize, constants prefetched
+                               : law_finalize(d, c, S, d.prop_full + c);
     // llr, strictly left to right (run.jl:271-277)
     double llr = ll_prop - ll_cur;
-    if (u.kernel == EXTMCMC_KERNEL_RW_UNIFORM) {
-        llr = llr + log_q_unif(u, eps, th);    // theta° -> theta
-        llr = llr - log_q_unif(u, eps, prop);  // theta -> theta°
-    } else {
-        double Sg[kMaxGaussCoords * kMaxGaussCoords], LA[kMaxGaussCoords * kMaxGaussCoords],
-            LB[kMaxGaussCoords * kMaxGaussCoords];
-        load_sigma(u, false, C, c, Sg);
-        bool ok = chol_lower_sym_upper(Sg, n, LA);
-        if (u.kernel == EXTMCMC_KERNEL_RW_GAUSS_MIX) {
-            load_sigma(u, true, C, c, Sg);
-            ok = chol_lower_sym_upper(Sg, n, LB) && ok;
-        }
-        if (!ok) {
-            *d.err_flag = 1;
-            llr = NAN;
-        } else {
-            llr = llr + log_q_any(u, eps, LA, LB, prop, th);   // theta° -> theta
-            llr = llr - log_q_any(u, eps, LA, LB, th, prop);   // theta -> theta°
-        }
-    }
-    llr = llr + log_prior(u, prop);
-    llr = llr - log_prior(u, th);
+    llr = llr + q_back;
+    llr = llr - q_fwd;
+    llr = llr + lp_prop;
+    llr = llr - lp_cur;
 
-    const double E = draw_exp(d, sd, c);
     const bool accepted = E > -llr;  // NaN compares false -> reject
     const double ll_new = accepted ? ll_prop : ll_cur;
     if (accepted)
         for (int i = 0; i < n; ++i) d.theta[(int64_t)u.coords[i] * C + c] = prop[i];
-    post_decision(d, sd, u, c, accepted, ll_new, ll_prop, u.kernel == EXTMCMC_KERNEL_RW_UNIFORM ? n : 0);
+    const int n_eps = u.kernel == EXTMCMC_KERNEL_RW_UNIFORM ? n : 0;
+    post_decision(d, sd, u, c, accepted, ll_new, ll_prop, n_eps, use_pf ? &pf : nullptr);
     // proposal of the NEXT schedule element of this block, fused here: the chain's thread
     // already holds its freshly committed state, and one launch per update step is saved
-    if (fuse_next) propose_chain(d, ctx_next.sd, ctx_next.u, c);
+    if (fuse_next) {
+        if (use_pf) {
+            const double *en = next_eps_ok ? eps_next
+                               : (ctx_next.sd.pidx == sd.pidx && ctx_next.u.kernel == EXTMCMC_KERNEL_RW_UNIFORM) ? pf.eps
+                                                                                                            : nullptr;
+            propose_chain(d, ctx_next.sd, ctx_next.u, c, pf.new_state, en);
+        } else {
+            propose_chain(d, ctx_next.sd, ctx_next.u, c);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------
@@ -877,10 +1028,22 @@ static inline int red_blocks_for(int64_t C, int sl) {
 }
 static inline int slices_for(const DevState &d) { return (!d.use_ssum && d.S * d.G > 16) ? 8 : 1; }
 void launch_accept(const DevState &d, const StepDesc *descs, int k, int fuse_next, cudaStream_t st) {
-    if (slices_for(d) == 8)
-        accept_kernel<8><<<red_blocks_for(d.C, 8), 256, 0, st>>>(d, descs, k, fuse_next);
-    else
-        accept_kernel<1><<<red_blocks_for(d.C, 1), 256, 0, st>>>(d, descs, k, fuse_next);
+    // PDL attribute: the accept kernel's prologue overlaps the tail of the sweep
+    cudaLaunchConfig_t cfg{};
+    cfg.blockDim = dim3(256);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = (pdl_mask() >> 1) & 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (slices_for(d) == 8) {
+        cfg.gridDim = dim3(red_blocks_for(d.C, 8));
+        cudaLaunchKernelEx(&cfg, accept_kernel<8>, d, descs, k, fuse_next);
+    } else {
+        cfg.gridDim = dim3(red_blocks_for(d.C, 1));
+        cudaLaunchKernelEx(&cfg, accept_kernel<1>, d, descs, k, fuse_next);
+    }
 }
 void launch_grad_finalize(const DevState &d, const double *src, double *ll_out, double *grad_out,
                           cudaStream_t st) {

@@ -5,6 +5,13 @@
 
 namespace extmcmc {
 
+// Which launches carry the programmatic-dependent-launch attribute: bit 0 sweep, bit 1 accept
+// (EXTMCMC_PDL environment variable).  Default 2: only the accept kernel starts early (its
+// prologue hides behind the sweep).  Letting the sweep start early too was measured 45 % SLOWER at
+// cfg 2: its CTAs land on SMs still holding accept blocks, the grid no longer fits in one
+// balanced wave of 4 CTAs per SM, and the second wave doubles the tail.
+int pdl_mask();
+
 enum { SWEEP_VARIANT_AUTO = 0, SWEEP_VARIANT_CHAINS = 1, SWEEP_VARIANT_OBS = 2 };
 
 struct SweepPlan {

@@ -27,6 +27,7 @@
 // groups, group g has its own per-chain mean mu[g][C] (gridDim.z = G), and with GRAD = true the
 // first-order sum  T = sum_i (x_i - mu)  is accumulated next to S for gradient-based updates.
 #include <cstdint>
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include "sweep.h"
 #include "tma.cuh"
@@ -63,14 +64,6 @@ sweep_gsn1d_chains_kernel(Gsn1dArgs a) {
     const int64_t len = hi - lo;
     const int n_tiles = (int)((len + TILE - 1) / TILE);
 
-    double m[R], acc[R], accT[GRAD ? R : 1];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const int64_t c = cbase + (int64_t)r * NT + tid;
-        m[r] = c < C ? mu[c] : 0.0;
-        acc[r] = 0.0;
-        if (GRAD) accT[r] = 0.0;
-    }
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) mbar_init(&bar[s], 1);
@@ -88,6 +81,20 @@ sweep_gsn1d_chains_kernel(Gsn1dArgs a) {
     };
     if (tid == 0)
         for (int t = 0; t < STAGES && t < n_tiles; ++t) issue(t);
+
+    // Everything above touches only the (constant) observations.  The per-chain means come from
+    // the preceding kernel (proposal / accept): under PDL this kernel may have started before
+    // that one finished, so wait for it here, then let our own successor start early.
+    griddep_wait();
+    griddep_launch_dependents();
+    double m[R], acc[R], accT[GRAD ? R : 1];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int64_t c = cbase + (int64_t)r * NT + tid;
+        m[r] = c < C ? mu[c] : 0.0;
+        acc[r] = 0.0;
+        if (GRAD) accT[r] = 0.0;
+    }
 
     for (int t = 0; t < n_tiles; ++t) {
         const int st = t % STAGES;
@@ -157,13 +164,6 @@ sweep_gsn1d_obs_kernel(Gsn1dArgs a) {
     const int64_t len = hi - lo;
     const int n_tiles = (int)((len + TILE - 1) / TILE);
 
-    double m[CB], acc[CB], accT[GRAD ? CB : 1];
-#pragma unroll
-    for (int c = 0; c < CB; ++c) {
-        m[c] = c < C ? mu[c] : 0.0;
-        acc[c] = 0.0;
-        if (GRAD) accT[c] = 0.0;
-    }
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) mbar_init(&bar[s], 1);
         mbar_fence_init();
@@ -180,6 +180,16 @@ sweep_gsn1d_obs_kernel(Gsn1dArgs a) {
     };
     if (tid == 0)
         for (int t = 0; t < STAGES && t < n_tiles; ++t) issue(t);
+
+    griddep_wait();               // the means below are written by the preceding kernel (PDL)
+    griddep_launch_dependents();
+    double m[CB], acc[CB], accT[GRAD ? CB : 1];
+#pragma unroll
+    for (int c = 0; c < CB; ++c) {
+        m[c] = c < C ? mu[c] : 0.0;
+        acc[c] = 0.0;
+        if (GRAD) accT[c] = 0.0;
+    }
 
     auto eat = [&](const double2 x) {
 #pragma unroll
@@ -256,13 +266,29 @@ constexpr size_t kObsSmem(int cb) {
     return (size_t)kObsStages * kObsTile * 8 + kObsStages * 8 + (size_t)2 * (kObsNT / 32) * cb * 8;
 }
 
+// launch with the PDL attribute: the kernel may be scheduled while its predecessor drains
+template <typename Kern>
+void launch_pdl(Kern kern, dim3 grid, int threads, size_t smem, cudaStream_t st, const Gsn1dArgs &a) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_mask() & 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, a);
+}
+
 template <int R>
 void launch_chains(const SweepPlan &pl, const Gsn1dArgs &a, bool grad, cudaStream_t st) {
     dim3 grid(pl.S, pl.groups, a.G);
     if (grad)
-        sweep_gsn1d_chains_kernel<R, kChainsNT, kChainsTile, kChainsStages, true><<<grid, kChainsNT, 0, st>>>(a);
+        launch_pdl(sweep_gsn1d_chains_kernel<R, kChainsNT, kChainsTile, kChainsStages, true>, grid, kChainsNT, 0, st, a);
     else
-        sweep_gsn1d_chains_kernel<R, kChainsNT, kChainsTile, kChainsStages, false><<<grid, kChainsNT, 0, st>>>(a);
+        launch_pdl(sweep_gsn1d_chains_kernel<R, kChainsNT, kChainsTile, kChainsStages, false>, grid, kChainsNT, 0, st, a);
 }
 template <int CB>
 cudaError_t prep_obs() {
@@ -276,13 +302,18 @@ template <int CB>
 void launch_obs(const SweepPlan &pl, const Gsn1dArgs &a, bool grad, cudaStream_t st) {
     dim3 grid(pl.S, 1, a.G);
     if (grad)
-        sweep_gsn1d_obs_kernel<CB, kObsNT, kObsTile, kObsStages, true><<<grid, kObsNT, kObsSmem(CB), st>>>(a);
+        launch_pdl(sweep_gsn1d_obs_kernel<CB, kObsNT, kObsTile, kObsStages, true>, grid, kObsNT, kObsSmem(CB), st, a);
     else
-        sweep_gsn1d_obs_kernel<CB, kObsNT, kObsTile, kObsStages, false><<<grid, kObsNT, kObsSmem(CB), st>>>(a);
+        launch_pdl(sweep_gsn1d_obs_kernel<CB, kObsNT, kObsTile, kObsStages, false>, grid, kObsNT, kObsSmem(CB), st, a);
 }
 }  // namespace
 
 // n_obs: observations of the LARGEST group (all of them when G = 1)
+int pdl_mask() {
+    static const int m = [] { const char *e = getenv("EXTMCMC_PDL"); return e ? atoi(e) : 2; }();
+    return m;
+}
+
 SweepPlan plan_sweep_gsn1d(int64_t C, int64_t n_obs, int force_variant, int num_sms, int G) {
     SweepPlan pl{};
     pl.G = G;

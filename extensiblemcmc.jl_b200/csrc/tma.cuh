@@ -42,4 +42,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     } while (!done);
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-
+// serialization attribute may start while its predecessor is still running; griddep_wait()
+// blocks until the predecessor has completed and its writes are visible, and
+// griddep_launch_dependents() lets the successor start early.  Both are no-ops for a kernel
+// launched without the attribute.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 }  // namespace extmcmc
