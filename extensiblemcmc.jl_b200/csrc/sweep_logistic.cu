@@ -28,8 +28,7 @@ namespace extmcmc {
 namespace {
 constexpr int kBM = 16;    // observations per tile (2 x 16 x (D+4) + 64 x (D+4) doubles fit 227 KB at D = 256)
 constexpr int kBN = 64;    // chains per CTA
-constexpr int kNC = 256;   // 8 warps; warp w owns chains 8w..8w+7 in both phases
-constexpr int kNT = kNC;   // (a 9th producer warp would round up to 12 warps of register allocation)
+constexpr int kNT = 512;   // 16 warps = 8 chain blocks x 2 halves (see the kernel comment)
 constexpr int kPad = 4;    // row padding (doubles) of the X tiles: 128-bit loads indexed (row tq, col 2 gq)
                            // and (row rho(gq), col 2 tq) are both bank-conflict free with stride D + 4
 constexpr int kPadT = 8;   // row padding of the Theta tile: 128-bit loads indexed (row gq, col 2 tq)
@@ -86,22 +85,38 @@ __device__ __forceinline__ void softplus_sigmoid(double z, double &sp, double &s
 template <int D>
 constexpr size_t logistic_smem() {
     return (size_t)kBN * (D + kPadT) * 8 + (size_t)2 * kBM * (D + kPad) * 8 + (size_t)kBM * kRPad * 8 +
-           2 * kBM * 8 + 4 * 8;
+           (size_t)(kNT / 32) * 64 * 8 + 2 * kBM * 8 + 4 * 8;
+}
+
+__device__ __forceinline__ void pair_sync(int id) {  // named barrier for the two warps of a chain block
+    asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
 }
 }  // namespace
 
+// 16 warps: warp (w8 = w % 8, h = w / 8).  The two warps of a pair share chain block w8 (8 chains):
+//   phase 1  each takes half of the feature range (k in [h D/2, (h+1) D/2)) for the whole 16 x 8
+//            Z block, the halves are exchanged through shared memory (the partner's half of the
+//            sum for MY 8 observations), pair barrier;
+//   epilogue each handles its own 8 observations (rows 8h .. 8h+7), writes its R rows, pair barrier;
+//   phase 2  each accumulates G for its half of the feature columns over all 16 observations.
+// Four warps per SM sub-partition instead of two: while one pair sits in its epilogue or at a
+// barrier, the others keep the MMA pipe busy.  G costs 64 registers per thread (D = 256), which is
+// what makes 512 threads x 128 registers possible.
 template <int D>
 __global__ void __launch_bounds__(kNT, 1) sweep_logistic_kernel(LogisticArgs a) {
     constexpr int LD = D + kPad, LDT = D + kPadT;
+    constexpr int NW = kNT / 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *Th = reinterpret_cast<double *>(smem_raw);   // [kBN][LDT]  Theta block, row = chain
     double *Xs = Th + kBN * LDT;                          // [2][kBM][LD] observation tiles
     double *Rs = Xs + 2 * kBM * LD;                       // [kBM][kRPad] residuals y - sigmoid(z)
-    double *ys = Rs + kBM * kRPad;                        // [2][kBM]
+    double *Zp = Rs + kBM * kRPad;                        // [NW][64]     partial Z handed to the partner
+    double *ys = Zp + NW * 64;                            // [2][kBM]
     uint64_t *bar = reinterpret_cast<uint64_t *>(ys + 2 * kBM);  // [2] full (TMA landed)
     unsigned int *done = reinterpret_cast<unsigned int *>(bar + 2);  // [2] warps done with a stage
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int w8 = w & 7, h = w >> 3;
     const int gq = lane >> 2, tq = lane & 3;  // mma fragment coordinates: group id, thread in group
     const int seg = blockIdx.x;
     const int64_t C = a.C;
@@ -128,8 +143,7 @@ __global__ void __launch_bounds__(kNT, 1) sweep_logistic_kernel(LogisticArgs a) 
 
     // One bulk copy per observation row (+ one for the y slice) into a 2-stage ring.  There is no
     // CTA-wide barrier in the main loop: each warp counts itself out of a stage when it is done
-    // with it, and the warp that completes the count (the last one) refills the stage, so nobody
-    // ever waits for a slower warp.
+    // with it, and the warp that completes the count (the last one) refills the stage.
     auto issue = [&](int t) {
         const int st = t & 1;
         const int64_t row0 = (t0 + t) * kBM;
@@ -142,10 +156,14 @@ __global__ void __launch_bounds__(kNT, 1) sweep_logistic_kernel(LogisticArgs a) 
     if (w == 0)
         for (int t = 0; t < 2 && t < n_tiles; ++t) issue(t);
 
-    double G[D / 8][2];
+    constexpr int NPH = D / 32;       // column pairs (16 features each) of this warp's half
+    double G[2 * NPH][2];
 #pragma unroll
-    for (int nb = 0; nb < D / 8; ++nb) G[nb][0] = G[nb][1] = 0.0;
-    double ll0 = 0.0, ll1 = 0.0;  // chains cbase + 8w + 2 tq + {0, 1}, rows gq, gq + 8, ...
+    for (int nb = 0; nb < 2 * NPH; ++nb) G[nb][0] = G[nb][1] = 0.0;
+    double ll0 = 0.0, ll1 = 0.0;  // chains cbase + 8 w8 + 2 tq + {0, 1}, observation rows 8h + rho(gq)
+    // fragment row gq stands for observation rho(gq) of the 8-block (bits 0 and 1 swapped): the two
+    // rows a quarter-warp touches are then 2 apart, which the D + 4 stride separates (128-bit loads)
+    const int rq = (gq & 4) | ((gq & 1) << 1) | ((gq >> 1) & 1);
 
     for (int t = 0; t < n_tiles; ++t) {
         const int st = t & 1;
@@ -153,28 +171,24 @@ __global__ void __launch_bounds__(kNT, 1) sweep_logistic_kernel(LogisticArgs a) 
         const double *X = Xs + st * kBM * LD;
         const int64_t row0 = (t0 + t) * kBM;
 
-        // ---- phase 1: Z[16 x 8(w)] = X[16 x D] . Th[8w.., :]^T  -------------------------------
-        // The k index of the MMA fragments is a relabelling of the real feature index: fragment
-        // slot tq of MMA e (e = 0, 1) of pair s stands for feature 8s + 2 tq + e, so that one
-        // LDS.128 per operand feeds two MMAs, and the two MMAs go to independent accumulators.
-        constexpr int MB = kBM / 8;
+        // ---- phase 1: half of the k range for Z[16 x 8(w8)] ---------------------------------------
+        // The k index of the MMA fragments is a relabelling of the real feature index: fragment slot
+        // tq of MMA e (e = 0, 1) of pair s stands for feature 8s + 2 tq + e, so that one LDS.128 per
+        // operand feeds two MMAs, and the two MMAs go to independent accumulators.
+        constexpr int MB = kBM / 8, KH = D / 2;
         double za[MB][2], zb[MB][2];
 #pragma unroll
         for (int m = 0; m < MB; ++m) za[m][0] = za[m][1] = zb[m][0] = zb[m][1] = 0.0;
-        // fragment row gq stands for observation rho(gq) of the 8-block (bits 0 and 1 swapped):
-        // the two rows a quarter-warp touches are then 2 apart, which the D + 4 stride separates
-        const int rq = (gq & 4) | ((gq & 1) << 1) | ((gq >> 1) & 1);
-        const double *Bp = Th + (8 * w + gq) * LDT + 2 * tq;
-        const double *Ap = X + rq * LD + 2 * tq;
-        // fragments are fetched one k-pair ahead into their own registers (software pipeline):
-        // the MMAs of step k never wait for the shared-memory loads of step k
+        const double *Bp = Th + (8 * w8 + gq) * LDT + h * KH + 2 * tq;
+        const double *Ap = X + rq * LD + h * KH + 2 * tq;
+        // fragments are fetched one k-pair ahead into their own registers (software pipeline)
         double2 b_cur = *reinterpret_cast<const double2 *>(Bp);
         double2 a_cur[MB];
 #pragma unroll
         for (int m = 0; m < MB; ++m) a_cur[m] = *reinterpret_cast<const double2 *>(Ap + (8 * m) * LD);
 #pragma unroll 8
-        for (int k0 = 0; k0 < D; k0 += 8) {
-            const int kn = k0 + 8 < D ? k0 + 8 : k0;
+        for (int k0 = 0; k0 < KH; k0 += 8) {
+            const int kn = k0 + 8 < KH ? k0 + 8 : k0;
             const double2 b_nxt = *reinterpret_cast<const double2 *>(Bp + kn);
             double2 a_nxt[MB];
 #pragma unroll
@@ -188,44 +202,54 @@ __global__ void __launch_bounds__(kNT, 1) sweep_logistic_kernel(LogisticArgs a) 
 #pragma unroll
             for (int m = 0; m < MB; ++m) a_cur[m] = a_nxt[m];
         }
-        double z[MB][2];
-#pragma unroll
-        for (int m = 0; m < MB; ++m) { z[m][0] = za[m][0] + zb[m][0]; z[m][1] = za[m][1] + zb[m][1]; }
-        // ---- epilogue: residuals and log-likelihood ------------------------------------------
-#pragma unroll
-        for (int m = 0; m < MB; ++m) {
-            const int r = 8 * m + rq;
+        // hand the partner its observations' half-sums, take mine (selects, no dynamic indexing)
+        const double s00 = za[0][0] + zb[0][0], s01 = za[0][1] + zb[0][1];
+        const double s10 = za[1][0] + zb[1][0], s11 = za[1][1] + zb[1][1];
+        {
+            double2 v;   // the partner's observation block is 1 - h
+            v.x = h ? s00 : s10;
+            v.y = h ? s01 : s11;
+            *reinterpret_cast<double2 *>(Zp + w * 64 + gq * 8 + 2 * tq) = v;
+        }
+        pair_sync(1 + w8);
+        double z[2];
+        {
+            const double2 v = *reinterpret_cast<const double2 *>(Zp + (w ^ 8) * 64 + gq * 8 + 2 * tq);
+            z[0] = (h ? s10 : s00) + v.x;
+            z[1] = (h ? s11 : s01) + v.y;
+        }
+        // ---- epilogue: residuals and log-likelihood of my 8 observations ---------------------------
+        {
+            const int r = 8 * h + rq;
             const bool live = row0 + r < a.n_obs;   // zero-padded rows must not contribute
             const double yv = ys[st * kBM + r];
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const double zz = z[m][j];
-                double sp, sg;
-                softplus_sigmoid(zz, sp, sg);
-                const double res = live ? yv - sg : 0.0;
-                const double lli = live ? yv * zz - sp : 0.0;
-                if (j == 0) ll0 += lli; else ll1 += lli;
-                Rs[r * kRPad + 8 * w + 2 * tq + j] = res;
-            }
+            double2 res;
+            double sp, sg;
+            softplus_sigmoid(z[0], sp, sg);
+            res.x = live ? yv - sg : 0.0;
+            ll0 += live ? yv * z[0] - sp : 0.0;
+            softplus_sigmoid(z[1], sp, sg);
+            res.y = live ? yv - sg : 0.0;
+            ll1 += live ? yv * z[1] - sp : 0.0;
+            *reinterpret_cast<double2 *>(Rs + r * kRPad + 8 * w8 + 2 * tq) = res;
         }
-        __syncwarp();  // the R columns 8w..8w+7 are produced and consumed by this warp only
+        pair_sync(1 + w8);   // both halves of R[:, 8 w8 ..] are in place
 
-        // ---- phase 2: G[8(w) x D] += R[:, 8w..]^T . X[16 x D]  ---------------------------------
+        // ---- phase 2: G[8(w8) x my half of D] += R[:, 8 w8..]^T . X[16 x my half] -------------------
         // Column relabelling: column gq of MMA e of pair P stands for feature 16 P + 2 gq + e
         // (one LDS.128 of X feeds two MMAs); undone when the partials are written.
 #pragma unroll
         for (int i0 = 0; i0 < kBM; i0 += 4) {
-            const double af = Rs[(i0 + tq) * kRPad + 8 * w + gq];
-            const double *Xr = X + (i0 + tq) * LD + 2 * gq;
-            // X fragments fetched four pairs ahead of the MMAs that use them
-            constexpr int NP = D / 16, AH = NP < 4 ? NP : 4;
+            const double af = Rs[(i0 + tq) * kRPad + 8 * w8 + gq];
+            const double *Xr = X + (i0 + tq) * LD + 16 * NPH * h + 2 * gq;
+            constexpr int AH = NPH < 4 ? NPH : 4;   // X fragments fetched AH pairs ahead of their MMAs
             double2 xq[AH];
 #pragma unroll
             for (int P = 0; P < AH; ++P) xq[P] = *reinterpret_cast<const double2 *>(Xr + 16 * P);
 #pragma unroll
-            for (int P = 0; P < NP; ++P) {
+            for (int P = 0; P < NPH; ++P) {
                 const double2 xv = xq[P % AH];
-                if (P + AH < NP) xq[P % AH] = *reinterpret_cast<const double2 *>(Xr + 16 * (P + AH));
+                if (P + AH < NPH) xq[P % AH] = *reinterpret_cast<const double2 *>(Xr + 16 * (P + AH));
                 dmma(G[2 * P][0], G[2 * P][1], af, xv.x);
                 dmma(G[2 * P + 1][0], G[2 * P + 1][1], af, xv.y);
             }
@@ -234,7 +258,7 @@ __global__ void __launch_bounds__(kNT, 1) sweep_logistic_kernel(LogisticArgs a) 
         unsigned int prev = 0u;
         if (lane == 0) prev = atomicAdd(&done[st], 1u);
         prev = __shfl_sync(0xffffffffu, prev, 0);
-        if (prev == kNC / 32 - 1) {          // last warp out of this stage: refill it
+        if (prev == NW - 1) {          // last warp out of this stage: refill it
             if (lane == 0) done[st] = 0u;
             __syncwarp();
             if (t + 2 < n_tiles) issue(t + 2);
@@ -242,25 +266,29 @@ __global__ void __launch_bounds__(kNT, 1) sweep_logistic_kernel(LogisticArgs a) 
     }
 
     // ---- write the partials of this (segment, chain block) -----------------------------------
-    // ll: rows are spread over gq (lane bits 2..4): xor-shuffle tree, fixed order
+    // ll: my 8 observation rows are spread over gq (lane bits 2..4): xor-shuffle tree, then the
+    // two halves of the pair are added in a fixed order (h = 0 first)
 #pragma unroll
     for (int o = 4; o < 32; o <<= 1) {
         ll0 += __shfl_xor_sync(0xffffffffu, ll0, o);
         ll1 += __shfl_xor_sync(0xffffffffu, ll1, o);
     }
-    if (gq == 0) {
-        const int64_t c = cbase + 8 * w + 2 * tq;
-        if (c < C) a.ll_part[(int64_t)seg * C + c] = ll0;
-        if (c + 1 < C) a.ll_part[(int64_t)seg * C + c + 1] = ll1;
+    __syncthreads();   // Zp is free: reuse it for the ll hand-over
+    if (h == 1 && gq == 0) { Zp[w8 * 8 + 2 * tq] = ll0; Zp[w8 * 8 + 2 * tq + 1] = ll1; }
+    __syncthreads();
+    if (h == 0 && gq == 0) {
+        const int64_t c = cbase + 8 * w8 + 2 * tq;
+        if (c < C) a.ll_part[(int64_t)seg * C + c] = ll0 + Zp[w8 * 8 + 2 * tq];
+        if (c + 1 < C) a.ll_part[(int64_t)seg * C + c + 1] = ll1 + Zp[w8 * 8 + 2 * tq + 1];
     }
-    const int64_t c = cbase + 8 * w + gq;
+    const int64_t c = cbase + 8 * w8 + gq;
     if (c < C) {
 #pragma unroll
-        for (int nb = 0; nb < D / 8; ++nb) {
+        for (int nb = 0; nb < 2 * NPH; ++nb) {
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 // accumulator (P = nb / 2, e = nb & 1), fragment column 2 tq + j -> feature index
-                const int k = 16 * (nb >> 1) + 2 * (2 * tq + j) + (nb & 1);
+                const int k = 16 * (NPH * h + (nb >> 1)) + 2 * (2 * tq + j) + (nb & 1);
                 if (k < a.d) a.g_part[((int64_t)seg * a.d + k) * C + c] = G[nb][j];
             }
         }
@@ -298,14 +326,13 @@ void launch(const SweepPlan &pl, const LogisticArgs &a, cudaStream_t st) {
 }  // namespace
 
 int logistic_padded_dim(int d) {
-    for (int D : {16, 32, 64, 128, 256})
+    for (int D : {32, 64, 128, 256})
         if (d <= D) return D;
     return 0;
 }
 
 cudaError_t sweep_logistic_init() {
     cudaError_t e;
-    if ((e = prep<16>()) != cudaSuccess) return e;
     if ((e = prep<32>()) != cudaSuccess) return e;
     if ((e = prep<64>()) != cudaSuccess) return e;
     if ((e = prep<128>()) != cudaSuccess) return e;
@@ -332,7 +359,6 @@ SweepPlan plan_sweep_logistic(int d, int64_t C, int64_t n_obs, int num_sms) {
 void launch_sweep_logistic(const SweepPlan &pl, const LogisticArgs &a, double *ll_out, double *grad_out,
                            cudaStream_t st) {
     switch (pl.D) {
-    case 16: launch<16>(pl, a, st); break;
     case 32: launch<32>(pl, a, st); break;
     case 64: launch<64>(pl, a, st); break;
     case 128: launch<128>(pl, a, st); break;
