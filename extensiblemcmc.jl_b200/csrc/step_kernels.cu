@@ -397,8 +397,12 @@ reduce_push_kernel(DevState d, const StepDesc *__restrict__ descs, int k) {
     __shared__ double sh[kRedThreads];
     __shared__ bool last;
     constexpr int kRedChains = kRedThreads / SL;
+    // PDL chain sweep -> reduce_push -> accept: start early, let the accept kernel start early
+    // too (its prologue then overlaps the sweep), and wait for the sweep before touching its sums
+    griddep_launch_dependents();
     const StepDesc sd = descs[k];
     const int parity = (int)(sd.seq & 1);
+    griddep_wait();
     const double tot = reduce_segments<SL>(d, sh);
     const int64_t c = (int64_t)blockIdx.x * kRedChains + (threadIdx.x % kRedChains);
     if ((threadIdx.x / kRedChains) == 0 && c < d.C) {
@@ -1065,10 +1069,21 @@ void launch_reduce_partials(const DevState &d, cudaStream_t st) {
         reduce_partials_kernel<1><<<red_blocks_for(d.C, 1), 256, 0, st>>>(d);
 }
 void launch_reduce_push(const DevState &d, const StepDesc *descs, int k, cudaStream_t st) {
-    if (d.S * d.G > 16)
-        reduce_push_kernel<8><<<red_blocks_for(d.C, 8), 256, 0, st>>>(d, descs, k);
-    else
-        reduce_push_kernel<1><<<red_blocks_for(d.C, 1), 256, 0, st>>>(d, descs, k);
+    cudaLaunchConfig_t cfg{};
+    cfg.blockDim = dim3(256);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = (pdl_mask() >> 1) & 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (d.S * d.G > 16) {
+        cfg.gridDim = dim3(red_blocks_for(d.C, 8));
+        cudaLaunchKernelEx(&cfg, reduce_push_kernel<8>, d, descs, k);
+    } else {
+        cfg.gridDim = dim3(red_blocks_for(d.C, 1));
+        cudaLaunchKernelEx(&cfg, reduce_push_kernel<1>, d, descs, k);
+    }
 }
 void launch_finalize_loglik(const DevState &d, double *ll_out, cudaStream_t st) {
     finalize_loglik_kernel<<<blocks_for(d.C), 256, 0, st>>>(d, ll_out);

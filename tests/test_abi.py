@@ -80,3 +80,32 @@ def test_unsupported_configurations_raise():
     assert (u.kernel, u.n_coords) == (_abi.KERNEL_MALA, 2)
     assert em.AdaptationMALA().to_abi().kind == _abi.ADAPT_MALA
     assert em.AdaptationMALA().target_accpt_rate == 0.574
+
+
+def _build_c_demo(tmpdir):
+    import subprocess
+    exe = os.path.join(tmpdir, "c_abi_demo")
+    subprocess.check_call(["gcc", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c_abi_demo.c"), "-o", exe, "-ldl", "-lm"])
+    return exe
+
+
+def test_plain_c_client_compiles_against_the_header(tmp_path):
+    # the boundary is usable from C alone (what a Julia ccall needs): compiles warning-free
+    # against include/extmcmc.h and resolves every symbol it uses from the shared library
+    import subprocess
+    exe = _build_c_demo(str(tmp_path))
+    r = subprocess.run([exe, _abi.LIB_PATH], capture_output=True, text=True)
+    if not _has_gpu():
+        assert r.returncode == 1 and "no CUDA device" in r.stderr      # fails loudly, no fallback
+
+
+@pytest.mark.gpu
+def test_plain_c_client_runs_the_sampler(tmp_path):
+    import subprocess
+    exe = _build_c_demo(str(tmp_path))
+    r = subprocess.run([exe, _abi.LIB_PATH], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    mu, var, xbar, s2, acc, eps0 = (float(v) for v in r.stdout.split())
+    assert abs(mu - xbar) < 0.02 and abs(var - s2) < 0.1          # posterior means: xbar, S/(n-3)
+    assert 0.15 < acc < 0.4 and eps0 != 0.5
