@@ -294,3 +294,53 @@ def test_full_size_cfg2_replay_parity():
             assert np.array_equal(full, np.broadcast_to(full[..., :1, :], full.shape)), k
         assert np.array_equal(g.eps(1)[:, :sub], o.eps(1)) and np.array_equal(g.eps(2)[:, :sub], o.eps(2))
     g.close()
+
+
+def test_device_generated_observations():
+    # extmcmc_generate_obs_normal (BASELINE cfg 5 generates its 1e9 observations in place): recover
+    # sum x and sum x^2 from log-likelihood evaluations and check them against N(1.5, 2^2); a split
+    # into two shards with global offsets must describe the very same data
+    import ctypes as C
+    lib = _abi.load()
+    n = 1_000_001
+
+    def sums(first, count):
+        mcmc = em.MCMC(cfg2_updates(), backend=em.CUDAMCMCBackend(n_chains=2, seed=1, history="none"))
+        from extensiblemcmc_jl_b200.mcmc import init_
+        init_(mcmc, 1, dict(P=em.GsnTargetLaw([0.0]), obs=em.DeviceGeneratedObs(count, 1.5, 2.0, 6, first)),
+              np.array([[0.0, 1.0], [1.0, 1.0]]))
+        ll = mcmc.workspace.eval_loglik()
+        mcmc.workspace.close()
+        S = -2.0 * (ll + 0.5 * count * math.log(2 * math.pi))       # S(mu) = sum (x - mu)^2 at var = 1
+        sx = (S[0] - S[1] + count) / 2.0
+        return sx, S[0]
+
+    sx, sxx = sums(0, n)
+    mean, var = sx / n, sxx / n - (sx / n) ** 2
+    assert abs(mean - 1.5) < 5 * 2.0 / math.sqrt(n) and abs(var - 4.0) < 5 * 4.0 * math.sqrt(2.0 / n)
+    a, b = sums(0, 400_001), sums(400_001, n - 400_001)              # odd split point on purpose
+    assert abs((a[0] + b[0]) - sx) < 1e-9 * abs(sx) and abs((a[1] + b[1]) - sxx) < 1e-9 * sxx
+
+
+def test_many_chains_indexing():
+    # 70 001 chains (not a multiple of anything): 64-bit indexing of the SoA arrays, ragged last CTA
+    x = _data(600, seed=11)
+    Cn = 70_001
+    th0 = theta_init_for(x, Cn)
+    ups = cfg2_updates(eps0=0.05, scale=5e-3, k=10, offset=2.0)
+    steps = list(em.MCMCSchedule(4, 2))
+    sub = np.r_[0:40, Cn - 40:Cn]                                   # first and last chains vs the oracle
+    o = orc.Oracle(em.GsnTargetLaw([0.0]), ups, x, th0[:, :40], 40, seed=5, chain_offset=0)
+    o2 = orc.Oracle(em.GsnTargetLaw([0.0]), ups, x, th0[:, Cn - 40:], 40, seed=5, chain_offset=Cn - 40)
+    r1, r2 = o.run(steps), o2.run(steps)
+    g = GpuSession(em.GsnTargetLaw([0.0]), ups, x, th0, Cn, seed=5, n_steps_hint=8)
+    props = np.zeros((8, 1, Cn)); exps = np.ones((8, Cn))
+    props[:, :, sub] = np.concatenate([r1["proposals"], r2["proposals"]], axis=2)
+    exps[:, sub] = np.concatenate([r1["exp_draws"], r2["exp_draws"]], axis=1)
+    props[:, 0, 40:Cn - 40] = np.where(np.arange(8)[:, None] % 2 == 0, th0[0, 40:Cn - 40], th0[1, 40:Cn - 40])
+    rg = g.run(steps, replay=(props, exps))
+    ref_theta = np.concatenate([r1["theta"], r2["theta"]], axis=2)
+    ref_acc = np.concatenate([r1["accepted"], r2["accepted"]], axis=1)
+    assert np.array_equal(rg["theta"][:, :, sub], ref_theta) and np.array_equal(rg["accepted"][:, sub], ref_acc)
+    assert np.isfinite(rg["ll"]).all()
+    g.close()
