@@ -241,6 +241,20 @@ int32_t enqueue_sweep(extmcmc_t h, bool instrument, bool grad = false, const dou
         LogisticArgs a{h->obs_dev, h->y_dev, h->n_obs_local, src, h->cfg.obs_dim, h->d.C, h->d.partial,
                        h->d.partial + (size_t)h->plan.S * h->d.C, h->plan.S};
         launch_sweep_logistic(h->plan, a, ll_dst, grad_dst, h->stream);
+        if (obs_sharded(h)) {
+            // every rank holds a slice of the rows of X: sum the per-chain log-likelihoods and the
+            // [d][C] gradients over the ranks ("allreduce of [C] ll and [C x d] grads")
+            NK(h, g_nccl.AllReduce(ll_dst, ll_dst, (size_t)h->d.C, ncclFloat64, ncclSum, h->comm, h->stream));
+            if (grad_dst)
+                NK(h, g_nccl.AllReduce(grad_dst, grad_dst, (size_t)h->cfg.obs_dim * h->d.C, ncclFloat64, ncclSum,
+                                       h->comm, h->stream));
+        }
+        h->launches += h->plan.launches;
+        if (instrument) {
+            CK(h, cudaEventRecord(ev.second, h->stream));
+            h->ev_pending.push_back(ev);
+        }
+        return EXTMCMC_OK;
     } else {
         launch_sweep_gsnmv(h->plan, h->obs_dev, h->n_obs_local, h->d.lawc, h->d.C, h->d.partial, h->stream);
     }
@@ -334,8 +348,9 @@ int32_t run_block_impl(extmcmc_t h, const extmcmc_step_t *steps, int32_t n_steps
         if (!h->upd_set[u]) return fail(h, EXTMCMC_EINVAL, "update " + std::to_string(u) + " not set");
     if (n_steps > h->cfg.history_window)
         return fail(h, EXTMCMC_EINVAL, "block longer than history_window");
-    if (h->any_mala && obs_sharded(h))
-        return fail(h, EXTMCMC_EUNSUPPORTED, "MALA updates with sharded observations are not implemented");
+    if (h->any_mala && obs_sharded(h) && h->cfg.law != EXTMCMC_LAW_LOGISTIC)
+        return fail(h, EXTMCMC_EUNSUPPORTED, "MALA updates with sharded observations are implemented for LOGISTIC only");
+    if (obs_sharded(h) && !h->comm) return fail(h, EXTMCMC_EINVAL, "EXTMCMC_SHARD_OBS needs extmcmc_comm_init first");
     for (int s = 0; s < n_steps; ++s)
         if (steps[s].pidx < 0 || steps[s].pidx >= h->cfg.n_updates || steps[s].mcmciter < 1)
             return fail(h, EXTMCMC_EINVAL, "step out of range");
@@ -493,8 +508,6 @@ int32_t extmcmc_create(const extmcmc_config_t *cfg, extmcmc_t *out) {
     case EXTMCMC_LAW_LOGISTIC:
         if (cfg->obs_dim != cfg->n_params || cfg->obs_dim < 1 || logistic_padded_dim(cfg->obs_dim) == 0)
             return fail(nullptr, EXTMCMC_EUNSUPPORTED, "LOGISTIC needs obs_dim = n_params = d with 1 <= d <= 256");
-        if (cfg->shard_mode == EXTMCMC_SHARD_OBS && cfg->world_size > 1)
-            return fail(nullptr, EXTMCMC_EUNSUPPORTED, "LOGISTIC with sharded observations is not implemented");
         break;
     case EXTMCMC_LAW_HIER_NORMAL:
         if (cfg->obs_dim != 1 || cfg->n_params < 3)
@@ -931,6 +944,8 @@ static size_t p2p_region_bytes(extmcmc_t h) {
 int32_t extmcmc_p2p_export(extmcmc_t h, uint8_t handle_out[64]) {
     if (!h || !handle_out) return EXTMCMC_EINVAL;
     if (!obs_sharded(h)) return fail(h, EXTMCMC_EINVAL, "peer exchange is for EXTMCMC_SHARD_OBS with world_size > 1");
+    if (h->cfg.law != EXTMCMC_LAW_GSN_IID_1D && h->cfg.law != EXTMCMC_LAW_GSN_MV)
+        return fail(h, EXTMCMC_EUNSUPPORTED, "peer exchange is implemented for the Gaussian laws");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
     CK(h, cudaSetDevice(h->cfg.device));
     if (!h->p2p_region) {
@@ -1191,7 +1206,8 @@ int32_t extmcmc_eval_grad(extmcmc_t h, double *ll_out, double *grad_out) {
     if (h->cfg.law != EXTMCMC_LAW_GSN_IID_1D && h->cfg.law != EXTMCMC_LAW_HIER_NORMAL &&
         h->cfg.law != EXTMCMC_LAW_LOGISTIC)
         return fail(h, EXTMCMC_EUNSUPPORTED, "this law has no device gradient");
-    if (obs_sharded(h)) return fail(h, EXTMCMC_EUNSUPPORTED, "gradients with sharded observations are not implemented");
+    if (obs_sharded(h) && h->cfg.law != EXTMCMC_LAW_LOGISTIC)
+        return fail(h, EXTMCMC_EUNSUPPORTED, "gradients with sharded observations are implemented for LOGISTIC only");
     CK(h, cudaSetDevice(h->cfg.device));
     int32_t rc;
     if ((rc = ensure_plan(h))) return rc;

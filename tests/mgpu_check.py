@@ -69,13 +69,37 @@ def main():
     p2p_same = bool(np.array_equal(shp["acc"], sh["acc"]) and np.array_equal(shp["theta"], sh["theta"]))
     fin_p = np.isfinite(sh["ll"])
     p2p_rel = float((np.abs(shp["ll"][fin_p] - sh["ll"][fin_p]) / np.abs(sh["ll"][fin_p])).max())
+    # 3. logistic regression (FP64 tensor-core kernel), rows of X sharded over the ranks, MALA:
+    #    per-chain ll and the [d][C] gradients are all-reduced; vs the single-GPU run the sums
+    #    differ in the last bits, so proposals agree to ~1e-12 and decisions agree
+    rng = np.random.default_rng(3)
+    dl, nl, Cl, Ml = 8, 4000, 96, 25
+    Xl = rng.standard_normal((nl, dl)) / np.sqrt(dl)
+    yl = (rng.random(nl) < 1.0 / (1.0 + np.exp(-Xl @ rng.standard_normal(dl)))).astype(np.float64)
+    mala = lambda: [em.MALAUpdate(0.2, list(range(1, dl + 1)), prior=em.StandardPrior(em.Normal(0.0, 10.0)),
+                                  adpt=em.AdaptationMALA(adapt_every_k_steps=5, scale=0.01, offset=1.0))]
+
+    def run_logi(backend, Xs, ys):
+        mcmc = em.MCMC(mala(), backend=backend)
+        ws, lws = em.run_(mcmc, Ml, dict(P=em.LogisticLaw(dl), obs=Xs, y=ys), np.zeros(dl))
+        out = (ws.sub_ws.state_history.copy(), ws.acc_all.copy(), ws.ll_all.copy())
+        ws.close()
+        return out
+    l1 = run_logi(em.CUDAMCMCBackend(n_chains=Cl, device=local, seed=4, block_len=10), Xl, yl)
+    f3, c3 = par.shard_obs(nl, rank, world)
+    lb = par.backend_for_rank(rank, world, local, Cl, shard="obs", comm_id=par.exchange_comm_id(dist), seed=4,
+                              block_len=10)
+    l2 = run_logi(lb, Xl[f3:f3 + c3], yl[f3:f3 + c3])
+    logi_ok = bool(np.array_equal(l1[1], l2[1]) and np.allclose(l1[0], l2[0], rtol=1e-9, atol=1e-11)
+                   and np.allclose(l1[2][np.isfinite(l1[2])], l2[2][np.isfinite(l1[2])], rtol=1e-10, atol=0))
     gathered = par.gather_chain_axis(dist, sh["theta"][..., :4])
     if rank == 0:
         report.update(obs_ll_rel_err=float(rel.max()) if same_dec else None, obs_decisions_equal=bool(same_dec),
                       obs_chains_with_flips=flips,
                       obs_ranks_identical=bool(all(np.array_equal(gathered[..., :4], gathered[..., 4 * r:4 * r + 4])
                                                    for r in range(world))))
-        report.update(p2p_matches_nccl=p2p_same, p2p_ll_rel_vs_nccl=p2p_rel)
+        report.update(p2p_matches_nccl=p2p_same, p2p_ll_rel_vs_nccl=p2p_rel, logistic_obs_sharded_ok=logi_ok)
+        ok &= logi_ok
         ok &= same_dec and rel.max() < 1e-10 and report["obs_ranks_identical"] and p2p_same and p2p_rel < 1e-12
         report["world"] = world
         print(json.dumps(report))
