@@ -588,11 +588,11 @@ def run_reference(args):
     from oracle import oracle as orc
     nthr = os.cpu_count() or 1
     x = cfg2_data()
-    n_chains = 2 * nthr                       # per step: 2 chains per thread x 1 iteration x N=1e6
+    n_chains = 8 * nthr                       # per step: 8 chains per thread x 1 iteration x N=1e6
     ups = cfg2_updates(em)
     o = orc.Oracle(em.GsnTargetLaw([0.0]), ups, x, cfg2_theta_init(x, n_chains), n_chains, seed=3)
     K, Wm = args.steps, max(args.warmup, 1)
-    K = min(K, 40)
+    K = min(K, 200)
     sched = list(em.MCMCSchedule(Wm + K, NU))
     o.run(sched[:Wm * NU], n_threads=nthr, record=False)
     t0 = time.perf_counter()
@@ -620,7 +620,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-iters", type=int, default=2000, help="iterations of the end-to-end job (BASELINE cfg2: 2000)")
-    ap.add_argument("--cpu-iters", type=int, default=150)
+    ap.add_argument("--cpu-iters", type=int, default=600, help="iterations of the single-core CPU baseline (~10 s)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-hbm", action="store_true")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"])
