@@ -355,13 +355,15 @@ __device__ __forceinline__ double reduce_segments(const DevState &d, double *sh 
     if (c < d.C) {
         const double *p = d.partial + c;
         const int nrows = d.S * d.G;   // all segments of all observation groups
+        // all loads of a batch are issued before the first add (memory-level parallelism: after a
+        // large sweep these come from DRAM); the adds stay in increasing row order
         int i = slice;
-        for (; i + 3 * kRedSlices < nrows; i += 4 * kRedSlices) {
-            const double a0 = p[(int64_t)i * d.C];
-            const double a1 = p[(int64_t)(i + kRedSlices) * d.C];
-            const double a2 = p[(int64_t)(i + 2 * kRedSlices) * d.C];
-            const double a3 = p[(int64_t)(i + 3 * kRedSlices) * d.C];
-            s += a0; s += a1; s += a2; s += a3;
+        for (; i + 7 * kRedSlices < nrows; i += 8 * kRedSlices) {
+            double a[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) a[q] = p[(int64_t)(i + q * kRedSlices) * d.C];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) s += a[q];
         }
         for (; i < nrows; i += kRedSlices) s += p[(int64_t)i * d.C];
     }
@@ -1030,7 +1032,12 @@ static inline int red_blocks_for(int64_t C, int sl) {
     const int ch = kRedThreads / sl;
     return (int)((C + ch - 1) / ch);
 }
-static inline int slices_for(const DevState &d) { return (!d.use_ssum && d.S * d.G > 16) ? 8 : 1; }
+// reduction slices per chain: 1 (thread per chain) for few segments; 8; 32 for a handful of chains
+// with hundreds of segments (cfg 5), so that the cold loads of the partial sums overlap
+static inline int slices_for(const DevState &d) {
+    if (d.use_ssum || d.S * d.G <= 16) return 1;
+    return d.C <= 8 ? 32 : 8;
+}
 void launch_accept(const DevState &d, const StepDesc *descs, int k, int fuse_next, cudaStream_t st) {
     // PDL attribute: the accept kernel's prologue overlaps the tail of the sweep
     cudaLaunchConfig_t cfg{};
@@ -1041,7 +1048,10 @@ void launch_accept(const DevState &d, const StepDesc *descs, int k, int fuse_nex
     attr[0].val.programmaticStreamSerializationAllowed = (pdl_mask() >> 1) & 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (slices_for(d) == 8) {
+    if (slices_for(d) == 32) {
+        cfg.gridDim = dim3(red_blocks_for(d.C, 32));
+        cudaLaunchKernelEx(&cfg, accept_kernel<32>, d, descs, k, fuse_next);
+    } else if (slices_for(d) == 8) {
         cfg.gridDim = dim3(red_blocks_for(d.C, 8));
         cudaLaunchKernelEx(&cfg, accept_kernel<8>, d, descs, k, fuse_next);
     } else {
