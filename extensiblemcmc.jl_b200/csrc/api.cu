@@ -79,6 +79,8 @@ struct extmcmc_handle {
     int64_t *goff_dev = nullptr, *glen_dev = nullptr;  // [G] padded group offsets / true lengths
     double *y_dev = nullptr;             // LOGISTIC: responses, padded like the rows of X
     int logi_D = 0;                      // LOGISTIC: padded feature dimension
+    unsigned int *tail_counter = nullptr; // CTA counter of the fused sweep tail
+    bool tail = false;                   // the obs-mapped sweep finishes the reduction itself
     bool grad_valid = false;             // grad_cur holds d ll/d theta of the CURRENT state
     bool any_mala = false;
     bool state_set = false;
@@ -168,6 +170,10 @@ void invalidate_graphs(extmcmc_t h) {
     h->graph_launches.clear();
 }
 
+bool obs_sharded(extmcmc_t h) {
+    return h->cfg.shard_mode == EXTMCMC_SHARD_OBS && h->cfg.world_size > 1;
+}
+
 int32_t ensure_plan(extmcmc_t h) {
     if (h->plan_valid) return EXTMCMC_OK;
     if (h->cfg.law == EXTMCMC_LAW_GSN_IID_1D || h->cfg.law == EXTMCMC_LAW_HIER_NORMAL)
@@ -179,6 +185,14 @@ int32_t ensure_plan(extmcmc_t h) {
     else
         return fail(h, EXTMCMC_EUNSUPPORTED, "law not implemented on the GPU path");
     h->d.S = h->plan.S;
+    // fused tail of the obs-mapped 1-D sweep (few chains, many segments): see sweep.h
+    h->tail = h->cfg.law == EXTMCMC_LAW_GSN_IID_1D && h->plan.variant == SWEEP_VARIANT_OBS;
+    if (h->tail && !h->tail_counter) {
+        int32_t rct = dev_alloc(h, &h->tail_counter, 1);
+        if (rct) return rct;
+        CK(h, cudaMemset(h->tail_counter, 0, sizeof(unsigned int)));
+    }
+    h->d.use_ssum = (obs_sharded(h) || h->cfg.law == EXTMCMC_LAW_LOGISTIC || h->tail) ? 1 : 0;
     // Gaussian laws: two quantities (second- and first-order sums) x G groups x S segments;
     // logistic: ll_part[S][C] followed by g_part[S][d][C]
     const size_t part_rows = h->cfg.law == EXTMCMC_LAW_LOGISTIC ? (size_t)h->plan.S * (h->cfg.obs_dim + 1)
@@ -217,10 +231,6 @@ int32_t ensure_total_obs(extmcmc_t h) {
     return EXTMCMC_OK;
 }
 
-bool obs_sharded(extmcmc_t h) {
-    return h->cfg.shard_mode == EXTMCMC_SHARD_OBS && h->cfg.world_size > 1;
-}
-
 // One likelihood sweep (+ cross-rank reduction when the observations are sharded).  Gaussian
 // laws read the law constants the proposal kernel left in lawc and leave per-segment sums in
 // `partial` (grad: also the first-order sums).  The logistic law reads the parameters from
@@ -229,13 +239,25 @@ int32_t enqueue_sweep(extmcmc_t h, bool instrument, bool grad = false, const dou
                       double *ll_dst = nullptr, double *grad_dst = nullptr,
                       const StepDesc *d_descs = nullptr, int k = 0) {
     std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+    bool tail_done = false;   // the sweep kernel itself reduced (and, with p2p, delivered) the sums
     if (instrument) {
         if (!h->ev_free.empty()) { ev = h->ev_free.back(); h->ev_free.pop_back(); }
         else { CK(h, cudaEventCreate(&ev.first)); CK(h, cudaEventCreate(&ev.second)); }
         CK(h, cudaEventRecord(ev.first, h->stream));
     }
     if (h->cfg.law == EXTMCMC_LAW_GSN_IID_1D || h->cfg.law == EXTMCMC_LAW_HIER_NORMAL) {
-        Gsn1dArgs a{h->obs_dev, h->goff_dev, h->glen_dev, h->d.G, h->d.lawc, h->d.C, h->d.partial, h->plan.S};
+        Gsn1dArgs a{};
+        a.obs = h->obs_dev; a.goff = h->goff_dev; a.glen = h->glen_dev; a.G = h->d.G;
+        a.mu = h->d.lawc; a.C = h->d.C; a.partial = h->d.partial; a.S = h->plan.S;
+        tail_done = h->tail && !grad;
+        if (tail_done) {
+            const bool push = obs_sharded(h) && h->d.p2p && d_descs;
+            a.tail_mode = push ? 2 : 1;
+            a.tail_counter = h->tail_counter; a.ssum = h->d.ssum;
+            a.peer_rx = h->d.peer_rx; a.peer_flag = h->d.peer_flag;
+            a.rank = h->cfg.rank; a.world = h->cfg.world_size;
+            a.descs = d_descs; a.k = k; a.epoch = h->d.epoch;
+        }
         launch_sweep_gsn1d(h->plan, a, grad, h->stream);
     } else if (h->cfg.law == EXTMCMC_LAW_LOGISTIC) {
         LogisticArgs a{h->obs_dev, h->y_dev, h->n_obs_local, src, h->cfg.obs_dim, h->d.C, h->d.partial,
@@ -265,12 +287,11 @@ int32_t enqueue_sweep(extmcmc_t h, bool instrument, bool grad = false, const dou
     }
     if (obs_sharded(h)) {
         if (h->d.p2p && d_descs) {
-            // our own exchange: peer stores + flags here, wait + ordered sum inside accept_kernel
-            launch_reduce_push(h->d, d_descs, k, h->stream);
-            h->launches += 1;
+            // our own exchange: peer stores + flags (in the sweep's fused tail, or here), wait +
+            // ordered sum inside accept_kernel
+            if (!tail_done) { launch_reduce_push(h->d, d_descs, k, h->stream); h->launches += 1; }
         } else {
-            launch_reduce_partials(h->d, h->stream);
-            h->launches += 1;
+            if (!tail_done) { launch_reduce_partials(h->d, h->stream); h->launches += 1; }
             NK(h, g_nccl.AllReduce(h->d.ssum, h->d.ssum, (size_t)h->d.C, ncclFloat64, ncclSum, h->comm,
                                    h->stream));
         }
@@ -1190,7 +1211,7 @@ int32_t extmcmc_eval_loglik(extmcmc_t h, double *ll_out) {
     } else {
         launch_prepare_current(h->d, h->stream);
         if ((rc = enqueue_sweep(h, h->cfg.instrument != 0))) return rc;
-        if (!obs_sharded(h)) { launch_reduce_partials(h->d, h->stream); h->launches += 1; }
+        if (!obs_sharded(h) && !h->tail) { launch_reduce_partials(h->d, h->stream); h->launches += 1; }
         launch_finalize_loglik(h->d, h->scratch_ll, h->stream);
         h->launches += 2;
     }

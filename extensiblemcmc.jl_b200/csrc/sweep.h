@@ -38,6 +38,19 @@ struct Gsn1dArgs {
     int64_t C;
     double *partial;
     int S;
+    // Optional fused tail of the "obs" mapping (G = 1, no gradient): the last CTA to finish adds
+    // the per-segment sums in a fixed order and either stores the totals to ssum[C] (tail_mode 1)
+    // or pushes them straight into every rank's exchange buffer over NVLink peer mappings and
+    // raises this rank's sequence flag there (tail_mode 2) -- compute and collective in one kernel.
+    int tail_mode;
+    unsigned int *tail_counter;
+    double *ssum;
+    double **peer_rx;
+    unsigned long long **peer_flag;
+    int rank, world;
+    const void *descs;       // StepDesc array of the block (device), element k names the step
+    int k;
+    unsigned long long epoch;
 };
 
 SweepPlan plan_sweep_gsn1d(int64_t C, int64_t n_obs_largest_group, int force_variant, int num_sms, int G);

@@ -29,6 +29,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cuda_runtime.h>
+#include "dev_state.cuh"
 #include "sweep.h"
 #include "tma.cuh"
 
@@ -254,6 +255,52 @@ sweep_gsn1d_obs_kernel(Gsn1dArgs a) {
             a.partial[(rows + row) * C + tid] = t2;
         }
     }
+    if (GRAD || a.tail_mode == 0) return;
+
+    // ---- fused tail: last CTA out reduces over the segments and delivers the totals ----------
+    __shared__ bool last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) last = atomicAdd(a.tail_counter, 1u) == gridDim.x * gridDim.z - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    // CB chains x (NT / CB) slices; slice j adds rows j, j + NS, ... (independent loads, L2-hot),
+    // then the slice sums are combined in slice order: a fixed order, like reduce_segments
+    constexpr int NS = NT / CB;
+    const int ch = tid % CB, sl = tid / CB;
+    double acc2 = 0.0;
+    if (ch < C)
+        for (int64_t i = sl; i < rows; i += NS) acc2 += __ldcg(a.partial + i * C + ch);
+    double *sh = reinterpret_cast<double *>(smem_raw);   // the tile ring is free now
+    sh[sl * CB + ch] = acc2;
+    __syncthreads();
+    if (tid < CB && tid < C) {
+        double tot = 0.0;
+        for (int j = 0; j < NS; ++j) tot += sh[j * CB + tid];
+        if (a.tail_mode == 1) {
+            a.ssum[tid] = tot;
+        } else {
+            const StepDesc *sd = reinterpret_cast<const StepDesc *>(a.descs) + a.k;
+            const int parity = (int)(sd->seq & 1);
+            const int64_t slot = ((int64_t)parity * a.world + a.rank) * C + tid;
+            for (int q = 0; q < a.world; ++q) a.peer_rx[q][slot] = tot;   // stores into peer memory
+        }
+    }
+    if (a.tail_mode == 2) {
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) {
+            const StepDesc *sd = reinterpret_cast<const StepDesc *>(a.descs) + a.k;
+            const int parity = (int)(sd->seq & 1);
+            const unsigned long long tag = (a.epoch << 40) | (unsigned long long)(sd->seq + 1);
+            for (int q = 0; q < a.world; ++q) {
+                unsigned long long *f = a.peer_flag[q] + (parity * a.world + a.rank);
+                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(tag) : "memory");
+            }
+        }
+    }
+    if (tid == 0) *a.tail_counter = 0u;
 }
 
 // ---------------------------------------------------------------------------------

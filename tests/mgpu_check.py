@@ -69,6 +69,20 @@ def main():
     p2p_same = bool(np.array_equal(shp["acc"], sh["acc"]) and np.array_equal(shp["theta"], sh["theta"]))
     fin_p = np.isfinite(sh["ll"])
     p2p_rel = float((np.abs(shp["ll"][fin_p] - sh["ll"][fin_p]) / np.abs(sh["ll"][fin_p])).max())
+    # 2c. few chains (observation-mapped sweep whose fused tail reduces and pushes the sums itself)
+    C6 = 6
+    th6 = th0[:, :C6]
+    s6 = run(em.CUDAMCMCBackend(n_chains=C6, device=local, seed=9, block_len=16), x, th6, M)
+    n6 = run(par.backend_for_rank(rank, world, local, C6, shard="obs", comm_id=par.exchange_comm_id(dist), seed=9,
+                                  block_len=16), x[first:first + cnt], th6, M)
+    p6 = run(par.backend_for_rank(rank, world, local, C6, shard="obs", comm_id=par.exchange_comm_id(dist), seed=9,
+                                  block_len=16, p2p_allgather=par.p2p_allgather_fn(dist)), x[first:first + cnt], th6, M)
+    fin6 = np.isfinite(s6["ll"])
+    few_ok = bool(np.array_equal(s6["acc"], n6["acc"]) and np.array_equal(s6["acc"], p6["acc"])
+                  and np.array_equal(s6["theta"], n6["theta"]) and np.array_equal(s6["theta"], p6["theta"])
+                  and np.allclose(s6["ll"][fin6], n6["ll"][fin6], rtol=1e-12, atol=0)
+                  and np.allclose(s6["ll"][fin6], p6["ll"][fin6], rtol=1e-12, atol=0))
+
     # 3. logistic regression (FP64 tensor-core kernel), rows of X sharded over the ranks, MALA:
     #    per-chain ll and the [d][C] gradients are all-reduced; vs the single-GPU run the sums
     #    differ in the last bits, so proposals agree to ~1e-12 and decisions agree
@@ -98,8 +112,9 @@ def main():
                       obs_chains_with_flips=flips,
                       obs_ranks_identical=bool(all(np.array_equal(gathered[..., :4], gathered[..., 4 * r:4 * r + 4])
                                                    for r in range(world))))
-        report.update(p2p_matches_nccl=p2p_same, p2p_ll_rel_vs_nccl=p2p_rel, logistic_obs_sharded_ok=logi_ok)
-        ok &= logi_ok
+        report.update(p2p_matches_nccl=p2p_same, p2p_ll_rel_vs_nccl=p2p_rel, logistic_obs_sharded_ok=logi_ok,
+                      few_chains_fused_tail_ok=few_ok)
+        ok &= logi_ok and few_ok
         ok &= same_dec and rel.max() < 1e-10 and report["obs_ranks_identical"] and p2p_same and p2p_rel < 1e-12
         report["world"] = world
         print(json.dumps(report))
