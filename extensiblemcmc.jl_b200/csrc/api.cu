@@ -306,38 +306,44 @@ int32_t enqueue_sweep(extmcmc_t h, bool instrument, bool grad = false, const dou
 // path make identical decisions.
 int32_t enqueue_steps(extmcmc_t h, const StepDesc *d_descs, const int *kinds, int n_steps,
                       bool instrument, bool &grad_valid) {
-    bool fused = false;  // the proposal of element k was already issued by accept(k-1)
+    bool fused = false;      // the proposal of element k was already issued by accept(k-1)
+    bool cur_prepared = false;  // accept(k-1) already wrote the law constants of the current state
     for (int k = 0; k < n_steps; ++k) {
         int32_t rc;
+        const bool next_mala = k + 1 < n_steps && kinds[k + 1] == EXTMCMC_KERNEL_MALA;
+        const bool next_rw = k + 1 < n_steps && kinds[k + 1] != EXTMCMC_KERNEL_MALA;
         if (kinds[k] == EXTMCMC_KERNEL_MALA) {
             const bool logi = h->cfg.law == EXTMCMC_LAW_LOGISTIC;
+            int finalize_cur = 0;
             if (!grad_valid) {
                 if (logi) {
                     if ((rc = enqueue_sweep(h, instrument, true, h->d.theta, h->scratch_ll, h->d.grad_cur))) return rc;
                 } else {
-                    launch_prepare_current(h->d, h->stream);
+                    // current-state gradient sweep; its sums are finished inside mala_propose
+                    if (!cur_prepared) { launch_prepare_current(h->d, h->stream); h->launches += 1; }
                     if ((rc = enqueue_sweep(h, instrument, true))) return rc;
-                    launch_grad_finalize(h->d, h->d.theta, h->scratch_ll, h->d.grad_cur, h->stream);
-                    h->launches += 2;
+                    finalize_cur = 1;
                 }
             }
-            launch_mala_propose(h->d, d_descs, k, h->stream);
+            launch_mala_propose(h->d, d_descs, k, finalize_cur, h->scratch_ll, h->stream);
             if (logi) {
                 if ((rc = enqueue_sweep(h, instrument, true, h->d.prop_full, h->d.ll_prop, h->d.grad_prop))) return rc;
             } else {
-                if ((rc = enqueue_sweep(h, instrument, true))) return rc;
-                launch_grad_finalize(h->d, h->d.prop_full, h->d.ll_prop, h->d.grad_prop, h->stream);
-                h->launches += 1;
+                if ((rc = enqueue_sweep(h, instrument, true))) return rc;   // finished inside mala_accept
             }
-            launch_mala_accept(h->d, d_descs, k, h->stream);
+            fused = next_rw;   // the next random-walk proposal rides on this accept kernel
+            launch_mala_accept(h->d, d_descs, k, logi ? 0 : 1, fused ? 1 : 0, h->stream);
             h->launches += 2;
             grad_valid = true;
-            fused = false;
+            cur_prepared = false;
         } else {
             if (!fused) { launch_propose(h->d, d_descs, k, h->stream); h->launches += 1; }
             if ((rc = enqueue_sweep(h, instrument, false, h->d.prop_full, h->d.ssum, nullptr, d_descs, k))) return rc;
-            fused = k + 1 < n_steps && kinds[k + 1] != EXTMCMC_KERNEL_MALA;
-            launch_accept(h->d, d_descs, k, fused ? 1 : 0, h->stream);
+            fused = next_rw;
+            // a MALA element follows and will need the law constants of the (then) current state for
+            // its gradient sweep: let this accept kernel write them (fuse_next = 2)
+            cur_prepared = next_mala && h->cfg.law != EXTMCMC_LAW_LOGISTIC;
+            launch_accept(h->d, d_descs, k, fused ? 1 : (cur_prepared ? 2 : 0), h->stream);
             h->launches += 1;
             grad_valid = false;
         }

@@ -707,7 +707,7 @@ accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fuse_ne
     // and prior terms and the Exp(1) draw are computed here, hidden behind the sweep.
     griddep_launch_dependents();
     load_step_ctx(&ctx, d, descs, k);
-    if (fuse_next) load_step_ctx(&ctx_next, d, descs, k + 1);
+    if (fuse_next == 1) load_step_ctx(&ctx_next, d, descs, k + 1);
     const int64_t c = (int64_t)blockIdx.x * kRedChains + (threadIdx.x % kRedChains);
     const bool worker = (threadIdx.x / kRedChains) == 0 && c < d.C;
     const StepDesc &sd = ctx.sd;
@@ -760,7 +760,7 @@ accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fuse_ne
         if (d.law == EXTMCMC_LAW_GSN_IID_1D) { law0 = d.lawc[C + c]; law1 = d.lawc[2 * C + c]; }
         // step sizes of the NEXT element's update (fused proposal); not when it is this very update,
         // whose eps the adaptation below may still change
-        if (fuse_next && ctx_next.sd.pidx != sd.pidx && ctx_next.u.kernel == EXTMCMC_KERNEL_RW_UNIFORM) {
+        if (fuse_next == 1 && ctx_next.sd.pidx != sd.pidx && ctx_next.u.kernel == EXTMCMC_KERNEL_RW_UNIFORM) {
             for (int i = 0; i < ctx_next.u.n_coords; ++i) eps_next[i] = ctx_next.u.eps[(int64_t)i * C + c];
             next_eps_ok = true;
         }
@@ -794,7 +794,9 @@ accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fuse_ne
     post_decision(d, sd, u, c, accepted, ll_new, ll_prop, n_eps, use_pf ? &pf : nullptr);
     // proposal of the NEXT schedule element of this block, fused here: the chain's thread
     // already holds its freshly committed state, and one launch per update step is saved
-    if (fuse_next) {
+    if (fuse_next == 2) {
+        law_prepare(d, c, d.theta + c, C);   // what prepare_current_kernel would do
+    } else if (fuse_next) {
         if (use_pf) {
             const double *en = next_eps_ok ? eps_next
                                : (ctx_next.sd.pidx == sd.pidx && ctx_next.u.kernel == EXTMCMC_KERNEL_RW_UNIFORM) ? pf.eps
@@ -820,11 +822,8 @@ accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fuse_ne
 //                d/dth_g = T_g - (th_g - mu)/tau^2, d/dmu = sum_g (th_g - mu)/tau^2,
 //                d/dtau = -G/tau + sum_g (th_g - mu)^2 / tau^3
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-grad_finalize_kernel(DevState d, const double *__restrict__ src, double *__restrict__ ll_out,
-                     double *__restrict__ grad_out) {
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= d.C) return;
+__device__ __forceinline__ void grad_finalize_chain(const DevState &d, int64_t c, const double *__restrict__ src,
+                                                    double *__restrict__ ll_out, double *__restrict__ grad_out) {
     const int64_t C = d.C;
     const int G = d.G, S = d.S;
     const int64_t rows = (int64_t)G * S;
@@ -857,6 +856,14 @@ grad_finalize_kernel(DevState d, const double *__restrict__ src, double *__restr
     }
 }
 
+__global__ void __launch_bounds__(128)
+grad_finalize_kernel(DevState d, const double *__restrict__ src, double *__restrict__ ll_out,
+                     double *__restrict__ grad_out) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= d.C) return;
+    grad_finalize_chain(d, c, src, ll_out, grad_out);
+}
+
 // d log prior / d theta_i for the priors that have one on the device
 __device__ __forceinline__ double prior_grad(const DevUpdate &u, double th) {
     if (u.prior == EXTMCMC_PRIOR_NORMAL) return -(th - u.prior_params[0]) / (u.prior_params[1] * u.prior_params[1]);
@@ -872,11 +879,15 @@ __device__ __forceinline__ double prior_logpdf1(const DevUpdate &u, double th) {
 
 // K5a: MALA proposal  theta° = theta + (tau^2/2) g(theta) + tau z,  g = grad(ll + log prior)
 __global__ void __launch_bounds__(128)
-mala_propose_kernel(DevState d, const StepDesc *__restrict__ descs, int k) {
+mala_propose_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int finalize_cur,
+                    double *__restrict__ ll_scratch) {
     __shared__ StepCtx ctx;
     load_step_ctx(&ctx, d, descs, k);
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= d.C) return;
+    // the sweep just before this kernel evaluated the CURRENT state: finish its sums here
+    // (gradient of the current state) instead of in a kernel of its own
+    if (finalize_cur) grad_finalize_chain(d, c, d.theta, ll_scratch, d.grad_cur);
     const StepDesc &sd = ctx.sd;
     const DevUpdate &u = ctx.u;
     const int64_t C = d.C;
@@ -911,11 +922,13 @@ mala_propose_kernel(DevState d, const StepDesc *__restrict__ descs, int k) {
 // K5b: MALA accept/reject.  log q(a -> b) = -|b - a - (tau^2/2) g(a)|^2 / (2 tau^2) (the
 // normalising constant is the same in both directions and is left out).
 __global__ void __launch_bounds__(128)
-mala_accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k) {
-    __shared__ StepCtx ctx;
+mala_accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int finalize_prop, int fuse_next) {
+    __shared__ StepCtx ctx, ctx_next;
     load_step_ctx(&ctx, d, descs, k);
+    if (fuse_next) load_step_ctx(&ctx_next, d, descs, k + 1);
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= d.C) return;
+    if (finalize_prop) grad_finalize_chain(d, c, d.prop_full, d.ll_prop, d.grad_prop);
     const StepDesc &sd = ctx.sd;
     const DevUpdate &u = ctx.u;
     const int64_t C = d.C;
@@ -954,6 +967,8 @@ mala_accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k) {
         for (int j = 0; j < d.p; ++j) d.grad_cur[(int64_t)j * C + c] = d.grad_prop[(int64_t)j * C + c];
     }
     post_decision(d, sd, u, c, accepted, ll_new, ll_prop, 1);
+    // next element is a random-walk update: issue its proposal here (one launch saved)
+    if (fuse_next) propose_chain(d, ctx_next.sd, ctx_next.u, c);
 }
 
 // ---------------------------------------------------------------------------------
@@ -1063,11 +1078,13 @@ void launch_grad_finalize(const DevState &d, const double *src, double *ll_out, 
                           cudaStream_t st) {
     grad_finalize_kernel<<<(int)((d.C + 127) / 128), 128, 0, st>>>(d, src, ll_out, grad_out);
 }
-void launch_mala_propose(const DevState &d, const StepDesc *descs, int k, cudaStream_t st) {
-    mala_propose_kernel<<<(int)((d.C + 127) / 128), 128, 0, st>>>(d, descs, k);
+void launch_mala_propose(const DevState &d, const StepDesc *descs, int k, int finalize_cur, double *ll_scratch,
+                         cudaStream_t st) {
+    mala_propose_kernel<<<(int)((d.C + 127) / 128), 128, 0, st>>>(d, descs, k, finalize_cur, ll_scratch);
 }
-void launch_mala_accept(const DevState &d, const StepDesc *descs, int k, cudaStream_t st) {
-    mala_accept_kernel<<<(int)((d.C + 127) / 128), 128, 0, st>>>(d, descs, k);
+void launch_mala_accept(const DevState &d, const StepDesc *descs, int k, int finalize_prop, int fuse_next,
+                        cudaStream_t st) {
+    mala_accept_kernel<<<(int)((d.C + 127) / 128), 128, 0, st>>>(d, descs, k, finalize_prop, fuse_next);
 }
 void launch_prepare_current(const DevState &d, cudaStream_t st) {
     prepare_current_kernel<<<blocks_for(d.C), 256, 0, st>>>(d);

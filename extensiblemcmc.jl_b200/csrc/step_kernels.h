@@ -9,8 +9,10 @@ void launch_propose(const DevState &d, const StepDesc *descs, int k, cudaStream_
 void launch_accept(const DevState &d, const StepDesc *descs, int k, int fuse_next, cudaStream_t st);
 void launch_prepare_current(const DevState &d, cudaStream_t st);
 void launch_grad_finalize(const DevState &d, const double *src, double *ll_out, double *grad_out, cudaStream_t st);
-void launch_mala_propose(const DevState &d, const StepDesc *descs, int k, cudaStream_t st);
-void launch_mala_accept(const DevState &d, const StepDesc *descs, int k, cudaStream_t st);
+void launch_mala_propose(const DevState &d, const StepDesc *descs, int k, int finalize_cur, double *ll_scratch,
+                         cudaStream_t st);
+void launch_mala_accept(const DevState &d, const StepDesc *descs, int k, int finalize_prop, int fuse_next,
+                        cudaStream_t st);
 void launch_reduce_partials(const DevState &d, cudaStream_t st);
 void launch_reduce_push(const DevState &d, const StepDesc *descs, int k, cudaStream_t st);
 void launch_finalize_loglik(const DevState &d, double *ll_out, cudaStream_t st);
