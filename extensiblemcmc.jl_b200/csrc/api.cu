@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -187,6 +188,7 @@ int32_t ensure_plan(extmcmc_t h) {
     h->d.S = h->plan.S;
     // fused tail of the obs-mapped 1-D sweep (few chains, many segments): see sweep.h
     h->tail = h->cfg.law == EXTMCMC_LAW_GSN_IID_1D && h->plan.variant == SWEEP_VARIANT_OBS;
+    if (const char *e = getenv("EXTMCMC_TAIL")) h->tail = h->tail && atoi(e) != 0;   // diagnostics
     if (h->tail && !h->tail_counter) {
         int32_t rct = dev_alloc(h, &h->tail_counter, 1);
         if (rct) return rct;
