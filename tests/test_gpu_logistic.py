@@ -98,3 +98,22 @@ def test_posterior_matches_oracle_under_own_philox():
     acc = ws.stats()["n_accept"].sum() / ws.stats()["n_prop"].sum()
     assert 0.35 < acc < 0.8
     ws.close()
+
+
+def test_full_size_cfg3_loglik_and_gradient():
+    """BASELINE cfg 3 at full size (d = 256, N = 1e6, 1024 chains): log-likelihood and gradient of
+    every chain in one sweep; 8 chains are checked against the numpy closed form (1e-10)."""
+    n, d, Cn = 1_000_000, 256, 1024
+    rng = np.random.default_rng(4)
+    X = rng.standard_normal((n, d)) / math.sqrt(d)
+    beta = rng.standard_normal(d)
+    y = (rng.random(n) < 1.0 / (1.0 + np.exp(-X @ beta))).astype(np.float64)
+    th0 = beta[:, None] + 0.05 * rng.standard_normal((d, Cn))
+    g = GpuSession(em.LogisticLaw(d), [em.MALAUpdate(0.02, list(range(1, d + 1)))], X, th0, Cn, y=y)
+    ll, gr = g.eval_grad()
+    sub = [0, 1, 63, 64, 500, 777, 1022, 1023]
+    llw, grw = _np_ll_grad(X, y, th0[:, sub])
+    assert np.allclose(ll[sub], llw, rtol=1e-10, atol=0)
+    assert np.allclose(gr[:, sub], grw, rtol=1e-9, atol=1e-8)
+    assert np.isfinite(ll).all() and np.isfinite(gr).all()
+    g.close()

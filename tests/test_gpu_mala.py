@@ -180,3 +180,27 @@ def test_mala_unsupported_combinations():
     with pytest.raises(_abi.ExtMCMCError) as ei:
         GpuSession(em.GsnTargetLaw([0.0]), [em.MALAUpdate(0.1, [1], prior=em.ImproperPosPrior())], x, [0.0, 1.0], 4)
     assert ei.value.code == _abi.EUNSUPPORTED
+
+
+def test_full_size_cfg4_replay_parity():
+    """BASELINE cfg 4 per-GPU size (8 groups x 4096 observations, 8192 chains) for 6 iterations of the
+    MALA + RW + RW-pos schedule: the oracle runs chains 0..255, the other chains are replicas."""
+    G, ng, Cn, sub, M = 8, 4096, 8192, 256, 6
+    y, grp, _ = _hier_data(G, ng, seed=5)
+    law = em.HierNormalLaw(G)
+    ups = _hier_updates(G, tau=0.03)
+    th_sub = _hier_theta0(G, sub)
+    steps = list(em.MCMCSchedule(M, 3))
+    o = orc.Oracle(law, ups, y, th_sub, sub, seed=3, y=grp)
+    ro = o.run(steps, n_threads=8)
+    reps = Cn // sub
+    g = GpuSession(law, ups, y, np.tile(th_sub, (1, reps)), Cn, seed=3, n_steps_hint=len(steps), y=grp)
+    rg = g.run(steps, replay=(np.tile(ro["proposals"], (1, 1, reps)), np.tile(ro["exp_draws"], (1, reps))))
+    from tests.parity import compare_histories
+    rep = compare_histories(ro, {k: v[..., :sub] for k, v in rg.items() if hasattr(v, "shape")})
+    assert rep["accept_mismatch"] == 0 and rep["near_ties"] == 0 and rep["theta_bitexact"], rep
+    assert rep["ll_rel_err"] < 1e-10, rep
+    full = rg["theta"].reshape(rg["theta"].shape[:-1] + (reps, sub))
+    assert np.array_equal(full, np.broadcast_to(full[..., :1, :], full.shape))
+    assert np.array_equal(g.eps(1)[:, :sub], o.eps(1))
+    g.close()
