@@ -1,7 +1,7 @@
-// K1 (proposal) and K3 (accept / commit / statistics / adaptation): one thread per
-// chain, everything SoA and coalesced across chains.  Compiled with -fmad=false: the
-// reference never contracts a*b+c, and the replay parity tests compare eps, running
-// moments and trajectories bit-for-bit against the CPU oracle.
+// K1 (proposal), K3 (accept / commit / statistics / adaptation) and the MALA kernels: one thread
+// per chain, everything SoA and coalesced across chains.  Compiled with -fmad=false: the reference
+// never contracts a*b+c, and the replay parity tests compare eps, running moments and
+// trajectories bit-for-bit against the CPU oracle.
 #include <cmath>
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -336,12 +336,12 @@ __global__ void __launch_bounds__(256) prepare_current_kernel(DevState d) {
     law_prepare(d, c, d.theta + c, d.C);
 }
 
-// Fixed-order reduction of partial[S][C] over the segments.  A 256-thread CTA owns 32
-// chains; slice j (0..7) adds segments j, j+8, j+16, ... (8 independent loads in flight per
-// thread), then the 8 slice sums are combined in slice order.  The order depends only on
-// S, never on timing, so results are reproducible run to run.
-// SL = 8 slices when there are many segments (cfg 2: S = 148), SL = 1 (plain thread per
-// chain, every thread stays busy in the accept phase) when S is small.
+// Fixed-order reduction of partial[.][C] over the segments (and observation groups).  A 256-thread
+// CTA owns 256 / SL chains; slice j of a chain adds rows j, j + SL, j + 2 SL, ... (loads issued in
+// batches of 8 before the first add), then the SL slice sums are combined in slice order.  The
+// order depends only on the row count and SL, never on timing, so results are reproducible.
+// SL = 1 (thread per chain) for few rows, 8 for many rows (cfg 2: 148), 32 for a handful of chains
+// with hundreds of rows (cfg 5).
 constexpr int kRedThreads = 256;
 
 
