@@ -84,7 +84,6 @@ __device__ __forceinline__ double log_q_unif(const DevUpdate &u, const double *e
 }
 
 // ---- Gaussian random walks (random_walk.jl:123-232), n <= kMaxGaussCoords -------------------
-constexpr double kTwoPi = 6.283185307179586476925286766559;
 
 // Lower Cholesky factor of Symmetric(S) (upper triangle of the column-major n x n S).
 __device__ __forceinline__ bool chol_lower_sym_upper(const double *S, int n, double *L) {
@@ -253,15 +252,16 @@ __device__ __forceinline__ void load_step_ctx(StepCtx *ctx, const DevState &d, c
 //     + set_proposal! (src/run.jl:221-240): writes the full proposal and the law
 //     constants the sweep consumes.
 // ---------------------------------------------------------------------------------
-// state_regs / eps_regs: optional register copies (current full state, this update's eps) that a
-// caller already holds; they spare the dependent global loads on the accept kernel's critical path.
+// state_regs / eps_regs: optional register (or shared-memory, element stride sstride) copies of the
+// current full state and of this update's eps that a caller already holds; they spare the dependent
+// global loads on the accept kernel's critical path.
 __device__ __forceinline__ void propose_chain(const DevState &d, const StepDesc &sd, const DevUpdate &u,
                                               int64_t c, const double *state_regs = nullptr,
-                                              const double *eps_regs = nullptr) {
+                                              const double *eps_regs = nullptr, int sstride = 1) {
     const int n = u.n_coords;
     double th[kMaxCoords], prop[kMaxCoords];
     for (int i = 0; i < n; ++i)
-        th[i] = state_regs ? state_regs[u.coords[i]] : d.theta[(int64_t)u.coords[i] * d.C + c];
+        th[i] = state_regs ? state_regs[u.coords[i] * sstride] : d.theta[(int64_t)u.coords[i] * d.C + c];
 
     uint32_t used = 0;
     if (d.rng_mode == EXTMCMC_RNG_REPLAY) {
@@ -315,7 +315,7 @@ __device__ __forceinline__ void propose_chain(const DevState &d, const StepDesc 
     for (int i = 0; i < n; ++i) d.prop_loc[(int64_t)i * d.C + c] = prop[i];
     // full proposal = current state with the update's coordinates replaced (run.jl:237-239)
     for (int j = 0; j < d.p; ++j)
-        d.prop_full[(int64_t)j * d.C + c] = state_regs ? state_regs[j] : d.theta[(int64_t)j * d.C + c];
+        d.prop_full[(int64_t)j * d.C + c] = state_regs ? state_regs[j * sstride] : d.theta[(int64_t)j * d.C + c];
     for (int i = 0; i < n; ++i) d.prop_full[(int64_t)u.coords[i] * d.C + c] = prop[i];
     law_prepare(d, c, d.prop_full + c, d.C);
 }
@@ -499,9 +499,57 @@ __device__ __forceinline__ void prefetch_chain(const DevState &d, const StepDesc
     pf.tot_acc = u.tot_acc[c];
 }
 
+// Cooperative path for models with more than a handful of parameters (cfg 4: p = 10, full p x p
+// covariance).  A CTA owns NCH chains; the chain's own thread stages the committed state and the
+// OLD running mean in shared memory (and writes the new mean), then, after a barrier, ALL threads
+// of the CTA update the NCH x p x p covariance entries -- same arithmetic, one entry per thread per
+// pass, coalesced along the chain axis -- instead of one thread walking p^2 dependent loads.
+constexpr int kCoopP = 32;   // largest p served this way (2 x kCoopP x NCH doubles of shared memory)
+struct CoopStage {
+    double *t;   // [p][nch] committed state
+    double *m;   // [p][nch] running mean before this step
+    int nch, ch;
+};
+
+template <int NCH>
+__device__ __forceinline__ void update_cov_coop(const DevState &d, int64_t N, int64_t c0, const double *sh_t,
+                                                const double *sh_m) {
+    const int p = d.p;
+    const int64_t C = d.C;
+    const double f_old = (double)(N - 1) / (double)N;
+    const double f_mean = (double)N / (double)(N + 1);
+    const double f_new = (double)(N + 1) / (double)N;
+    const int total = NCH * p * p;
+    const int nt = (int)blockDim.x;
+    for (int i0 = threadIdx.x; i0 < total; i0 += 4 * nt) {
+        double cv[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int i = i0 + q * nt;
+            const int ch = i % NCH, e = i / NCH;
+            cv[q] = (i < total && c0 + ch < C) ? d.cov[(int64_t)e * C + c0 + ch] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int i = i0 + q * nt;
+            const int ch = i % NCH, e = i / NCH;
+            if (i < total && c0 + ch < C) {
+                const int a = e % p, b = e / p;
+                const double ta = sh_t[a * NCH + ch], tb = sh_t[b * NCH + ch];
+                const double ma_old = sh_m[a * NCH + ch], mb_old = sh_m[b * NCH + ch];
+                const double ma_new = ma_old * f_mean + ta / (double)(N + 1);
+                const double mb_new = mb_old * f_mean + tb / (double)(N + 1);
+                const double old_sum_sq = f_old * cv[q] + ma_old * mb_old;
+                const double new_sum_sq = old_sum_sq + (ta * tb) / (double)N;
+                d.cov[(int64_t)e * C + c0 + ch] = new_sum_sq - f_new * (ma_new * mb_new);
+            }
+        }
+    }
+}
+
 __device__ __forceinline__ void post_decision(const DevState &d, const StepDesc &sd, const DevUpdate &u,
                                               int64_t c, bool accepted, double ll_new, double ll_prop,
-                                              int n_eps, Prefetch *pf = nullptr) {
+                                              int n_eps, Prefetch *pf = nullptr, const CoopStage *cs = nullptr) {
     const int64_t C = d.C;
     d.ll[c] = ll_new;
     // history row (state_history / state_proposal_history / ll_history / acceptance_history)
@@ -570,17 +618,38 @@ __device__ __forceinline__ void post_decision(const DevState &d, const StepDesc 
         }
         return;
     }
-    for (int j = 0; j < d.p; ++j) {
-        d.h_theta[(slot * d.p + j) * C + c] = d.theta[(int64_t)j * C + c];
-        d.h_prop[(slot * d.p + j) * C + c] = d.prop_full[(int64_t)j * C + c];
+    const int64_t N = sd.stat_n;
+    // history row + (cooperative path) staging; loads in batches of 4 ahead of the stores
+    for (int j0 = 0; j0 < d.p; j0 += 4) {
+        double t[4], pr[4], m[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (j0 + q < d.p) {
+                t[q] = d.theta[(int64_t)(j0 + q) * C + c];
+                pr[q] = d.prop_full[(int64_t)(j0 + q) * C + c];
+                if (cs) m[q] = d.mean[(int64_t)(j0 + q) * C + c];
+            }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (j0 + q < d.p) {
+                const int j = j0 + q;
+                d.h_theta[(slot * d.p + j) * C + c] = t[q];
+                d.h_prop[(slot * d.p + j) * C + c] = pr[q];
+                if (cs) {
+                    cs->t[j * cs->nch + cs->ch] = t[q];
+                    cs->m[j * cs->nch + cs->ch] = m[q];
+                    // new running mean (chain_statistics.jl:46); the covariance entries follow in
+                    // update_cov_coop from the staged old mean
+                    d.mean[(int64_t)j * C + c] = m[q] * ((double)N / (double)(N + 1)) + t[q] / (double)(N + 1);
+                }
+            }
     }
     d.h_ll[slot * C + c] = ll_new;
     d.h_llp[slot * C + c] = ll_prop;
     d.h_acc[slot * C + c] = accepted ? 1 : 0;
 
     // update_stats! (chain_statistics.jl:46-51), verbatim arithmetic
-    const int64_t N = sd.stat_n;
-    if (d.stats_mode != 2) {
+    if (d.stats_mode != 2 && !cs) {
         const double f_old = (double)(N - 1) / (double)N;
         const double f_mean = (double)N / (double)(N + 1);
         const double f_new = (double)(N + 1) / (double)N;
@@ -701,6 +770,9 @@ accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fuse_ne
     constexpr int kRedChains = kRedThreads / SL;
     __shared__ double sh[kRedThreads];
     __shared__ StepCtx ctx, ctx_next;
+    // staging of the cooperative covariance update (only the sliced layouts have spare threads)
+    constexpr int kStage = SL >= 8 ? kCoopP * kRedChains : 1;
+    __shared__ double sh_t[kStage], sh_m[kStage];
     // PDL: this kernel may have been scheduled while the likelihood sweep is still running.
     // Everything up to griddep_wait() only READS state that was final before the sweep started
     // (chain state, proposal, step sizes, law constants, RNG counters) -- the transition-density
@@ -775,23 +847,32 @@ accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fuse_ne
     } else {
         S = reduce_segments<SL>(d, sh);
     }
-    if (!worker) return;
-    const double ll_prop = (use_pf && d.law == EXTMCMC_LAW_GSN_IID_1D)
-                               ? (double)d.n_obs_total * law0 - S * law1   // = law_finalize, constants prefetched
-                               : law_finalize(d, c, S, d.prop_full + c);
-    // llr, strictly left to right (run.jl:271-277)
-    double llr = ll_prop - ll_cur;
-    llr = llr + q_back;
-    llr = llr - q_fwd;
-    llr = llr + lp_prop;
-    llr = llr - lp_cur;
+    // full covariance of a model with more than kPreP parameters: all slices share the work
+    const bool coop = SL >= 8 && !use_pf && d.stats_mode == 0 && d.p <= kCoopP;   // CTA-uniform
+    if (worker) {
+        const double ll_prop = (use_pf && d.law == EXTMCMC_LAW_GSN_IID_1D)
+                                   ? (double)d.n_obs_total * law0 - S * law1   // = law_finalize, constants prefetched
+                                   : law_finalize(d, c, S, d.prop_full + c);
+        // llr, strictly left to right (run.jl:271-277)
+        double llr = ll_prop - ll_cur;
+        llr = llr + q_back;
+        llr = llr - q_fwd;
+        llr = llr + lp_prop;
+        llr = llr - lp_cur;
 
-    const bool accepted = E > -llr;  // NaN compares false -> reject
-    const double ll_new = accepted ? ll_prop : ll_cur;
-    if (accepted)
-        for (int i = 0; i < n; ++i) d.theta[(int64_t)u.coords[i] * C + c] = prop[i];
-    const int n_eps = u.kernel == EXTMCMC_KERNEL_RW_UNIFORM ? n : 0;
-    post_decision(d, sd, u, c, accepted, ll_new, ll_prop, n_eps, use_pf ? &pf : nullptr);
+        const bool accepted = E > -llr;  // NaN compares false -> reject
+        const double ll_new = accepted ? ll_prop : ll_cur;
+        if (accepted)
+            for (int i = 0; i < n; ++i) d.theta[(int64_t)u.coords[i] * C + c] = prop[i];
+        const int n_eps = u.kernel == EXTMCMC_KERNEL_RW_UNIFORM ? n : 0;
+        const CoopStage cs{sh_t, sh_m, kRedChains, (int)(threadIdx.x % kRedChains)};
+        post_decision(d, sd, u, c, accepted, ll_new, ll_prop, n_eps, use_pf ? &pf : nullptr, coop ? &cs : nullptr);
+    }
+    if (coop) {
+        __syncthreads();
+        update_cov_coop<kRedChains>(d, sd.stat_n, (int64_t)blockIdx.x * kRedChains, sh_t, sh_m);
+    }
+    if (!worker) return;
     // proposal of the NEXT schedule element of this block, fused here: the chain's thread
     // already holds its freshly committed state, and one launch per update step is saved
     if (fuse_next == 2) {
@@ -802,6 +883,8 @@ accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fuse_ne
                                : (ctx_next.sd.pidx == sd.pidx && ctx_next.u.kernel == EXTMCMC_KERNEL_RW_UNIFORM) ? pf.eps
                                                                                                             : nullptr;
             propose_chain(d, ctx_next.sd, ctx_next.u, c, pf.new_state, en);
+        } else if (coop) {
+            propose_chain(d, ctx_next.sd, ctx_next.u, c, sh_t + (threadIdx.x % kRedChains), nullptr, kRedChains);
         } else {
             propose_chain(d, ctx_next.sd, ctx_next.u, c);
         }
@@ -856,6 +939,56 @@ __device__ __forceinline__ void grad_finalize_chain(const DevState &d, int64_t c
     }
 }
 
+// The MALA step kernels run as CTAs of kMalaChains chains x kMalaSlices slices (256 threads): the
+// slices share the per-group segment sums of the hierarchical law and the covariance update, the
+// chain's own thread (slice 0) does the scalar work.  Same sums, same order as grad_finalize_chain.
+constexpr int kMalaChains = 32, kMalaSlices = 8;
+constexpr int kCoopG = 16;   // most observation groups reduced this way
+__device__ __forceinline__ void grad_finalize_coop(const DevState &d, int64_t c0, const double *__restrict__ src,
+                                                   double *__restrict__ ll_out, double *__restrict__ grad_out,
+                                                   double *sh2, double *sh1 /*[kCoopG][kMalaChains] each*/) {
+    const int ch = threadIdx.x % kMalaChains, slice = threadIdx.x / kMalaChains;
+    const int64_t c = c0 + ch, C = d.C;
+    const int G = d.G, S = d.S;
+    if (d.law != EXTMCMC_LAW_HIER_NORMAL || G > kCoopG) {   // CTA-uniform
+        if (slice == 0 && c < C) grad_finalize_chain(d, c, src, ll_out, grad_out);
+        return;
+    }
+    const int64_t rows = (int64_t)G * S;
+    if (c < C)
+        for (int g = slice; g < G; g += kMalaSlices) {
+            const double *p2 = d.partial + ((int64_t)g * S) * C + c;
+            const double *p1 = d.partial + (rows + (int64_t)g * S) * C + c;
+            double s2 = 0.0, s1 = 0.0;
+            int i = 0;
+            for (; i + 3 < S; i += 4) {   // loads first, adds in segment order
+                double a[4], b[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { a[q] = p2[(int64_t)(i + q) * C]; b[q] = p1[(int64_t)(i + q) * C]; }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { s2 += a[q]; s1 += b[q]; }
+            }
+            for (; i < S; ++i) { s2 += p2[(int64_t)i * C]; s1 += p1[(int64_t)i * C]; }
+            sh2[g * kMalaChains + ch] = s2;
+            sh1[g * kMalaChains + ch] = s1;
+        }
+    __syncthreads();
+    if (slice != 0 || c >= C) return;
+    const double mu = src[(int64_t)G * C + c], tau = src[(int64_t)(G + 1) * C + c];
+    const double it2 = 1.0 / (tau * tau);
+    double s2_tot = 0.0, dmu = 0.0, dev2 = 0.0;
+    for (int g = 0; g < G; ++g) {
+        s2_tot += sh2[g * kMalaChains + ch];
+        const double dv = src[(int64_t)g * C + c] - mu;
+        grad_out[(int64_t)g * C + c] = sh1[g * kMalaChains + ch] - dv * it2;
+        dmu += dv * it2;
+        dev2 += dv * dv;
+    }
+    grad_out[(int64_t)G * C + c] = dmu;
+    grad_out[(int64_t)(G + 1) * C + c] = -(double)G / tau + dev2 * it2 / tau;
+    ll_out[c] = law_finalize(d, c, s2_tot, src + c);
+}
+
 __global__ void __launch_bounds__(128)
 grad_finalize_kernel(DevState d, const double *__restrict__ src, double *__restrict__ ll_out,
                      double *__restrict__ grad_out) {
@@ -878,22 +1011,30 @@ __device__ __forceinline__ double prior_logpdf1(const DevUpdate &u, double th) {
 }
 
 // K5a: MALA proposal  theta° = theta + (tau^2/2) g(theta) + tau z,  g = grad(ll + log prior)
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kMalaChains * kMalaSlices)
 mala_propose_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int finalize_cur,
                     double *__restrict__ ll_scratch) {
     __shared__ StepCtx ctx;
+    __shared__ double sh2[kCoopG * kMalaChains], sh1[kCoopG * kMalaChains];
     load_step_ctx(&ctx, d, descs, k);
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= d.C) return;
+    const int64_t c0 = (int64_t)blockIdx.x * kMalaChains;
+    const int64_t c = c0 + threadIdx.x % kMalaChains;
     // the sweep just before this kernel evaluated the CURRENT state: finish its sums here
     // (gradient of the current state) instead of in a kernel of its own
-    if (finalize_cur) grad_finalize_chain(d, c, d.theta, ll_scratch, d.grad_cur);
+    if (finalize_cur) grad_finalize_coop(d, c0, d.theta, ll_scratch, d.grad_cur, sh2, sh1);
+    if (threadIdx.x >= kMalaChains || c >= d.C) return;
     const StepDesc &sd = ctx.sd;
     const DevUpdate &u = ctx.u;
     const int64_t C = d.C;
     const int n = u.n_coords;
     const double tau = u.eps[c], h2 = tau * tau / 2.0;
-    for (int j = 0; j < d.p; ++j) d.prop_full[(int64_t)j * C + c] = d.theta[(int64_t)j * C + c];
+    for (int j0 = 0; j0 < d.p; j0 += 4) {   // prop_full <- theta, loads ahead of the stores
+        double t[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) if (j0 + q < d.p) t[q] = d.theta[(int64_t)(j0 + q) * C + c];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) if (j0 + q < d.p) d.prop_full[(int64_t)(j0 + q) * C + c] = t[q];
+    }
     if (d.rng_mode == EXTMCMC_RNG_REPLAY) {
         for (int i = 0; i < n; ++i)
             d.prop_full[(int64_t)u.coords_dev[i] * C + c] = d.rp_prop[((int64_t)sd.replay_row * d.p_u_max + i) * C + c];
@@ -921,30 +1062,38 @@ mala_propose_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int f
 
 // K5b: MALA accept/reject.  log q(a -> b) = -|b - a - (tau^2/2) g(a)|^2 / (2 tau^2) (the
 // normalising constant is the same in both directions and is left out).
-__global__ void __launch_bounds__(128)
-mala_accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int finalize_prop, int fuse_next) {
-    __shared__ StepCtx ctx, ctx_next;
-    load_step_ctx(&ctx, d, descs, k);
-    if (fuse_next) load_step_ctx(&ctx_next, d, descs, k + 1);
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= d.C) return;
-    if (finalize_prop) grad_finalize_chain(d, c, d.prop_full, d.ll_prop, d.grad_prop);
+// mala_decide: the chain's own thread -- decision, commit, history, counters; with sh_t != nullptr
+// the covariance update is left to update_cov_coop (see CoopStage).
+__device__ __forceinline__ void mala_decide(const DevState &d, const StepCtx &ctx, int64_t c, double *sh_t,
+                                            double *sh_m, int ch) {
     const StepDesc &sd = ctx.sd;
     const DevUpdate &u = ctx.u;
     const int64_t C = d.C;
     const int n = u.n_coords;
     const double tau = u.eps[c], h2 = tau * tau / 2.0;
     double qf = 0.0, qb = 0.0, lp_prop = 0.0, lp_cur = 0.0;
-    for (int i = 0; i < n; ++i) {
-        const int64_t j = u.coords_dev[i];
-        const double a = d.theta[j * C + c], b = d.prop_full[j * C + c];
-        const double ga = d.grad_cur[j * C + c] + prior_grad(u, a);
-        const double gb = d.grad_prop[j * C + c] + prior_grad(u, b);
-        const double rf = b - a - h2 * ga, rb = a - b - h2 * gb;
-        qf += rf * rf;
-        qb += rb * rb;
-        lp_prop += prior_logpdf1(u, b);
-        lp_cur += prior_logpdf1(u, a);
+    for (int i0 = 0; i0 < n; i0 += 2) {   // loads of two coordinates in flight; sums in index order
+        double a[2], b[2], ga[2], gb[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+            if (i0 + q < n) {
+                const int64_t j = u.coords_dev[i0 + q];
+                a[q] = d.theta[j * C + c];
+                b[q] = d.prop_full[j * C + c];
+                ga[q] = d.grad_cur[j * C + c];
+                gb[q] = d.grad_prop[j * C + c];
+            }
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+            if (i0 + q < n) {
+                const double gaq = ga[q] + prior_grad(u, a[q]);
+                const double gbq = gb[q] + prior_grad(u, b[q]);
+                const double rf = b[q] - a[q] - h2 * gaq, rb = a[q] - b[q] - h2 * gbq;
+                qf += rf * rf;
+                qb += rb * rb;
+                lp_prop += prior_logpdf1(u, b[q]);
+                lp_cur += prior_logpdf1(u, a[q]);
+            }
     }
     const double inv = 1.0 / (2.0 * tau * tau);
     qf = -qf * inv;  // theta -> theta°
@@ -964,11 +1113,41 @@ mala_accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fi
             const int64_t j = u.coords_dev[i];
             d.theta[j * C + c] = d.prop_full[j * C + c];
         }
-        for (int j = 0; j < d.p; ++j) d.grad_cur[(int64_t)j * C + c] = d.grad_prop[(int64_t)j * C + c];
+        for (int j0 = 0; j0 < d.p; j0 += 4) {   // grad_cur <- grad_prop
+            double g[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (j0 + q < d.p) g[q] = d.grad_prop[(int64_t)(j0 + q) * C + c];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (j0 + q < d.p) d.grad_cur[(int64_t)(j0 + q) * C + c] = g[q];
+        }
     }
-    post_decision(d, sd, u, c, accepted, ll_new, ll_prop, 1);
+    const CoopStage cs{sh_t, sh_m, kMalaChains, ch};
+    post_decision(d, sd, u, c, accepted, ll_new, ll_prop, 1, nullptr, sh_t ? &cs : nullptr);
+}
+
+__global__ void __launch_bounds__(kMalaChains * kMalaSlices)
+mala_accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int finalize_prop, int fuse_next) {
+    __shared__ StepCtx ctx, ctx_next;
+    __shared__ double sh2[kCoopG * kMalaChains], sh1[kCoopG * kMalaChains];
+    __shared__ double sh_t[kCoopP * kMalaChains], sh_m[kCoopP * kMalaChains];
+    load_step_ctx(&ctx, d, descs, k);
+    if (fuse_next) load_step_ctx(&ctx_next, d, descs, k + 1);
+    const int64_t c0 = (int64_t)blockIdx.x * kMalaChains;
+    const int ch = threadIdx.x % kMalaChains;
+    const int64_t c = c0 + ch;
+    if (finalize_prop) grad_finalize_coop(d, c0, d.prop_full, d.ll_prop, d.grad_prop, sh2, sh1);
+    const bool worker = threadIdx.x < kMalaChains && c < d.C;
+    const bool coop = d.stats_mode == 0 && d.p <= kCoopP;   // CTA-uniform
+    if (worker) mala_decide(d, ctx, c, coop ? sh_t : nullptr, sh_m, ch);
+    if (coop) {
+        __syncthreads();
+        update_cov_coop<kMalaChains>(d, ctx.sd.stat_n, c0, sh_t, sh_m);
+    }
     // next element is a random-walk update: issue its proposal here (one launch saved)
-    if (fuse_next) propose_chain(d, ctx_next.sd, ctx_next.u, c);
+    if (worker && fuse_next) {
+        if (coop) propose_chain(d, ctx_next.sd, ctx_next.u, c, sh_t + ch, nullptr, kMalaChains);
+        else propose_chain(d, ctx_next.sd, ctx_next.u, c);
+    }
 }
 
 // ---------------------------------------------------------------------------------
@@ -1050,7 +1229,9 @@ static inline int red_blocks_for(int64_t C, int sl) {
 // reduction slices per chain: 1 (thread per chain) for few segments; 8; 32 for a handful of chains
 // with hundreds of segments (cfg 5), so that the cold loads of the partial sums overlap
 static inline int slices_for(const DevState &d) {
-    if (d.use_ssum || d.S * d.G <= 16) return 1;
+    // a full covariance of more than kPreP parameters is updated by all slices (update_cov_coop)
+    const bool coop = !(d.p <= kPreP && d.n_haario == 0) && d.stats_mode == 0 && d.p <= kCoopP;
+    if (!coop && (d.use_ssum || d.S * d.G <= 16)) return 1;
     return d.C <= 8 ? 32 : 8;
 }
 void launch_accept(const DevState &d, const StepDesc *descs, int k, int fuse_next, cudaStream_t st) {
@@ -1080,11 +1261,13 @@ void launch_grad_finalize(const DevState &d, const double *src, double *ll_out, 
 }
 void launch_mala_propose(const DevState &d, const StepDesc *descs, int k, int finalize_cur, double *ll_scratch,
                          cudaStream_t st) {
-    mala_propose_kernel<<<(int)((d.C + 127) / 128), 128, 0, st>>>(d, descs, k, finalize_cur, ll_scratch);
+    mala_propose_kernel<<<(int)((d.C + kMalaChains - 1) / kMalaChains), kMalaChains * kMalaSlices, 0, st>>>(
+        d, descs, k, finalize_cur, ll_scratch);
 }
 void launch_mala_accept(const DevState &d, const StepDesc *descs, int k, int finalize_prop, int fuse_next,
                         cudaStream_t st) {
-    mala_accept_kernel<<<(int)((d.C + 127) / 128), 128, 0, st>>>(d, descs, k, finalize_prop, fuse_next);
+    mala_accept_kernel<<<(int)((d.C + kMalaChains - 1) / kMalaChains), kMalaChains * kMalaSlices, 0, st>>>(
+        d, descs, k, finalize_prop, fuse_next);
 }
 void launch_prepare_current(const DevState &d, cudaStream_t st) {
     prepare_current_kernel<<<blocks_for(d.C), 256, 0, st>>>(d);

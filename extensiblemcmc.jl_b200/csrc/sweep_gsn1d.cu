@@ -373,13 +373,27 @@ SweepPlan plan_sweep_gsn1d(int64_t C, int64_t n_obs, int force_variant, int num_
     if (chains) {
         // chains per thread: the largest R in {8,4,2,1} that still yields >= 2 CTAs per SM
         // (small N limits the number of segments, so small problems trade registers for CTAs)
-        const int64_t max_S = (n_pairs + 255) / 256;  // >= 512 observations per segment
+        const int64_t max_S = (n_pairs + 127) / 128;  // >= 256 observations per segment
         int R = 8, S = 1, groups = 1;
         for (;; R >>= 1) {
             groups = (int)((C + (int64_t)kChainsNT * R - 1) / ((int64_t)kChainsNT * R));
             S = (num_sms * 4 + groups * G - 1) / (groups * G);
             if (S > max_S) S = (int)max_S;
             if (S < 1) S = 1;
+            // The FP64 pipe of an SM is shared by its resident CTAs, so the sweep lasts as long as
+            // the busiest SM: ceil(CTAs / SMs) segments of ceil(n_pairs / S) pairs (+ ~32 pairs of
+            // per-CTA prologue).  Pick the S near the target that minimises that product -- with
+            // grouped data (cfg 4: 64 x S CTAs) the nearest multiple of the SM count is not S itself.
+            {
+                auto cost = [&](int s_) {
+                    const int64_t ctas = (int64_t)groups * G * s_;
+                    return ((ctas + num_sms - 1) / num_sms) * ((n_pairs + s_ - 1) / s_ + 32);
+                };
+                int best = S;
+                for (int s_ = S > 3 ? S - 3 : 1; s_ <= S + 3 && s_ <= max_S; ++s_)
+                    if (cost(s_) < cost(best)) best = s_;
+                S = best;
+            }
             const bool fits = C >= (int64_t)kChainsNT * R;      // no mostly-empty thread tiles
             if (force_R ? R == force_R : (R == 1 || (fits && (int64_t)groups * S * G >= 2 * num_sms))) break;
             if (R == 1) break;

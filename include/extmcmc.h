@@ -199,7 +199,7 @@ int32_t extmcmc_abi_version(void);
 /* Replaces the user's law object + its observations: data = (P = law, obs = ...)
  * (src/workspaces.jl:229-237).  Row-major obs[n_obs][obs_dim]; y = responses (LOGISTIC)
  * or the 0-based group index of every observation, sorted ascending (HIER_NORMAL);
- * NULL otherwise.  The library copies.
+ * NULL otherwise.  The library copies.  n_obs >= 1 (EXTMCMC_EINVAL otherwise).
  * Under EXTMCMC_SHARD_OBS each rank uploads only its own slice. */
 int32_t extmcmc_upload_obs(extmcmc_t h, const double *obs, int64_t n_obs,
                            int32_t obs_dim, const double *y);

@@ -42,7 +42,7 @@ const char *oracle_last_error(void);
 /*
  * Run n_steps schedule elements for every chain (chain loop outermost, as the
  * reference would run C separate samplers).  n_threads > 1 distributes chains
- * over OpenMP threads (results do not depend on it).
+ * over a pthread pool (results do not depend on it).
  *
  * rng_mode EXTMCMC_RNG_PHILOX: draws come from the per-chain Philox stream; if
  *   rec_proposals / rec_exp are non-NULL the local proposals
