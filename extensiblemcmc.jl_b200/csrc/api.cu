@@ -250,7 +250,11 @@ int32_t enqueue_sweep(extmcmc_t h, bool instrument, bool grad = false, const dou
     if (h->cfg.law == EXTMCMC_LAW_GSN_IID_1D || h->cfg.law == EXTMCMC_LAW_HIER_NORMAL) {
         Gsn1dArgs a{};
         a.obs = h->obs_dev; a.goff = h->goff_dev; a.glen = h->glen_dev; a.G = h->d.G;
-        a.mu = h->d.lawc; a.C = h->d.C; a.partial = h->d.partial; a.S = h->plan.S;
+        // per-chain means: the law constants for the iid law; theta_1..G of the evaluated state
+        // itself (src, [p][C]) for the hierarchical law
+        a.mu = h->cfg.law == EXTMCMC_LAW_HIER_NORMAL ? src : h->d.lawc;
+        if (!a.mu) return fail(h, EXTMCMC_EINVAL, "internal: sweep without a source state");
+        a.C = h->d.C; a.partial = h->d.partial; a.S = h->plan.S;
         tail_done = h->tail && !grad;
         if (tail_done) {
             const bool push = obs_sharded(h) && h->d.p2p && d_descs;
@@ -322,8 +326,9 @@ int32_t enqueue_steps(extmcmc_t h, const StepDesc *d_descs, const int *kinds, in
                     if ((rc = enqueue_sweep(h, instrument, true, h->d.theta, h->scratch_ll, h->d.grad_cur))) return rc;
                 } else {
                     // current-state gradient sweep; its sums are finished inside mala_propose
-                    if (!cur_prepared) { launch_prepare_current(h->d, h->stream); h->launches += 1; }
-                    if ((rc = enqueue_sweep(h, instrument, true))) return rc;
+                    const bool hier = h->cfg.law == EXTMCMC_LAW_HIER_NORMAL;   // no law constants to prepare
+                    if (!cur_prepared && !hier) { launch_prepare_current(h->d, h->stream); h->launches += 1; }
+                    if ((rc = enqueue_sweep(h, instrument, true, h->d.theta))) return rc;
                     finalize_cur = 1;
                 }
             }
@@ -331,7 +336,7 @@ int32_t enqueue_steps(extmcmc_t h, const StepDesc *d_descs, const int *kinds, in
             if (logi) {
                 if ((rc = enqueue_sweep(h, instrument, true, h->d.prop_full, h->d.ll_prop, h->d.grad_prop))) return rc;
             } else {
-                if ((rc = enqueue_sweep(h, instrument, true))) return rc;   // finished inside mala_accept
+                if ((rc = enqueue_sweep(h, instrument, true, h->d.prop_full))) return rc;   // finished inside mala_accept
             }
             fused = next_rw;   // the next random-walk proposal rides on this accept kernel
             launch_mala_accept(h->d, d_descs, k, logi ? 0 : 1, fused ? 1 : 0, h->stream);
@@ -344,7 +349,7 @@ int32_t enqueue_steps(extmcmc_t h, const StepDesc *d_descs, const int *kinds, in
             fused = next_rw;
             // a MALA element follows and will need the law constants of the (then) current state for
             // its gradient sweep: let this accept kernel write them (fuse_next = 2)
-            cur_prepared = next_mala && h->cfg.law != EXTMCMC_LAW_LOGISTIC;
+            cur_prepared = next_mala && h->cfg.law != EXTMCMC_LAW_LOGISTIC && h->cfg.law != EXTMCMC_LAW_HIER_NORMAL;
             launch_accept(h->d, d_descs, k, fused ? 1 : (cur_prepared ? 2 : 0), h->stream);
             h->launches += 1;
             grad_valid = false;
@@ -1218,7 +1223,7 @@ int32_t extmcmc_eval_loglik(extmcmc_t h, double *ll_out) {
         if ((rc = enqueue_sweep(h, h->cfg.instrument != 0, false, h->d.theta, h->scratch_ll, nullptr))) return rc;
     } else {
         launch_prepare_current(h->d, h->stream);
-        if ((rc = enqueue_sweep(h, h->cfg.instrument != 0))) return rc;
+        if ((rc = enqueue_sweep(h, h->cfg.instrument != 0, false, h->d.theta))) return rc;
         if (!obs_sharded(h) && !h->tail) { launch_reduce_partials(h->d, h->stream); h->launches += 1; }
         launch_finalize_loglik(h->d, h->scratch_ll, h->stream);
         h->launches += 2;
@@ -1245,7 +1250,7 @@ int32_t extmcmc_eval_grad(extmcmc_t h, double *ll_out, double *grad_out) {
         if ((rc = enqueue_sweep(h, h->cfg.instrument != 0, true, h->d.theta, h->scratch_ll, h->d.grad_cur))) return rc;
     } else {
         launch_prepare_current(h->d, h->stream);
-        if ((rc = enqueue_sweep(h, h->cfg.instrument != 0, true))) return rc;
+        if ((rc = enqueue_sweep(h, h->cfg.instrument != 0, true, h->d.theta))) return rc;
         launch_grad_finalize(h->d, h->d.theta, h->scratch_ll, h->d.grad_cur, h->stream);
         h->launches += 2;
     }

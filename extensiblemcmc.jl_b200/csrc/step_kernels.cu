@@ -167,7 +167,7 @@ __device__ __forceinline__ void law_prepare(const DevState &d, int64_t c, const 
         d.lawc[d.C + c] = c0;
         d.lawc[2 * d.C + c] = inv2;
     } else if (d.law == EXTMCMC_LAW_HIER_NORMAL) {
-        for (int g = 0; g < d.G; ++g) d.lawc[(int64_t)g * d.C + c] = full[(int64_t)g * stride];
+        // no constants: the sweep reads theta_1..G straight from the state array it is given
         const double tau = full[(int64_t)(d.G + 1) * stride];
         if (!(tau > 0.0) || isinf(tau)) *d.err_flag = 1;
     } else if (d.law == EXTMCMC_LAW_GSN_MV) {
@@ -506,8 +506,8 @@ __device__ __forceinline__ void prefetch_chain(const DevState &d, const StepDesc
 // pass, coalesced along the chain axis -- instead of one thread walking p^2 dependent loads.
 constexpr int kCoopP = 32;   // largest p served this way (2 x kCoopP x NCH doubles of shared memory)
 struct CoopStage {
-    double *t;   // [p][nch] committed state
-    double *m;   // [p][nch] running mean before this step
+    double *t;   // [p][nch] committed state (also feeds the fused next proposal)
+    double *m;   // [p][nch] running mean before this step; nullptr unless the full covariance is kept
     int nch, ch;
 };
 
@@ -619,15 +619,23 @@ __device__ __forceinline__ void post_decision(const DevState &d, const StepDesc 
         return;
     }
     const int64_t N = sd.stat_n;
-    // history row + (cooperative path) staging; loads in batches of 4 ahead of the stores
+    const double f_old = (double)(N - 1) / (double)N;
+    const double f_mean = (double)N / (double)(N + 1);
+    const double f_new = (double)(N + 1) / (double)N;
+    const bool coop_full = cs && cs->m;        // full covariance left to update_cov_coop
+    const bool diag = d.stats_mode == 1;
+    // History row, staging and -- diagonal statistics / cooperative path -- update_stats!
+    // (chain_statistics.jl:46-51, verbatim arithmetic); loads in batches of 4 ahead of the stores
+    // (the stores may alias the loads as far as the compiler knows, so a plain loop serialises).
     for (int j0 = 0; j0 < d.p; j0 += 4) {
-        double t[4], pr[4], m[4];
+        double t[4], pr[4], m[4], cv[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q)
             if (j0 + q < d.p) {
                 t[q] = d.theta[(int64_t)(j0 + q) * C + c];
                 pr[q] = d.prop_full[(int64_t)(j0 + q) * C + c];
-                if (cs) m[q] = d.mean[(int64_t)(j0 + q) * C + c];
+                if (coop_full || diag) m[q] = d.mean[(int64_t)(j0 + q) * C + c];
+                if (diag) cv[q] = d.cov[(int64_t)(j0 + q) * C + c];
             }
 #pragma unroll
         for (int q = 0; q < 4; ++q)
@@ -635,12 +643,16 @@ __device__ __forceinline__ void post_decision(const DevState &d, const StepDesc 
                 const int j = j0 + q;
                 d.h_theta[(slot * d.p + j) * C + c] = t[q];
                 d.h_prop[(slot * d.p + j) * C + c] = pr[q];
-                if (cs) {
-                    cs->t[j * cs->nch + cs->ch] = t[q];
-                    cs->m[j * cs->nch + cs->ch] = m[q];
-                    // new running mean (chain_statistics.jl:46); the covariance entries follow in
-                    // update_cov_coop from the staged old mean
-                    d.mean[(int64_t)j * C + c] = m[q] * ((double)N / (double)(N + 1)) + t[q] / (double)(N + 1);
+                if (cs) cs->t[j * cs->nch + cs->ch] = t[q];
+                if (coop_full) cs->m[j * cs->nch + cs->ch] = m[q];
+                if (coop_full || diag) {
+                    const double m_new = m[q] * f_mean + t[q] / (double)(N + 1);
+                    if (diag) {
+                        const double old_sum_sq = f_old * cv[q] + m[q] * m[q];
+                        const double new_sum_sq = old_sum_sq + (t[q] * t[q]) / (double)N;
+                        d.cov[(int64_t)j * C + c] = new_sum_sq - f_new * (m_new * m_new);
+                    }
+                    d.mean[(int64_t)j * C + c] = m_new;
                 }
             }
     }
@@ -648,37 +660,22 @@ __device__ __forceinline__ void post_decision(const DevState &d, const StepDesc 
     d.h_llp[slot * C + c] = ll_prop;
     d.h_acc[slot * C + c] = accepted ? 1 : 0;
 
-    // update_stats! (chain_statistics.jl:46-51), verbatim arithmetic
-    if (d.stats_mode != 2 && !cs) {
-        const double f_old = (double)(N - 1) / (double)N;
-        const double f_mean = (double)N / (double)(N + 1);
-        const double f_new = (double)(N + 1) / (double)N;
+    // full covariance by this thread alone (more than kCoopP parameters, or no spare threads)
+    if (d.stats_mode == 0 && !coop_full) {
         const int p = d.p;
-        if (d.stats_mode == 0) {
-            // covariance first (it needs the old mean), column by column
-            for (int b = 0; b < p; ++b) {
-                const double tb = d.theta[(int64_t)b * C + c];
-                const double mb_old = d.mean[(int64_t)b * C + c];
-                const double mb_new = mb_old * f_mean + tb / (double)(N + 1);
-                for (int a = 0; a < p; ++a) {
-                    const double ta = d.theta[(int64_t)a * C + c];
-                    const double ma_old = d.mean[(int64_t)a * C + c];
-                    const double ma_new = ma_old * f_mean + ta / (double)(N + 1);
-                    const int64_t idx = ((int64_t)(a + b * p)) * C + c;
-                    const double old_sum_sq = f_old * d.cov[idx] + ma_old * mb_old;
-                    const double new_sum_sq = old_sum_sq + (ta * tb) / (double)N;
-                    d.cov[idx] = new_sum_sq - f_new * (ma_new * mb_new);
-                }
-            }
-        } else {
+        // covariance first (it needs the old mean), column by column
+        for (int b = 0; b < p; ++b) {
+            const double tb = d.theta[(int64_t)b * C + c];
+            const double mb_old = d.mean[(int64_t)b * C + c];
+            const double mb_new = mb_old * f_mean + tb / (double)(N + 1);
             for (int a = 0; a < p; ++a) {
                 const double ta = d.theta[(int64_t)a * C + c];
                 const double ma_old = d.mean[(int64_t)a * C + c];
                 const double ma_new = ma_old * f_mean + ta / (double)(N + 1);
-                const int64_t idx = (int64_t)a * C + c;
-                const double old_sum_sq = f_old * d.cov[idx] + ma_old * ma_old;
-                const double new_sum_sq = old_sum_sq + (ta * ta) / (double)N;
-                d.cov[idx] = new_sum_sq - f_new * (ma_new * ma_new);
+                const int64_t idx = ((int64_t)(a + b * p)) * C + c;
+                const double old_sum_sq = f_old * d.cov[idx] + ma_old * mb_old;
+                const double new_sum_sq = old_sum_sq + (ta * tb) / (double)N;
+                d.cov[idx] = new_sum_sq - f_new * (ma_new * mb_new);
             }
         }
         for (int a = 0; a < p; ++a) {
@@ -848,7 +845,8 @@ accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fuse_ne
         S = reduce_segments<SL>(d, sh);
     }
     // full covariance of a model with more than kPreP parameters: all slices share the work
-    const bool coop = SL >= 8 && !use_pf && d.stats_mode == 0 && d.p <= kCoopP;   // CTA-uniform
+    const bool stage = SL >= 8 && !use_pf && d.p <= kCoopP;   // CTA-uniform
+    const bool coop = stage && d.stats_mode == 0;
     if (worker) {
         const double ll_prop = (use_pf && d.law == EXTMCMC_LAW_GSN_IID_1D)
                                    ? (double)d.n_obs_total * law0 - S * law1   // = law_finalize, constants prefetched
@@ -865,8 +863,8 @@ accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fuse_ne
         if (accepted)
             for (int i = 0; i < n; ++i) d.theta[(int64_t)u.coords[i] * C + c] = prop[i];
         const int n_eps = u.kernel == EXTMCMC_KERNEL_RW_UNIFORM ? n : 0;
-        const CoopStage cs{sh_t, sh_m, kRedChains, (int)(threadIdx.x % kRedChains)};
-        post_decision(d, sd, u, c, accepted, ll_new, ll_prop, n_eps, use_pf ? &pf : nullptr, coop ? &cs : nullptr);
+        const CoopStage cs{sh_t, coop ? sh_m : nullptr, kRedChains, (int)(threadIdx.x % kRedChains)};
+        post_decision(d, sd, u, c, accepted, ll_new, ll_prop, n_eps, use_pf ? &pf : nullptr, stage ? &cs : nullptr);
     }
     if (coop) {
         __syncthreads();
@@ -883,7 +881,7 @@ accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fuse_ne
                                : (ctx_next.sd.pidx == sd.pidx && ctx_next.u.kernel == EXTMCMC_KERNEL_RW_UNIFORM) ? pf.eps
                                                                                                             : nullptr;
             propose_chain(d, ctx_next.sd, ctx_next.u, c, pf.new_state, en);
-        } else if (coop) {
+        } else if (stage) {
             propose_chain(d, ctx_next.sd, ctx_next.u, c, sh_t + (threadIdx.x % kRedChains), nullptr, kRedChains);
         } else {
             propose_chain(d, ctx_next.sd, ctx_next.u, c);
@@ -919,6 +917,7 @@ __device__ __forceinline__ void grad_finalize_chain(const DevState &d, int64_t c
         grad_out[C + c] = -(double)d.n_obs_total / (2.0 * var) + s2 / (2.0 * var * var);
     } else if (d.law == EXTMCMC_LAW_HIER_NORMAL) {
         const double mu = src[(int64_t)G * C + c], tau = src[(int64_t)(G + 1) * C + c];
+        if (!(tau > 0.0) || isinf(tau)) *d.err_flag = 1;   // the current state never went through law_prepare
         const double it2 = 1.0 / (tau * tau);
         double s2_tot = 0.0, dmu = 0.0, dev2 = 0.0;
         for (int g = 0; g < G; ++g) {
@@ -975,6 +974,7 @@ __device__ __forceinline__ void grad_finalize_coop(const DevState &d, int64_t c0
     __syncthreads();
     if (slice != 0 || c >= C) return;
     const double mu = src[(int64_t)G * C + c], tau = src[(int64_t)(G + 1) * C + c];
+    if (!(tau > 0.0) || isinf(tau)) *d.err_flag = 1;   // the current state never went through law_prepare
     const double it2 = 1.0 / (tau * tau);
     double s2_tot = 0.0, dmu = 0.0, dev2 = 0.0;
     for (int g = 0; g < G; ++g) {
@@ -1062,8 +1062,8 @@ mala_propose_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int f
 
 // K5b: MALA accept/reject.  log q(a -> b) = -|b - a - (tau^2/2) g(a)|^2 / (2 tau^2) (the
 // normalising constant is the same in both directions and is left out).
-// mala_decide: the chain's own thread -- decision, commit, history, counters; with sh_t != nullptr
-// the covariance update is left to update_cov_coop (see CoopStage).
+// mala_decide: the chain's own thread -- decision, commit, history, counters; sh_t / sh_m: staging
+// (see CoopStage; with sh_m the covariance update is left to update_cov_coop).
 __device__ __forceinline__ void mala_decide(const DevState &d, const StepCtx &ctx, int64_t c, double *sh_t,
                                             double *sh_m, int ch) {
     const StepDesc &sd = ctx.sd;
@@ -1137,15 +1137,16 @@ mala_accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fi
     const int64_t c = c0 + ch;
     if (finalize_prop) grad_finalize_coop(d, c0, d.prop_full, d.ll_prop, d.grad_prop, sh2, sh1);
     const bool worker = threadIdx.x < kMalaChains && c < d.C;
-    const bool coop = d.stats_mode == 0 && d.p <= kCoopP;   // CTA-uniform
-    if (worker) mala_decide(d, ctx, c, coop ? sh_t : nullptr, sh_m, ch);
+    const bool stage = d.p <= kCoopP;   // CTA-uniform
+    const bool coop = stage && d.stats_mode == 0;
+    if (worker) mala_decide(d, ctx, c, stage ? sh_t : nullptr, coop ? sh_m : nullptr, ch);
     if (coop) {
         __syncthreads();
         update_cov_coop<kMalaChains>(d, ctx.sd.stat_n, c0, sh_t, sh_m);
     }
     // next element is a random-walk update: issue its proposal here (one launch saved)
     if (worker && fuse_next) {
-        if (coop) propose_chain(d, ctx_next.sd, ctx_next.u, c, sh_t + ch, nullptr, kMalaChains);
+        if (stage) propose_chain(d, ctx_next.sd, ctx_next.u, c, sh_t + ch, nullptr, kMalaChains);
         else propose_chain(d, ctx_next.sd, ctx_next.u, c);
     }
 }
@@ -1230,8 +1231,9 @@ static inline int red_blocks_for(int64_t C, int sl) {
 // with hundreds of segments (cfg 5), so that the cold loads of the partial sums overlap
 static inline int slices_for(const DevState &d) {
     // a full covariance of more than kPreP parameters is updated by all slices (update_cov_coop)
-    const bool coop = !(d.p <= kPreP && d.n_haario == 0) && d.stats_mode == 0 && d.p <= kCoopP;
-    if (!coop && (d.use_ssum || d.S * d.G <= 16)) return 1;
+    // (and its state is staged in shared memory for the fused next proposal)
+    const bool stage = !(d.p <= kPreP && d.n_haario == 0) && d.p <= kCoopP;
+    if (!stage && (d.use_ssum || d.S * d.G <= 16)) return 1;
     return d.C <= 8 ? 32 : 8;
 }
 void launch_accept(const DevState &d, const StepDesc *descs, int k, int fuse_next, cudaStream_t st) {
