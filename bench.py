@@ -509,7 +509,7 @@ def run_cfg34(args):
     def make(instrument):
         mcmc = em.MCMC(ups, backend=em.CUDAMCMCBackend(n_chains=C, chain_offset=rank * C, device=local, seed=7,
                                                        history="none", block_len=NUc, use_graphs=not instrument,
-                                                       instrument=instrument, stats_mode=1))
+                                                       instrument=instrument))   # stats: full covariance for p <= 16, variances beyond
         init_(mcmc, 1, data, th0)
         return mcmc.workspace
     K, Wm = args.steps, max(args.warmup, 3)

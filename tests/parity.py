@@ -49,6 +49,7 @@ class GpuSession:
         cfg.use_graphs = cfg_kw.pop("use_graphs", 0)
         for k, v in cfg_kw.items():
             setattr(cfg, k, v)
+        self.stats_mode = int(cfg.stats_mode)
         self.h = _abi.Handle()
         rc = self.lib.extmcmc_create(C.byref(cfg), C.byref(self.h))
         if rc:
@@ -124,8 +125,9 @@ class GpuSession:
         self.ck(self.lib.extmcmc_get_stats(self.h, _abi.dptr(mean), _abi.dptr(cov), _abi.dptr(ra),
                                            na.ctypes.data_as(_abi.c_int64_p),
                                            npr.ctypes.data_as(_abi.c_int64_p)))
-        return dict(mean=mean, cov=cov.reshape(p, p, Cn).transpose(1, 0, 2), rolling_ar=ra,
-                    n_accept=na, n_prop=npr)
+        # stats_mode 1 keeps the variances only: the library fills the first p rows
+        cov = cov[:p] if self.stats_mode == 1 else cov.reshape(p, p, Cn).transpose(1, 0, 2)
+        return dict(mean=mean, cov=cov, rolling_ar=ra, n_accept=na, n_prop=npr)
 
     def eps(self, u):
         n = self.p_u[u - 1]
@@ -210,7 +212,8 @@ def replay_compare(x, n_chains, n_iters, seed=1, updates=None, theta_init=None, 
         rep["eps_max_rel"] = max([float(np.max(np.abs(o.eps(u) - g.eps(u)) / np.maximum(np.abs(o.eps(u)), 1e-300)))
                                   for u in with_state] or [0.0])
         rep["mean_bitexact"] = bool(np.array_equal(so["mean"], sg["mean"]))
-        rep["cov_bitexact"] = bool(np.array_equal(so["cov"], sg["cov"]))
+        cov_o = np.einsum("aac->ac", so["cov"]) if g.stats_mode == 1 else so["cov"]
+        rep["cov_bitexact"] = bool(np.array_equal(cov_o, sg["cov"]))
         rep["rolling_ar_bitexact"] = bool(np.array_equal(so["rolling_ar"], sg["rolling_ar"]))
         rep["counts_equal"] = bool(np.array_equal(so["n_accept"], sg["n_accept"]) and
                                    np.array_equal(so["n_prop"], sg["n_prop"]))

@@ -118,6 +118,16 @@ def test_cfg4_schedule_replay_parity(n_chains, ragged):
     _clean(rep)
 
 
+def test_cfg4_schedule_replay_parity_variances_only():
+    # stats_mode = 1 (running mean + variances; what bench.py's cfg3 run uses): the variances are
+    # the diagonal of the reference's covariance recursion, bit for bit
+    G = 8
+    y, grp, _ = _hier_data(G, 256)
+    rep = replay_compare(y, 150, 20, seed=13, updates=_hier_updates(G), law=em.HierNormalLaw(G), y=grp,
+                         theta_init=_hier_theta0(G, 150), history_window=64, stats_mode=1)
+    _clean(rep)
+
+
 def test_mala_accepts_everything_as_tau_goes_to_zero():
     G = 4
     y, grp, _ = _hier_data(G, 100, seed=8)
