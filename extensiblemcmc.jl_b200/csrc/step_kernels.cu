@@ -508,16 +508,16 @@ constexpr int kCoopP = 32;   // largest p served this way (2 x kCoopP x NCH doub
 struct CoopStage {
     double *t;   // [p][nch] committed state (also feeds the fused next proposal)
     double *m;   // [p][nch] running mean before this step; nullptr unless the full covariance is kept
+    double *mn;  // [p][nch] running mean after this step (spares two divisions per covariance entry)
     int nch, ch;
 };
 
 template <int NCH>
 __device__ __forceinline__ void update_cov_coop(const DevState &d, int64_t N, int64_t c0, const double *sh_t,
-                                                const double *sh_m) {
+                                                const double *sh_m, const double *sh_n) {
     const int p = d.p;
     const int64_t C = d.C;
     const double f_old = (double)(N - 1) / (double)N;
-    const double f_mean = (double)N / (double)(N + 1);
     const double f_new = (double)(N + 1) / (double)N;
     const int total = NCH * p * p;
     const int nt = (int)blockDim.x;
@@ -537,8 +537,7 @@ __device__ __forceinline__ void update_cov_coop(const DevState &d, int64_t N, in
                 const int a = e % p, b = e / p;
                 const double ta = sh_t[a * NCH + ch], tb = sh_t[b * NCH + ch];
                 const double ma_old = sh_m[a * NCH + ch], mb_old = sh_m[b * NCH + ch];
-                const double ma_new = ma_old * f_mean + ta / (double)(N + 1);
-                const double mb_new = mb_old * f_mean + tb / (double)(N + 1);
+                const double ma_new = sh_n[a * NCH + ch], mb_new = sh_n[b * NCH + ch];
                 const double old_sum_sq = f_old * cv[q] + ma_old * mb_old;
                 const double new_sum_sq = old_sum_sq + (ta * tb) / (double)N;
                 d.cov[(int64_t)e * C + c0 + ch] = new_sum_sq - f_new * (ma_new * mb_new);
@@ -644,9 +643,9 @@ __device__ __forceinline__ void post_decision(const DevState &d, const StepDesc 
                 d.h_theta[(slot * d.p + j) * C + c] = t[q];
                 d.h_prop[(slot * d.p + j) * C + c] = pr[q];
                 if (cs) cs->t[j * cs->nch + cs->ch] = t[q];
-                if (coop_full) cs->m[j * cs->nch + cs->ch] = m[q];
                 if (coop_full || diag) {
                     const double m_new = m[q] * f_mean + t[q] / (double)(N + 1);
+                    if (coop_full) { cs->m[j * cs->nch + cs->ch] = m[q]; cs->mn[j * cs->nch + cs->ch] = m_new; }
                     if (diag) {
                         const double old_sum_sq = f_old * cv[q] + m[q] * m[q];
                         const double new_sum_sq = old_sum_sq + (t[q] * t[q]) / (double)N;
@@ -769,7 +768,7 @@ accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fuse_ne
     __shared__ StepCtx ctx, ctx_next;
     // staging of the cooperative covariance update (only the sliced layouts have spare threads)
     constexpr int kStage = SL >= 8 ? kCoopP * kRedChains : 1;
-    __shared__ double sh_t[kStage], sh_m[kStage];
+    __shared__ double sh_t[kStage], sh_m[kStage], sh_n[kStage];
     // PDL: this kernel may have been scheduled while the likelihood sweep is still running.
     // Everything up to griddep_wait() only READS state that was final before the sweep started
     // (chain state, proposal, step sizes, law constants, RNG counters) -- the transition-density
@@ -863,12 +862,12 @@ accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fuse_ne
         if (accepted)
             for (int i = 0; i < n; ++i) d.theta[(int64_t)u.coords[i] * C + c] = prop[i];
         const int n_eps = u.kernel == EXTMCMC_KERNEL_RW_UNIFORM ? n : 0;
-        const CoopStage cs{sh_t, coop ? sh_m : nullptr, kRedChains, (int)(threadIdx.x % kRedChains)};
+        const CoopStage cs{sh_t, coop ? sh_m : nullptr, sh_n, kRedChains, (int)(threadIdx.x % kRedChains)};
         post_decision(d, sd, u, c, accepted, ll_new, ll_prop, n_eps, use_pf ? &pf : nullptr, stage ? &cs : nullptr);
     }
     if (coop) {
         __syncthreads();
-        update_cov_coop<kRedChains>(d, sd.stat_n, (int64_t)blockIdx.x * kRedChains, sh_t, sh_m);
+        update_cov_coop<kRedChains>(d, sd.stat_n, (int64_t)blockIdx.x * kRedChains, sh_t, sh_m, sh_n);
     }
     if (!worker) return;
     // proposal of the NEXT schedule element of this block, fused here: the chain's thread
@@ -1065,7 +1064,7 @@ mala_propose_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int f
 // mala_decide: the chain's own thread -- decision, commit, history, counters; sh_t / sh_m: staging
 // (see CoopStage; with sh_m the covariance update is left to update_cov_coop).
 __device__ __forceinline__ void mala_decide(const DevState &d, const StepCtx &ctx, int64_t c, double *sh_t,
-                                            double *sh_m, int ch) {
+                                            double *sh_m, double *sh_n, int ch) {
     const StepDesc &sd = ctx.sd;
     const DevUpdate &u = ctx.u;
     const int64_t C = d.C;
@@ -1121,7 +1120,7 @@ __device__ __forceinline__ void mala_decide(const DevState &d, const StepCtx &ct
             for (int q = 0; q < 4; ++q) if (j0 + q < d.p) d.grad_cur[(int64_t)(j0 + q) * C + c] = g[q];
         }
     }
-    const CoopStage cs{sh_t, sh_m, kMalaChains, ch};
+    const CoopStage cs{sh_t, sh_m, sh_n, kMalaChains, ch};
     post_decision(d, sd, u, c, accepted, ll_new, ll_prop, 1, nullptr, sh_t ? &cs : nullptr);
 }
 
@@ -1129,7 +1128,7 @@ __global__ void __launch_bounds__(kMalaChains * kMalaSlices)
 mala_accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int finalize_prop, int fuse_next) {
     __shared__ StepCtx ctx, ctx_next;
     __shared__ double sh2[kCoopG * kMalaChains], sh1[kCoopG * kMalaChains];
-    __shared__ double sh_t[kCoopP * kMalaChains], sh_m[kCoopP * kMalaChains];
+    __shared__ double sh_t[kCoopP * kMalaChains], sh_m[kCoopP * kMalaChains], sh_n[kCoopP * kMalaChains];
     load_step_ctx(&ctx, d, descs, k);
     if (fuse_next) load_step_ctx(&ctx_next, d, descs, k + 1);
     const int64_t c0 = (int64_t)blockIdx.x * kMalaChains;
@@ -1139,10 +1138,10 @@ mala_accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fi
     const bool worker = threadIdx.x < kMalaChains && c < d.C;
     const bool stage = d.p <= kCoopP;   // CTA-uniform
     const bool coop = stage && d.stats_mode == 0;
-    if (worker) mala_decide(d, ctx, c, stage ? sh_t : nullptr, coop ? sh_m : nullptr, ch);
+    if (worker) mala_decide(d, ctx, c, stage ? sh_t : nullptr, coop ? sh_m : nullptr, sh_n, ch);
     if (coop) {
         __syncthreads();
-        update_cov_coop<kMalaChains>(d, ctx.sd.stat_n, c0, sh_t, sh_m);
+        update_cov_coop<kMalaChains>(d, ctx.sd.stat_n, c0, sh_t, sh_m, sh_n);
     }
     // next element is a random-walk update: issue its proposal here (one launch saved)
     if (worker && fuse_next) {
