@@ -18,7 +18,9 @@
 // 2-stage ring and is used by BOTH phases, so X is read from L2/HBM once per (chain block,
 // sweep).  Theta_blk stays resident in shared memory for the whole kernel.  Partial ll / G per
 // (segment, chain) are reduced in fixed order by logistic_finalize_kernel: deterministic.
+#include <cmath>
 #include <cstdint>
+#include <cstring>
 #include <cuda_runtime.h>
 #include "sweep.h"
 #include "tma.cuh"
@@ -40,52 +42,58 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
         : "d"(a), "d"(b));
 }
 
-// softplus(z) = log(1 + e^z) and sigmoid(z) in one go, ~60 FP64 instructions (the libm route
-// exp + log1p + divide costs ~4x more and made the epilogue, not the tensor pipe, the critical
-// path of a warp).  e = exp(-|z|) by 2^k * Taylor-13 on |r| <= ln2/2; log(1 + e) = 2 atanh(s),
-// s = e/(2 + e) <= 1/3, odd series to s^35; one shared reciprocal.  Max relative error vs
-// long-double libm over z in [-60, 60] and the tails: softplus 4.8e-16, sigmoid 3.7e-16.
-__device__ __forceinline__ void softplus_sigmoid(double z, double &sp, double &sg) {
-    const double x = -fabs(z);
-    double kf = rint(x * 1.4426950408889634074);
-    kf = fmax(kf, -1000.0);
-    double r = fma(-kf, 6.93147180369123816490e-01, x);
-    r = fma(-kf, 1.90821492927058770002e-10, r);
-    double p = 1.0 / 6227020800.0;
-    p = fma(p, r, 1.0 / 479001600.0);
-    p = fma(p, r, 1.0 / 39916800.0);
-    p = fma(p, r, 1.0 / 3628800.0);
-    p = fma(p, r, 1.0 / 362880.0);
-    p = fma(p, r, 1.0 / 40320.0);
-    p = fma(p, r, 1.0 / 5040.0);
-    p = fma(p, r, 1.0 / 720.0);
+// softplus(z) = log(1 + e^z) and sigmoid(z) in one go, ~31 FP64 instructions + 3 table loads (the
+// libm route exp + log1p + divide costs ~8x more and made the epilogue, not the tensor pipe, the
+// critical path of a warp; the FP64 pipe shares its datapath with DMMA, so every instruction saved
+// here is MMA time).
+//   e = exp(-|z|) = 2^m * 2^(j/32) * exp(r):  k = rint(-|z| 32/ln2) by the magic-number add,
+//       j = k mod 32 (table E2), m = k div 32 (into the exponent field), |r| <= ln2/64, degree 6.
+//   1 + e in [1, 2]: interval idx of width 1/128, c = 10-bit reciprocal of its midpoint (table RC,
+//       RC[0] = 1), rr = (1 + e) c - 1 = fma(e, c, c - 1) exactly formed, |rr| <= 2^-7;
+//       log(1 + e) = -log c (table LG) + log1p(rr), degree 7;
+//       1/(1 + e) = c / (1 + rr) = c (1 - rr)(1 + rr^2)(1 + rr^4)   (error rr^8 <= 2^-56).
+// Max relative error vs long-double libm over z in [-700, 700] (4e7 samples incl. the tails, host
+// replica of this code): softplus 5.0e-16, sigmoid 6.5e-16.
+constexpr int kTabE2 = 0, kTabRC = 32, kTabLG = 160, kTabN = 288;
+__device__ double g_sp_tab[kTabN];
+
+__device__ __forceinline__ void softplus_sigmoid(double z, double &sp, double &sg, const double *tab) {
+    const double x = fmax(-fabs(z), -700.0);
+    const double kMagic = 6755399441055744.0;   // 1.5 * 2^52: the low word of t is rint(x * 32/ln2)
+    const double t = fma(x, 46.166241308446828384, kMagic);
+    const int ki = __double2loint(t);
+    const double kf = t - kMagic;
+    double r = fma(-kf, 6.93147180369123816490e-01 / 32.0, x);
+    r = fma(-kf, 1.90821492927058770002e-10 / 32.0, r);
+    double p = 1.0 / 720.0;
     p = fma(p, r, 1.0 / 120.0);
     p = fma(p, r, 1.0 / 24.0);
     p = fma(p, r, 1.0 / 6.0);
     p = fma(p, r, 0.5);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
-    double e = __longlong_as_double(__double_as_longlong(p) + ((long long)kf << 52));
-    if (x < -700.0) e = 0.0;
-    const double t1 = 1.0 + e, t2 = 2.0 + e;
-    const double rc = 1.0 / (t1 * t2);
-    const double inv = t2 * rc;            // 1 / (1 + e)
+    const double ep = tab[kTabE2 + (ki & 31)] * p;   // in [1, 2)
+    const double e = __hiloint2double(__double2hiint(ep) + ((ki >> 5) << 20), __double2loint(ep));
+    const int hi = __double2hiint(1.0 + e);
+    const int idx = hi >= 0x40000000 ? 127 : (hi >> 13) & 127;
+    const double c = tab[kTabRC + idx];
+    const double rr = fma(e, c, c - 1.0), r2 = rr * rr;
+    double q = 1.0 / 7.0;
+    q = fma(q, rr, -1.0 / 6.0);
+    q = fma(q, rr, 1.0 / 5.0);
+    q = fma(q, rr, -1.0 / 4.0);
+    q = fma(q, rr, 1.0 / 3.0);
+    q = fma(q, rr, -0.5);
+    sp = fmax(z, 0.0) + (tab[kTabLG + idx] + fma(q, r2, rr));
+    const double a1 = 1.0 - rr, b1 = fma(a1, r2, a1);
+    const double inv = c * fma(b1, r2 * r2, b1);   // 1 / (1 + e)
     sg = z >= 0.0 ? inv : e * inv;
-    const double s = e * (t1 * rc), s2 = s * s;   // e / (2 + e)
-    double q = 1.0 / 35.0;
-    q = fma(q, s2, 1.0 / 33.0); q = fma(q, s2, 1.0 / 31.0); q = fma(q, s2, 1.0 / 29.0);
-    q = fma(q, s2, 1.0 / 27.0); q = fma(q, s2, 1.0 / 25.0); q = fma(q, s2, 1.0 / 23.0);
-    q = fma(q, s2, 1.0 / 21.0); q = fma(q, s2, 1.0 / 19.0); q = fma(q, s2, 1.0 / 17.0);
-    q = fma(q, s2, 1.0 / 15.0); q = fma(q, s2, 1.0 / 13.0); q = fma(q, s2, 1.0 / 11.0);
-    q = fma(q, s2, 1.0 / 9.0);  q = fma(q, s2, 1.0 / 7.0);  q = fma(q, s2, 1.0 / 5.0);
-    q = fma(q, s2, 1.0 / 3.0);  q = fma(q, s2, 1.0);
-    sp = fmax(z, 0.0) + 2.0 * s * q;
 }
 
 template <int D>
 constexpr size_t logistic_smem() {
     return (size_t)kBN * (D + kPadT) * 8 + (size_t)2 * kBM * (D + kPad) * 8 + (size_t)kBM * kRPad * 8 +
-           (size_t)(kNT / 32) * 64 * 8 + 2 * kBM * 8 + 4 * 8;
+           (size_t)(kNT / 32) * 64 * 8 + 2 * kBM * 8 + kTabN * 8 + 4 * 8;
 }
 
 __device__ __forceinline__ void pair_sync(int id) {  // named barrier for the two warps of a chain block
@@ -112,7 +120,8 @@ __global__ void __launch_bounds__(kNT, 1) sweep_logistic_kernel(LogisticArgs a) 
     double *Rs = Xs + 2 * kBM * LD;                       // [kBM][kRPad] residuals y - sigmoid(z)
     double *Zp = Rs + kBM * kRPad;                        // [NW][64]     partial Z handed to the partner
     double *ys = Zp + NW * 64;                            // [2][kBM]
-    uint64_t *bar = reinterpret_cast<uint64_t *>(ys + 2 * kBM);  // [2] full (TMA landed)
+    double *tab = ys + 2 * kBM;                           // [kTabN]      softplus/sigmoid tables
+    uint64_t *bar = reinterpret_cast<uint64_t *>(tab + kTabN);   // [2] full (TMA landed)
     unsigned int *done = reinterpret_cast<unsigned int *>(bar + 2);  // [2] warps done with a stage
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -133,6 +142,7 @@ __global__ void __launch_bounds__(kNT, 1) sweep_logistic_kernel(LogisticArgs a) 
         const int64_t gc = cbase + c;
         Th[c * LDT + k] = (k < a.d && gc < C) ? a.theta[(int64_t)k * C + gc] : 0.0;
     }
+    if (tid < kTabN) tab[tid] = g_sp_tab[tid];
     if (tid == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
@@ -225,10 +235,10 @@ __global__ void __launch_bounds__(kNT, 1) sweep_logistic_kernel(LogisticArgs a) 
             const double yv = ys[st * kBM + r];
             double2 res;
             double sp, sg;
-            softplus_sigmoid(z[0], sp, sg);
+            softplus_sigmoid(z[0], sp, sg, tab);
             res.x = live ? yv - sg : 0.0;
             ll0 += live ? yv * z[0] - sp : 0.0;
-            softplus_sigmoid(z[1], sp, sg);
+            softplus_sigmoid(z[1], sp, sg, tab);
             res.y = live ? yv - sg : 0.0;
             ll1 += live ? yv * z[1] - sp : 0.0;
             *reinterpret_cast<double2 *>(Rs + r * kRPad + 8 * w8 + 2 * tq) = res;
@@ -333,6 +343,22 @@ int logistic_padded_dim(int d) {
 
 cudaError_t sweep_logistic_init() {
     cudaError_t e;
+    {
+        // tables of softplus_sigmoid, rounded from extended precision
+        double tabh[kTabN];
+        for (int j = 0; j < 32; ++j) tabh[kTabE2 + j] = (double)exp2l((long double)j / 32.0L);
+        for (int j = 0; j < 128; ++j) {
+            double c = (double)(1.0L / (1.0L + ((long double)j + 0.5L) / 128.0L));
+            uint64_t b;
+            memcpy(&b, &c, 8);
+            b = (b + (1ull << 41)) & ~((1ull << 42) - 1);   // 10 significant bits
+            memcpy(&c, &b, 8);
+            if (j == 0) c = 1.0;                              // rr = e exactly on the first interval
+            tabh[kTabRC + j] = c;
+            tabh[kTabLG + j] = (double)(-logl((long double)c));
+        }
+        if ((e = cudaMemcpyToSymbol(g_sp_tab, tabh, sizeof tabh)) != cudaSuccess) return e;
+    }
     if ((e = prep<32>()) != cudaSuccess) return e;
     if ((e = prep<64>()) != cudaSuccess) return e;
     if ((e = prep<128>()) != cudaSuccess) return e;
