@@ -109,3 +109,23 @@ def test_plain_c_client_runs_the_sampler(tmp_path):
     mu, var, xbar, s2, acc, eps0 = (float(v) for v in r.stdout.split())
     assert abs(mu - xbar) < 0.02 and abs(var - s2) < 0.1          # posterior means: xbar, S/(n-3)
     assert 0.15 < acc < 0.4 and eps0 != 0.5
+
+
+def test_product_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under the package (Python host mirror, CUDA
+    sources, Makefile) may import, include, link or dlopen it, and the loader has no CPU fallback."""
+    import pathlib
+    import re
+
+    pkg = pathlib.Path(__file__).resolve().parents[1] / "extensiblemcmc.jl_b200"
+    pat = re.compile(r"(^\s*(from|import)\s+\S*oracle)|(#include\s*[\"<][^\">]*oracle)|libextmcmc_oracle|extmcmc_oracle\.")
+    offenders = []
+    for f in pkg.rglob("*"):
+        if f.is_file() and (f.suffix in {".py", ".cu", ".cuh", ".h", ".cpp"} or f.name == "Makefile"):
+            for ln, line in enumerate(f.read_text(errors="ignore").splitlines(), 1):
+                if pat.search(line):
+                    offenders.append(f"{f.relative_to(pkg)}:{ln}: {line.strip()}")
+    assert not offenders, offenders
+    src = (pkg / "_abi.py").read_text()
+    assert "raise" in src            # a missing library is an error ...
+    assert not re.search(r"except\s+OSError\s*:\s*\n\s*(pass|return None)", src)   # ... never swallowed
