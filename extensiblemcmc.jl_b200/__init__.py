@@ -18,7 +18,7 @@ from .hier_normal import HierNormalLaw
 from .logistic import LogisticLaw
 from .workspaces import (CUDAMCMCBackend, CUDAGlobalWorkspace, CUDALocalWorkspace,
                          DeviceGeneratedObs, init_global_workspace, create_workspace,
-                         create_workspaces, state, state_prop, ll, ll_prop, accepted, llr,
+                         create_workspaces, state, state_prop, ll, ll_prop, accepted, set_accepted_, llr,
                          estim_mean, estim_cov, num_mcmc_steps, num_updt, name_of_update, summary)
 from .callbacks import Callback, SavingCallback, REPLCallback
 from .mcmc import MCMC, init_

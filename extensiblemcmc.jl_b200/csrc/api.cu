@@ -267,7 +267,7 @@ int32_t enqueue_sweep(extmcmc_t h, bool instrument, bool grad = false, const dou
         launch_sweep_gsn1d(h->plan, a, grad, h->stream);
     } else if (h->cfg.law == EXTMCMC_LAW_LOGISTIC) {
         LogisticArgs a{h->obs_dev, h->y_dev, h->n_obs_local, src, h->cfg.obs_dim, h->d.C, h->d.partial,
-                       h->d.partial + (size_t)h->plan.S * h->d.C, h->plan.S};
+                       h->d.partial + (size_t)h->plan.S * h->d.C, h->plan.S, h->plan.n_cta};
         launch_sweep_logistic(h->plan, a, ll_dst, grad_dst, h->stream);
         if (obs_sharded(h)) {
             // every rank holds a slice of the rows of X: sum the per-chain log-likelihoods and the

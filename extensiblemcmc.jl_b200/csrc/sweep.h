@@ -22,6 +22,7 @@ struct SweepPlan {
     int launches;      // kernel launches per sweep
     int D;             // observation dimension (general-d Gaussian law)
     int G;             // observation groups (hierarchical law; 1 otherwise)
+    int n_cta;         // logistic: persistent CTAs
     const char *name;
 };
 
@@ -65,7 +66,7 @@ void launch_sweep_gsnmv(const SweepPlan &pl, const double *obs, int64_t n_obs, c
 
 // Logistic regression.  X: row-major [n_pad][D] with D = logistic_padded_dim(d) and n_pad a
 // multiple of 16 (zero rows / columns beyond n_obs / d); y: [n_pad]; theta: SoA [d][C];
-// ll_part [S][C], g_part [S][d][C].
+// ll_part [S][C], g_part [S][d][C], S = partial slots per block of 64 chains.
 struct LogisticArgs {
     const double *X;
     const double *y;
@@ -75,7 +76,8 @@ struct LogisticArgs {
     int64_t C;
     double *ll_part;
     double *g_part;
-    int S;
+    int S;        // partial slots per chain block
+    int n_cta;    // persistent CTAs sharing the flattened (chain block, tile) units
 };
 int logistic_padded_dim(int d);
 cudaError_t sweep_logistic_init();

@@ -96,6 +96,20 @@ constexpr size_t logistic_smem() {
            (size_t)(kNT / 32) * 64 * 8 + 2 * kBM * 8 + kTabN * 8 + 4 * 8;
 }
 
+// Work split.  The (chain block, observation tile) pairs are flattened block-major into
+// U = blocks * T units and CTA c takes units [c U / n_cta, (c + 1) U / n_cta): every SM gets the same
+// number of tiles whatever the number of chain blocks (cfg 3: 16 blocks on 148 SMs; a (segments x
+// blocks) grid would leave 4 SMs idle), at the price of at most one extra Theta load for a CTA
+// whose range straddles two blocks.  A CTA's part of one block is a "piece"; piece j of a block
+// writes partial slot j, and the finalize kernel adds the slots of a block in order.
+__host__ __device__ __forceinline__ int64_t unit_lo(int64_t c, int64_t U, int n_cta) { return c * U / n_cta; }
+__host__ __device__ __forceinline__ int cta_of_unit(int64_t x, int64_t U, int n_cta) {
+    int64_t c = x * n_cta / U;
+    while (c + 1 < n_cta && unit_lo(c + 1, U, n_cta) <= x) ++c;
+    while (c > 0 && unit_lo(c, U, n_cta) > x) --c;
+    return (int)c;
+}
+
 __device__ __forceinline__ void pair_sync(int id) {  // named barrier for the two warps of a chain block
     asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
 }
@@ -127,21 +141,11 @@ __global__ void __launch_bounds__(kNT, 1) sweep_logistic_kernel(LogisticArgs a) 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int w8 = w & 7, h = w >> 3;
     const int gq = lane >> 2, tq = lane & 3;  // mma fragment coordinates: group id, thread in group
-    const int seg = blockIdx.x;
     const int64_t C = a.C;
-    const int64_t cbase = (int64_t)blockIdx.y * kBN;
+    const int64_t T = (a.n_obs + kBM - 1) / kBM;            // tiles per chain block
+    const int64_t U = (int64_t)((C + kBN - 1) / kBN) * T;   // flattened (block, tile) units
+    const int64_t u_end = unit_lo((int64_t)blockIdx.x + 1, U, a.n_cta);
 
-    // tiles of this segment
-    const int64_t n_tiles_all = (a.n_obs + kBM - 1) / kBM;
-    const int64_t t0 = (int64_t)seg * n_tiles_all / a.S, t1 = (int64_t)(seg + 1) * n_tiles_all / a.S;
-    const int n_tiles = (int)(t1 - t0);
-
-    // Theta block -> shared (coalesced over chains), zero beyond d or beyond C
-    for (int idx = tid; idx < kBN * D; idx += kNT) {
-        const int k = idx / kBN, c = idx % kBN;
-        const int64_t gc = cbase + c;
-        Th[c * LDT + k] = (k < a.d && gc < C) ? a.theta[(int64_t)k * C + gc] : 0.0;
-    }
     if (tid < kTabN) tab[tid] = g_sp_tab[tid];
     if (tid == 0) {
         mbar_init(&bar[0], 1);
@@ -149,13 +153,34 @@ __global__ void __launch_bounds__(kNT, 1) sweep_logistic_kernel(LogisticArgs a) 
         done[0] = done[1] = 0u;
         mbar_fence_init();
     }
+    constexpr int NPH = D / 32;       // column pairs (16 features each) of this warp's half
+    // fragment row gq stands for observation rho(gq) of the 8-block (bits 0 and 1 swapped): the two
+    // rows a quarter-warp touches are then 2 apart, which the D + 4 stride separates (128-bit loads)
+    const int rq = (gq & 4) | ((gq & 1) << 1) | ((gq >> 1) & 1);
+    int tt = 0;   // tiles consumed so far by this CTA: the ring's stage and phase run on across pieces
+
+  for (int64_t u = unit_lo(blockIdx.x, U, a.n_cta); u < u_end;) {
+    // ---- one piece: chain block blk, tiles [t0, t0 + n_tiles) ----------------------------------
+    const int64_t blk = u / T, t0 = u - blk * T;
+    const int n_tiles = (int)((T - t0 < u_end - u) ? (T - t0) : (u_end - u));
+    const int seg = (int)blockIdx.x - cta_of_unit(blk * T, U, a.n_cta);   // partial slot of this piece
+    const int64_t cbase = blk * kBN;
+    u += n_tiles;
+
+    __syncthreads();   // the previous piece is completely done with Theta, the stages and Zp
+    // Theta block -> shared (coalesced over chains), zero beyond d or beyond C
+    for (int idx = tid; idx < kBN * D; idx += kNT) {
+        const int k = idx / kBN, c = idx % kBN;
+        const int64_t gc = cbase + c;
+        Th[c * LDT + k] = (k < a.d && gc < C) ? a.theta[(int64_t)k * C + gc] : 0.0;
+    }
     __syncthreads();
 
     // One bulk copy per observation row (+ one for the y slice) into a 2-stage ring.  There is no
     // CTA-wide barrier in the main loop: each warp counts itself out of a stage when it is done
     // with it, and the warp that completes the count (the last one) refills the stage.
     auto issue = [&](int t) {
-        const int st = t & 1;
+        const int st = (tt + t) & 1;
         const int64_t row0 = (t0 + t) * kBM;
         if (lane == 0) mbar_expect_tx(&bar[st], (uint32_t)(kBM * D * 8 + kBM * 8));
         __syncwarp();
@@ -166,18 +191,14 @@ __global__ void __launch_bounds__(kNT, 1) sweep_logistic_kernel(LogisticArgs a) 
     if (w == 0)
         for (int t = 0; t < 2 && t < n_tiles; ++t) issue(t);
 
-    constexpr int NPH = D / 32;       // column pairs (16 features each) of this warp's half
     double G[2 * NPH][2];
 #pragma unroll
     for (int nb = 0; nb < 2 * NPH; ++nb) G[nb][0] = G[nb][1] = 0.0;
     double ll0 = 0.0, ll1 = 0.0;  // chains cbase + 8 w8 + 2 tq + {0, 1}, observation rows 8h + rho(gq)
-    // fragment row gq stands for observation rho(gq) of the 8-block (bits 0 and 1 swapped): the two
-    // rows a quarter-warp touches are then 2 apart, which the D + 4 stride separates (128-bit loads)
-    const int rq = (gq & 4) | ((gq & 1) << 1) | ((gq >> 1) & 1);
 
     for (int t = 0; t < n_tiles; ++t) {
-        const int st = t & 1;
-        mbar_wait(&bar[st], (uint32_t)(t >> 1) & 1u);
+        const int st = (tt + t) & 1;
+        mbar_wait(&bar[st], (uint32_t)((tt + t) >> 1) & 1u);
         const double *X = Xs + st * kBM * LD;
         const int64_t row0 = (t0 + t) * kBM;
 
@@ -303,6 +324,8 @@ __global__ void __launch_bounds__(kNT, 1) sweep_logistic_kernel(LogisticArgs a) 
             }
         }
     }
+    tt += n_tiles;
+  }   // pieces
 }
 
 // ll[c] = sum_s ll_part[s][c];  grad[k][c] = sum_s g_part[s][k][c]  (fixed order)
@@ -312,12 +335,15 @@ logistic_finalize_kernel(LogisticArgs a, double *__restrict__ ll_out, double *__
     const int64_t C = a.C;
     if (idx >= (int64_t)(a.d + 1) * C) return;
     const int64_t row = idx / C, c = idx % C;
+    // pieces of this chain's block (see the work split above)
+    const int64_t T = (a.n_obs + kBM - 1) / kBM, U = (int64_t)((C + kBN - 1) / kBN) * T, blk = c / kBN;
+    const int np = cta_of_unit((blk + 1) * T - 1, U, a.n_cta) - cta_of_unit(blk * T, U, a.n_cta) + 1;
     double s = 0.0;
     if (row == a.d) {
-        for (int i = 0; i < a.S; ++i) s += a.ll_part[(int64_t)i * C + c];
+        for (int i = 0; i < np; ++i) s += a.ll_part[(int64_t)i * C + c];
         ll_out[c] = s;
     } else {
-        for (int i = 0; i < a.S; ++i) s += a.g_part[((int64_t)i * a.d + row) * C + c];
+        for (int i = 0; i < np; ++i) s += a.g_part[((int64_t)i * a.d + row) * C + c];
         if (grad_out) grad_out[row * C + c] = s;
     }
 }
@@ -330,8 +356,7 @@ cudaError_t prep() {
 }
 template <int D>
 void launch(const SweepPlan &pl, const LogisticArgs &a, cudaStream_t st) {
-    dim3 grid(pl.S, pl.groups);
-    sweep_logistic_kernel<D><<<grid, kNT, logistic_smem<D>(), st>>>(a);
+    sweep_logistic_kernel<D><<<a.n_cta, kNT, logistic_smem<D>(), st>>>(a);
 }
 }  // namespace
 
@@ -372,11 +397,11 @@ SweepPlan plan_sweep_logistic(int d, int64_t C, int64_t n_obs, int num_sms) {
     pl.variant = SWEEP_VARIANT_CHAINS;
     pl.R = kBN;
     pl.groups = (int)((C + kBN - 1) / kBN);
-    const int64_t n_tiles = (n_obs + kBM - 1) / kBM;
-    int S = num_sms / pl.groups;  // one CTA per SM (the tiles take ~215 KB of shared memory)
-    if (S < 1) S = 1;
-    if (S > n_tiles) S = (int)n_tiles;
-    pl.S = S;
+    const int64_t n_tiles = (n_obs + kBM - 1) / kBM, U = (int64_t)pl.groups * n_tiles;
+    // one persistent CTA per SM (the tiles take ~215 KB of shared memory), each with an equal share
+    // of the flattened (chain block, tile) units; S = partial slots per chain block
+    pl.n_cta = (int)(U < num_sms ? U : num_sms);
+    pl.S = (pl.n_cta + pl.groups - 1) / pl.groups + 1;
     pl.launches = 2;  // sweep + finalize
     pl.name = "logistic_dmma";
     return pl;

@@ -368,6 +368,11 @@ def accepted(ws, i):
     return _hist_or_raise(ws.acceptance_history)[i - 1]
 
 
+def set_accepted_(ws, i, v):                                     # set_accepted! workspaces.jl:299-303
+    """Overwrite the host mirror of acceptance_history[i] (the device keeps its own record)."""
+    _hist_or_raise(ws.acceptance_history)[i - 1] = v
+
+
 def llr(ws, i):                                                  # workspaces.jl:378
     return np.sum(ll_prop(ws, i) - ll(ws, i), axis=0)
 

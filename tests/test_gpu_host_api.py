@@ -30,6 +30,16 @@ def test_reference_smoke_shape():
     assert not np.isnan(ws.sub_ws.state_history).any()
     assert len(lws) == 2 and lws[0].acceptance_history.shape == (1000, 1)
     assert lws[0].acceptance_history[0, 0]                       # first proposal always accepted
+    # the accessors of src/workspaces.jl:91-136,294-385 on the finished run
+    assert em.num_mcmc_steps(ws) == 1000 and em.num_updt(ws) == 2
+    assert em.name_of_update(lws[0]) == "RandomWalkUpdate"
+    assert em.state(ws).shape == (2, 1) and em.state(lws[1]).shape == (1, 1)
+    assert em.estim_mean(ws).shape == (2, 1) and em.estim_cov(ws).shape == (2, 2, 1)
+    assert bool(em.accepted(lws[0], 1)[0]) is True
+    assert np.isfinite(em.ll(lws[0], 500)).all() and np.isfinite(em.ll_prop(lws[0], 500)).all()
+    assert em.llr(lws[0], 500).shape == (1,)
+    em.set_accepted_(lws[0], 1, False)                            # set_accepted! :299-303
+    assert not lws[0].acceptance_history[0, 0]
     ws.close()
 
 
