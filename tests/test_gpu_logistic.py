@@ -29,7 +29,10 @@ def _np_ll_grad(X, y, th):
     return ll, g
 
 
-@pytest.mark.parametrize("n,d,n_chains", [(1000, 8, 64), (777, 20, 100), (2049, 64, 130), (600, 256, 70), (50, 3, 5)])
+# the last three exercise the flattened work split: more chain blocks than SMs (a CTA walks several
+# whole blocks), a single tile per block, and one block whose tiles are spread over all CTAs
+@pytest.mark.parametrize("n,d,n_chains", [(1000, 8, 64), (777, 20, 100), (2049, 64, 130), (600, 256, 70), (50, 3, 5),
+                                          (100, 8, 64 * 150 + 5), (10, 5, 700), (5000, 12, 33)])
 def test_loglik_and_gradient(n, d, n_chains):
     X, y, beta = _data(n, d)
     law = em.LogisticLaw(d)
