@@ -57,53 +57,103 @@ def cfg2_theta_init(x, n_chains, offset=0):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock, power and throttle reasons sampled DURING the timed region: NVML polled every 20 ms
+    from a thread of this process (nvidia-smi -lms as the fallback; same counters).  A timed region
+    shorter than a few sampling periods is followed by an untimed continuation of the very same
+    steps (`extend`) until three samples under load exist; the JSON says so in `window`."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, gpu_index):
-        self.idx, self.proc, self.lines = gpu_index, None, []
+        self.idx, self.proc, self.rows = gpu_index, None, []     # rows: (sm, sm_max, watts, reasons)
+        self.nv, self.dev, self.run, self.t = None, None, False, None
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.idx).uuid)
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+        except Exception:
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.idx)
 
     def start(self):
+        self.run = True
+        try:
+            self.nv, self.dev = self._nvml_handle()
+            self._sample_nvml()                                  # fails here, not in the thread
+            self.rows.clear()
+            self.t = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nv = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                  "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t = threading.Thread(target=self._read_smi, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _sample_nvml(self):
+        nv, d = self.nv, self.dev
+        sm = float(nv.nvmlDeviceGetClockInfo(d, nv.NVML_CLOCK_SM))
+        smax = float(nv.nvmlDeviceGetMaxClockInfo(d, nv.NVML_CLOCK_SM))
+        watts = nv.nvmlDeviceGetPowerUsage(d) / 1000.0
+        mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(d)
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        self.rows.append((sm, smax, watts, {k for k, b in bits.items() if mask & b}))
 
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons, power = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [v.strip() for v in ln.split(",")]
+    def _poll_nvml(self):
+        while self.run:
+            try:
+                self._sample_nvml()
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def _read_smi(self):
+        for line in self.proc.stdout:
+            f = [v.strip() for v in line.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+                self.rows.append((float(f[1]), float(f[2]), float(f[3]),
+                                  {nm for nm, v in zip(self.NAMES, f[5:9]) if v.lower().startswith("active")}))
             except ValueError:
                 continue
-            for nm, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": float(max(smax)) if smax else None,
-                "power_w_max": float(max(power)) if power else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+
+    def stop(self, extend=None):
+        if self.nv is None and not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        n_timed = len(self.rows)
+        window = "timed region"
+        if extend is not None and n_timed < 3:
+            t_end = time.monotonic() + 2.0
+            while len(self.rows) < 3 and time.monotonic() < t_end:
+                extend()
+            window = "timed region + untimed continuation of the same steps (region shorter than 3 samples)"
+        self.run = False
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        if self.t is not None:
+            self.t.join(timeout=1.0)
+        rows = list(self.rows)
+        reasons = set().union(*[r[3] for r in rows]) if rows else set()
+        return {"sm_mhz": float(np.median([r[0] for r in rows])) if rows else None,
+                "sm_max_mhz": float(max(r[1] for r in rows)) if rows else None,
+                "power_w_max": float(max(r[2] for r in rows)) if rows else None,
+                "samples": len(rows), "samples_in_timed_region": n_timed, "window": window,
+                "source": "nvml" if self.nv is not None else "nvidia-smi", "reasons": sorted(reasons)}
 
 
 def measured_peaks():
@@ -137,13 +187,14 @@ def make_ws(em, x, n_chains, chain_offset, device, **bk):
     return mcmc.workspace
 
 
-def timed_steps(ws, _abi, C, K, W, flush=True):
-    """W warm-up + K timed steps (one MCMC iteration each).  Every timed step is bracketed by
-    its own CUDA event pair on the library stream (the L2 flush before it is outside the pair);
-    nothing synchronises the host inside the loop.  Returns the summed device ms."""
+def timed_steps(ws, _abi, C, K, W, flush=True, it0=1):
+    """W warm-up + K timed steps (one MCMC iteration each, iterations it0, it0 + 1, ...).  Every
+    timed step is bracketed by its own CUDA event pair on the library stream (the L2 flush before
+    it is outside the pair); nothing synchronises the host inside the loop.  Returns the summed
+    device ms."""
     import ctypes
     lib, h = ws.lib, ws.handle
-    it = 1
+    it = it0
     for _ in range(W):
         ws._ck(lib.extmcmc_run_block(h, steps_for(None, _abi, it, 1), NU)); it += 1
     ws.sync()
@@ -207,9 +258,13 @@ def run_ours(args):
     l1 = ws.lib.extmcmc_launch_count(ws.handle)
     sampler.start()
     barrier()
-    ms_total = timed_steps(ws, _abi, C, K, 0)
+    ms_total = timed_steps(ws, _abi, C, K, 0, it0=Wm + 1)
     barrier()
-    clocks = sampler.stop()
+    ext = [Wm + 1 + K]   # a timed region shorter than three samples: keep the same load going, untimed
+
+    def hold():
+        timed_steps(ws, _abi, C, 20, 0, it0=ext[0]); ext[0] += 20
+    clocks = sampler.stop(extend=hold)
     launches = int(ws.lib.extmcmc_launch_count(ws.handle) - l1)
     t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -379,10 +434,15 @@ def run_cfg5(args):
     torch.cuda.synchronize()
     sampler.start()
     l0 = ws.lib.extmcmc_launch_count(ws.handle)
-    ms_total = timed_steps(ws, _abi, C, K, 0, flush=False)
+    ms_total = timed_steps(ws, _abi, C, K, 0, flush=False, it0=Wm + 1)
     launches = int(ws.lib.extmcmc_launch_count(ws.handle) - l0)
     torch.cuda.synchronize()
-    clocks = sampler.stop()
+    ext = [Wm + 1 + K]
+
+    def hold():
+        timed_steps(ws, _abi, C, 10, 0, flush=False, it0=ext[0]); ext[0] += 10
+    # ranks exchange sums every step under observation sharding: no rank-local continuation there
+    clocks = sampler.stop(extend=hold if world == 1 else None)
     t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -432,7 +492,7 @@ def run_cfg5(args):
         "gpu_launches": launches, "clocks": clocks}))
 
 
-def _generic_timed(ws, _abi, n_updates, K, W):
+def _generic_timed(ws, _abi, n_updates, K, W, it0=1):
     """W warm-up + K timed MCMC iterations of an n_updates-element schedule (one graph block per
     iteration, one CUDA event pair per iteration)."""
     import ctypes
@@ -446,7 +506,7 @@ def _generic_timed(ws, _abi, n_updates, K, W):
             arr[pj].prev_pidx = -1 if first else (pj - 1 if pj else n_updates - 1)
             arr[pj].prev_mcmciter = 0 if first else (it if pj else it - 1)
         return arr
-    it = 1
+    it = it0
     for _ in range(W):
         ws._ck(lib.extmcmc_run_block(h, block(it), n_updates)); it += 1
     ws.sync()
@@ -521,10 +581,14 @@ def run_cfg34(args):
     torch.cuda.synchronize()
     sampler.start()
     l0 = ws.lib.extmcmc_launch_count(ws.handle)
-    ms_total = _generic_timed(ws, _abi, NUc, K, 0)
+    ms_total = _generic_timed(ws, _abi, NUc, K, 0, it0=Wm + 1)
     launches = int(ws.lib.extmcmc_launch_count(ws.handle) - l0)
     torch.cuda.synchronize()
-    clocks = sampler.stop()
+    ext = [Wm + 1 + K]
+
+    def hold():
+        _generic_timed(ws, _abi, NUc, 5, 0, it0=ext[0]); ext[0] += 5
+    clocks = sampler.stop(extend=hold)
     variant = ws.lib.extmcmc_sweep_variant_name(ws.handle).decode()
     pk64, pkmma = ctypes.c_double(), ctypes.c_double()
     ws._ck(ws.lib.extmcmc_measure_fp64_peak(ws.handle, ctypes.byref(pk64)))
