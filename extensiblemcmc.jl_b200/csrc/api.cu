@@ -436,7 +436,7 @@ int32_t run_block_impl(extmcmc_t h, const extmcmc_step_t *steps, int32_t n_steps
         CK(h, cudaMalloc(&sl.d_descs, sizeof(StepDesc) * cap));
         sl.cap = cap;
     }
-    const int W = h->d.W, NU = h->cfg.n_updates;
+    const int W = h->d.W;
     for (int s = 0; s < n_steps; ++s) {
         StepDesc &sd = sl.h_descs[s];
         const int u = steps[s].pidx;
@@ -458,7 +458,6 @@ int32_t run_block_impl(extmcmc_t h, const extmcmc_step_t *steps, int32_t n_steps
         }
         h->ra_iter[u] = it;
         tag = it;
-        (void)NU;
     }
 
     std::vector<int> kinds(n_steps);
