@@ -899,8 +899,9 @@ int32_t oracle_get_eps(oracle_t h, int32_t u, double *eps) {
 
 int32_t oracle_loglik_grad(oracle_t h, const double *theta, int64_t n_eval, double *ll_out, double *grad_out) {
     if (h->cfg.law == EXTMCMC_LAW_GSN_MV) return EXTMCMC_EUNSUPPORTED;
+    if (h->p < 1 || h->p > 256) return EXTMCMC_EINVAL;
     for (int64_t c = 0; c < n_eval; ++c) {
-        double th[256], g[256];
+        double th[256] = {0.0}, g[256] = {0.0};
         int bad = 0;
         for (int k = 0; k < h->p; ++k) th[k] = theta[(int64_t)k * n_eval + c];
         ll_out[c] = law_loglik_grad(h, th, g, &bad);
