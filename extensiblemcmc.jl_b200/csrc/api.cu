@@ -787,7 +787,7 @@ int32_t extmcmc_set_update(extmcmc_t h, int32_t u, const extmcmc_update_t *upd) 
             for (int i = 0; i < upd->n_coords; ++i)
                 if (upd->pos[i]) return fail(h, EXTMCMC_EUNSUPPORTED, "MALA on positivity-constrained coordinates is not implemented");
     }
-    if (upd->prior < EXTMCMC_PRIOR_IMPROPER || upd->prior > EXTMCMC_PRIOR_PRODUCT)
+    if (upd->prior < EXTMCMC_PRIOR_IMPROPER || upd->prior > EXTMCMC_PRIOR_CAUCHY)
         return fail(h, EXTMCMC_EUNSUPPORTED, "prior not implemented on the GPU path");
     if (upd->prior == EXTMCMC_PRIOR_PRODUCT) {
         // {K, then per factor: kind, dim, p0, p1}; the dims must tile the update's coordinates
@@ -798,7 +798,7 @@ int32_t extmcmc_set_update(extmcmc_t h, int32_t u, const extmcmc_update_t *upd) 
         int tot = 0;
         for (int k = 0; k < K; ++k) {
             const int kind = (int)upd->prior_params[1 + 4 * k], dim = (int)upd->prior_params[2 + 4 * k];
-            if (kind < EXTMCMC_PRIOR_IMPROPER || kind > EXTMCMC_PRIOR_UNIFORM || dim < 1)
+            if (kind < EXTMCMC_PRIOR_IMPROPER || kind > EXTMCMC_PRIOR_CAUCHY || kind == EXTMCMC_PRIOR_PRODUCT || dim < 1)
                 return fail(h, EXTMCMC_EUNSUPPORTED, "ProductPrior factor not implemented on the GPU path");
             tot += dim;
         }
@@ -817,9 +817,13 @@ int32_t extmcmc_set_update(extmcmc_t h, int32_t u, const extmcmc_update_t *upd) 
     if (!upd->coords || !upd->step) return fail(h, EXTMCMC_EINVAL, "coords/step missing");
     if (upd->n_prior_params > kMaxPriorParams || (upd->n_prior_params > 0 && !upd->prior_params))
         return fail(h, EXTMCMC_EINVAL, "bad prior parameters");
-    if ((upd->prior == EXTMCMC_PRIOR_NORMAL || upd->prior == EXTMCMC_PRIOR_GAMMA ||
-         upd->prior == EXTMCMC_PRIOR_UNIFORM) && upd->n_prior_params < 2)
-        return fail(h, EXTMCMC_EINVAL, "prior needs two parameters");
+    {
+        // parameters each StandardPrior family reads (the ProductPrior layout was checked above)
+        const int pk = upd->prior;
+        const int need = (pk == EXTMCMC_PRIOR_IMPROPER || pk == EXTMCMC_PRIOR_IMPROPER_POS || pk == EXTMCMC_PRIOR_PRODUCT) ? 0
+                       : pk == EXTMCMC_PRIOR_EXPONENTIAL ? 1 : 2;
+        if (upd->n_prior_params < need) return fail(h, EXTMCMC_EINVAL, "prior parameters missing");
+    }
     if (upd->adapt.kind != EXTMCMC_ADAPT_NONE && upd->adapt.adapt_every_k_steps < 1)
         return fail(h, EXTMCMC_EINVAL, "adapt_every_k_steps must be >= 1");
     CK(h, cudaSetDevice(h->cfg.device));

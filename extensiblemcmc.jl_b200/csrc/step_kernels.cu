@@ -53,6 +53,53 @@ __device__ __forceinline__ double log_prior_family(int kind, const double *pp, c
         }
         return s;
     }
+    case EXTMCMC_PRIOR_EXPONENTIAL: { /* Exponential(scale): log(rate) - rate x, rate = 1/scale; -Inf for x < 0 */
+        const double rate = 1.0 / pp[0];
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) {
+            if (!(th[i] >= 0.0)) return -INFINITY;
+            s += log(rate) - rate * th[i];
+        }
+        return s;
+    }
+    case EXTMCMC_PRIOR_INV_GAMMA: { /* InverseGamma(a, sc): a log sc - lgamma(a) - (a + 1) log x - sc/x */
+        const double a = pp[0], sc = pp[1];
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) {
+            if (!(th[i] > 0.0)) return -INFINITY;
+            s += a * log(sc) - lgamma(a) - (a + 1.0) * log(th[i]) - sc / th[i];
+        }
+        return s;
+    }
+    case EXTMCMC_PRIOR_BETA: { /* Beta(a, b): (a-1) log x + (b-1) log1p(-x) - logbeta(a, b) on (0, 1) */
+        const double a = pp[0], b = pp[1];
+        const double lbeta = lgamma(a) + lgamma(b) - lgamma(a + b);
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) {
+            if (!(th[i] > 0.0 && th[i] < 1.0)) return -INFINITY;
+            s += (a - 1.0) * log(th[i]) + (b - 1.0) * log1p(-th[i]) - lbeta;
+        }
+        return s;
+    }
+    case EXTMCMC_PRIOR_LOGNORMAL: { /* LogNormal(m, sd): logpdf(Normal(m, sd), log x) - log x */
+        const double m = pp[0], sd = pp[1];
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) {
+            if (!(th[i] > 0.0)) return -INFINITY;
+            const double lx = log(th[i]), z = (lx - m) / sd;
+            s += (-(z * z + kLog2Pi) / 2.0 - log(sd)) - lx;
+        }
+        return s;
+    }
+    case EXTMCMC_PRIOR_CAUCHY: { /* Cauchy(m, sc): -(log1p(z^2) + log(pi) + log(sc)) */
+        const double m = pp[0], sc = pp[1];
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) {
+            const double z = (th[i] - m) / sc;
+            s += -(log1p(z * z) + 1.1447298858494001741434273513531 + log(sc));
+        }
+        return s;
+    }
     }
     return NAN;
 }

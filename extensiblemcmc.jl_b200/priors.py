@@ -40,6 +40,36 @@ class Uniform:
         self.a, self.b = float(a), float(b)
 
 
+class Exponential:
+    """Stand-in for Distributions.Exponential(scale)."""
+    def __init__(self, scale=1.0):
+        self.scale = float(scale)
+
+
+class InverseGamma:
+    """Stand-in for Distributions.InverseGamma(shape, scale)."""
+    def __init__(self, shape=1.0, scale=1.0):
+        self.shape, self.scale = float(shape), float(scale)
+
+
+class Beta:
+    """Stand-in for Distributions.Beta(alpha, beta)."""
+    def __init__(self, alpha=1.0, beta=1.0):
+        self.alpha, self.beta = float(alpha), float(beta)
+
+
+class LogNormal:
+    """Stand-in for Distributions.LogNormal(mu, sigma)."""
+    def __init__(self, mu=0.0, sigma=1.0):
+        self.mu, self.sigma = float(mu), float(sigma)
+
+
+class Cauchy:
+    """Stand-in for Distributions.Cauchy(mu, sigma)."""
+    def __init__(self, mu=0.0, sigma=1.0):
+        self.mu, self.sigma = float(mu), float(sigma)
+
+
 class StandardPrior(Prior):                           # priors.jl:35-39
     """StandardPrior(dist): `dist` is applied independently to each coordinate of the
     update (an iid product)."""
@@ -54,15 +84,25 @@ class StandardPrior(Prior):                           # priors.jl:35-39
             return _abi.PRIOR_GAMMA, np.array([d.shape, d.scale])
         if isinstance(d, Uniform):
             return _abi.PRIOR_UNIFORM, np.array([d.a, d.b])
+        if isinstance(d, Exponential):
+            return _abi.PRIOR_EXPONENTIAL, np.array([d.scale])
+        if isinstance(d, InverseGamma):
+            return _abi.PRIOR_INV_GAMMA, np.array([d.shape, d.scale])
+        if isinstance(d, Beta):
+            return _abi.PRIOR_BETA, np.array([d.alpha, d.beta])
+        if isinstance(d, LogNormal):
+            return _abi.PRIOR_LOGNORMAL, np.array([d.mu, d.sigma])
+        if isinstance(d, Cauchy):
+            return _abi.PRIOR_CAUCHY, np.array([d.mu, d.sigma])
         raise NotImplementedError(
-            f"StandardPrior({type(d).__name__}) is not implemented on the GPU path "
-            "(supported: Normal, Gamma, Uniform)")
+            f"StandardPrior({type(d).__name__}) is not implemented on the GPU path (supported: Normal, "
+            "Gamma, Uniform, Exponential, InverseGamma, Beta, LogNormal, Cauchy)")
 
 
 class ProductPrior(Prior):                            # priors.jl:60-88
     """ProductPrior(dists, dims): factor k applies to the next dims[k] coordinates of the update
     (consecutive index groups, priors.jl:66-78).  Each factor is an ImproperPrior /
-    ImproperPosPrior or one of the Normal / Gamma / Uniform stand-ins (iid within its group)."""
+    ImproperPosPrior or one of the distribution stand-ins above (iid within its group)."""
 
     def __init__(self, dists, dims):
         self.dists, self.dims = tuple(dists), tuple(int(d) for d in dims)

@@ -84,9 +84,16 @@ enum {
                                        params = {shape, scale}; -Inf for th <= 0      */
     EXTMCMC_PRIOR_UNIFORM      = 4, /* StandardPrior(Uniform(a, b)) iid product,
                                        params = {a, b}; -Inf outside [a, b]           */
-    EXTMCMC_PRIOR_PRODUCT      = 5  /* ProductPrior(dists, dims), priors.jl:60-88: factors over
+    EXTMCMC_PRIOR_PRODUCT      = 5, /* ProductPrior(dists, dims), priors.jl:60-88: factors over
                                        consecutive coordinate groups; params = {K, then per
-                                       factor: kind (one of the above), dim, p0, p1}, K <= 8 */
+                                       factor: kind (any other kind), dim, p0, p1}, K <= 8    */
+    /* further StandardPrior families (iid product over the update's coordinates; the closed
+       forms of Distributions.jl's logpdf, -Inf outside the support)                           */
+    EXTMCMC_PRIOR_EXPONENTIAL  = 6, /* Exponential(scale): params = {scale}                    */
+    EXTMCMC_PRIOR_INV_GAMMA    = 7, /* InverseGamma(shape, scale)                              */
+    EXTMCMC_PRIOR_BETA         = 8, /* Beta(alpha, beta)                                       */
+    EXTMCMC_PRIOR_LOGNORMAL    = 9, /* LogNormal(mu, sigma)                                    */
+    EXTMCMC_PRIOR_CAUCHY       = 10 /* Cauchy(mu, sigma)                                       */
 };
 
 /* ---- adaptation schemes (src/transition_kernels/adaptation.jl) ----------- */

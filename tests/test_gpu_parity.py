@@ -85,6 +85,19 @@ def test_replay_no_adaptation_and_priors():
     _assert_clean(rep)
 
 
+def test_replay_further_prior_families():
+    # Exponential / InverseGamma / Beta / LogNormal / Cauchy, alone and inside a ProductPrior
+    x = _data(2000, seed=9, mean=0.5, sd=0.6)
+    ups = [em.RandomWalkUpdate(em.UniformRandomWalk([0.05]), [1], prior=em.StandardPrior(em.Beta(2.0, 3.0))),
+           em.RandomWalkUpdate(em.UniformRandomWalk([0.08], [True]), [2], prior=em.StandardPrior(em.InverseGamma(3.0, 1.0))),
+           em.RandomWalkUpdate(em.UniformRandomWalk([0.04, 0.06], [False, True]), [1, 2],
+                               prior=em.ProductPrior([em.Cauchy(0.4, 0.5), em.LogNormal(-1.0, 0.7)], [1, 1])),
+           em.RandomWalkUpdate(em.UniformRandomWalk([0.08], [True]), [2], prior=em.StandardPrior(em.Exponential(0.5)))]
+    th0 = np.repeat(np.array([[0.5], [0.36]]), 80, axis=1)
+    rep = replay_compare(x, 80, 30, seed=11, updates=ups, theta_init=th0)
+    _assert_clean(rep)
+
+
 def test_product_prior_and_support_redraw():
     # ProductPrior over a joint update (priors.jl:60-88); the Uniform factor has bounded support, so
     # the oracle's own stream exercises the whole-vector redraw of proposal! (updates.jl:193-195)

@@ -32,6 +32,17 @@ def test_julia_style_float_printing():
     assert float(_jl(0.1 + 0.2)) == 0.1 + 0.2
 
 
+def test_oracle_beta_prior_against_scipy():
+    # support (0, 1): probe from a state inside it; a proposal outside has log prior -Inf
+    x = np.array([0.3, -0.2, 0.9])
+    ups = [em.RandomWalkUpdate(em.UniformRandomWalk([0.1]), [2], prior=em.StandardPrior(em.Beta(2.5, 4.0)))]
+    o = orc.Oracle(em.GsnTargetLaw([0.0]), ups, x, [1.0, 0.4], n_chains=1)
+    r = o.run(list(em.MCMCSchedule(3, 1)), replay=(np.array([[[0.4]], [[0.55]], [[1.2]]]), np.array([[1.0], [1e9], [1e-9]])))
+    want = (r["ll_prop"][1, 0] - r["ll"][0, 0]) + stats.beta.logpdf(0.55, 2.5, 4.0) - stats.beta.logpdf(0.4, 2.5, 4.0)
+    assert abs(r["llr"][1, 0] - want) < 1e-12 * max(1.0, abs(want))
+    assert r["llr"][2, 0] == -np.inf and not r["accepted"][2, 0]
+
+
 def test_product_prior_translation():
     kind, pp = em.ProductPrior([em.Normal(1.0, 2.0), em.ImproperPosPrior(), em.Uniform(0.0, 3.0)], [2, 1, 1]).to_abi()
     assert kind == _abi.PRIOR_PRODUCT
@@ -49,6 +60,12 @@ def test_oracle_priors_against_scipy():
         (em.StandardPrior(em.Gamma(2.5, 1.5)), lambda t: stats.gamma.logpdf(t, 2.5, scale=1.5).sum()),
         (em.StandardPrior(em.Uniform(0.0, 4.0)), lambda t: stats.uniform.logpdf(t, 0.0, 4.0).sum()),
         (em.ImproperPosPrior(), lambda t: -np.log(t).sum()),
+        (em.StandardPrior(em.Exponential(1.7)), lambda t: stats.expon.logpdf(t, scale=1.7).sum()),
+        (em.StandardPrior(em.InverseGamma(3.0, 2.5)), lambda t: stats.invgamma.logpdf(t, 3.0, scale=2.5).sum()),
+        (em.StandardPrior(em.LogNormal(0.3, 0.8)), lambda t: stats.lognorm.logpdf(t, 0.8, scale=np.exp(0.3)).sum()),
+        (em.StandardPrior(em.Cauchy(0.5, 1.5)), lambda t: stats.cauchy.logpdf(t, 0.5, 1.5).sum()),
+        (em.ProductPrior([em.Cauchy(1.0, 2.0), em.InverseGamma(2.0, 1.0)], [1, 1]),
+         lambda t: stats.cauchy.logpdf(t[0], 1.0, 2.0) + stats.invgamma.logpdf(t[1], 2.0, scale=1.0)),
         (em.ProductPrior([em.Normal(0.0, 1.0), em.Gamma(2.0, 2.0)], [1, 1]),
          lambda t: stats.norm.logpdf(t[0]) + stats.gamma.logpdf(t[1], 2.0, scale=2.0)),
     ]
