@@ -58,6 +58,30 @@ mutable struct CUDAGlobalWorkspace{T} <: eMCMC.GlobalWorkspace{T}
     data
 end
 
+# (EXTMCMC_PRIOR_* kind, parameters) of a reference prior (src/priors.jl:18-88); params(dist) of
+# Distributions.jl returns exactly the parameter order the ABI documents.
+using Distributions
+const PRIOR_KIND = Dict(Normal => 2, Gamma => 3, Uniform => 4, Exponential => 6, InverseGamma => 7,
+                        Beta => 8, LogNormal => 9, Cauchy => 10)
+prior_abi(::eMCMC.ImproperPrior) = (Int32(0), Float64[])
+prior_abi(::eMCMC.ImproperPosPrior) = (Int32(1), Float64[])
+function prior_abi(pr::eMCMC.StandardPrior)
+    for (T, k) in PRIOR_KIND
+        pr.dist isa T && return (Int32(k), Float64[params(pr.dist)...])
+    end
+    error("StandardPrior($(typeof(pr.dist))) not implemented on the GPU path")
+end
+function prior_abi(pr::eMCMC.ProductPrior)                  # {K, then per factor: kind, dim, p0, p1}
+    out = Float64[length(pr.dists)]
+    for (dist, idx) in zip(pr.dists, pr.idx)
+        k, pp = prior_abi(dist isa eMCMC.Prior ? dist : eMCMC.StandardPrior(dist))
+        k == 5 && error("nested ProductPrior not implemented on the GPU path")
+        append!(out, (Float64(k), Float64(length(idx)), get(pp, 1, 0.0), get(pp, 2, 0.0)))
+    end
+    (Int32(5), out)
+end
+prior_abi(pr) = error("prior $(typeof(pr)) not implemented on the GPU path")
+
 law_id(P::eMCMC.GsnTargetLaw) = length(P.P.μ) == 1 ? Int32(1) : Int32(2)
 law_id(P) = error("target law $(typeof(P)) is not implemented on the GPU path")
 
@@ -74,14 +98,13 @@ function eMCMC.init_global_workspace(b::CUDAMCMCBackend, M, updates::Vector{<:eM
         rw isa eMCMC.UniformRandomWalk || error("transition kernel $(typeof(rw)) not implemented on the GPU path")
         coords = Int32.(collect(updt.coords) .- 1)       # 0-based at the ABI
         eps = Float64.(collect(rw.ϵ)); pos = UInt8.(collect(rw.pos))
-        prior = updt.prior isa eMCMC.ImproperPrior ? Int32(0) :
-                updt.prior isa eMCMC.ImproperPosPrior ? Int32(1) :
-                error("prior $(typeof(updt.prior)) not implemented on the GPU path")
+        prior, pp = prior_abi(updt.prior)
         a = updt.adpt
         adapt = a isa eMCMC.NoAdaptation ? Adapt(0, 100, 0.234, 1.0, 1e-12, 1e7, 1e2) :
                 Adapt(1, a.adapt_every_k_steps, a.target_accpt_rate, a.scale, a.min, a.max, a.offset)
-        GC.@preserve coords eps pos begin
-            upd = Update(1, length(coords), pointer(coords), pointer(eps), pointer(pos), prior, 0, C_NULL, adapt)
+        GC.@preserve coords eps pos pp begin
+            upd = Update(1, length(coords), pointer(coords), pointer(eps), pointer(pos), prior,
+                         length(pp), isempty(pp) ? C_NULL : pointer(pp), adapt)
             check(h[], ccall((:extmcmc_set_update, LIB), Int32, (Ptr{Cvoid}, Int32, Ref{Update}), h[], u - 1, upd))
         end
     end
