@@ -56,6 +56,7 @@ mutable struct CUDAGlobalWorkspace{T} <: eMCMC.GlobalWorkspace{T}
     acceptance_history::Array{UInt8,3}
     block_len::Int
     data
+    n_local::Int                           # local workspaces created so far (their pidx)
 end
 
 # (EXTMCMC_PRIOR_* kind, parameters) of a reference prior (src/priors.jl:18-88); params(dist) of
@@ -114,7 +115,7 @@ function eMCMC.init_global_workspace(b::CUDAMCMCBackend, M, updates::Vector{<:eM
     θ0 = repeat(reshape(θinit, 1, p), C, 1)              # [C, p] column-major == chain fastest
     GC.@preserve θ0 check(h[], ccall((:extmcmc_set_state, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), h[], θ0))
     ws = CUDAGlobalWorkspace{T}(h[], permutedims(θ0), zeros(T, C, p, NU, M), zeros(T, C, p, NU, M),
-                                zeros(C, NU, M), zeros(C, NU, M), zeros(UInt8, C, NU, M), b.block_len, data)
+                                zeros(C, NU, M), zeros(C, NU, M), zeros(UInt8, C, NU, M), b.block_len, data, 0)
     finalizer(w -> ccall((:extmcmc_destroy, LIB), Int32, (Ptr{Cvoid},), w.handle), ws)
     ws
 end
@@ -124,10 +125,21 @@ end
 struct CUDALocalWorkspace{T} <: eMCMC.LocalWorkspace{T}
     gws::CUDAGlobalWorkspace{T}; pidx::Int; name::String
 end
-eMCMC.create_workspace(::CUDAMCMCBackend, updt, gws::CUDAGlobalWorkspace{T}, M) where T =
-    CUDALocalWorkspace{T}(gws, 0, string(eMCMC.remove_curly(typeof(updt))))
+# create_workspaces (src/workspaces.jl:362-371) calls this once per update, in schedule order
+function eMCMC.create_workspace(::CUDAMCMCBackend, updt, gws::CUDAGlobalWorkspace{T}, M) where T
+    gws.n_local += 1
+    CUDALocalWorkspace{T}(gws, gws.n_local, string(eMCMC.remove_curly(typeof(updt))))
+end
 eMCMC.accepted(ws::CUDALocalWorkspace, i::Int) = ws.gws.acceptance_history[:, ws.pidx, i] .!= 0
+eMCMC.set_accepted!(ws::CUDALocalWorkspace, i::Int, v) = (ws.gws.acceptance_history[:, ws.pidx, i] .= v)
+eMCMC.ll(ws::CUDALocalWorkspace, i::Int) = ws.gws.ll_history[:, ws.pidx, i]
+eMCMC.ll°(ws::CUDALocalWorkspace, i::Int) = ws.gws.llprop_history[:, ws.pidx, i]
 eMCMC.name_of_update(ws::CUDALocalWorkspace) = ws.name
+eMCMC.state(ws::CUDAGlobalWorkspace) = ws.state
+eMCMC.state(ws::CUDAGlobalWorkspace, step) = ws.state_history[:, :, step.pidx, step.mcmciter]
+eMCMC.state°(ws::CUDAGlobalWorkspace, step) = ws.state_proposal_history[:, :, step.pidx, step.mcmciter]
+eMCMC.num_mcmc_steps(ws::CUDAGlobalWorkspace) = size(ws.state_history, 4)
+eMCMC.num_updt(ws::CUDAGlobalWorkspace) = size(ws.state_history, 3)
 
 # __run!: walk the schedule on the host, ship blocks; callbacks define the sync points.
 function eMCMC.__run!(gws::CUDAGlobalWorkspace, local_wss, updates, schedule, callbacks)
