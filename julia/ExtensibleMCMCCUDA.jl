@@ -141,6 +141,18 @@ eMCMC.state°(ws::CUDAGlobalWorkspace, step) = ws.state_proposal_history[:, :, s
 eMCMC.num_mcmc_steps(ws::CUDAGlobalWorkspace) = size(ws.state_history, 4)
 eMCMC.num_updt(ws::CUDAGlobalWorkspace) = size(ws.state_history, 3)
 
+# estim_mean / estim_cov (src/workspaces.jl:121-136): GenericChainStats of every chain,
+# mean [C, p], cov [C, p, p] (the ABI fills chain-fastest; entry (a, b) at a + b p)
+function chain_stats(ws::CUDAGlobalWorkspace)
+    p, C = size(ws.state); NU = eMCMC.num_updt(ws)
+    m = zeros(C, p); cv = zeros(C, p * p); ra = zeros(C, NU); na = zeros(Int64, C, NU); np = zeros(Int64, C, NU)
+    GC.@preserve m cv ra na np check(ws.handle, ccall((:extmcmc_get_stats, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}), ws.handle, m, cv, ra, na, np))
+    (mean = m, cov = reshape(cv, C, p, p), rolling_ar = ra, n_accept = na, n_prop = np)
+end
+eMCMC.estim_mean(ws::CUDAGlobalWorkspace) = chain_stats(ws).mean
+eMCMC.estim_cov(ws::CUDAGlobalWorkspace) = chain_stats(ws).cov
+
 # __run!: walk the schedule on the host, ship blocks; callbacks define the sync points.
 function eMCMC.__run!(gws::CUDAGlobalWorkspace, local_wss, updates, schedule, callbacks)
     block = Step[]; seq = Ref(0)
