@@ -265,6 +265,15 @@ def test_unsupported_requests_raise():
         GpuSession(big, [em.RandomWalkUpdate(em.GaussianRandomWalk(np.eye(9)), list(range(1, 10)))],
                    np.zeros((5, 3)), big.theta, 4)
     assert ei.value.code == _abi.EUNSUPPORTED
+    # an empty observation set is refused loudly (EINVAL), as is running before any upload
+    cfg.law, cfg.obs_dim, cfg.n_params = _abi.LAW_GSN_IID_1D, 1, 2
+    assert lib.extmcmc_create(C.byref(cfg), C.byref(h)) == 0
+    empty = np.zeros(1)
+    assert lib.extmcmc_upload_obs(h, _abi.dptr(empty), 0, 1, None) == _abi.EINVAL
+    step = orc.steps_array(list(em.MCMCSchedule(1, 1)))
+    assert lib.extmcmc_run_block(h, step, 1) == _abi.EINVAL
+    assert b"observations" in lib.extmcmc_last_error(h)
+    lib.extmcmc_destroy(h)
 
 
 def test_history_ring_staleness():
