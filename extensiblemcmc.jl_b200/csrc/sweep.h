@@ -18,7 +18,7 @@ struct SweepPlan {
     int variant;       // SWEEP_VARIANT_*
     int R;             // chains per thread ("chains") or chains per CTA pass ("obs")
     int groups;        // chain groups (grid.y for "chains", launches for "obs")
-    int S;             // observation segments = rows of partial[S][C]
+    int S;             // observation segments = rows of partial[S][C] (logistic: partial slots per chain block)
     int launches;      // kernel launches per sweep
     int D;             // observation dimension (general-d Gaussian law)
     int G;             // observation groups (hierarchical law; 1 otherwise)
