@@ -1,7 +1,9 @@
-// K1 (proposal), K3 (accept / commit / statistics / adaptation) and the MALA kernels: one thread
-// per chain, everything SoA and coalesced across chains.  Compiled with -fmad=false: the reference
-// never contracts a*b+c, and the replay parity tests compare eps, running moments and
-// trajectories bit-for-bit against the CPU oracle.
+// K1 (proposal), K3 (accept / commit / statistics / adaptation) and the MALA kernels.  One thread
+// owns a chain's scalar work (everything SoA, coalesced across chains); the reductions of the
+// sweep's partial sums and the covariance update of mid-sized models are shared by the 8 "slices"
+// (threads) a CTA assigns to every chain.  Compiled with -fmad=false: the reference never
+// contracts a*b+c, and the replay parity tests compare eps, running moments and trajectories
+// bit-for-bit against the CPU oracle.
 #include <cmath>
 #include <cstdint>
 #include <cuda_runtime.h>
