@@ -1064,7 +1064,11 @@ mala_propose_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int f
                     double *__restrict__ ll_scratch) {
     __shared__ StepCtx ctx;
     __shared__ double sh2[kCoopG * kMalaChains], sh1[kCoopG * kMalaChains];
+    // PDL (as in accept_kernel): the schedule element and update entry are staged while the
+    // preceding sweep is still running; nothing the predecessor writes is read before the wait
+    griddep_launch_dependents();
     load_step_ctx(&ctx, d, descs, k);
+    griddep_wait();
     const int64_t c0 = (int64_t)blockIdx.x * kMalaChains;
     const int64_t c = c0 + threadIdx.x % kMalaChains;
     // the sweep just before this kernel evaluated the CURRENT state: finish its sums here
@@ -1178,8 +1182,10 @@ mala_accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fi
     __shared__ StepCtx ctx, ctx_next;
     __shared__ double sh2[kCoopG * kMalaChains], sh1[kCoopG * kMalaChains];
     __shared__ double sh_t[kCoopP * kMalaChains], sh_m[kCoopP * kMalaChains], sh_n[kCoopP * kMalaChains];
+    griddep_launch_dependents();
     load_step_ctx(&ctx, d, descs, k);
     if (fuse_next) load_step_ctx(&ctx_next, d, descs, k + 1);
+    griddep_wait();   // the gradient sweep of the proposal has finished
     const int64_t c0 = (int64_t)blockIdx.x * kMalaChains;
     const int ch = threadIdx.x % kMalaChains;
     const int64_t c = c0 + ch;
@@ -1311,13 +1317,29 @@ void launch_grad_finalize(const DevState &d, const double *src, double *ll_out, 
 }
 void launch_mala_propose(const DevState &d, const StepDesc *descs, int k, int finalize_cur, double *ll_scratch,
                          cudaStream_t st) {
-    mala_propose_kernel<<<(int)((d.C + kMalaChains - 1) / kMalaChains), kMalaChains * kMalaSlices, 0, st>>>(
-        d, descs, k, finalize_cur, ll_scratch);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)((d.C + kMalaChains - 1) / kMalaChains));
+    cfg.blockDim = dim3(kMalaChains * kMalaSlices);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = (pdl_mask() >> 1) & 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, mala_propose_kernel, d, descs, k, finalize_cur, ll_scratch);
 }
 void launch_mala_accept(const DevState &d, const StepDesc *descs, int k, int finalize_prop, int fuse_next,
                         cudaStream_t st) {
-    mala_accept_kernel<<<(int)((d.C + kMalaChains - 1) / kMalaChains), kMalaChains * kMalaSlices, 0, st>>>(
-        d, descs, k, finalize_prop, fuse_next);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)((d.C + kMalaChains - 1) / kMalaChains));
+    cfg.blockDim = dim3(kMalaChains * kMalaSlices);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = (pdl_mask() >> 1) & 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, mala_accept_kernel, d, descs, k, finalize_prop, fuse_next);
 }
 void launch_prepare_current(const DevState &d, cudaStream_t st) {
     prepare_current_kernel<<<blocks_for(d.C), 256, 0, st>>>(d);
