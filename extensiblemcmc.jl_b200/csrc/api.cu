@@ -109,6 +109,7 @@ struct extmcmc_handle {
     double *flush_buf = nullptr;
     int64_t flush_n = 0;
     double *scratch_ll = nullptr;  // [C]
+    double *gsum = nullptr;        // [2][G][C] all-reduced per-group sums of a gradient sweep (obs sharding)
     // asynchronous history fetch
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t fetch_ready = nullptr, fetch_done = nullptr;
@@ -201,6 +202,9 @@ int32_t ensure_plan(extmcmc_t h) {
                                                                 : (size_t)2 * h->d.G * h->plan.S;
     int32_t rc = dev_alloc(h, &h->d.partial, part_rows * h->d.C);
     if (rc) return rc;
+    if (obs_sharded(h) && !h->gsum &&
+        (h->cfg.law == EXTMCMC_LAW_GSN_IID_1D || h->cfg.law == EXTMCMC_LAW_HIER_NORMAL))
+        if ((rc = dev_alloc(h, &h->gsum, (size_t)2 * h->d.G * h->d.C))) return rc;
     h->plan_valid = true;
     invalidate_graphs(h);
     return EXTMCMC_OK;
@@ -291,7 +295,14 @@ int32_t enqueue_sweep(extmcmc_t h, bool instrument, bool grad = false, const dou
         CK(h, cudaEventRecord(ev.second, h->stream));
         h->ev_pending.push_back(ev);
     }
-    if (obs_sharded(h)) {
+    if (obs_sharded(h) && grad) {
+        // gradient sweep of a Gaussian law: the consumers (MALA kernels, extmcmc_eval_grad) need the
+        // sums per observation group and of both orders, over all ranks
+        launch_reduce_group_sums(h->d, h->gsum, h->stream);
+        h->launches += 1;
+        NK(h, g_nccl.AllReduce(h->gsum, h->gsum, (size_t)2 * h->d.G * h->d.C, ncclFloat64, ncclSum, h->comm,
+                               h->stream));
+    } else if (obs_sharded(h)) {
         if (h->d.p2p && d_descs) {
             // our own exchange: peer stores + flags (in the sweep's fused tail, or here), wait +
             // ordered sum inside accept_kernel
@@ -310,6 +321,14 @@ int32_t enqueue_sweep(extmcmc_t h, bool instrument, bool grad = false, const dou
 // MALA element: [current-state gradient sweep if grad_cur is stale] propose, gradient sweep,
 // finalize, accept.  grad_valid is threaded through so that a captured graph and the eager
 // path make identical decisions.
+// What the gradient consumers see: under observation sharding the all-reduced per-group sums stand
+// in for the partial buffer (one "segment" per group).
+DevState grad_view(extmcmc_t h) {
+    DevState v = h->d;
+    if (obs_sharded(h) && h->cfg.law != EXTMCMC_LAW_LOGISTIC) { v.partial = h->gsum; v.S = 1; }
+    return v;
+}
+
 int32_t enqueue_steps(extmcmc_t h, const StepDesc *d_descs, const int *kinds, int n_steps,
                       bool instrument, bool &grad_valid) {
     bool fused = false;      // the proposal of element k was already issued by accept(k-1)
@@ -332,14 +351,15 @@ int32_t enqueue_steps(extmcmc_t h, const StepDesc *d_descs, const int *kinds, in
                     finalize_cur = 1;
                 }
             }
-            launch_mala_propose(h->d, d_descs, k, finalize_cur, h->scratch_ll, h->stream);
+            const DevState gv = grad_view(h);
+            launch_mala_propose(gv, d_descs, k, finalize_cur, h->scratch_ll, h->stream);
             if (logi) {
                 if ((rc = enqueue_sweep(h, instrument, true, h->d.prop_full, h->d.ll_prop, h->d.grad_prop))) return rc;
             } else {
                 if ((rc = enqueue_sweep(h, instrument, true, h->d.prop_full))) return rc;   // finished inside mala_accept
             }
             fused = next_rw;   // the next random-walk proposal rides on this accept kernel
-            launch_mala_accept(h->d, d_descs, k, logi ? 0 : 1, fused ? 1 : 0, h->stream);
+            launch_mala_accept(gv, d_descs, k, logi ? 0 : 1, fused ? 1 : 0, h->stream);
             h->launches += 2;
             grad_valid = true;
             cur_prepared = false;
@@ -382,8 +402,6 @@ int32_t run_block_impl(extmcmc_t h, const extmcmc_step_t *steps, int32_t n_steps
         if (!h->upd_set[u]) return fail(h, EXTMCMC_EINVAL, "update " + std::to_string(u) + " not set");
     if (n_steps > h->cfg.history_window)
         return fail(h, EXTMCMC_EINVAL, "block longer than history_window");
-    if (h->any_mala && obs_sharded(h) && h->cfg.law != EXTMCMC_LAW_LOGISTIC)
-        return fail(h, EXTMCMC_EUNSUPPORTED, "MALA updates with sharded observations are implemented for LOGISTIC only");
     if (obs_sharded(h) && !h->comm) return fail(h, EXTMCMC_EINVAL, "EXTMCMC_SHARD_OBS needs extmcmc_comm_init first");
     for (int s = 0; s < n_steps; ++s)
         if (steps[s].pidx < 0 || steps[s].pidx >= h->cfg.n_updates || steps[s].mcmciter < 1)
@@ -545,8 +563,6 @@ int32_t extmcmc_create(const extmcmc_config_t *cfg, extmcmc_t *out) {
     case EXTMCMC_LAW_HIER_NORMAL:
         if (cfg->obs_dim != 1 || cfg->n_params < 3)
             return fail(nullptr, EXTMCMC_EINVAL, "HIER_NORMAL needs obs_dim = 1 and n_params = G + 2 >= 3");
-        if (cfg->shard_mode == EXTMCMC_SHARD_OBS && cfg->world_size > 1)
-            return fail(nullptr, EXTMCMC_EUNSUPPORTED, "HIER_NORMAL with sharded observations is not implemented");
         break;
     default:
         // the reference's convention for a missing method: error("... not implemented")
@@ -1243,8 +1259,7 @@ int32_t extmcmc_eval_grad(extmcmc_t h, double *ll_out, double *grad_out) {
     if (h->cfg.law != EXTMCMC_LAW_GSN_IID_1D && h->cfg.law != EXTMCMC_LAW_HIER_NORMAL &&
         h->cfg.law != EXTMCMC_LAW_LOGISTIC)
         return fail(h, EXTMCMC_EUNSUPPORTED, "this law has no device gradient");
-    if (obs_sharded(h) && h->cfg.law != EXTMCMC_LAW_LOGISTIC)
-        return fail(h, EXTMCMC_EUNSUPPORTED, "gradients with sharded observations are implemented for LOGISTIC only");
+    if (obs_sharded(h) && !h->comm) return fail(h, EXTMCMC_EINVAL, "EXTMCMC_SHARD_OBS needs extmcmc_comm_init first");
     CK(h, cudaSetDevice(h->cfg.device));
     int32_t rc;
     if ((rc = ensure_plan(h))) return rc;
@@ -1254,7 +1269,7 @@ int32_t extmcmc_eval_grad(extmcmc_t h, double *ll_out, double *grad_out) {
     } else {
         launch_prepare_current(h->d, h->stream);
         if ((rc = enqueue_sweep(h, h->cfg.instrument != 0, true, h->d.theta))) return rc;
-        launch_grad_finalize(h->d, h->d.theta, h->scratch_ll, h->d.grad_cur, h->stream);
+        launch_grad_finalize(grad_view(h), h->d.theta, h->scratch_ll, h->d.grad_cur, h->stream);
         h->launches += 2;
     }
     h->grad_valid = true;

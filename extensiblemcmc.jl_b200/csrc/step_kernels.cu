@@ -427,6 +427,28 @@ __device__ __forceinline__ double reduce_segments(const DevState &d, double *sh 
     return tot;  // valid in threads with slice == 0
 }
 
+// Per-group sums of both orders, out[q][g][c] = sum_i partial[q][g*S + i][c] (segment order): what a
+// rank contributes to the all-reduce of a gradient sweep under observation sharding.  The MALA
+// kernels then read `out` as a partial buffer with one segment per group.
+__global__ void __launch_bounds__(256) reduce_group_sums_kernel(DevState d, double *__restrict__ out) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t C = d.C;
+    if (idx >= (int64_t)2 * d.G * C) return;
+    const int64_t r = idx / C, c = idx % C;          // r = q * G + g
+    const double *p = d.partial + (r * d.S) * C + c;  // rows (q G + g) S .. + S of partial[2][G S][C]
+    double s = 0.0;
+    int i = 0;
+    for (; i + 3 < d.S; i += 4) {
+        double a[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) a[q] = p[(int64_t)(i + q) * C];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) s += a[q];
+    }
+    for (; i < d.S; ++i) s += p[(int64_t)i * C];
+    out[idx] = s;
+}
+
 template <int SL>
 __global__ void __launch_bounds__(256) reduce_partials_kernel(DevState d) {
     __shared__ double sh[kRedThreads];
@@ -1343,6 +1365,10 @@ void launch_mala_accept(const DevState &d, const StepDesc *descs, int k, int fin
 }
 void launch_prepare_current(const DevState &d, cudaStream_t st) {
     prepare_current_kernel<<<blocks_for(d.C), 256, 0, st>>>(d);
+}
+void launch_reduce_group_sums(const DevState &d, double *out, cudaStream_t st) {
+    const int64_t n = (int64_t)2 * d.G * d.C;
+    reduce_group_sums_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(d, out);
 }
 void launch_reduce_partials(const DevState &d, cudaStream_t st) {
     if (d.S * d.G > 16)

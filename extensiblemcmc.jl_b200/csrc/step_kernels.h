@@ -14,6 +14,7 @@ void launch_mala_propose(const DevState &d, const StepDesc *descs, int k, int fi
 void launch_mala_accept(const DevState &d, const StepDesc *descs, int k, int finalize_prop, int fuse_next,
                         cudaStream_t st);
 void launch_reduce_partials(const DevState &d, cudaStream_t st);
+void launch_reduce_group_sums(const DevState &d, double *out, cudaStream_t st);
 void launch_reduce_push(const DevState &d, const StepDesc *descs, int k, cudaStream_t st);
 void launch_finalize_loglik(const DevState &d, double *ll_out, cudaStream_t st);
 void launch_generate_obs_normal(double *obs, int64_t first, int64_t n, double mean, double sd,

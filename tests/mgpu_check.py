@@ -8,6 +8,8 @@
 2. observations shard + NCCL all-reduce: every rank holds identical chains; log-likelihoods
    agree with the single-GPU sweep within 1e-10 relative, decisions agree (a different
    summation association can only flip a near-tie; flips are counted and reported).
+3. logistic law, rows sharded, MALA: ll and gradients all-reduced.
+4. hierarchical law, observations sharded, MALA + walks: per-group sums all-reduced.
 Prints one JSON line on rank 0 and exits non-zero on failure.
 """
 import json
@@ -106,6 +108,34 @@ def main():
     l2 = run_logi(lb, Xl[f3:f3 + c3], yl[f3:f3 + c3])
     logi_ok = bool(np.array_equal(l1[1], l2[1]) and np.allclose(l1[0], l2[0], rtol=1e-9, atol=1e-11)
                    and np.allclose(l1[2][np.isfinite(l1[2])], l2[2][np.isfinite(l1[2])], rtol=1e-10, atol=0))
+    # 4. gradient sweeps of the Gaussian laws under observation sharding: the per-group sums of both
+    #    orders are all-reduced before the MALA kernels finish ll and gradient (cfg 4 schedule: MALA on
+    #    theta_1..G, walks on mu and tau).  Contiguous slices of group-sorted data: ranks see different
+    #    (possibly no) observations of a group.
+    G, ng, Ch, Mh = 4, 300, 64, 30
+    rng = np.random.default_rng(5)
+    tg = rng.standard_normal(G)
+    yh = np.concatenate([tg[g] + rng.standard_normal(ng) for g in range(G)])
+    gh = np.repeat(np.arange(G), ng).astype(np.float64)
+    hier_ups = lambda: [em.MALAUpdate(0.1, list(range(1, G + 1)),
+                                      adpt=em.AdaptationMALA(adapt_every_k_steps=6, scale=0.004, offset=1.0)),
+                        em.RandomWalkUpdate(em.UniformRandomWalk([0.4]), [G + 1]),
+                        em.RandomWalkUpdate(em.UniformRandomWalk([0.4], [True]), [G + 2], prior=em.ImproperPosPrior())]
+    thh = np.concatenate([np.zeros(G), [0.0, 1.0]])
+
+    def run_hier(backend, ys, gs):
+        mcmc = em.MCMC(hier_ups(), backend=backend)
+        ws, lws = em.run_(mcmc, Mh, dict(P=em.HierNormalLaw(G), obs=ys, groups=gs), thh)
+        out = (ws.sub_ws.state_history.copy(), ws.acc_all.copy(), ws.ll_all.copy())
+        ws.close()
+        return out
+    h1 = run_hier(em.CUDAMCMCBackend(n_chains=Ch, device=local, seed=8, block_len=9), yh, gh)
+    f4, c4 = par.shard_obs(len(yh), rank, world)
+    h2 = run_hier(par.backend_for_rank(rank, world, local, Ch, shard="obs", comm_id=par.exchange_comm_id(dist),
+                                       seed=8, block_len=9), yh[f4:f4 + c4], gh[f4:f4 + c4])
+    finh = np.isfinite(h1[2])
+    hier_ok = bool(np.array_equal(h1[1], h2[1]) and np.allclose(h1[0], h2[0], rtol=1e-9, atol=1e-11)
+                   and np.allclose(h1[2][finh], h2[2][finh], rtol=1e-10, atol=0))
     gathered = par.gather_chain_axis(dist, sh["theta"][..., :4])
     if rank == 0:
         report.update(obs_ll_rel_err=float(rel.max()) if same_dec else None, obs_decisions_equal=bool(same_dec),
@@ -113,8 +143,8 @@ def main():
                       obs_ranks_identical=bool(all(np.array_equal(gathered[..., :4], gathered[..., 4 * r:4 * r + 4])
                                                    for r in range(world))))
         report.update(p2p_matches_nccl=p2p_same, p2p_ll_rel_vs_nccl=p2p_rel, logistic_obs_sharded_ok=logi_ok,
-                      few_chains_fused_tail_ok=few_ok)
-        ok &= logi_ok and few_ok
+                      few_chains_fused_tail_ok=few_ok, hier_mala_obs_sharded_ok=hier_ok)
+        ok &= logi_ok and few_ok and hier_ok
         ok &= same_dec and rel.max() < 1e-10 and report["obs_ranks_identical"] and p2p_same and p2p_rel < 1e-12
         report["world"] = world
         print(json.dumps(report))
