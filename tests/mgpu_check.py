@@ -10,6 +10,7 @@
    summation association can only flip a near-tie; flips are counted and reported).
 3. logistic law, rows sharded, MALA: ll and gradients all-reduced.
 4. hierarchical law, observations sharded, MALA + walks: per-group sums all-reduced.
+5. general-d Gaussian law, rows sharded.
 Prints one JSON line on rank 0 and exits non-zero on failure.
 """
 import json
@@ -136,6 +137,29 @@ def main():
     finh = np.isfinite(h1[2])
     hier_ok = bool(np.array_equal(h1[1], h2[1]) and np.allclose(h1[0], h2[0], rtol=1e-9, atol=1e-11)
                    and np.allclose(h1[2][finh], h2[2][finh], rtol=1e-10, atol=0))
+    # 5. general-d Gaussian law (theta = [mu; vec Sigma]) with the rows of the data sharded
+    dm, nm, Cm, Mm = 3, 1500, 80, 20
+    rng = np.random.default_rng(7)
+    Am = rng.standard_normal((dm, dm))
+    Sm = Am @ Am.T / dm + np.eye(dm)
+    Xm = rng.multivariate_normal(np.zeros(dm), Sm, size=nm)
+    mv_ups = lambda: [em.RandomWalkUpdate(em.UniformRandomWalk([0.1]), [k + 1]) for k in range(dm)] + \
+                     [em.RandomWalkUpdate(em.UniformRandomWalk([0.1], [True]), [dm + 1], prior=em.ImproperPosPrior())]
+    mv_law = em.GsnTargetLaw(np.zeros(dm), Sm)
+
+    def run_mv(backend, Xs):
+        mcmc = em.MCMC(mv_ups(), backend=backend)
+        ws, lws = em.run_(mcmc, Mm, dict(P=mv_law, obs=Xs), mv_law.theta)
+        out = (ws.sub_ws.state_history.copy(), ws.acc_all.copy(), ws.ll_all.copy())
+        ws.close()
+        return out
+    m1 = run_mv(em.CUDAMCMCBackend(n_chains=Cm, device=local, seed=11, block_len=8), Xm)
+    f5, c5 = par.shard_obs(nm, rank, world)
+    m2 = run_mv(par.backend_for_rank(rank, world, local, Cm, shard="obs", comm_id=par.exchange_comm_id(dist),
+                                     seed=11, block_len=8), Xm[f5:f5 + c5])
+    finm = np.isfinite(m1[2])
+    mv_ok = bool(np.array_equal(m1[1], m2[1]) and np.array_equal(m1[0], m2[0])
+                 and np.allclose(m1[2][finm], m2[2][finm], rtol=1e-10, atol=0))
     gathered = par.gather_chain_axis(dist, sh["theta"][..., :4])
     if rank == 0:
         report.update(obs_ll_rel_err=float(rel.max()) if same_dec else None, obs_decisions_equal=bool(same_dec),
@@ -143,8 +167,9 @@ def main():
                       obs_ranks_identical=bool(all(np.array_equal(gathered[..., :4], gathered[..., 4 * r:4 * r + 4])
                                                    for r in range(world))))
         report.update(p2p_matches_nccl=p2p_same, p2p_ll_rel_vs_nccl=p2p_rel, logistic_obs_sharded_ok=logi_ok,
-                      few_chains_fused_tail_ok=few_ok, hier_mala_obs_sharded_ok=hier_ok)
-        ok &= logi_ok and few_ok and hier_ok
+                      few_chains_fused_tail_ok=few_ok, hier_mala_obs_sharded_ok=hier_ok,
+                      gsnmv_obs_sharded_ok=mv_ok)
+        ok &= logi_ok and few_ok and hier_ok and mv_ok
         ok &= same_dec and rel.max() < 1e-10 and report["obs_ranks_identical"] and p2p_same and p2p_rel < 1e-12
         report["world"] = world
         print(json.dumps(report))
