@@ -14,6 +14,10 @@ value    device-resident throughput: K steps timed with CUDA events on the libra
 e2e      the whole cfg 2 job through the reference-facing API `run_(mcmc, M, data, theta0)`
          with host buffers: observation upload, every block launch, and the copy of every
          history row back to the host are inside the timed region.
+extra    sub-records of the same JSON line: `strong_cfg5` (BASELINE cfg 5: N = 1e9 observations
+         sharded over the ranks, NCCL all-reduce and the library's fused NVLink exchange, with an
+         in-run cross-rank parity check), and at N = 1 `cfg3` / `cfg4` (logistic regression on the
+         FP64 tensor path; hierarchical model with the mixed MALA / random-walk schedule).
 """
 import argparse
 import json
@@ -27,8 +31,11 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly one JSON line: keep NCCL's version banner out of it
-os.environ["NCCL_DEBUG"] = os.environ.get("EXTMCMC_NCCL_DEBUG", "WARN")
+# stdout carries exactly one JSON line.  NCCL's INFO log (communicator lines with `nranks N`) goes
+# to stderr instead of being silenced, so the ranks of every communicator stay observable.
+os.environ.setdefault("NCCL_DEBUG", os.environ.get("EXTMCMC_NCCL_DEBUG", "INFO"))
+os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 N_OBS = 1_000_000
 CHAINS_PER_GPU = 4096

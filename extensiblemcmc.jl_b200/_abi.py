@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libextmcmc_cuda.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # status codes
 OK, EINVAL, EUNSUPPORTED, ECUDA, ENCCL, EOOM, EDOMAIN, ESTALE = 0, -1, -2, -3, -4, -5, -6, -7
@@ -22,6 +22,7 @@ KERNEL_RW_UNIFORM, KERNEL_RW_GAUSS, KERNEL_RW_GAUSS_MIX, KERNEL_MALA = 1, 2, 3, 
 # priors
 PRIOR_IMPROPER, PRIOR_IMPROPER_POS, PRIOR_NORMAL, PRIOR_GAMMA, PRIOR_UNIFORM, PRIOR_PRODUCT = 0, 1, 2, 3, 4, 5
 PRIOR_EXPONENTIAL, PRIOR_INV_GAMMA, PRIOR_BETA, PRIOR_LOGNORMAL, PRIOR_CAUCHY = 6, 7, 8, 9, 10
+PRIOR_MVNORMAL = 11
 # adaptation
 ADAPT_NONE, ADAPT_UNIF_RW, ADAPT_HAARIO, ADAPT_MALA = 0, 1, 2, 3
 # sharding
@@ -95,6 +96,8 @@ class Config(C.Structure):
 
 
 Handle = C.c_void_p
+# double f(double lambda, int64 N, int64 mcmc_iter, void *user): HaarioTypeAdaptation's weight schedule
+LambdaFn = C.CFUNCTYPE(C.c_double, C.c_double, C.c_int64, C.c_int64, C.c_void_p)
 
 # name -> (restype, argtypes); every symbol declared in include/extmcmc.h
 SIGNATURES = {
@@ -106,6 +109,8 @@ SIGNATURES = {
     "extmcmc_generate_obs_normal": (C.c_int32, [Handle, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_uint64]),
     "extmcmc_set_update": (C.c_int32, [Handle, C.c_int32, C.POINTER(Update)]),
     "extmcmc_set_state": (C.c_int32, [Handle, c_double_p]),
+    "extmcmc_set_seed": (C.c_int32, [Handle, C.c_uint64]),
+    "extmcmc_set_lambda_fn": (C.c_int32, [Handle, C.c_int32, LambdaFn, C.c_void_p]),
     "extmcmc_comm_unique_id": (C.c_int32, [c_uint8_p]),
     "extmcmc_comm_init": (C.c_int32, [Handle, c_uint8_p]),
     "extmcmc_p2p_export": (C.c_int32, [Handle, c_uint8_p]),

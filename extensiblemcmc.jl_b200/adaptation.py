@@ -91,7 +91,10 @@ def isequal_except(a, b, *args):                         # adaptation.jl:223-235
 
 class HaarioTypeAdaptation(Adaptation):
     """HaarioTypeAdaptation(state; adapt_every_k_steps=100, scale=2.38^2, f) --
-    adaptation.jl:372-397 (device path: next round)."""
+    adaptation.jl:372-397.  Runs on the device (running mean / covariance of the transformed
+    sub-state, Sigma_B readjusted every k own turns); the weight schedule `f(lambda, N, iter)` is a
+    host closure: lambda is shared by all chains and N, iter are schedule facts, so the library calls
+    `f` back on the host at every readjustment (extmcmc_set_lambda_fn)."""
 
     def __init__(self, state, adapt_every_k_steps=100, scale=2.38 ** 2, f=None):
         n = int(np.size(state))
@@ -103,11 +106,14 @@ class HaarioTypeAdaptation(Adaptation):
         self._default_f = f is None
         self.f = f if f is not None else (lambda x, y, z: x)
 
+    def lambda_callback(self):
+        """ctypes callback for extmcmc_set_lambda_fn (None for the default, constant lambda)."""
+        if self._default_f:
+            return None
+        f = self.f
+        return _abi.LambdaFn(lambda lam, N, it, _user: float(f(lam, int(N), int(it))))
+
     def to_abi(self):
-        if not self._default_f:
-            raise NotImplementedError(
-                "HaarioTypeAdaptation with a user closure f(lambda, N, iter) cannot cross the C ABI; "
-                "only the default f = (x, y, z) -> x (constant lambda) is implemented on the GPU path")
         # NB the reference's readjust! ignores `scale` and uses 2.38^2 / length(rw) (adaptation.jl:423)
         return _abi.Adapt(_abi.ADAPT_HAARIO, self.adapt_every_k_steps, 0.0, self.scale, 0.0, 0.0, 0.0)
 

@@ -18,6 +18,7 @@
 
 #include "../../include/extmcmc.h"
 #include "dev_state.cuh"
+#include "block_kernels.h"
 #include "step_kernels.h"
 #include "sweep.h"
 
@@ -96,6 +97,19 @@ struct extmcmc_handle {
     std::vector<int64_t> ra_iter;   // [NU] mcmciter at which the update last ran (0 = never)
     std::vector<int64_t> acc_tag;   // [NU][W] mcmciter stored in the ring slot (0 = never)
     std::vector<int64_t> haario_M;  // [NU] HaarioTypeAdaptation.M (own-turn counter, adaptation.jl:378)
+    // GaussianRandomWalkMix.lambda per update and its schedule f(lambda, N, iter) (adaptation.jl:385,
+    // 422-426): evaluated on the host at every readjustment, shipped with the step descriptor
+    std::vector<double> lambda;
+    std::vector<extmcmc_lambda_fn> lambda_fn;
+    std::vector<void *> lambda_user;
+    int64_t xseq_next = 0;          // executed steps since handle creation (never reset)
+    // persistent block kernels (block_kernels.cu)
+    bool blk_planned = false;
+    bool res_ok = false, obsblk_ok = false;
+    ResidentPlan res_plan{};
+    int obsblk_grid = 0;
+    unsigned long long *blk_go = nullptr;
+    unsigned int *blk_counter = nullptr;
     // replay staging
     double *rp_prop = nullptr, *rp_exp = nullptr;
     size_t rp_prop_cap = 0, rp_exp_cap = 0;
@@ -198,15 +212,58 @@ int32_t ensure_plan(extmcmc_t h) {
     h->d.use_ssum = (obs_sharded(h) || h->cfg.law == EXTMCMC_LAW_LOGISTIC || h->tail) ? 1 : 0;
     // Gaussian laws: two quantities (second- and first-order sums) x G groups x S segments;
     // logistic: ll_part[S][C] followed by g_part[S][d][C]
-    const size_t part_rows = h->cfg.law == EXTMCMC_LAW_LOGISTIC ? (size_t)h->plan.S * (h->cfg.obs_dim + 1)
-                                                                : (size_t)2 * h->d.G * h->plan.S;
+    size_t part_rows = h->cfg.law == EXTMCMC_LAW_LOGISTIC ? (size_t)h->plan.S * (h->cfg.obs_dim + 1)
+                                                          : (size_t)2 * h->d.G * h->plan.S;
+    part_rows = std::max(part_rows, (size_t)h->num_sms * 3);   // segments of the observation-mapped block kernel
     int32_t rc = dev_alloc(h, &h->d.partial, part_rows * h->d.C);
     if (rc) return rc;
     if (obs_sharded(h) && !h->gsum &&
         (h->cfg.law == EXTMCMC_LAW_GSN_IID_1D || h->cfg.law == EXTMCMC_LAW_HIER_NORMAL))
         if ((rc = dev_alloc(h, &h->gsum, (size_t)2 * h->d.G * h->d.C))) return rc;
     h->plan_valid = true;
+    h->blk_planned = false;
     invalidate_graphs(h);
+    return EXTMCMC_OK;
+}
+
+// Which schedule blocks run as ONE persistent kernel (block_kernels.cu) instead of a kernel sequence
+// per element.  cfg.sweep_variant: 0 = automatic, 3 = chain-resident kernel whenever it is
+// applicable (tests: also with few chains), 4 = observation-mapped block kernel likewise, any
+// other value pins the per-step path.
+int32_t plan_block_kernels(extmcmc_t h) {
+    if (h->blk_planned) return EXTMCMC_OK;
+    h->blk_planned = true;
+    h->res_ok = h->obsblk_ok = false;
+    const int sv = h->cfg.sweep_variant;
+    if (sv != 0 && sv != 3 && sv != 4) return EXTMCMC_OK;
+    if (const char *e = getenv("EXTMCMC_BLOCK_KERNELS")) if (atoi(e) == 0) return EXTMCMC_OK;   // diagnostics
+    const bool gsn1d = h->cfg.law == EXTMCMC_LAW_GSN_IID_1D || h->cfg.law == EXTMCMC_LAW_HIER_NORMAL;
+    if (!gsn1d || h->d.n_haario > 0) return EXTMCMC_OK;
+    bool all_unif = true, all_unif_or_mala = true;
+    for (int u = 0; u < h->cfg.n_updates; ++u) {
+        const int kk = h->upd_host[u].kernel;
+        if (kk != EXTMCMC_KERNEL_RW_UNIFORM) all_unif = false;
+        if (kk != EXTMCMC_KERNEL_RW_UNIFORM && kk != EXTMCMC_KERNEL_MALA) all_unif_or_mala = false;
+    }
+    if (all_unif_or_mala && !obs_sharded(h) && sv != 4)
+        h->res_ok = plan_resident(h->d, h->num_sms, sv == 3, &h->res_plan);
+    if (!h->res_ok && all_unif && h->cfg.law == EXTMCMC_LAW_GSN_IID_1D && h->d.C <= 32 && sv != 3 &&
+        (sv == 4 || h->plan.variant == SWEEP_VARIANT_OBS) && (!obs_sharded(h) || h->d.p2p)) {
+        int cb = 1;
+        while (cb < h->d.C) cb <<= 1;
+        cudaError_t e = plan_obs_block(cb, h->num_sms, h->n_obs_local, &h->obsblk_grid);
+        if (e == cudaSuccess) {
+            if (!h->blk_go) {
+                int32_t rc;
+                if ((rc = dev_alloc(h, &h->blk_go, 1)) || (rc = dev_alloc(h, &h->blk_counter, 1))) return rc;
+                CK(h, cudaMemset(h->blk_go, 0, sizeof(unsigned long long)));
+                CK(h, cudaMemset(h->blk_counter, 0, sizeof(unsigned int)));
+            }
+            h->obsblk_ok = true;
+        } else {
+            cudaGetLastError();
+        }
+    }
     return EXTMCMC_OK;
 }
 
@@ -266,7 +323,7 @@ int32_t enqueue_sweep(extmcmc_t h, bool instrument, bool grad = false, const dou
             a.tail_counter = h->tail_counter; a.ssum = h->d.ssum;
             a.peer_rx = h->d.peer_rx; a.peer_flag = h->d.peer_flag;
             a.rank = h->cfg.rank; a.world = h->cfg.world_size;
-            a.descs = d_descs; a.k = k; a.epoch = h->d.epoch;
+            a.descs = d_descs; a.k = k;
         }
         launch_sweep_gsn1d(h->plan, a, grad, h->stream);
     } else if (h->cfg.law == EXTMCMC_LAW_LOGISTIC) {
@@ -411,6 +468,11 @@ int32_t run_block_impl(extmcmc_t h, const extmcmc_step_t *steps, int32_t n_steps
     if ((rc = ensure_plan(h))) return rc;
     if ((rc = upload_updates(h))) return rc;
     if ((rc = ensure_total_obs(h))) return rc;
+    if ((rc = plan_block_kernels(h))) return rc;
+    // a history fetch still in flight reads ring slots this block is about to overwrite: order the
+    // block after the copy (callers that keep 2 x block_len rows never get here)
+    if (h->fetch_active && h->seq_next + n_steps - h->d.H > h->fetch_lo)
+        CK(h, cudaStreamWaitEvent(h->stream, h->fetch_done, 0));
 
     if (h->d.rng_mode != rng_mode) { h->d.rng_mode = rng_mode; invalidate_graphs(h); }
     if (rng_mode == EXTMCMC_RNG_REPLAY) {
@@ -455,27 +517,44 @@ int32_t run_block_impl(extmcmc_t h, const extmcmc_step_t *steps, int32_t n_steps
         sl.cap = cap;
     }
     const int W = h->d.W;
-    for (int s = 0; s < n_steps; ++s) {
-        StepDesc &sd = sl.h_descs[s];
-        const int u = steps[s].pidx;
-        const int64_t it = steps[s].mcmciter;
-        sd.mcmciter = it;
-        sd.seq = h->seq_next + s;
-        sd.stat_n = sd.seq + 1;  // GenericChainStats.N starts at 1 (chain_statistics.jl:34)
-        sd.pidx = u;
-        sd.first = steps[s].prev_pidx < 0 ? 1 : 0;
-        const int64_t prev_it = it - 1 > 1 ? it - 1 : 1;
-        sd.ra_prev_valid = (h->ra_iter[u] == prev_it && prev_it != it) ? 1 : 0;
-        int64_t &tag = h->acc_tag[(size_t)u * W + (size_t)(it % W)];
-        sd.acc_out_valid = (it > W && tag == it - W) ? 1 : 0;
-        sd.replay_row = s;
-        sd.haario_ready = 0;
-        if (h->upd_host[u].adapt_kind == EXTMCMC_ADAPT_HAARIO) {
-            // register_only_on_my_turn(::Val{true}, ::Haario): M += 1; time_to_update: M >= k -> M = 0
-            if (++h->haario_M[u] >= h->upd_host[u].adapt_every_k) { sd.haario_ready = 1; h->haario_M[u] = 0; }
+    int n_sweeps = 0;
+    {
+        bool gv = h->grad_valid;
+        for (int s = 0; s < n_steps; ++s) {
+            StepDesc &sd = sl.h_descs[s];
+            const int u = steps[s].pidx;
+            const int64_t it = steps[s].mcmciter;
+            sd.mcmciter = it;
+            sd.seq = h->seq_next + s;
+            sd.stat_n = sd.seq + 1;  // GenericChainStats.N starts at 1 (chain_statistics.jl:34)
+            sd.xseq = h->xseq_next + s;
+            sd.pidx = u;
+            sd.first = steps[s].prev_pidx < 0 ? 1 : 0;
+            const int64_t prev_it = it - 1 > 1 ? it - 1 : 1;
+            sd.ra_prev_valid = (h->ra_iter[u] == prev_it && prev_it != it) ? 1 : 0;
+            int64_t &tag = h->acc_tag[(size_t)u * W + (size_t)(it % W)];
+            sd.acc_out_valid = (it > W && tag == it - W) ? 1 : 0;
+            sd.replay_row = s;
+            sd.haario_ready = 0;
+            sd.lambda = h->lambda[u];
+            sd.pad_ = 0;
+            if (h->upd_host[u].adapt_kind == EXTMCMC_ADAPT_HAARIO) {
+                // register_only_on_my_turn(::Val{true}, ::Haario): M += 1; time_to_update: M >= k -> M = 0
+                if (++h->haario_M[u] >= h->upd_host[u].adapt_every_k) {
+                    sd.haario_ready = 1;
+                    h->haario_M[u] = 0;
+                    // readjust!: rw.lambda = f(rw.lambda, adpt.N, mcmc_iter) with adpt.N already
+                    // incremented by this step's registration (adaptation.jl:413,425)
+                    if (h->lambda_fn[u]) h->lambda[u] = h->lambda_fn[u](h->lambda[u], sd.stat_n + 1, it, h->lambda_user[u]);
+                }
+            }
+            const bool mala = h->upd_host[u].kernel == EXTMCMC_KERNEL_MALA;
+            sd.need_cur_grad = (mala && !gv) ? 1 : 0;
+            n_sweeps += mala ? 1 + sd.need_cur_grad : 1;
+            gv = mala;
+            h->ra_iter[u] = it;
+            tag = it;
         }
-        h->ra_iter[u] = it;
-        tag = it;
     }
 
     std::vector<int> kinds(n_steps);
@@ -488,7 +567,43 @@ int32_t run_block_impl(extmcmc_t h, const extmcmc_step_t *steps, int32_t n_steps
     hash = (hash ^ (unsigned long long)n_steps) * 1099511628211ull;
     const bool instrument = h->cfg.instrument != 0;
     const bool use_graph = h->cfg.use_graphs && !instrument && rng_mode == EXTMCMC_RNG_PHILOX;
-    if (!use_graph) {
+    if (h->res_ok || h->obsblk_ok) {
+        // the whole block in one persistent kernel
+        CK(h, cudaMemcpyAsync(sl.d_descs, sl.h_descs, sizeof(StepDesc) * n_steps, cudaMemcpyHostToDevice, h->stream));
+        std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+        if (instrument) {
+            if (!h->ev_free.empty()) { ev = h->ev_free.back(); h->ev_free.pop_back(); }
+            else { CK(h, cudaEventCreate(&ev.first)); CK(h, cudaEventCreate(&ev.second)); }
+        }
+        if (h->res_ok) {
+            ResidentArgs a{};
+            a.d = h->d;
+            a.d.S = 1;
+            a.descs = sl.d_descs; a.n_steps = n_steps; a.n_sweeps = n_sweeps;
+            a.obs = h->obs_dev; a.goff = h->goff_dev; a.glen = h->glen_dev; a.G = h->d.G;
+            a.ll_scratch = h->scratch_ll;
+            if (instrument) CK(h, cudaEventRecord(ev.first, h->stream));
+            CK(h, launch_resident_block(h->res_plan, a, h->stream));
+            h->launches += 1;
+        } else {
+            ObsBlockArgs a{};
+            a.d = h->d;
+            a.descs = sl.d_descs; a.n_steps = n_steps;
+            a.obs = h->obs_dev; a.n_obs = h->n_obs_local;
+            a.go = h->blk_go; a.counter = h->blk_counter;
+            launch_obs_block_first(h->d, sl.d_descs, h->blk_go, h->blk_counter, h->stream);
+            if (instrument) CK(h, cudaEventRecord(ev.first, h->stream));
+            int cb = 1;
+            while (cb < h->d.C) cb <<= 1;
+            CK(h, launch_obs_block(cb, h->obsblk_grid, a, h->stream));
+            h->launches += 2;
+        }
+        if (instrument) {
+            CK(h, cudaEventRecord(ev.second, h->stream));
+            h->ev_pending.push_back(ev);
+        }
+        h->grad_valid = kinds[n_steps - 1] == EXTMCMC_KERNEL_MALA;
+    } else if (!use_graph) {
         CK(h, cudaMemcpyAsync(sl.d_descs, sl.h_descs, sizeof(StepDesc) * n_steps,
                               cudaMemcpyHostToDevice, h->stream));
         if ((rc = enqueue_steps(h, sl.d_descs, kinds.data(), n_steps, instrument, h->grad_valid))) return rc;
@@ -526,6 +641,7 @@ int32_t run_block_impl(extmcmc_t h, const extmcmc_step_t *steps, int32_t n_steps
     CK(h, cudaEventRecord(sl.done, h->stream));
     sl.in_flight = true;
     h->seq_next += n_steps;
+    h->xseq_next += n_steps;
     return EXTMCMC_OK;
 }
 
@@ -552,7 +668,7 @@ int32_t extmcmc_create(const extmcmc_config_t *cfg, extmcmc_t *out) {
         break;
     case EXTMCMC_LAW_GSN_MV:
         if (cfg->obs_dim < 2 || cfg->obs_dim > kMaxObsDim)
-            return fail(nullptr, EXTMCMC_EUNSUPPORTED, "GSN_MV on the GPU path needs 2 <= obs_dim <= 8 (d = 1: GSN_IID_1D)");
+            return fail(nullptr, EXTMCMC_EUNSUPPORTED, "GSN_MV on the GPU path needs 2 <= obs_dim <= 16 (d = 1: GSN_IID_1D)");
         if (cfg->n_params != cfg->obs_dim * (cfg->obs_dim + 1))
             return fail(nullptr, EXTMCMC_EINVAL, "GSN_MV needs n_params = d (d + 1)");
         break;
@@ -649,6 +765,19 @@ int32_t extmcmc_create(const extmcmc_config_t *cfg, extmcmc_t *out) {
     h->ra_iter.assign(NU, 0);
     h->acc_tag.assign((size_t)NU * d.W, 0);
     h->haario_M.assign(NU, 0);
+    h->lambda.assign(NU, 0.0);
+    h->lambda_fn.assign(NU, nullptr);
+    h->lambda_user.assign(NU, nullptr);
+    if (cfg->law == EXTMCMC_LAW_GSN_MV && (rc = dev_alloc(h, &d.mv_L, (size_t)cfg->obs_dim * cfg->obs_dim * C)))
+        return bail(rc);
+    {
+        // bounded wait for the peers' sums under observation sharding (and for the go-flag of the
+        // observation-mapped block kernel): generous, because ordinary host skew (a rank inside a
+        // callback, a first-block graph capture) delays a peer's launch, not only a dead rank
+        const char *e = getenv("EXTMCMC_P2P_TIMEOUT_MS");
+        const double ms = e ? atof(e) : 30000.0;
+        d.p2p_timeout_ns = (unsigned long long)((ms > 1.0 ? ms : 1.0) * 1e6);
+    }
     *out = h;
     return EXTMCMC_OK;
 #undef CKC
@@ -786,11 +915,28 @@ int32_t extmcmc_generate_obs_normal(extmcmc_t h, int64_t first, int64_t n_obs, d
     return EXTMCMC_OK;
 }
 
+// Per-chain SoA scratch of the Gaussian walks, Haario registration and MvNormal priors: three
+// columns of n doubles per chain (step_device.cuh).  Grown on demand, never shrunk.
+static int32_t ensure_gw_scratch(extmcmc_t h, int n) {
+    if (n <= h->d.gw_n) return EXTMCMC_OK;
+    CK(h, cudaStreamSynchronize(h->stream));
+    double *p = nullptr;
+    int32_t rc = dev_alloc(h, &p, (size_t)3 * n * h->d.C);
+    if (rc) return rc;
+    h->d.gw = p;
+    h->d.gw_n = n;
+    invalidate_graphs(h);
+    return EXTMCMC_OK;
+}
+
 int32_t extmcmc_set_update(extmcmc_t h, int32_t u, const extmcmc_update_t *upd) {
     if (!h || !upd) return EXTMCMC_EINVAL;
     if (u < 0 || u >= h->cfg.n_updates) return fail(h, EXTMCMC_EINVAL, "update index out of range");
+    // ---- validation first: a failed call leaves the update as it was -----------------------------
     const bool gauss = upd->kernel == EXTMCMC_KERNEL_RW_GAUSS || upd->kernel == EXTMCMC_KERNEL_RW_GAUSS_MIX;
     const bool mala = upd->kernel == EXTMCMC_KERNEL_MALA;
+    const bool mix = upd->kernel == EXTMCMC_KERNEL_RW_GAUSS_MIX;
+    const bool haario = upd->adapt.kind == EXTMCMC_ADAPT_HAARIO;
     if (upd->kernel != EXTMCMC_KERNEL_RW_UNIFORM && !gauss && !mala)
         return fail(h, EXTMCMC_EUNSUPPORTED, "transition kernel not implemented on the GPU path");
     if (mala) {
@@ -803,14 +949,19 @@ int32_t extmcmc_set_update(extmcmc_t h, int32_t u, const extmcmc_update_t *upd) 
             for (int i = 0; i < upd->n_coords; ++i)
                 if (upd->pos[i]) return fail(h, EXTMCMC_EUNSUPPORTED, "MALA on positivity-constrained coordinates is not implemented");
     }
-    if (upd->prior < EXTMCMC_PRIOR_IMPROPER || upd->prior > EXTMCMC_PRIOR_CAUCHY)
+    if (upd->prior < EXTMCMC_PRIOR_IMPROPER || upd->prior > EXTMCMC_PRIOR_MVNORMAL)
         return fail(h, EXTMCMC_EUNSUPPORTED, "prior not implemented on the GPU path");
+    if (upd->n_coords < 1 || upd->n_coords > (mala ? std::min(h->cfg.n_params, 32768) : kMaxCoords))
+        return fail(h, EXTMCMC_EUNSUPPORTED, mala ? "1 <= n_coords <= min(n_params, 32768) for MALA"
+                                                  : "1 <= n_coords <= 32 for random-walk updates on the GPU path");
+    if (!upd->coords || !upd->step) return fail(h, EXTMCMC_EINVAL, "coords/step missing");
+    const int nc = upd->n_coords, nn = nc * nc;
     if (upd->prior == EXTMCMC_PRIOR_PRODUCT) {
         // {K, then per factor: kind, dim, p0, p1}; the dims must tile the update's coordinates
         if (upd->n_prior_params < 1 || !upd->prior_params) return fail(h, EXTMCMC_EINVAL, "ProductPrior parameters missing");
         const int K = (int)upd->prior_params[0];
         if (K < 1 || K > kMaxPriorFactors || upd->n_prior_params != 1 + 4 * K)
-            return fail(h, EXTMCMC_EUNSUPPORTED, "ProductPrior: 1 <= factors <= 8");
+            return fail(h, EXTMCMC_EUNSUPPORTED, "ProductPrior: 1 <= factors <= 16");
         int tot = 0;
         for (int k = 0; k < K; ++k) {
             const int kind = (int)upd->prior_params[1 + 4 * k], dim = (int)upd->prior_params[2 + 4 * k];
@@ -818,75 +969,84 @@ int32_t extmcmc_set_update(extmcmc_t h, int32_t u, const extmcmc_update_t *upd) 
                 return fail(h, EXTMCMC_EUNSUPPORTED, "ProductPrior factor not implemented on the GPU path");
             tot += dim;
         }
-        if (tot != upd->n_coords) return fail(h, EXTMCMC_EINVAL, "ProductPrior dims must add up to length(coords)");
+        if (tot != nc) return fail(h, EXTMCMC_EINVAL, "ProductPrior dims must add up to length(coords)");
+    } else if (upd->prior == EXTMCMC_PRIOR_MVNORMAL) {
+        if (upd->n_prior_params != nc + nn || !upd->prior_params)
+            return fail(h, EXTMCMC_EINVAL, "MvNormal prior needs {mu[p_u], L[p_u * p_u]}");
+        for (int i = 0; i < nc; ++i)
+            if (!(upd->prior_params[nc + i + i * nc] > 0.0))
+                return fail(h, EXTMCMC_EINVAL, "MvNormal prior: the Cholesky factor must have a positive diagonal");
+    } else {
+        if (upd->n_prior_params > kMaxPriorParams || (upd->n_prior_params > 0 && !upd->prior_params))
+            return fail(h, EXTMCMC_EINVAL, "bad prior parameters");
+        // parameters each StandardPrior family reads
+        const int pk = upd->prior;
+        const int need = (pk == EXTMCMC_PRIOR_IMPROPER || pk == EXTMCMC_PRIOR_IMPROPER_POS) ? 0
+                       : pk == EXTMCMC_PRIOR_EXPONENTIAL ? 1 : 2;
+        if (upd->n_prior_params < need) return fail(h, EXTMCMC_EINVAL, "prior parameters missing");
     }
     // readjust! exists only for (UniformRandomWalk, AdaptationUnifRW) and
     // (GaussianRandomWalkMix, HaarioTypeAdaptation): adaptation.jl:273,422
     if (!(upd->adapt.kind == EXTMCMC_ADAPT_NONE ||
           (upd->adapt.kind == EXTMCMC_ADAPT_MALA && mala) ||
           (upd->adapt.kind == EXTMCMC_ADAPT_UNIF_RW && upd->kernel == EXTMCMC_KERNEL_RW_UNIFORM) ||
-          (upd->adapt.kind == EXTMCMC_ADAPT_HAARIO && upd->kernel == EXTMCMC_KERNEL_RW_GAUSS_MIX)))
+          (upd->adapt.kind == EXTMCMC_ADAPT_HAARIO && mix)))
         return fail(h, EXTMCMC_EUNSUPPORTED, "adaptation not implemented for this transition kernel");
-    if (upd->n_coords < 1 || upd->n_coords > (mala ? h->cfg.n_params : gauss ? kMaxGaussCoords : kMaxCoords))
-        return fail(h, EXTMCMC_EUNSUPPORTED, gauss ? "1 <= n_coords <= 8 for Gaussian random walks on the GPU path"
-                                                    : "1 <= n_coords <= 16 for random-walk updates");
-    if (!upd->coords || !upd->step) return fail(h, EXTMCMC_EINVAL, "coords/step missing");
-    if (upd->n_prior_params > kMaxPriorParams || (upd->n_prior_params > 0 && !upd->prior_params))
-        return fail(h, EXTMCMC_EINVAL, "bad prior parameters");
-    {
-        // parameters each StandardPrior family reads (the ProductPrior layout was checked above)
-        const int pk = upd->prior;
-        const int need = (pk == EXTMCMC_PRIOR_IMPROPER || pk == EXTMCMC_PRIOR_IMPROPER_POS || pk == EXTMCMC_PRIOR_PRODUCT) ? 0
-                       : pk == EXTMCMC_PRIOR_EXPONENTIAL ? 1 : 2;
-        if (upd->n_prior_params < need) return fail(h, EXTMCMC_EINVAL, "prior parameters missing");
-    }
     if (upd->adapt.kind != EXTMCMC_ADAPT_NONE && upd->adapt.adapt_every_k_steps < 1)
         return fail(h, EXTMCMC_EINVAL, "adapt_every_k_steps must be >= 1");
-    CK(h, cudaSetDevice(h->cfg.device));
-    const int64_t C = h->d.C;
-    const int W = h->d.W;
-    DevUpdate &t = h->upd_host[u];
-    const bool fresh = !h->upd_set[u];
-    if (!fresh && t.n_coords != upd->n_coords) return fail(h, EXTMCMC_EINVAL, "cannot change n_coords of an update");
-    t.kernel = upd->kernel; t.n_coords = upd->n_coords; t.prior = upd->prior;
-    t.adapt_kind = upd->adapt.kind;
-    for (int i = 0; i < upd->n_coords; ++i) {
+    for (int i = 0; i < nc; ++i) {
         if (upd->coords[i] < 0 || upd->coords[i] >= h->cfg.n_params)
             return fail(h, EXTMCMC_EINVAL, "coordinate out of range");
         if (!gauss && !mala && !(upd->step[i] > 0.0))  // UniformRandomWalk: @assert all(eps .> 0.0), random_walk.jl:50
             return fail(h, EXTMCMC_EINVAL, "eps must be > 0");
-        if (i < kMaxCoords) {
-            t.coords[i] = upd->coords[i];
-            t.pos[i] = upd->pos ? upd->pos[i] : 0;
-        }
     }
+    if (mix && !(upd->step[2 * nn] >= 0.0 && upd->step[2 * nn] <= 1.0))   // @assert 0 <= lambda <= 1, random_walk.jl:199
+        return fail(h, EXTMCMC_EINVAL, "lambda must be in [0, 1]");
+    if (mala && !(upd->step[0] > 0.0)) return fail(h, EXTMCMC_EINVAL, "MALA step tau must be > 0");
+    const bool fresh = !h->upd_set[u];
+    {
+        const DevUpdate &cur = h->upd_host[u];
+        if (!fresh && cur.n_coords != nc) return fail(h, EXTMCMC_EINVAL, "cannot change n_coords of an update");
+        if (!fresh && ((mix && !cur.sigB) || (gauss && !cur.sigA) || (haario && !cur.hmean) ||
+                       (upd->prior == EXTMCMC_PRIOR_MVNORMAL && !cur.prior_dev)))
+            return fail(h, EXTMCMC_EINVAL, "cannot change the kernel or prior family of an update");
+    }
+
+    // ---- build the new entry in a copy; it replaces the old one only when everything succeeded ----
+    CK(h, cudaSetDevice(h->cfg.device));
+    const int64_t C = h->d.C;
+    const int W = h->d.W;
+    DevUpdate t = h->upd_host[u];
+    t.kernel = upd->kernel; t.n_coords = nc; t.prior = upd->prior;
+    t.adapt_kind = upd->adapt.kind;
+    for (int i = 0; i < nc && i < kMaxCoords; ++i) {
+        t.coords[i] = upd->coords[i];
+        t.pos[i] = upd->pos ? upd->pos[i] : 0;
+    }
+    const bool mvn = upd->prior == EXTMCMC_PRIOR_MVNORMAL;
     for (int i = 0; i < kMaxPriorParams; ++i)
-        t.prior_params[i] = i < upd->n_prior_params ? upd->prior_params[i] : 0.0;
+        t.prior_params[i] = (!mvn && i < upd->n_prior_params) ? upd->prior_params[i] : 0.0;
     t.adapt_every_k = upd->adapt.adapt_every_k_steps;
     t.target = upd->adapt.target_accpt_rate; t.scale = upd->adapt.scale;
     t.vmin = upd->adapt.min; t.vmax = upd->adapt.max; t.offset = upd->adapt.offset;
     int32_t rc = 0;
-    const int nc = upd->n_coords, nn = nc * nc;
-    const bool mix = upd->kernel == EXTMCMC_KERNEL_RW_GAUSS_MIX;
-    const bool haario = upd->adapt.kind == EXTMCMC_ADAPT_HAARIO;
-    if (mix && !(upd->step[2 * nn] >= 0.0 && upd->step[2 * nn] <= 1.0))   // @assert 0 <= lambda <= 1, random_walk.jl:199
-        return fail(h, EXTMCMC_EINVAL, "lambda must be in [0, 1]");
-    if (mala && !(upd->step[0] > 0.0)) return fail(h, EXTMCMC_EINVAL, "MALA step tau must be > 0");
     if (fresh) {
+        double *pd = nullptr;
         if ((rc = dev_alloc(h, &t.coords_dev, (size_t)nc)) ||
             (rc = dev_alloc(h, &t.eps, (size_t)nc * C)) ||
             (rc = dev_alloc(h, &t.adapt_prop, (size_t)C)) || (rc = dev_alloc(h, &t.adapt_acc, (size_t)C)) ||
             (rc = dev_alloc(h, &t.tot_prop, (size_t)C)) || (rc = dev_alloc(h, &t.tot_acc, (size_t)C)) ||
             (rc = dev_alloc(h, &t.ra_val, (size_t)C)) || (rc = dev_alloc(h, &t.acc_ring, (size_t)W * C)))
             return rc;
-        if (gauss && (rc = dev_alloc(h, &t.sigA, (size_t)nn))) return rc;
-        if (mix && (rc = dev_alloc(h, &t.sigB, (size_t)nn * C))) return rc;
+        if (gauss && ((rc = dev_alloc(h, &t.sigA, (size_t)nn)) || (rc = dev_alloc(h, &t.LA, (size_t)nn)))) return rc;
+        if (mix && ((rc = dev_alloc(h, &t.sigB, (size_t)nn * C)) || (rc = dev_alloc(h, &t.LB, (size_t)nn * C)))) return rc;
         if (haario && ((rc = dev_alloc(h, &t.hmean, (size_t)nc * C)) || (rc = dev_alloc(h, &t.hcov, (size_t)nn * C)))) return rc;
-    } else if ((mix && !t.sigB) || (gauss && !t.sigA) || (haario && !t.hmean)) {
-        return fail(h, EXTMCMC_EINVAL, "cannot change the kernel family of an update");
+        if (mvn) { if ((rc = dev_alloc(h, &pd, (size_t)(nc + nn)))) return rc; t.prior_dev = pd; }
     }
+    if ((gauss || haario || mvn) && (rc = ensure_gw_scratch(h, nc))) return rc;
     CK(h, cudaStreamSynchronize(h->stream));
     CK(h, cudaMemcpy(t.coords_dev, upd->coords, sizeof(int32_t) * nc, cudaMemcpyHostToDevice));
+    if (mvn) CK(h, cudaMemcpy(const_cast<double *>(t.prior_dev), upd->prior_params, sizeof(double) * (nc + nn), cudaMemcpyHostToDevice));
     if (mala) {
         std::vector<double> tau0((size_t)C, upd->step[0]);   // one step size tau per chain
         CK(h, cudaMemcpy(t.eps, tau0.data(), tau0.size() * sizeof(double), cudaMemcpyHostToDevice));
@@ -897,26 +1057,32 @@ int32_t extmcmc_set_update(extmcmc_t h, int32_t u, const extmcmc_update_t *upd) 
         CK(h, cudaMemcpy(t.eps, eps0.data(), eps0.size() * sizeof(double), cudaMemcpyHostToDevice));
     } else {
         CK(h, cudaMemcpy(t.sigA, upd->step, sizeof(double) * nn, cudaMemcpyHostToDevice));
+        launch_chol_factor(t.sigA, t.LA, nc, 1, 1, h->stream);          // L_A, once: Sigma_A never changes
         if (mix) {
             std::vector<double> sb((size_t)nn * C);
             for (int k = 0; k < nn; ++k) std::fill_n(sb.begin() + (size_t)k * C, C, upd->step[nn + k]);
             CK(h, cudaMemcpy(t.sigB, sb.data(), sb.size() * sizeof(double), cudaMemcpyHostToDevice));
-            t.lambda = upd->step[2 * nn];
+            launch_chol_factor(t.sigB, t.LB, nc, C, C, h->stream);      // L_B per chain (rewritten at every readjust!)
         }
+        CK(h, cudaGetLastError());
+        CK(h, cudaStreamSynchronize(h->stream));
         if (haario) {
             CK(h, cudaMemset(t.hmean, 0, sizeof(double) * nc * C));
             CK(h, cudaMemset(t.hcov, 0, sizeof(double) * nn * C));
         }
     }
-    h->haario_M[u] = 0;
     CK(h, cudaMemset(t.adapt_prop, 0, sizeof(int32_t) * C));
     CK(h, cudaMemset(t.adapt_acc, 0, sizeof(int32_t) * C));
     CK(h, cudaMemset(t.tot_prop, 0, sizeof(int64_t) * C));
     CK(h, cudaMemset(t.tot_acc, 0, sizeof(int64_t) * C));
     CK(h, cudaMemset(t.ra_val, 0, sizeof(double) * C));
     CK(h, cudaMemset(t.acc_ring, 0, (size_t)W * C));
+    h->upd_host[u] = t;
+    h->lambda[u] = mix ? upd->step[2 * nn] : 0.0;
+    h->haario_M[u] = 0;
     h->upd_set[u] = true;
     h->upd_dirty = true;
+    h->blk_planned = false;
     int nh = 0;
     h->any_mala = false;
     for (int v = 0; v < h->cfg.n_updates; ++v) {
@@ -924,6 +1090,22 @@ int32_t extmcmc_set_update(extmcmc_t h, int32_t u, const extmcmc_update_t *upd) 
         if (h->upd_set[v] && h->upd_host[v].adapt_kind == EXTMCMC_ADAPT_HAARIO) ++nh;
     }
     if (nh != h->d.n_haario) { h->d.n_haario = nh; invalidate_graphs(h); }
+    return EXTMCMC_OK;
+}
+
+int32_t extmcmc_set_seed(extmcmc_t h, uint64_t seed) {
+    if (!h) return EXTMCMC_EINVAL;
+    h->cfg.seed = seed;
+    h->d.seed = seed;
+    invalidate_graphs(h);   // the key is baked into the kernel arguments
+    return EXTMCMC_OK;
+}
+
+int32_t extmcmc_set_lambda_fn(extmcmc_t h, int32_t u, extmcmc_lambda_fn f, void *user) {
+    if (!h) return EXTMCMC_EINVAL;
+    if (u < 0 || u >= h->cfg.n_updates) return fail(h, EXTMCMC_EINVAL, "update index out of range");
+    h->lambda_fn[u] = f;
+    h->lambda_user[u] = user;
     return EXTMCMC_OK;
 }
 
@@ -956,8 +1138,6 @@ int32_t extmcmc_set_state(extmcmc_t h, const double *theta) {
     }
     std::fill(h->haario_M.begin(), h->haario_M.end(), 0);
     h->seq_next = 0;
-    h->d.epoch += 1;
-    invalidate_graphs(h);   // the epoch is baked into the kernel arguments
     h->grad_valid = false;
     if (h->fetch_active) { cudaEventSynchronize(h->fetch_done); h->fetch_active = false; }
     std::fill(h->ra_iter.begin(), h->ra_iter.end(), 0);
@@ -1065,10 +1245,9 @@ int32_t extmcmc_sync(extmcmc_t h) {
     if (rc) return rc;
     int32_t flag = 0;
     CK(h, cudaMemcpy(&flag, h->d.err_flag, sizeof flag, cudaMemcpyDeviceToHost));
-    if (flag == 2) {
-        CK(h, cudaMemset(h->d.err_flag, 0, sizeof flag));
-        return fail(h, EXTMCMC_ENCCL, "peer exchange timed out: a rank did not deliver its partial sums");
-    }
+    if (flag == 2)   // sticky until extmcmc_set_state: nothing has been committed since the failed exchange
+        return fail(h, EXTMCMC_ENCCL, "peer exchange timed out: a rank did not deliver its partial sums; "
+                                      "no step has been committed since (extmcmc_set_state to start over)");
     if (flag) {
         CK(h, cudaMemset(h->d.err_flag, 0, sizeof flag));
         return fail(h, EXTMCMC_EDOMAIN,
@@ -1342,7 +1521,7 @@ int32_t extmcmc_flush_l2(extmcmc_t h) {
 int32_t extmcmc_measure_fp64_peak(extmcmc_t h, double *tflops_out) {
     if (!h || !tflops_out) return EXTMCMC_EINVAL;
     CK(h, cudaSetDevice(h->cfg.device));
-    const int iters = 20000;
+    const int iters = 16000;   // multiple of the unroll factor 8
     double best = 0.0;
     for (int rep = 0; rep < 4; ++rep) {
         CK(h, cudaEventRecord(h->t0, h->stream));
@@ -1351,7 +1530,7 @@ int32_t extmcmc_measure_fp64_peak(extmcmc_t h, double *tflops_out) {
         CK(h, cudaEventSynchronize(h->t1));
         float ms = 0.f;
         CK(h, cudaEventElapsedTime(&ms, h->t0, h->t1));
-        const double flops = (double)h->num_sms * 8 * 256 * 8.0 * iters * 2.0;
+        const double flops = (double)h->num_sms * 8 * 256 * 16.0 * iters * 2.0;
         if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
     }
     *tflops_out = best;
@@ -1381,7 +1560,21 @@ int32_t extmcmc_measure_dmma_peak(extmcmc_t h, double *tflops_out) {
 const char *extmcmc_sweep_variant_name(extmcmc_t h) {
     if (!h) return "";
     if (!h->plan_valid && h->obs_dev) ensure_plan(h);
-    return h->plan_valid ? h->plan.name : "unplanned";
+    if (!h->plan_valid) return "unplanned";
+    bool all_set = true;
+    for (int u = 0; u < h->cfg.n_updates; ++u) all_set = all_set && h->upd_set[u];
+    if (all_set && plan_block_kernels(h) == EXTMCMC_OK) {
+        if (h->res_ok) {
+            static const char *rn[] = {"", "", "", "", "resident_R4", "resident_R5", "resident_R6", "resident_R7", "resident_R8"};
+            return rn[h->res_plan.R];
+        }
+        if (h->obsblk_ok) {
+            const int64_t C = h->d.C;
+            return C <= 1 ? "obs_block_C1" : C <= 2 ? "obs_block_C2" : C <= 4 ? "obs_block_C4"
+                 : C <= 8 ? "obs_block_C8" : C <= 16 ? "obs_block_C16" : "obs_block_C32";
+        }
+    }
+    return h->plan.name;
 }
 
 }  // extern "C"

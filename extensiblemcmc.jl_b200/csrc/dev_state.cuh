@@ -14,11 +14,10 @@
 
 namespace extmcmc {
 
-constexpr int kMaxCoords = 16;      // p_u limit of the scalar per-chain step kernels
-constexpr int kMaxGaussCoords = 8; // p_u limit of the Gaussian random walks on the device
-constexpr int kMaxPriorFactors = 8;  // ProductPrior factors
+constexpr int kMaxCoords = 32;       // p_u limit of the random-walk updates (MALA: unlimited, coords_dev)
+constexpr int kMaxPriorFactors = 16; // ProductPrior factors
 constexpr int kMaxPriorParams = 1 + 4 * kMaxPriorFactors;
-constexpr int kMaxObsDim = 8;       // general-d Gaussian law on the device: d <= 8
+constexpr int kMaxObsDim = 16;       // general-d Gaussian law on the device: d <= 16
 
 // One update as the kernels see it (constant per run; lives in a device table).
 struct DevUpdate {
@@ -26,6 +25,7 @@ struct DevUpdate {
     int32_t coords[kMaxCoords];
     uint8_t pos[kMaxCoords];
     double  prior_params[kMaxPriorParams];
+    const double *prior_dev; // MVNORMAL prior: { mu[n], L[n*n] column-major lower Cholesky factor } (device)
     int32_t adapt_every_k;
     double  target, scale, vmin, vmax, offset;
     double *eps;          // [n_coords][C] per-chain step size (rw.eps, adapted in place)
@@ -35,10 +35,13 @@ struct DevUpdate {
     int64_t *tot_acc;     // [C]
     double  *ra_val;      // [C] latest rolling acceptance rate of this update
     uint8_t *acc_ring;    // [W][C] acceptance bits of the last W iterations
-    // Gaussian random walks (random_walk.jl:123-232)
+    // Gaussian random walks (random_walk.jl:123-232).  The Cholesky factors are cached: L_A once
+    // per set_update (Sigma_A is shared by all chains and never changes), L_B per chain whenever
+    // the Haario adaptation rewrites Sigma_B (L_B[0] = NaN marks "not positive definite").
     double *sigA;         // [n*n] column-major, shared by all chains (GaussianRandomWalk.Sigma / gsn_A)
+    double *LA;           // [n*n] lower Cholesky factor of Symmetric(sigA) (upper triangle), column-major
     double *sigB;         // [n*n][C] per chain (gsn_B.Sigma, rewritten by the Haario adaptation)
-    double  lambda;       // GaussianRandomWalkMix.lambda
+    double *LB;           // [n*n][C] per chain factor of sigB
     double *hmean;        // [n][C]   HaarioTypeAdaptation.mean
     double *hcov;         // [n*n][C] HaarioTypeAdaptation.cov
     int32_t *coords_dev;  // [n_coords] device copy of coords (MALA: n_coords may exceed kMaxCoords)
@@ -49,12 +52,17 @@ struct StepDesc {
     int64_t mcmciter;       // 1-based, enters compute_delta (adaptation.jl:312-319)
     int64_t seq;            // executed-step sequence number since set_state
     int64_t stat_n;         // GenericChainStats.N before this step (= seq + 1)
+    int64_t xseq;           // executed-step sequence number since handle creation (never reset:
+                            // parity and tag of the cross-rank exchange, go-flag of the block kernels)
+    double  lambda;         // GaussianRandomWalkMix.lambda in force at this step (host-evaluated f_lambda)
     int32_t pidx;           // 0-based update index
     int32_t first;          // prev_pidx === nothing: ll stays -Inf (run.jl:76,109)
     int32_t ra_prev_valid;  // rolling_ar[max(1, iter-1)][pidx] was written (else 0.0)
     int32_t acc_out_valid;  // acceptance_history[iter - W] of this update was written
     int32_t replay_row;     // row of this step in the replay buffers
     int32_t haario_ready;   // this step brings the update's own-turn counter M to k (adaptation.jl:416-420)
+    int32_t need_cur_grad;  // MALA: the gradient at the current state is stale (another update moved it)
+    int32_t pad_;
 };
 
 struct DevState {
@@ -78,6 +86,11 @@ struct DevState {
     double *prop_full;      // [p][C] full proposal = theta with coords replaced (run.jl:237-239)
     double *lawc;           // [lawc_k][C] per-chain law constants of the proposal
     uint32_t *n_used;       // [C] uniforms consumed by the proposal (next index = Exp draw)
+    // per-chain scratch of the Gaussian walks / MvNormal priors / general-d law (SoA, so that a
+    // thread-per-chain triangular solve stays coalesced and nothing lives in local memory)
+    double *gw;             // [3 * gw_n][C]: z | t | m
+    int32_t gw_n;
+    double *mv_L;           // [d*d][C] Cholesky scratch of the general-d law
     // sweep output
     double *partial;        // [2][G*S][C] per-segment partial sums: q = 0 second-order, q = 1 first-order
     int32_t S;
@@ -97,16 +110,19 @@ struct DevState {
     const double *rp_exp;   // [rows][C]
     // fused cross-GPU exchange of the per-chain sums under observation sharding (no NCCL on the
     // hot path): every rank pushes its sums into slot [parity][rank] of every peer's rx buffer
-    // over NVLink peer mappings and raises a sequence flag; the accept kernel waits for all
-    // flags and adds the slots in rank order (identical totals on every rank).
+    // over NVLink peer mappings and raises a sequence flag; the consumer waits for all flags and
+    // adds the slots in rank order (identical totals on every rank).  parity = xseq & 1,
+    // tag = xseq + 1: xseq is never reset, so a slot is only reused two exchanges later, after
+    // every rank has consumed it.
     int32_t p2p, rank, world;
-    uint64_t epoch;                     // bumped by set_state so stale flags never match
     double **peer_rx;                   // [world] -> rx[2][world][C] of each rank
     unsigned long long **peer_flag;     // [world] -> flag[2][world] of each rank
     double *my_rx;
     unsigned long long *my_flag;
     unsigned int *push_counter;
+    unsigned long long p2p_timeout_ns;  // bounded wait for the peers' flags
     int32_t *err_flag;      // sticky: 1 = a chain left the law's domain, 2 = peer exchange timed out
+                            // (2: every later step is a no-op until the host has seen it)
     DevUpdate *upd;         // [NU]
 };
 

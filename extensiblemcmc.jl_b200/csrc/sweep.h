@@ -51,7 +51,6 @@ struct Gsn1dArgs {
     int rank, world;
     const void *descs;       // StepDesc array of the block (device), element k names the step
     int k;
-    unsigned long long epoch;
 };
 
 SweepPlan plan_sweep_gsn1d(int64_t C, int64_t n_obs_largest_group, int force_variant, int num_sms, int G);

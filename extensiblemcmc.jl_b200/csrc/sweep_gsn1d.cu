@@ -282,7 +282,7 @@ sweep_gsn1d_obs_kernel(Gsn1dArgs a) {
             a.ssum[tid] = tot;
         } else {
             const StepDesc *sd = reinterpret_cast<const StepDesc *>(a.descs) + a.k;
-            const int parity = (int)(sd->seq & 1);
+            const int parity = (int)(sd->xseq & 1);
             const int64_t slot = ((int64_t)parity * a.world + a.rank) * C + tid;
             for (int q = 0; q < a.world; ++q) a.peer_rx[q][slot] = tot;   // stores into peer memory
         }
@@ -292,8 +292,8 @@ sweep_gsn1d_obs_kernel(Gsn1dArgs a) {
         __syncthreads();
         if (tid == 0) {
             const StepDesc *sd = reinterpret_cast<const StepDesc *>(a.descs) + a.k;
-            const int parity = (int)(sd->seq & 1);
-            const unsigned long long tag = (a.epoch << 40) | (unsigned long long)(sd->seq + 1);
+            const int parity = (int)(sd->xseq & 1);
+            const unsigned long long tag = (unsigned long long)(sd->xseq + 1);
             for (int q = 0; q < a.world; ++q) {
                 unsigned long long *f = a.peer_flag[q] + (parity * a.world + a.rank);
                 asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(tag) : "memory");

@@ -70,9 +70,22 @@ class Cauchy:
         self.mu, self.sigma = float(mu), float(sigma)
 
 
+class MvNormal:
+    """Stand-in for Distributions.MvNormal(mu, Sigma): a joint prior over the whole coordinate
+    block of an update (priors.jl:35-39 wraps any Distributions object).  The host factorises
+    Sigma = L L'; the device whitens with L, as PDMats does."""
+    def __init__(self, mu, Sigma):
+        self.mu = np.atleast_1d(np.asarray(mu, dtype=np.float64)).copy()
+        self.Sigma = np.atleast_2d(np.asarray(Sigma, dtype=np.float64)).copy()
+        n = self.mu.size
+        if self.Sigma.shape != (n, n):
+            raise ValueError("MvNormal: Sigma must be length(mu) x length(mu)")
+        self.L = np.linalg.cholesky(self.Sigma)       # raises if not positive definite (PosDefException)
+
+
 class StandardPrior(Prior):                           # priors.jl:35-39
-    """StandardPrior(dist): `dist` is applied independently to each coordinate of the
-    update (an iid product)."""
+    """StandardPrior(dist): a univariate `dist` is applied independently to each coordinate of
+    the update (an iid product); an MvNormal covers the update's coordinate block jointly."""
     def __init__(self, dist):
         self.dist = dist
 
@@ -94,9 +107,12 @@ class StandardPrior(Prior):                           # priors.jl:35-39
             return _abi.PRIOR_LOGNORMAL, np.array([d.mu, d.sigma])
         if isinstance(d, Cauchy):
             return _abi.PRIOR_CAUCHY, np.array([d.mu, d.sigma])
+        if isinstance(d, MvNormal):
+            # {mu[n], L[n*n] column-major}
+            return _abi.PRIOR_MVNORMAL, np.concatenate([d.mu, np.ascontiguousarray(d.L.T).ravel()])
         raise NotImplementedError(
             f"StandardPrior({type(d).__name__}) is not implemented on the GPU path (supported: Normal, "
-            "Gamma, Uniform, Exponential, InverseGamma, Beta, LogNormal, Cauchy)")
+            "Gamma, Uniform, Exponential, InverseGamma, Beta, LogNormal, Cauchy, MvNormal)")
 
 
 class ProductPrior(Prior):                            # priors.jl:60-88
@@ -113,8 +129,8 @@ class ProductPrior(Prior):                            # priors.jl:60-88
         for dist, dim in zip(self.dists, self.dims):
             pr = dist if isinstance(dist, Prior) else StandardPrior(dist)
             kind, pp = pr.to_abi()
-            if kind == _abi.PRIOR_PRODUCT:
-                raise NotImplementedError("nested ProductPrior is not implemented on the GPU path")
+            if kind in (_abi.PRIOR_PRODUCT, _abi.PRIOR_MVNORMAL):
+                raise NotImplementedError("ProductPrior factors must be iid families on the GPU path")
             pp = list(pp) + [0.0, 0.0]
             out += [float(kind), float(dim), pp[0], pp[1]]
         return _abi.PRIOR_PRODUCT, np.array(out)

@@ -34,7 +34,7 @@ class UniformRandomWalk(RandomWalk):
 
 
 class GaussianRandomWalk(RandomWalk):
-    """GaussianRandomWalk(Sigma, pos) -- random_walk.jl:123-134 (device path: next round)."""
+    """GaussianRandomWalk(Sigma, pos) -- random_walk.jl:123-134."""
 
     abi_kernel = _abi.KERNEL_RW_GAUSS
 

@@ -66,6 +66,17 @@ class CUDAMCMCBackend(MCMCBackend):
         # callable bytes -> [bytes of every rank, rank order]; enables the library's own NVLink
         # peer exchange of the per-chain sums instead of ncclAllReduce (shard_mode="obs")
         self.p2p_allgather = p2p_allgather
+        self.runs_started = 0
+
+
+def _run_seed(seed, run):
+    """Philox key of the run-th run of a backend: the seed itself for run 0, a SplitMix64 mix after."""
+    if run == 0:
+        return seed & 0xFFFFFFFFFFFFFFFF
+    z = (seed + run * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    return z ^ (z >> 31)
 
 
 class _GlobalSub:
@@ -117,7 +128,10 @@ class CUDAGlobalWorkspace(GlobalWorkspace):
         cfg.n_updates = self.NU
         cfg.law = law.abi_law()
         cfg.obs_dim = law.obs_dim
-        cfg.seed = backend.seed
+        # the reference advances a global RNG from run to run; a counter RNG restarts, so every
+        # further run of the same backend gets its own key (run 0 keeps the user's seed)
+        cfg.seed = _run_seed(backend.seed, backend.runs_started)
+        backend.runs_started += 1
         cfg.shard_mode = _abi.SHARD_OBS if backend.shard_mode == "obs" else _abi.SHARD_CHAINS
         cfg.rank, cfg.world_size = backend.rank, backend.world_size
         self.block_len = max(1, backend.block_len)
@@ -154,6 +168,10 @@ class CUDAGlobalWorkspace(GlobalWorkspace):
                 self._keep.append(keep)
                 self._kernels.append(u.kernel)
                 self._ck(lib.extmcmc_set_update(self.handle, i, C.byref(u)))
+                cb = getattr(getattr(updt, "adpt", None), "lambda_callback", lambda: None)()
+                if cb is not None:                              # HaarioTypeAdaptation(...; f = ...)
+                    self._keep.append(cb)
+                    self._ck(lib.extmcmc_set_lambda_fn(self.handle, i, cb, None))
             if isinstance(obs, DeviceGeneratedObs):
                 self._ck(lib.extmcmc_generate_obs_normal(self.handle, obs.first, obs.n, obs.mean, obs.sd, obs.seed))
                 self.n_obs = obs.n

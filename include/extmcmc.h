@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define EXTMCMC_ABI_VERSION 1
+#define EXTMCMC_ABI_VERSION 2
 
 /* ---- status codes -------------------------------------------------------- */
 enum {
@@ -86,14 +86,19 @@ enum {
                                        params = {a, b}; -Inf outside [a, b]           */
     EXTMCMC_PRIOR_PRODUCT      = 5, /* ProductPrior(dists, dims), priors.jl:60-88: factors over
                                        consecutive coordinate groups; params = {K, then per
-                                       factor: kind (any other kind), dim, p0, p1}, K <= 8    */
+                                       factor: kind (any iid family), dim, p0, p1}, K <= 16   */
     /* further StandardPrior families (iid product over the update's coordinates; the closed
        forms of Distributions.jl's logpdf, -Inf outside the support)                           */
     EXTMCMC_PRIOR_EXPONENTIAL  = 6, /* Exponential(scale): params = {scale}                    */
     EXTMCMC_PRIOR_INV_GAMMA    = 7, /* InverseGamma(shape, scale)                              */
     EXTMCMC_PRIOR_BETA         = 8, /* Beta(alpha, beta)                                       */
     EXTMCMC_PRIOR_LOGNORMAL    = 9, /* LogNormal(mu, sigma)                                    */
-    EXTMCMC_PRIOR_CAUCHY       = 10 /* Cauchy(mu, sigma)                                       */
+    EXTMCMC_PRIOR_CAUCHY       = 10, /* Cauchy(mu, sigma)                                      */
+    EXTMCMC_PRIOR_MVNORMAL     = 11  /* StandardPrior(MvNormal(mu, Sigma)) on the whole coordinate
+                                        block of a joint update (priors.jl:35-39 wraps any
+                                        Distributions object): params = {mu[p_u], L[p_u*p_u]}, L the
+                                        lower Cholesky factor of Sigma, column-major (the host side
+                                        factorises; the device whitens, as PDMats does)            */
 };
 
 /* ---- adaptation schemes (src/transition_kernels/adaptation.jl) ----------- */
@@ -142,7 +147,8 @@ typedef struct extmcmc_update {
     const double  *step;          /* RW_UNIFORM: eps[p_u] (UniformRandomWalk.eps);
                                      RW_GAUSS: Sigma[p_u*p_u] column-major;
                                      RW_GAUSS_MIX: Sigma_A, Sigma_B, lambda
-                                     (2*p_u*p_u + 1); MALA: tau[1]                 */
+                                     (2*p_u*p_u + 1); MALA: tau[1].
+                                     p_u <= 32 for the random walks, any p_u for MALA */
     const uint8_t *pos;           /* [p_u] 1 = coordinate restricted to be positive */
     int32_t        prior;         /* EXTMCMC_PRIOR_*                               */
     int32_t        n_prior_params;
@@ -217,8 +223,21 @@ int32_t extmcmc_generate_obs_normal(extmcmc_t h, int64_t first, int64_t n_obs,
 /* Replaces RandomWalkUpdate(rw, coords; prior, adpt) src/updates.jl:170-182. */
 int32_t extmcmc_set_update(extmcmc_t h, int32_t u, const extmcmc_update_t *upd);
 /* theta[p * n_chains] chain-major SoA; replaces theta_init (src/run.jl:34-45).
- * Resets ll to -Inf (src/workspaces.jl:425), counters, moments and history. */
+ * Resets ll to -Inf (src/workspaces.jl:425), counters, moments and history.  The Philox
+ * counters restart too: a caller that runs the sampler again on the same handle (warm-up,
+ * then sampling) and wants fresh draws -- the reference advances a global RNG between runs --
+ * calls extmcmc_set_seed first (the Python and Julia mirrors derive a new seed per run). */
 int32_t extmcmc_set_state(extmcmc_t h, const double *theta);
+/* Replaces the Philox key of the handle (cfg.seed). */
+int32_t extmcmc_set_seed(extmcmc_t h, uint64_t seed);
+/* HaarioTypeAdaptation's weight schedule lambda <- f(lambda, N, mcmc_iter) (the `f` keyword of
+ * the constructor, adaptation.jl:385; applied by readjust!, :422-426).  lambda is shared by all
+ * chains and N, mcmc_iter are schedule facts, so the library evaluates f on the HOST, on the
+ * calling thread, inside extmcmc_run_block, once per readjustment of update u, and ships the
+ * value with the step -- any closure works (Julia: @cfunction).  NULL restores the default
+ * f = (lambda, N, iter) -> lambda. */
+typedef double (*extmcmc_lambda_fn)(double lambda, int64_t N, int64_t mcmc_iter, void *user);
+int32_t extmcmc_set_lambda_fn(extmcmc_t h, int32_t u, extmcmc_lambda_fn f, void *user);
 
 /* ---- multi-rank (one process per GPU) ------------------------------------ */
 /* Fills 128 bytes with an NCCL unique id (rank 0 calls it and ships the bytes

@@ -76,7 +76,9 @@ typedef struct {
     int32_t kernel, n_coords, prior, n_prior_params;
     int32_t *coords;
     uint8_t *pos;
-    double prior_params[40];
+    double *prior_params;  /* [n_prior_params] */
+    extmcmc_lambda_fn lambda_fn;  /* HaarioTypeAdaptation's f(lambda, N, iter), adaptation.jl:385; NULL = default */
+    void *lambda_user;
     extmcmc_adapt_t adapt;
     int32_t step_len; /* doubles of step-size state per chain */
     double *step0;    /* initial step-size state [step_len] */
@@ -178,7 +180,7 @@ int32_t oracle_create(const extmcmc_config_t *cfg, const extmcmc_update_t *updat
             oracle_destroy(h);
             return EXTMCMC_EUNSUPPORTED;
         }
-        if (s->prior < EXTMCMC_PRIOR_IMPROPER || s->prior > EXTMCMC_PRIOR_CAUCHY) {
+        if (s->prior < EXTMCMC_PRIOR_IMPROPER || s->prior > EXTMCMC_PRIOR_MVNORMAL) {
             /* reference: error("logpdf not implemented for prior ...") src/priors.jl:11-13 */
             set_err("oracle: prior not implemented");
             oracle_destroy(h);
@@ -195,13 +197,15 @@ int32_t oracle_create(const extmcmc_config_t *cfg, const extmcmc_update_t *updat
             /* UniformRandomWalk asserts all(eps .> 0), random_walk.jl:50 */
             if (s->kernel == EXTMCMC_KERNEL_RW_UNIFORM && !(s->step[i] > 0.0)) { set_err("eps must be > 0"); oracle_destroy(h); return EXTMCMC_EINVAL; }
         }
-        for (int i = 0; i < s->n_prior_params && i < 40; ++i) t->prior_params[i] = s->prior_params[i];
+        t->prior_params = xcalloc(s->n_prior_params > 0 ? s->n_prior_params : 1, sizeof(double));
+        for (int i = 0; i < s->n_prior_params; ++i) t->prior_params[i] = s->prior_params[i];
+        if (s->prior == EXTMCMC_PRIOR_MVNORMAL && s->n_prior_params != s->n_coords * (s->n_coords + 1)) { set_err("oracle: MvNormal prior needs {mu[n], L[n*n]}"); oracle_destroy(h); return EXTMCMC_EINVAL; }
         {
             const int nn = s->n_coords * s->n_coords;
             t->step_len = s->kernel == EXTMCMC_KERNEL_RW_UNIFORM ? s->n_coords
                         : s->kernel == EXTMCMC_KERNEL_MALA ? 1
                         : s->kernel == EXTMCMC_KERNEL_RW_GAUSS ? nn : 2 * nn + 1;
-            if ((s->kernel == EXTMCMC_KERNEL_RW_GAUSS || s->kernel == EXTMCMC_KERNEL_RW_GAUSS_MIX) && s->n_coords > 16) { set_err("oracle: Gaussian walks need n_coords <= 16"); oracle_destroy(h); return EXTMCMC_EINVAL; }
+            if ((s->kernel == EXTMCMC_KERNEL_RW_GAUSS || s->kernel == EXTMCMC_KERNEL_RW_GAUSS_MIX) && s->n_coords > 32) { set_err("oracle: Gaussian walks need n_coords <= 32"); oracle_destroy(h); return EXTMCMC_EINVAL; }
             if (s->adapt.kind == EXTMCMC_ADAPT_HAARIO) {
                 t->hmean = xcalloc((size_t)C * s->n_coords, sizeof(double));   /* zero(state), adaptation.jl:388 */
                 t->hcov = xcalloc((size_t)C * nn, sizeof(double));
@@ -237,7 +241,7 @@ int32_t oracle_create(const extmcmc_config_t *cfg, const extmcmc_update_t *updat
 
 void oracle_destroy(oracle_t h) {
     if (!h) return;
-    if (h->upd) for (int u = 0; u < h->NU; ++u) { free(h->upd[u].coords); free(h->upd[u].pos); free(h->upd[u].step0);
+    if (h->upd) for (int u = 0; u < h->NU; ++u) { free(h->upd[u].coords); free(h->upd[u].pos); free(h->upd[u].step0); free(h->upd[u].prior_params);
                                                   free(h->upd[u].hmean); free(h->upd[u].hcov); free(h->upd[u].hM); }
     if (h->step) for (int u = 0; u < h->NU; ++u) free(h->step[u]);
     free(h->upd); free(h->step); free(h->obs); free(h->y); free(h->theta); free(h->ll);
@@ -474,7 +478,12 @@ static double log_prior_family(int kind, const double *pp, const double *th, int
     return NAN;
 }
 
+static double mvn_logpdf_chol(const double *L, int n, const double *mu, const double *x);
+
 static double log_prior(const orc_update_t *u, const double *th) {
+    /* StandardPrior(MvNormal(mu, Sigma)): logpdf by whitening with the Cholesky factor (PDMats), priors.jl:35-39 */
+    if (u->prior == EXTMCMC_PRIOR_MVNORMAL)
+        return mvn_logpdf_chol(u->prior_params + u->n_coords, u->n_coords, u->prior_params, th);
     if (u->prior != EXTMCMC_PRIOR_PRODUCT) return log_prior_family(u->prior, u->prior_params, th, u->n_coords);
     /* logpdf(prior::ProductPrior, th): lp = 0.0; lp += logpdf(dist_k, th[idx_k]), priors.jl:82-88 */
     const int K = (int)u->prior_params[0];
@@ -524,7 +533,7 @@ static int chol_lower_sym_upper(const double *S, int n, double *L) {
 
 /* logpdf(MvNormal(mu, L L'), x) = -(n log 2pi + 2 sum log L_ii)/2 - |L \ (x - mu)|^2 / 2 */
 static double mvn_logpdf_chol(const double *L, int n, const double *mu, const double *x) {
-    double z[16], sq = 0.0, logdet = 0.0;
+    double z[32], sq = 0.0, logdet = 0.0;
     for (int r = 0; r < n; ++r) {
         double a = x[r] - mu[r];
         for (int k = 0; k < r; ++k) a -= L[r + k * n] * z[k];
@@ -539,7 +548,7 @@ static double mvn_logpdf_chol(const double *L, int n, const double *mu, const do
  * (the reference log/exp-transforms in place and perturbs the state by ulps). */
 static double log_q_gauss(const uint8_t *pos, int n, const double *Sigma, const double *from,
                           const double *to, int *bad) {
-    double L[256], tf[16], tt[16], logJ = 0.0;
+    double L[1024], tf[32], tt[32], logJ = 0.0;
     if (!chol_lower_sym_upper(Sigma, n, L)) { *bad = 1; return NAN; }
     double s = 0.0;
     for (int i = 0; i < n; ++i) if (pos[i]) s += log(to[i]);     /* _logjacobian: -sum(log.(to[pos])) */
@@ -563,7 +572,7 @@ static double log_q(const orc_update_t *u, const double *step, const double *fro
 /* rand(rw::GaussianRandomWalk, theta) random_walk.jl:145-151: theta° = exp-back(log-transform(theta) + L z) */
 static void gauss_propose(const uint8_t *pos, int n, const double *Sigma, const double *th,
                           const double *z, double *out, int *bad) {
-    double L[256];
+    double L[1024];
     if (!chol_lower_sym_upper(Sigma, n, L)) { *bad = 1; for (int i = 0; i < n; ++i) out[i] = NAN; return; }
     for (int i = 0; i < n; ++i) {
         double t = pos[i] ? log(th[i]) : th[i];
@@ -663,7 +672,7 @@ static void chain_step(struct oracle_handle *h, int64_t c, const extmcmc_step_t 
                     double r = oracle_uniform(h->cfg.seed, gchain, st->mcmciter, u_idx, j++);
                     if (r <= eps[2 * n * n]) Sig = eps + n * n;
                 }
-                double z[16];
+                double z[32];
                 for (int q = 0; q < n; q += 2) {          /* randn via Box-Muller on the uniform stream */
                     double u1 = oracle_uniform(h->cfg.seed, gchain, st->mcmciter, u_idx, j++);
                     double u2 = oracle_uniform(h->cfg.seed, gchain, st->mcmciter, u_idx, j++);
@@ -815,7 +824,7 @@ static void chain_step(struct oracle_handle *h, int64_t c, const extmcmc_step_t 
         const int m = w->n_coords;
         double *hm = w->hmean + c * m, *hc = w->hcov + c * m * m;
         if (v == u_idx) w->hM[c] += 1;                           /* my turn: M += 1, :401-404 */
-        double t[16], old_m[16];
+        double t[32], old_m[32];
         for (int i = 0; i < m; ++i) { double x = theta[w->coords[i]]; t[i] = w->pos[i] ? log(x) : x; }
         const int64_t N = h->statN[c] - 1;                       /* adpt.N: starts at 1, +1 per register */
         const double f_old = (double)(N - 1) / (double)N, f_mean = (double)N / (double)(N + 1);
@@ -832,7 +841,12 @@ static void chain_step(struct oracle_handle *h, int64_t c, const extmcmc_step_t 
             w->hM[c] = 0;
             double *SigB = h->step[v] + c * w->step_len + m * m;
             for (int k = 0; k < m * m; ++k) SigB[k] = (2.38 * 2.38) / (double)m * hc[k];   /* 2.38^2/length(rw)*cov :423 */
-            /* lambda = f_lambda(lambda, N, iter): the default closure returns lambda unchanged (:385) */
+            /* rw.lambda = adpt.f_lambda(rw.lambda, adpt.N, mcmc_iter) (:425); adpt.N was incremented by
+             * this step's register! (:413); the default closure returns lambda unchanged (:385) */
+            if (w->lambda_fn) {
+                double *lam = h->step[v] + c * w->step_len + 2 * m * m;
+                *lam = w->lambda_fn(*lam, h->statN[c], st->mcmciter, w->lambda_user);
+            }
         }
     }
 }
@@ -911,6 +925,13 @@ int32_t oracle_run_block(oracle_t h, const extmcmc_step_t *steps, int32_t n_step
     run_job_t job = {h, steps, n_steps, &io, NULL, NULL, 0, 0};
     parallel_chains(run_worker, &job, h->C, n_threads);
     return h->domain_err ? EXTMCMC_EDOMAIN : EXTMCMC_OK;
+}
+
+int32_t oracle_set_lambda_fn(oracle_t h, int32_t u, extmcmc_lambda_fn f, void *user) {
+    if (!h || u < 0 || u >= h->NU) return EXTMCMC_EINVAL;
+    h->upd[u].lambda_fn = f;
+    h->upd[u].lambda_user = user;
+    return EXTMCMC_OK;
 }
 
 int32_t oracle_get_state(oracle_t h, double *theta, double *ll) {

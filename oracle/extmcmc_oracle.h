@@ -60,6 +60,8 @@ int32_t oracle_run_block(oracle_t h, const extmcmc_step_t *steps, int32_t n_step
                          uint8_t *accepted_hist, double *llr_hist,
                          int32_t n_threads);
 
+/* HaarioTypeAdaptation's weight schedule f(lambda, N, iter) of update u (NULL: default). */
+int32_t oracle_set_lambda_fn(oracle_t h, int32_t u, extmcmc_lambda_fn f, void *user);
 int32_t oracle_get_state(oracle_t h, double *theta, double *ll);
 int32_t oracle_get_stats(oracle_t h, double *mean, double *cov, double *rolling_ar,
                          int64_t *n_accept, int64_t *n_prop);

@@ -40,6 +40,8 @@ def load():
     lib.oracle_run_block.restype = C.c_int32
     lib.oracle_run_block.argtypes = [H, C.POINTER(_abi.Step), C.c_int32, C.c_int32, C.c_int32,
                                      dp, dp, dp, dp, dp, dp, u8p, dp, C.c_int32]
+    lib.oracle_set_lambda_fn.restype = C.c_int32
+    lib.oracle_set_lambda_fn.argtypes = [H, C.c_int32, _abi.LambdaFn, C.c_void_p]
     lib.oracle_get_state.restype = C.c_int32
     lib.oracle_get_state.argtypes = [H, dp, dp]
     lib.oracle_get_stats.restype = C.c_int32
@@ -119,6 +121,11 @@ class Oracle:
                                _abi.dptr(theta_init), C.byref(self.h))
         if rc != 0:
             raise OracleError(rc, lib.oracle_last_error().decode())
+        for i, u in enumerate(updates):                 # HaarioTypeAdaptation(...; f = ...)
+            cb = getattr(getattr(u, "adpt", None), "lambda_callback", lambda: None)()
+            if cb is not None:
+                self._keep.append(cb)
+                lib.oracle_set_lambda_fn(self.h, i, cb, None)
 
     def __del__(self):
         if getattr(self, "h", None):

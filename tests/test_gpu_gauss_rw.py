@@ -108,8 +108,9 @@ def test_unsupported_pairings_raise():
         with pytest.raises(_abi.ExtMCMCError) as ei:
             GpuSession(em.GsnTargetLaw([0.0]), [u], x, [0.0, 1.0], 4)
         assert ei.value.code == _abi.EUNSUPPORTED
-    with pytest.raises(NotImplementedError):
-        em.HaarioTypeAdaptation([0.0], f=lambda lam, n, it: 0.5 * lam).to_abi()
+    # a user closure f(lambda, N, iter) is served by a host callback (extmcmc_set_lambda_fn)
+    assert em.HaarioTypeAdaptation([0.0], f=lambda lam, n, it: 0.5 * lam).lambda_callback() is not None
+    assert em.HaarioTypeAdaptation([0.0]).lambda_callback() is None
 
 
 def test_singular_adapted_covariance_is_a_domain_error():

@@ -40,10 +40,10 @@ def _assert_clean(rep):
     (300, 3001, 40, 12, "gsn1d_chains_R2"),    # odd N, ragged chain group
     (700, 5000, 25, 14, "gsn1d_chains_R4"),
     (1100, 2050, 25, 18, "gsn1d_chains_R8"),   # 2 chain groups, second one ragged
-    (2100, 60000, 12, 0, "gsn1d_chains_R8"),   # what the planner itself picks for a mid-size problem
-    (5, 20001, 60, 0, "gsn1d_obs_C8"),         # few chains: observation-mapped kernel
-    (1, 4097, 120, 0, "gsn1d_obs_C1"),         # the reference's shape: one chain
-    (20, 9000, 40, 0, "gsn1d_obs_C32"),
+    (2100, 60000, 12, 1, "gsn1d_chains_R8"),   # what the per-step planner picks for a mid-size problem
+    (5, 20001, 60, 2, "gsn1d_obs_C8"),         # few chains: observation-mapped kernel
+    (1, 4097, 120, 2, "gsn1d_obs_C1"),         # the reference's shape: one chain
+    (20, 9000, 40, 2, "gsn1d_obs_C32"),
 ])
 def test_replay_parity(n_chains, n_obs, n_iters, force, variant):
     rep = replay_compare(_data(n_obs, seed=n_chains), n_chains, n_iters, seed=n_chains + 1,
@@ -165,7 +165,7 @@ def test_loglik_full_size_against_sufficient_statistics():
     n, Cn = 1_000_000, 4096
     x = _data(n, seed=2)
     th0 = theta_init_for(x, Cn)
-    s = GpuSession(em.GsnTargetLaw([0.0]), cfg2_updates(), x, th0, Cn)
+    s = GpuSession(em.GsnTargetLaw([0.0]), cfg2_updates(), x, th0, Cn, sweep_variant=1)
     got = s.eval_loglik()
     assert s.variant() == "gsn1d_chains_R8"
     xl = x.astype(np.longdouble)
@@ -261,9 +261,9 @@ def test_unsupported_requests_raise():
     assert lib.extmcmc_create(C.byref(cfg), C.byref(h)) == _abi.EUNSUPPORTED
     x = _data(50)
     with pytest.raises(_abi.ExtMCMCError) as ei:
-        big = em.GsnTargetLaw(np.zeros(3))      # 12 parameters: a 9-coordinate Gaussian walk exceeds the device limit
-        GpuSession(big, [em.RandomWalkUpdate(em.GaussianRandomWalk(np.eye(9)), list(range(1, 10)))],
-                   np.zeros((5, 3)), big.theta, 4)
+        big = em.GsnTargetLaw(np.zeros(6))      # 42 parameters: a 33-coordinate walk exceeds the device limit (32)
+        GpuSession(big, [em.RandomWalkUpdate(em.GaussianRandomWalk(np.eye(33)), list(range(1, 34)))],
+                   np.zeros((5, 6)), big.theta, 4)
     assert ei.value.code == _abi.EUNSUPPORTED
     # an empty observation set is refused loudly (EINVAL), as is running before any upload
     cfg.law, cfg.obs_dim, cfg.n_params = _abi.LAW_GSN_IID_1D, 1, 2
@@ -303,7 +303,8 @@ def test_full_size_cfg2_replay_parity():
     o = orc.Oracle(em.GsnTargetLaw([0.0]), ups, x, th_sub, sub, seed=3)
     ro = o.run(steps, n_threads=8)
     reps = Cn // sub
-    g = GpuSession(em.GsnTargetLaw([0.0]), ups, x, np.tile(th_sub, (1, reps)), Cn, seed=3, n_steps_hint=len(steps))
+    g = GpuSession(em.GsnTargetLaw([0.0]), ups, x, np.tile(th_sub, (1, reps)), Cn, seed=3, n_steps_hint=len(steps),
+                   sweep_variant=1)     # the per-step kernels (the resident block kernel: test_gpu_block_kernels.py)
     assert g.variant() == "gsn1d_chains_R8"
     rg = g.run(steps, replay=(np.tile(ro["proposals"], (1, 1, reps)), np.tile(ro["exp_draws"], (1, reps))))
     first = {k: v[..., :sub] for k, v in rg.items() if hasattr(v, "shape")}
