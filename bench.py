@@ -225,11 +225,233 @@ def timed_steps(ws, _abi, C, K, W, flush=True, it0=1):
     return total
 
 
+def ncu_traffic(kernel_substr, csv_name):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one kernel launch, read at run time from the
+    committed summary of an `ncu --set full` capture (tools/ncu_summary.py) under profiles/."""
+    path = os.path.join(ROOT, "profiles", csv_name)
+    try:
+        import csv
+        tot, unit_scale = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        seen = set()
+        for row in csv.DictReader(open(path)):
+            if kernel_substr in row["kernel"] and row["metric"] in ("dram__bytes_read.sum", "dram__bytes_write.sum") \
+                    and row["metric"] not in seen:
+                seen.add(row["metric"])
+                tot += float(row["value"].replace(",", "")) * unit_scale.get(row["unit"], 1.0)
+        if len(seen) == 2:
+            return tot, f"profiles/{csv_name} (ncu --set full capture of this kernel at this shape, parsed at run time)"
+    except Exception:
+        pass
+    return None, f"profiles/{csv_name} not found or without dram__bytes rows"
+
+
+def fp64_peaks(ws, clocks, n_sms=148):
+    """FP64 peak two ways: the FMA micro-benchmark run in this process, and lanes x clock
+    (SMs x 64 FP64 lanes x 2 flop x the SM clock sampled under load)."""
+    import ctypes
+    pk = ctypes.c_double()
+    ws._ck(ws.lib.extmcmc_measure_fp64_peak(ws.handle, ctypes.byref(pk)))
+    mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0
+    return pk.value, n_sms * 64 * 2 * mhz * 1e6 / 1e12
+
+
+def measure_cfg5(args, em, _abi, par, dist, rank, world, local, peaks, peak_src):
+    """BASELINE cfg 5: ONE dataset of N = 1e9 Gaussian observations generated on the device,
+    sharded by observations over the ranks (strong scaling), C = 8 replicated chains, two adaptive
+    random-walk updates per iteration.  Per update step the per-chain partial sums of all ranks are
+    combined: `nccl` = ncclAllReduce between the sweep and the accept kernel; `p2p` = the library's
+    own exchange (stores into every peer over NVLink + flags, inside the persistent block kernel).
+    In-run checks: every rank ends in the same state with the same decision counts, and the
+    sharded log-likelihood of a 2^24-observation prefix equals the single-rank one."""
+    import ctypes
+    import torch
+    from extensiblemcmc_jl_b200.mcmc import init_
+    n_total, C, iters, blk_iters = args.cfg5_n_obs, 8, args.cfg5_iters, 10
+    first, cnt = par.shard_obs(n_total, rank, world)
+    mk = lambda: em.AdaptationUnifRW([0.0], adapt_every_k_steps=50, target_accpt_rate=0.234,
+                                     scale=5e-4 / 30, min=1e-7 / 30, max=1e7, offset=100.0)
+    ups = lambda: [em.RandomWalkUpdate(em.UniformRandomWalk([5e-3 / 30]), [1], adpt=mk()),
+                   em.RandomWalkUpdate(em.UniformRandomWalk([5e-3 / 30], [True]), [2], prior=em.ImproperPosPrior(), adpt=mk())]
+    th0 = np.repeat(np.array([[1.5], [4.0]]), C, axis=1) * (1.0 + 1e-4 * np.arange(C))[None, :]
+
+    def backend(mode, n_chains=C, **kw):
+        if world == 1:
+            return em.CUDAMCMCBackend(n_chains=n_chains, device=local, seed=6, history="none", **kw)
+        extra = {"p2p_allgather": par.p2p_allgather_fn(dist)} if mode == "p2p" else {}
+        return par.backend_for_rank(rank, world, local, n_chains, shard="obs", comm_id=par.exchange_comm_id(dist),
+                                    seed=6, history="none", **extra, **kw)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    out = {"n_obs_total": n_total, "n_obs_per_gpu": cnt, "chains": C, "iters": iters,
+           "block": f"{blk_iters} iterations ({blk_iters * NU} schedule elements) per extmcmc_run_block", "modes": {}}
+    for mode in (["single"] if world == 1 else ["nccl", "p2p"]):
+        mcmc = em.MCMC(ups(), backend=backend(mode, block_len=blk_iters * NU, use_graphs=True))
+        init_(mcmc, 1, dict(P=em.GsnTargetLaw([0.0]), obs=em.DeviceGeneratedObs(cnt, 1.5, 2.0, 6, first)), th0)
+        ws = mcmc.workspace
+        lib, h = ws.lib, ws.handle
+        it = 1
+        for _ in range(2):                                     # warm-up: graph capture / first launches
+            ws._ck(lib.extmcmc_run_block(h, steps_for(None, _abi, it, blk_iters), blk_iters * NU)); it += blk_iters
+        ws.sync()
+        sampler = ClockSampler(local)
+        barrier()
+        sampler.start()
+        l0 = lib.extmcmc_launch_count(h)
+        ws._ck(lib.extmcmc_event_record(h, 0))
+        for _ in range(iters // blk_iters):
+            ws._ck(lib.extmcmc_run_block(h, steps_for(None, _abi, it, blk_iters), blk_iters * NU)); it += blk_iters
+        ws._ck(lib.extmcmc_event_record(h, 1))
+        ws.sync()
+        ms = ctypes.c_float()
+        ws._ck(lib.extmcmc_event_elapsed(h, 0, 1, ctypes.byref(ms)))
+        launches = int(lib.extmcmc_launch_count(h) - l0)
+        clocks = sampler.stop()
+        t = torch.tensor([ms.value], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+        n_it = (iters // blk_iters) * blk_iters
+        # every rank must hold the same chains: state and decision counts, bit for bit
+        th, ll = ws.refresh_state()
+        st = ws.stats()
+        sig = np.concatenate([th.ravel(), ll, st["n_accept"].ravel().astype(np.float64)])
+        same = True
+        if dist is not None:
+            g = [torch.zeros(sig.size, dtype=torch.float64, device="cuda") for _ in range(world)]
+            dist.all_gather(g, torch.tensor(sig, device="cuda"))
+            same = all(bool(torch.equal(g[0], q)) for q in g[1:])
+        variant = lib.extmcmc_sweep_variant_name(h).decode()
+        ws.close()
+        step_s = ms_total * 1e-3 / (n_it * NU)
+        gbs = 8.0 * cnt / step_s / 1e9
+        out["modes"][mode] = {
+            "ms_per_iteration": ms_total / n_it, "value": C * n_it * NU * float(n_total) / (ms_total * 1e-3),
+            "unit": "chain-step*obs/s", "kernel": variant, "gpu_launches": launches,
+            "hbm_gbs_per_gpu": gbs, "hbm_frac_per_gpu": gbs / peaks["hbm_gbs"], "hbm_peak": peaks["hbm_gbs"],
+            "hbm_peak_source": peak_src,
+            "hbm_note": "8 B x observations of this rank / whole update-step time (sweep + exchange + decision)",
+            "decisions_equal_across_ranks": bool(same), "accept_rate": float(st["n_accept"].sum() / max(st["n_prop"].sum(), 1)),
+            "clocks": clocks}
+        barrier()
+    # ---- sharded vs single-rank log-likelihood on a 2^24-observation prefix --------------------
+    n_pre = min(1 << 24, n_total)
+    thp = np.repeat(np.array([[1.5], [4.0]]), C, axis=1) * (1.0 + 0.01 * np.arange(C))[None, :]
+    if world > 1:
+        pf, pc = par.shard_obs(n_pre, rank, world)
+        m1 = em.MCMC(ups(), backend=backend("nccl", use_graphs=False))
+        init_(m1, 1, dict(P=em.GsnTargetLaw([0.0]), obs=em.DeviceGeneratedObs(pc, 1.5, 2.0, 6, pf)), thp)
+        ll_sh = m1.workspace.eval_loglik()
+        m1.workspace.close()
+        rel = None
+        if rank == 0:
+            m2 = em.MCMC(ups(), backend=em.CUDAMCMCBackend(n_chains=C, device=local, seed=6, history="none", use_graphs=False))
+            init_(m2, 1, dict(P=em.GsnTargetLaw([0.0]), obs=em.DeviceGeneratedObs(n_pre, 1.5, 2.0, 6, 0)), thp)
+            ll_1 = m2.workspace.eval_loglik()
+            m2.workspace.close()
+            rel = float(np.max(np.abs(ll_sh - ll_1) / np.abs(ll_1)))
+        out["ll_rel_vs_single_rank"] = rel
+        out["ll_check"] = f"extmcmc_eval_loglik on the first 2^24 observations: sharded over {world} ranks (NCCL) vs rank 0 alone"
+        barrier()
+    return out
+
+
+def measure_cfg34(args, workload, em, _abi, local, steps):
+    """BASELINE cfg 3 (logistic regression d = 256, N = 1e6, 1024 chains, MALA, FP64 tensor-core GEMMs)
+    or cfg 4 (hierarchical normal, 8 groups x 4096 observations, MALA + 2 random-walk updates, 8192
+    chains per GPU) on one GPU: ms per iteration and the roofline of its dominant kernel."""
+    import ctypes
+    from extensiblemcmc_jl_b200.mcmc import init_
+    rng = np.random.default_rng(4 if workload == "cfg3" else 5)
+    if workload == "cfg3":
+        C, d, N = 1024, 256, args.cfg3_n_obs
+        X = rng.standard_normal((N, d)) / np.sqrt(d)
+        beta = rng.standard_normal(d)
+        y = (rng.random(N) < 1.0 / (1.0 + np.exp(-X @ beta))).astype(np.float64)
+        data = dict(P=em.LogisticLaw(d), obs=X, y=y)
+        ups = [em.MALAUpdate(0.02, list(range(1, d + 1)), prior=em.StandardPrior(em.Normal(0.0, 10.0)),
+                             adpt=em.AdaptationMALA(adapt_every_k_steps=20, scale=1e-3, min=1e-5, offset=2.0))]
+        th0 = 0.01 * np.random.default_rng(40).standard_normal((d, C))
+        n_obs, flops_per_iter, sweeps_per_iter = N, 4.0 * d * C * N, 1
+        desc = f"BASELINE cfg3: logistic regression d={d}, N={N:.3g}, {C} chains/GPU, MALAUpdate on all coordinates"
+    else:
+        C, G, ng = 8192, 8, 4096
+        tg = rng.standard_normal(G)
+        yv = np.concatenate([tg[g] + rng.standard_normal(ng) for g in range(G)])
+        data = dict(P=em.HierNormalLaw(G), obs=yv, groups=np.repeat(np.arange(G), ng))
+        ups = [em.MALAUpdate(0.02, list(range(1, G + 1)), adpt=em.AdaptationMALA(adapt_every_k_steps=50, scale=1e-3, min=1e-5)),
+               em.RandomWalkUpdate(em.UniformRandomWalk([0.3]), [G + 1], adpt=em.AdaptationUnifRW([0.0], adapt_every_k_steps=50, scale=0.02)),
+               em.RandomWalkUpdate(em.UniformRandomWalk([0.3], [True]), [G + 2], prior=em.ImproperPosPrior(),
+                                   adpt=em.AdaptationUnifRW([0.0], adapt_every_k_steps=50, scale=0.02))]
+        th0 = np.concatenate([np.zeros(G), [0.0, 1.0]])
+        # per iteration: 2 gradient sweeps (3 FP64 instructions per chain x observation: x - mu, the
+        # square and the first-order sum) + 2 plain sweeps (2 instructions) = 10 issue slots = 20 "flop"
+        # at the FMA rate the peak is quoted in
+        n_obs, flops_per_iter, sweeps_per_iter = G * ng, 2.0 * 10.0 * C * G * ng, 4
+        desc = (f"BASELINE cfg4: hierarchical normal, {G} groups x {ng} obs, {C} chains/GPU, "
+                "schedule MALA(theta_1..8) + RW(mu) + RW-pos(tau), full 10 x 10 running covariance")
+    NUc = len(ups)
+
+    def make(instrument):
+        mcmc = em.MCMC(ups, backend=em.CUDAMCMCBackend(n_chains=C, device=local, seed=7, history="none", block_len=NUc,
+                                                       use_graphs=not instrument, instrument=instrument))
+        init_(mcmc, 1, data, th0)
+        return mcmc.workspace
+    K, Wm = steps, 3
+    ws = make(False)
+    sampler = ClockSampler(local)
+    _generic_timed(ws, _abi, NUc, 0, Wm)
+    sampler.start()
+    l0 = ws.lib.extmcmc_launch_count(ws.handle)
+    ms_total = _generic_timed(ws, _abi, NUc, K, 0, it0=Wm + 1)
+    launches = int(ws.lib.extmcmc_launch_count(ws.handle) - l0)
+    ext = [Wm + 1 + K]
+
+    def hold():
+        _generic_timed(ws, _abi, NUc, 5, 0, it0=ext[0]); ext[0] += 5
+    clocks = sampler.stop(extend=hold)
+    variant = ws.lib.extmcmc_sweep_variant_name(ws.handle).decode()
+    pk64, lanes = fp64_peaks(ws, clocks)
+    pkmma = ctypes.c_double()
+    ws._ck(ws.lib.extmcmc_measure_dmma_peak(ws.handle, ctypes.byref(pkmma)))
+    acc = ws.stats()["n_accept"].sum(axis=1) / np.maximum(ws.stats()["n_prop"].sum(axis=1), 1)
+    ws.close()
+    wi = make(True)
+    _generic_timed(wi, _abi, NUc, 0, Wm)
+    msw, nl = ctypes.c_float(), ctypes.c_int64()
+    wi._ck(wi.lib.extmcmc_get_sweep_time(wi.handle, ctypes.byref(msw), ctypes.byref(nl)))
+    step_ms = _generic_timed(wi, _abi, NUc, min(K, 20), 0)
+    wi._ck(wi.lib.extmcmc_get_sweep_time(wi.handle, ctypes.byref(msw), ctypes.byref(nl)))
+    kern_ms = msw.value / max(nl.value, 1)
+    wi.close()
+    launches_per_iter = nl.value / float(min(K, 20))
+    peak = max(pkmma.value, pk64, lanes) if workload == "cfg3" else max(pk64, lanes)
+    ach = flops_per_iter / launches_per_iter / (kern_ms * 1e-3) / 1e12
+    return {
+        "workload": desc, "ms_per_step": ms_total / K, "steps": K,
+        "value": float(C) * K * NUc * n_obs / (ms_total * 1e-3), "unit": "chain-step*obs/s",
+        "roofline": {"kernel": variant, "bound": "tensor" if workload == "cfg3" else "fp64",
+                     "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None,
+                     "peak_source": "largest of: FP64 DMMA / FMA micro-benchmarks in this process, SMs x 64 lanes x 2 x SM clock under load",
+                     "fp64_fma_probe": pk64, "fp64_dmma_probe": pkmma.value, "peak_lanes_x_clock": lanes,
+                     "avg_launch_ms": kern_ms, "launches_timed": int(nl.value),
+                     "launches_per_iteration": launches_per_iter, "sweeps_per_iteration": sweeps_per_iter,
+                     "share_of_step": msw.value / step_ms if step_ms else None,
+                     "algorithmic_flops_per_iteration": flops_per_iter,
+                     "floor_ms_per_iteration": flops_per_iter / (peak * 1e12) * 1e3 if peak else None,
+                     "traffic": None, "traffic_source": "not captured (the data set is L2 / shared-memory resident)" if workload == "cfg4"
+                     else "see profiles/ (ncu --set full of the logistic sweep)"},
+        "accept_rate_per_update": [float(a) for a in acc], "gpu_launches": launches, "clocks": clocks}
+
+
 def run_ours(args):
     import ctypes
     import torch
     import extensiblemcmc_jl_b200 as em
-    from extensiblemcmc_jl_b200 import _abi
+    from extensiblemcmc_jl_b200 import _abi, parallel as par
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -255,13 +477,12 @@ def run_ours(args):
     x = cfg2_data()
     peaks, peak_src = measured_peaks()
 
-    # ---- value: device-resident, CUDA-graph blocks, L2 flushed between steps ----------
+    # ---- value: device-resident, one persistent kernel per iteration, L2 flushed between steps ----
     ws = make_ws(em, x, C, rank * C, local, block_len=NU, use_graphs=True)
     variant = ws.lib.extmcmc_sweep_variant_name(ws.handle).decode()
     sampler = ClockSampler(local)
     barrier()
-    l0 = ws.lib.extmcmc_launch_count(ws.handle)
-    timed_steps(ws, _abi, C, 0, Wm)                # warm-up (graph capture, clocks)
+    timed_steps(ws, _abi, C, 0, Wm)                # warm-up (first launches, clocks)
     l1 = ws.lib.extmcmc_launch_count(ws.handle)
     sampler.start()
     barrier()
@@ -272,52 +493,59 @@ def run_ours(args):
     def hold():
         timed_steps(ws, _abi, C, 20, 0, it0=ext[0]); ext[0] += 20
     clocks = sampler.stop(extend=hold)
-    launches = int(ws.lib.extmcmc_launch_count(ws.handle) - l1)
+    # kernels launched by the timed steps themselves (the untimed continuation above excluded)
+    launches = int((ws.lib.extmcmc_launch_count(ws.handle) - l1) * K / max(ext[0] - (Wm + 1), 1))
     t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     units = float(world) * C * K * NU * N_OBS
     value = units / (ms_total * 1e-3)
-    fp64_peak = ctypes.c_double()
-    ws._ck(ws.lib.extmcmc_measure_fp64_peak(ws.handle, ctypes.byref(fp64_peak)))
+    fp64_probe, lanes_peak = fp64_peaks(ws, clocks)
     ws.close()
 
-    # ---- roofline of the dominant kernel: every sweep launch bracketed by events ------
+    # ---- roofline of the dominant kernel: every launch of it bracketed by events --------------
     wsi = make_ws(em, x, C, rank * C, local, block_len=NU, use_graphs=False, instrument=True)
     timed_steps(wsi, _abi, C, 0, Wm)
     msw, nl = ctypes.c_float(), ctypes.c_int64()
     wsi._ck(wsi.lib.extmcmc_get_sweep_time(wsi.handle, ctypes.byref(msw), ctypes.byref(nl)))
-    step_ms_instr = timed_steps(wsi, _abi, C, min(K, 50), 0)
+    n_instr = min(K, 50)
+    step_ms_instr = timed_steps(wsi, _abi, C, n_instr, 0)
     wsi._ck(wsi.lib.extmcmc_get_sweep_time(wsi.handle, ctypes.byref(msw), ctypes.byref(nl)))
-    sweep_ms = msw.value / max(nl.value, 1)
+    kern_ms = msw.value / max(nl.value, 1)
+    sweeps_per_launch = n_instr * NU / max(nl.value, 1)     # 2: one launch runs both update steps of an iteration
     sweep_share = msw.value / step_ms_instr if step_ms_instr > 0 else None
     wsi.close()
-    flops = 3.0 * C * N_OBS                      # 1 SUB + 1 FMA per chain x observation
-    ach_tf = flops / (sweep_ms * 1e-3) / 1e12
+    flops = 3.0 * C * N_OBS * sweeps_per_launch    # 1 SUB + 1 FMA per chain x observation
+    ach_tf = flops / (kern_ms * 1e-3) / 1e12
+    fp64_peak = max(fp64_probe, lanes_peak)
+    traffic, traffic_src = ncu_traffic("resident_block_kernel", "ncu_full_resident_r02.csv")
     roofline = {
-        "kernel": variant, "bound": "fp64", "achieved": ach_tf, "peak": fp64_peak.value,
-        "unit": "TFLOP/s", "frac": ach_tf / fp64_peak.value if fp64_peak.value else None,
-        "peak_source": "FP64 FMA micro-benchmark run in this process (not in MEASURED_PEAKS.json)",
-        # 2 FP64 issue slots (DADD + DFMA) per pair; the FMA-rate peak counts 2 flop per slot
-        "issue_frac": (2.0 * C * N_OBS / (sweep_ms * 1e-3)) / (fp64_peak.value * 1e12 / 2.0) if fp64_peak.value else None,
-        "avg_launch_ms": sweep_ms, "launches_timed": int(nl.value), "share_of_step": sweep_share,
-        # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture of this
-        # kernel at this shape (profiles/README_r01.md); algorithmic bytes = 8e6
-        "traffic": 8.046592e6,
-        "hbm": {"achieved": 8.0 * N_OBS / (sweep_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
-                "unit": "GB/s", "frac": 8.0 * N_OBS / (sweep_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+        "kernel": variant, "bound": "fp64", "achieved": ach_tf, "peak": fp64_peak,
+        "unit": "TFLOP/s", "frac": ach_tf / fp64_peak if fp64_peak else None,
+        "peak_source": "larger of the FP64 FMA micro-benchmark run in this process and SMs x 64 lanes x 2 flop x SM clock "
+                       "sampled under load (MEASURED_PEAKS.json has no FP64 figure)",
+        "fp64_fma_probe": fp64_probe, "peak_lanes_x_clock": lanes_peak,
+        # 2 FP64 issue slots (DADD + DFMA) per chain x observation against 3 flop counted: the
+        # formulation's ceiling is 0.75 of the FMA-rate peak; issue_frac is the fraction of that ceiling
+        "issue_frac": (2.0 * C * N_OBS * sweeps_per_launch / (kern_ms * 1e-3)) / (fp64_peak * 1e12 / 2.0) if fp64_peak else None,
+        "avg_launch_ms": kern_ms, "launches_timed": int(nl.value), "update_steps_per_launch": sweeps_per_launch,
+        "share_of_step": sweep_share,
+        "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": 8.0 * N_OBS,
+        "traffic": traffic, "traffic_source": traffic_src,
+        "hbm": {"achieved": 8.0 * N_OBS / (kern_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                "unit": "GB/s", "frac": 8.0 * N_OBS / (kern_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                 "peak_source": peak_src + " (MEASURED_PEAKS.json)" if peak_src == "measured" else "fallback"},
     }
 
-    # ---- the HBM-bound regime of the same kernel family (cfg 5 shape on one GPU) ------
+    # ---- the HBM-bound regime of the same kernel family (cfg 5 shape on one GPU) ------------------
     roofline_hbm = None
     if rank == 0 and not args.skip_hbm:
         n5, c5 = 1 << 28, 8                       # 2 GiB of observations, 8 chains
         ups = cfg2_updates(em)
         from extensiblemcmc_jl_b200.mcmc import init_
         m5 = em.MCMC(ups, backend=em.CUDAMCMCBackend(n_chains=c5, device=local, seed=6, history="none",
-                                                     block_len=NU, use_graphs=False, instrument=True))
+                                                     block_len=NU, use_graphs=False, instrument=True, sweep_variant=2))
         init_(m5, 1, dict(P=em.GsnTargetLaw([0.0]), obs=em.DeviceGeneratedObs(n5, 1.5, 2.0, 6)),
               np.repeat(np.array([[1.5], [4.0]]), c5, axis=1))
         w5 = m5.workspace
@@ -329,16 +557,16 @@ def run_ours(args):
         w5._ck(w5.lib.extmcmc_get_sweep_time(w5.handle, ctypes.byref(msw), ctypes.byref(nl)))
         t5 = msw.value / max(nl.value, 1)
         gbs = 8.0 * n5 / (t5 * 1e-3) / 1e9
+        tr5, tr5_src = ncu_traffic("sweep_gsn1d_obs_kernel", "ncu_full_obs_r01.csv")
         roofline_hbm = {"kernel": w5.lib.extmcmc_sweep_variant_name(w5.handle).decode(),
                         "workload": f"cfg5 shape on 1 GPU: C={c5}, N=2^28 (2 GiB > L2)", "bound": "hbm",
                         "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                         "frac": gbs / peaks["hbm_gbs"], "avg_launch_ms": t5,
                         "peak_source": peak_src,
-                        # ncu --set full (profiles/README_r01.md): 2.147561e9 read + 4.2e6 write
-                        "traffic": 2.151769e9, "algorithmic_bytes": 8.0 * n5}
+                        "traffic": tr5, "traffic_source": tr5_src, "algorithmic_bytes": 8.0 * n5}
         w5.close()
 
-    # ---- e2e: the whole job through run_() with host buffers --------------------------
+    # ---- e2e: the whole job through run_() with host buffers --------------------------------------
     M = args.e2e_iters
     th0 = cfg2_theta_init(x, C, rank * C)
 
@@ -367,8 +595,20 @@ def run_ours(args):
         ess_per_sec = float(ess.mean() * C * world / wall)
     acc_rate = float(np.mean([l.acceptance_history.mean() for l in lws_e]))
     ws_e.close()
+    barrier()
 
-    # ---- CPU baseline: the oracle (a port of the reference's algorithm), 1 core -------
+    # ---- BASELINE cfg 5 (observations sharded, strong scaling, cross-rank exchange) ----------------
+    strong_cfg5 = None
+    if not args.skip_cfg5:
+        strong_cfg5 = measure_cfg5(args, em, _abi, par, dist, rank, world, local, peaks, peak_src)
+
+    # ---- BASELINE cfg 3 / cfg 4 on one GPU ----------------------------------------------------------
+    cfg3 = cfg4 = None
+    if rank == 0 and world == 1 and not args.skip_extras:
+        cfg4 = measure_cfg34(args, "cfg4", em, _abi, local, args.cfg4_steps)
+        cfg3 = measure_cfg34(args, "cfg3", em, _abi, local, args.cfg3_steps)
+
+    # ---- CPU baseline: the oracle (a port of the reference's algorithm), 1 core -------------------
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
         cpu = cpu_oracle_rate(x, n_chains=8, n_iters=args.cpu_iters, n_threads=1)
@@ -398,109 +638,13 @@ def run_ours(args):
                 "what": "run_(mcmc, M, data, theta0): obs upload + all blocks + every history row copied to host"},
         "ess_per_sec": ess_per_sec, "accept_rate": acc_rate,
         "gpu_launches": launches, "clocks": clocks,
+        "strong_cfg5": strong_cfg5, "cfg3": cfg3, "cfg4": cfg4,
     }
     print(json.dumps(out))
 
 
-def run_cfg5(args):
-    """Secondary workload (BASELINE cfg 5): one dataset of N observations generated on the
-    device, sharded by observations over the ranks; C = 8 replicated chains; the per-chain
-    partial sums are all-reduced (NCCL) once per update step.  Strong scaling in N."""
-    import torch
-    import extensiblemcmc_jl_b200 as em
-    from extensiblemcmc_jl_b200 import _abi, parallel as par
-    from extensiblemcmc_jl_b200.mcmc import init_
-    rank, world, local = par.env_rank_world()
-    torch.cuda.set_device(local)
-    dist = None
-    cid = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        cid = par.exchange_comm_id(dist)
-    n_total, C = args.n_obs, 8
-    first, cnt = par.shard_obs(n_total, rank, world)
-    mk = lambda: em.AdaptationUnifRW([0.0], adapt_every_k_steps=50, target_accpt_rate=0.234,
-                                     scale=5e-4 / 30, min=1e-7 / 30, max=1e7, offset=100.0)
-    ups = [em.RandomWalkUpdate(em.UniformRandomWalk([5e-3 / 30]), [1], adpt=mk()),
-           em.RandomWalkUpdate(em.UniformRandomWalk([5e-3 / 30], [True]), [2], prior=em.ImproperPosPrior(), adpt=mk())]
-    bk = par.backend_for_rank(rank, world, local, C, shard="obs" if world > 1 else "chains", comm_id=cid,
-                              seed=6, history="none", block_len=NU, use_graphs=True,
-                              **({"p2p_allgather": par.p2p_allgather_fn(dist)} if (world > 1 and args.p2p) else {}))
-    if world == 1:
-        bk = em.CUDAMCMCBackend(n_chains=C, device=local, seed=6, history="none", block_len=NU, use_graphs=True)
-    mcmc = em.MCMC(ups, backend=bk)
-    init_(mcmc, 1, dict(P=em.GsnTargetLaw([0.0]), obs=em.DeviceGeneratedObs(cnt, 1.5, 2.0, 6, first)),
-          np.repeat(np.array([[1.5], [4.0]]), C, axis=1))
-    ws = mcmc.workspace
-    K, Wm = args.steps, max(args.warmup, 3)
-    sampler = ClockSampler(local)
-    timed_steps(ws, _abi, C, 0, Wm, flush=False)
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
-    sampler.start()
-    l0 = ws.lib.extmcmc_launch_count(ws.handle)
-    ms_total = timed_steps(ws, _abi, C, K, 0, flush=False, it0=Wm + 1)
-    launches = int(ws.lib.extmcmc_launch_count(ws.handle) - l0)
-    torch.cuda.synchronize()
-    ext = [Wm + 1 + K]
-
-    def hold():
-        timed_steps(ws, _abi, C, 10, 0, flush=False, it0=ext[0]); ext[0] += 10
-    # ranks exchange sums every step under observation sharding: no rank-local continuation there
-    clocks = sampler.stop(extend=hold if world == 1 else None)
-    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.barrier()
-    ms_total = float(t.item())
-    variant = ws.lib.extmcmc_sweep_variant_name(ws.handle).decode()
-    ws.close()
-    # the sweep kernel alone (every launch bracketed by events; single rank only: the instrumented
-    # handle cannot replay graphs)
-    sweep_only_ms = None
-    if world == 1:
-        import ctypes
-        bki = em.CUDAMCMCBackend(n_chains=C, device=local, seed=6, history="none", block_len=NU,
-                                 use_graphs=False, instrument=True)
-        mi = em.MCMC(ups, backend=bki)
-        init_(mi, 1, dict(P=em.GsnTargetLaw([0.0]), obs=em.DeviceGeneratedObs(cnt, 1.5, 2.0, 6, first)),
-              np.repeat(np.array([[1.5], [4.0]]), C, axis=1))
-        wi = mi.workspace
-        msw, nl = ctypes.c_float(), ctypes.c_int64()
-        timed_steps(wi, _abi, C, 0, 3, flush=False)
-        wi._ck(wi.lib.extmcmc_get_sweep_time(wi.handle, ctypes.byref(msw), ctypes.byref(nl)))
-        timed_steps(wi, _abi, C, 10, 0, flush=False)
-        wi._ck(wi.lib.extmcmc_get_sweep_time(wi.handle, ctypes.byref(msw), ctypes.byref(nl)))
-        sweep_only_ms = msw.value / max(nl.value, 1)
-        wi.close()
-    if dist is not None:
-        dist.destroy_process_group()
-    if rank != 0:
-        return
-    peaks, peak_src = measured_peaks()
-    sweep_s = ms_total * 1e-3 / (K * NU)
-    gbs = 8.0 * cnt / sweep_s / 1e9
-    print(json.dumps({
-        "metric": "chain-steps x obs/sec", "value": C * K * NU * float(n_total) / (ms_total * 1e-3),
-        "unit": "chain-step*obs/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms_total / K,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"BASELINE cfg5: N={n_total:.3g} Gaussian observations generated on device, sharded "
-                               f"by observations over {world} GPU(s), C=8 replicated chains, "
-                               + ("fused NVLink peer exchange" if args.p2p else "NCCL all-reduce") +
-                               " of partial sums per update step", "l2": "inputs larger than L2, no flush"},
-        "roofline": {"kernel": variant, "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": gbs / peaks["hbm_gbs"], "peak_source": peak_src,
-                     "note": "per-GPU bytes of one update step / whole update-step time (sweep + reduce + all-reduce + accept)",
-                     "sweep_kernel_ms": sweep_only_ms,
-                     "sweep_kernel_frac": (8.0 * cnt / (sweep_only_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]) if sweep_only_ms else None,
-                     "traffic": None},
-        "gpu_launches": launches, "clocks": clocks}))
-
-
 def _generic_timed(ws, _abi, n_updates, K, W, it0=1):
-    """W warm-up + K timed MCMC iterations of an n_updates-element schedule (one graph block per
+    """W warm-up + K timed MCMC iterations of an n_updates-element schedule (one block per
     iteration, one CUDA event pair per iteration)."""
     import ctypes
     lib, h = ws.lib, ws.handle
@@ -529,111 +673,31 @@ def _generic_timed(ws, _abi, n_updates, K, W, it0=1):
     return total
 
 
-def run_cfg34(args):
-    """Secondary workloads: BASELINE cfg 3 (logistic regression, d=256, N=1e6, 1024 chains, MALA,
-    FP64 tensor-core GEMMs) and cfg 4 (hierarchical normal, 8 groups x 4096 obs, MALA + 2 RW
-    updates, 8192 chains per GPU).  Chains shard over the ranks; no collective."""
-    import ctypes
+def run_secondary(args):
+    """Stand-alone runs of the secondary workloads (`--workload cfg3|cfg4|cfg5`): the same
+    measurements the default run attaches as sub-records, printed as one JSON line."""
     import torch
     import extensiblemcmc_jl_b200 as em
     from extensiblemcmc_jl_b200 import _abi, parallel as par
-    from extensiblemcmc_jl_b200.mcmc import init_
     rank, world, local = par.env_rank_world()
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    rng = np.random.default_rng(4 if args.workload == "cfg3" else 5)
-    if args.workload == "cfg3":
-        C, d, N = 1024, 256, args.n_obs if args.n_obs != 1_000_000_000 else 1_000_000
-        X = rng.standard_normal((N, d)) / np.sqrt(d)
-        beta = rng.standard_normal(d)
-        y = (rng.random(N) < 1.0 / (1.0 + np.exp(-X @ beta))).astype(np.float64)
-        law, data = em.LogisticLaw(d), None
-        data = dict(P=law, obs=X, y=y)
-        ups = [em.MALAUpdate(0.02, list(range(1, d + 1)), prior=em.StandardPrior(em.Normal(0.0, 10.0)),
-                             adpt=em.AdaptationMALA(adapt_every_k_steps=20, scale=1e-3, min=1e-5, offset=2.0))]
-        th0 = 0.01 * np.random.default_rng(40 + rank).standard_normal((d, C))
-        n_obs, flops_per_sweep = N, 4.0 * d * C * N
-        desc = f"BASELINE cfg3: logistic regression d={d}, N={N:.3g}, {C} chains/GPU, MALAUpdate on all coordinates"
+    peaks, peak_src = measured_peaks()
+    if args.workload == "cfg5":
+        rec = measure_cfg5(args, em, _abi, par, dist, rank, world, local, peaks, peak_src)
     else:
-        C, G, ng = 8192, 8, 4096
-        tg = rng.standard_normal(G)
-        yv = np.concatenate([tg[g] + rng.standard_normal(ng) for g in range(G)])
-        law = em.HierNormalLaw(G)
-        data = dict(P=law, obs=yv, groups=np.repeat(np.arange(G), ng))
-        ups = [em.MALAUpdate(0.02, list(range(1, G + 1)), adpt=em.AdaptationMALA(adapt_every_k_steps=50, scale=1e-3, min=1e-5)),
-               em.RandomWalkUpdate(em.UniformRandomWalk([0.3]), [G + 1], adpt=em.AdaptationUnifRW([0.0], adapt_every_k_steps=50, scale=0.02)),
-               em.RandomWalkUpdate(em.UniformRandomWalk([0.3], [True]), [G + 2], prior=em.ImproperPosPrior(),
-                                   adpt=em.AdaptationUnifRW([0.0], adapt_every_k_steps=50, scale=0.02))]
-        th0 = np.concatenate([np.zeros(G), [0.0, 1.0]])
-        n_obs, flops_per_sweep = G * ng, 4.0 * C * G * ng
-        desc = (f"BASELINE cfg4: hierarchical normal, {G} groups x {ng} obs, {C} chains/GPU, "
-                "schedule MALA(theta_1..8) + RW(mu) + RW-pos(tau)")
-    NUc = len(ups)
-
-    def make(instrument):
-        mcmc = em.MCMC(ups, backend=em.CUDAMCMCBackend(n_chains=C, chain_offset=rank * C, device=local, seed=7,
-                                                       history="none", block_len=NUc, use_graphs=not instrument,
-                                                       instrument=instrument))   # stats: full covariance for p <= 16, variances beyond
-        init_(mcmc, 1, data, th0)
-        return mcmc.workspace
-    K, Wm = args.steps, max(args.warmup, 3)
-    ws = make(False)
-    sampler = ClockSampler(local)
-    _generic_timed(ws, _abi, NUc, 0, Wm)
+        if world > 1:
+            raise SystemExit("cfg3 / cfg4 shard by chains (no collective): run them on one GPU, or the default bench for scaling")
+        rec = measure_cfg34(args, args.workload, em, _abi, local, args.steps)
     if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
-    sampler.start()
-    l0 = ws.lib.extmcmc_launch_count(ws.handle)
-    ms_total = _generic_timed(ws, _abi, NUc, K, 0, it0=Wm + 1)
-    launches = int(ws.lib.extmcmc_launch_count(ws.handle) - l0)
-    torch.cuda.synchronize()
-    ext = [Wm + 1 + K]
-
-    def hold():
-        _generic_timed(ws, _abi, NUc, 5, 0, it0=ext[0]); ext[0] += 5
-    clocks = sampler.stop(extend=hold)
-    variant = ws.lib.extmcmc_sweep_variant_name(ws.handle).decode()
-    pk64, pkmma = ctypes.c_double(), ctypes.c_double()
-    ws._ck(ws.lib.extmcmc_measure_fp64_peak(ws.handle, ctypes.byref(pk64)))
-    ws._ck(ws.lib.extmcmc_measure_dmma_peak(ws.handle, ctypes.byref(pkmma)))
-    acc = ws.stats()["n_accept"].sum(axis=1) / np.maximum(ws.stats()["n_prop"].sum(axis=1), 1)
-    ws.close()
-    wi = make(True)
-    _generic_timed(wi, _abi, NUc, 0, Wm)
-    msw, nl = ctypes.c_float(), ctypes.c_int64()
-    wi._ck(wi.lib.extmcmc_get_sweep_time(wi.handle, ctypes.byref(msw), ctypes.byref(nl)))
-    step_ms = _generic_timed(wi, _abi, NUc, min(K, 20), 0)
-    wi._ck(wi.lib.extmcmc_get_sweep_time(wi.handle, ctypes.byref(msw), ctypes.byref(nl)))
-    sweep_ms = msw.value / max(nl.value, 1)
-    wi.close()
-    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.barrier()
         dist.destroy_process_group()
-    ms_total = float(t.item())
-    if rank != 0:
-        return
-    peak = pkmma.value if args.workload == "cfg3" else pk64.value
-    ach = flops_per_sweep / (sweep_ms * 1e-3) / 1e12
-    print(json.dumps({
-        "metric": "chain-steps x obs/sec", "value": float(world) * C * K * NUc * n_obs / (ms_total * 1e-3),
-        "unit": "chain-step*obs/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms_total / K,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "l2": "no flush: the design matrix (2 GB) exceeds L2" if args.workload == "cfg3"
-                   else "no flush: 256 KB of observations are L2/shared-memory resident by design"},
-        "roofline": {"kernel": variant, "bound": "tensor" if args.workload == "cfg3" else "fp64",
-                     "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None,
-                     "peak_source": ("FP64 DMMA (mma.sync m8n8k4) micro-benchmark in this process" if args.workload == "cfg3"
-                                     else "FP64 FMA micro-benchmark in this process"),
-                     "fp64_fma_peak": pk64.value, "fp64_dmma_peak": pkmma.value, "avg_launch_ms": sweep_ms,
-                     "launches_timed": int(nl.value), "share_of_step": msw.value / step_ms if step_ms else None,
-                     "algorithmic_flops_per_launch": flops_per_sweep, "traffic": None},
-        "accept_rate_per_update": [float(a) for a in acc], "gpu_launches": launches, "clocks": clocks}))
+    if rank == 0:
+        rec["n_gpus"] = world
+        print(json.dumps(rec))
 
 
 def cpu_oracle_rate(x, n_chains, n_iters, n_threads):
@@ -672,6 +736,21 @@ def run_reference(args):
     value = n_chains * K * NU * float(N_OBS) / dt
     sample = (f"{n_chains} chains x 1 iteration of cfg2 (N=1e6, 2 updates) per step, {K} steps, "
               f"{nthr} threads; oracle = CPU restatement of ExtensibleMCMC.jl's algorithm (Julia unavailable)")
+    # ESS/s (BASELINE.json's second metric): effective samples per chain-iteration from a full-length
+    # cfg2 trace of one chain per thread (M iterations, second half kept, Geyer estimator, minimum
+    # over the parameters -- the same definition as the GPU arm) x the chain-iterations/s timed above
+    ess_per_sec = ess_note = None
+    if not args.skip_ess:
+        M = args.ref_ess_iters
+        oe = orc.Oracle(em.GsnTargetLaw([0.0]), cfg2_updates(em), x, cfg2_theta_init(x, nthr), nthr, seed=3)
+        te = time.perf_counter()
+        re_ = oe.run(list(em.MCMCSchedule(M, NU)), n_threads=nthr, record=False)
+        te = time.perf_counter() - te
+        tr = re_["theta"].reshape(M, NU, 2, nthr)[M // 2:, 1]
+        ess_iter = float(em.ess_geyer(tr).min(axis=0).mean() / (M - M // 2))
+        ess_per_sec = ess_iter * (n_chains * K / dt)
+        ess_note = (f"ESS per chain-iteration {ess_iter:.4g} from {nthr} chains x {M} iterations of cfg2 "
+                    f"(second half; {te:.1f} s of CPU time, untimed) x chain-iterations/s of the timed steps")
     print(json.dumps({
         "impl": "reference", "metric": "chain-steps x obs/sec", "value": value, "unit": "chain-step*obs/s",
         "n_gpus": args.gpus, "steps": K, "warmup": Wm, "ms_per_step": dt / K * 1e3,
@@ -680,6 +759,7 @@ def run_reference(args):
                                "2 adaptive uniform random-walk updates per iteration", "n_obs": N_OBS},
         "cpu_baseline": {"value": value, "unit": "chain-step*obs/s", "cores": nthr, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "chain-step*obs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "ess_per_sec": ess_per_sec, "ess_note": ess_note,
         "gpu_launches": 0,
     }))
 
@@ -694,16 +774,21 @@ def main():
     ap.add_argument("--cpu-iters", type=int, default=600, help="iterations of the single-core CPU baseline (~10 s)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-hbm", action="store_true")
+    ap.add_argument("--skip-cfg5", action="store_true", help="no strong_cfg5 sub-record")
+    ap.add_argument("--skip-extras", action="store_true", help="no cfg3 / cfg4 sub-records (N = 1 only anyway)")
+    ap.add_argument("--skip-ess", action="store_true", help="reference arm: no ESS/s trace")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"])
-    ap.add_argument("--p2p", action="store_true", help="cfg5: the library's NVLink peer exchange instead of ncclAllReduce")
-    ap.add_argument("--n-obs", type=int, default=1_000_000_000, help="cfg5 only: total observations")
+    ap.add_argument("--cfg5-n-obs", type=int, default=1_000_000_000, help="cfg5: total observations over all ranks")
+    ap.add_argument("--cfg5-iters", type=int, default=300, help="cfg5: timed MCMC iterations per exchange mode")
+    ap.add_argument("--cfg3-n-obs", type=int, default=1_000_000)
+    ap.add_argument("--cfg3-steps", type=int, default=5)
+    ap.add_argument("--cfg4-steps", type=int, default=400)
+    ap.add_argument("--ref-ess-iters", type=int, default=2000, help="reference arm: iterations of the ESS trace")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
-    elif args.workload == "cfg5":
-        run_cfg5(args)
-    elif args.workload in ("cfg3", "cfg4"):
-        run_cfg34(args)
+    elif args.workload != "cfg2":
+        run_secondary(args)
     else:
         run_ours(args)
 

@@ -106,10 +106,13 @@ struct extmcmc_handle {
     // persistent block kernels (block_kernels.cu)
     bool blk_planned = false;
     bool res_ok = false, obsblk_ok = false;
-    ResidentPlan res_plan{};
-    int obsblk_grid = 0;
+    TeamPlan res_plan{};
+    ObsBlockPlan obsblk_plan{};
     unsigned long long *blk_go = nullptr;
     unsigned int *blk_counter = nullptr;
+    unsigned int *team_sync = nullptr;   // team barrier counters + half-sweep flags (zeroed per launch)
+    long long *team_prof = nullptr;      // EXTMCMC_TEAM_PROF: per-CTA cycle breakdown, printed at destroy
+    size_t team_sync_cap = 0;
     // replay staging
     double *rp_prop = nullptr, *rp_exp = nullptr;
     size_t rp_prop_cap = 0, rp_exp_cap = 0;
@@ -215,6 +218,7 @@ int32_t ensure_plan(extmcmc_t h) {
     size_t part_rows = h->cfg.law == EXTMCMC_LAW_LOGISTIC ? (size_t)h->plan.S * (h->cfg.obs_dim + 1)
                                                           : (size_t)2 * h->d.G * h->plan.S;
     part_rows = std::max(part_rows, (size_t)h->num_sms * 3);   // segments of the observation-mapped block kernel
+    part_rows = std::max(part_rows, (size_t)2 * h->d.G * 4);   // members of a team of the team-resident block kernel
     int32_t rc = dev_alloc(h, &h->d.partial, part_rows * h->d.C);
     if (rc) return rc;
     if (obs_sharded(h) && !h->gsum &&
@@ -245,13 +249,33 @@ int32_t plan_block_kernels(extmcmc_t h) {
         if (kk != EXTMCMC_KERNEL_RW_UNIFORM) all_unif = false;
         if (kk != EXTMCMC_KERNEL_RW_UNIFORM && kk != EXTMCMC_KERNEL_MALA) all_unif_or_mala = false;
     }
-    if (all_unif_or_mala && !obs_sharded(h) && sv != 4)
-        h->res_ok = plan_resident(h->d, h->num_sms, sv == 3, &h->res_plan);
-    if (!h->res_ok && all_unif && h->cfg.law == EXTMCMC_LAW_GSN_IID_1D && h->d.C <= 32 && sv != 3 &&
-        (sv == 4 || h->plan.variant == SWEEP_VARIANT_OBS) && (!obs_sharded(h) || h->d.p2p)) {
-        int cb = 1;
-        while (cb < h->d.C) cb <<= 1;
-        cudaError_t e = plan_obs_block(cb, h->num_sms, h->n_obs_local, &h->obsblk_grid);
+    // The team-resident kernel is opt-in (sweep_variant 3): measured on B200 it does not beat the
+    // per-step kernels -- with observations of the cfg 2 size every CTA-level stream of them is bound
+    // by L2 -> SM delivery, and with small data (cfg 4) the FP64-latency-bound scalar phases are not
+    // hidden well enough ("Persistent block kernels").
+    if (all_unif_or_mala && !obs_sharded(h) && sv == 3) {
+        h->res_ok = plan_team(h->d, h->upd_host.data(), h->num_sms, true, &h->res_plan);
+        if (h->res_ok && getenv("EXTMCMC_TEAM_PROF") && !h->team_prof) {
+            int32_t rc = dev_alloc(h, &h->team_prof, (size_t)h->res_plan.n_cta * 8);
+            if (rc) return rc;
+            CK(h, cudaMemset(h->team_prof, 0, sizeof(long long) * h->res_plan.n_cta * 8));
+        }
+        if (h->res_ok) {
+            const size_t words = team_sync_words(h->res_plan);
+            if (words > h->team_sync_cap) {
+                int32_t rc = dev_alloc(h, &h->team_sync, words);
+                if (rc) return rc;
+                h->team_sync_cap = words;
+            }
+        }
+    }
+    // The observation-mapped block kernel: automatic where the per-step fixed cost matters, i.e. when
+    // observations are sharded over ranks and the library's own peer exchange is on; opt-in
+    // (sweep_variant 4) on a single rank, where the sweep itself dominates.
+    const bool obs_auto = sv == 0 && obs_sharded(h) && h->d.p2p && h->plan.variant == SWEEP_VARIANT_OBS;
+    if (!h->res_ok && all_unif && h->cfg.law == EXTMCMC_LAW_GSN_IID_1D && h->d.C <= 32 && (sv == 4 || obs_auto) &&
+        (!obs_sharded(h) || h->d.p2p)) {
+        cudaError_t e = plan_obs_block(h->d, h->upd_host.data(), h->num_sms, h->n_obs_local, &h->obsblk_plan);
         if (e == cudaSuccess) {
             if (!h->blk_go) {
                 int32_t rc;
@@ -576,14 +600,17 @@ int32_t run_block_impl(extmcmc_t h, const extmcmc_step_t *steps, int32_t n_steps
             else { CK(h, cudaEventCreate(&ev.first)); CK(h, cudaEventCreate(&ev.second)); }
         }
         if (h->res_ok) {
-            ResidentArgs a{};
+            TeamArgs a{};
             a.d = h->d;
-            a.d.S = 1;
+            a.d.S = h->res_plan.ts;        // the members of a team are the "segments" of the partial sums
             a.descs = sl.d_descs; a.n_steps = n_steps; a.n_sweeps = n_sweeps;
             a.obs = h->obs_dev; a.goff = h->goff_dev; a.glen = h->glen_dev; a.G = h->d.G;
             a.ll_scratch = h->scratch_ll;
+            a.sync = h->team_sync;
+            a.prof = h->team_prof;
+            CK(h, cudaMemsetAsync(h->team_sync, 0, team_sync_words(h->res_plan) * sizeof(unsigned int), h->stream));
             if (instrument) CK(h, cudaEventRecord(ev.first, h->stream));
-            CK(h, launch_resident_block(h->res_plan, a, h->stream));
+            CK(h, launch_team_block(h->res_plan, a, h->stream));
             h->launches += 1;
         } else {
             ObsBlockArgs a{};
@@ -591,12 +618,9 @@ int32_t run_block_impl(extmcmc_t h, const extmcmc_step_t *steps, int32_t n_steps
             a.descs = sl.d_descs; a.n_steps = n_steps;
             a.obs = h->obs_dev; a.n_obs = h->n_obs_local;
             a.go = h->blk_go; a.counter = h->blk_counter;
-            launch_obs_block_first(h->d, sl.d_descs, h->blk_go, h->blk_counter, h->stream);
             if (instrument) CK(h, cudaEventRecord(ev.first, h->stream));
-            int cb = 1;
-            while (cb < h->d.C) cb <<= 1;
-            CK(h, launch_obs_block(cb, h->obsblk_grid, a, h->stream));
-            h->launches += 2;
+            CK(h, launch_obs_block(h->obsblk_plan, a, h->stream));
+            h->launches += 1;
         }
         if (instrument) {
             CK(h, cudaEventRecord(ev.second, h->stream));
@@ -726,7 +750,7 @@ int32_t extmcmc_create(const extmcmc_config_t *cfg, extmcmc_t *out) {
     DevState &d = h->d;
     const int64_t C = cfg->n_chains;
     const int p = cfg->n_params, NU = cfg->n_updates;
-    d.C = C; d.chain_offset = cfg->chain_offset; d.p = p; d.NU = NU;
+    d.C = C; d.gC = C; d.g0 = 0; d.chain_offset = cfg->chain_offset; d.p = p; d.NU = NU;
     d.W = cfg->roll_window > 0 ? cfg->roll_window : 100;
     d.H = cfg->history_window;
     d.law = cfg->law; d.stats_mode = cfg->stats_mode; d.rng_mode = EXTMCMC_RNG_PHILOX;
@@ -787,6 +811,25 @@ int32_t extmcmc_destroy(extmcmc_t h) {
     if (!h) return EXTMCMC_OK;
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->team_prof) {
+        // diagnostics: where the CTAs of the team kernel spent their cycles (mean over CTAs and launches)
+        const int n = h->res_plan.n_cta;
+        std::vector<long long> pr((size_t)n * 8);
+        if (cudaMemcpy(pr.data(), h->team_prof, pr.size() * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            double s[7] = {0, 0, 0, 0, 0, 0, 0}, runs = 0, mx = 0, mn = 1e300;
+            for (int b = 0; b < n; ++b) {
+                double tot = 0;
+                for (int i = 0; i < 7; ++i) { s[i] += (double)pr[(size_t)b * 8 + i]; tot += (double)pr[(size_t)b * 8 + i]; }
+                runs += (double)pr[(size_t)b * 8 + 7];
+                if (pr[(size_t)b * 8 + 7]) { const double t = tot / pr[(size_t)b * 8 + 7]; mx = std::max(mx, t); mn = std::min(mn, t); }
+            }
+            if (runs > 0)
+                fprintf(stderr, "[extmcmc team kernel] cycles per launch per CTA: sweep %.0f, barrier-before %.0f, barrier-after %.0f, "
+                                "propose %.0f, accept %.0f, cov+sync %.0f, ctx %.0f; total min %.0f max %.0f over CTAs; %d CTAs, ts %d, stages %d\n",
+                        s[0] / runs, s[1] / runs, s[2] / runs, s[3] / runs, s[4] / runs, s[5] / runs, s[6] / runs, mn, mx, n,
+                        h->res_plan.ts, h->res_plan.stages);
+        }
+    }
     invalidate_graphs(h);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     for (void *p : h->p2p_opened) cudaIpcCloseMemHandle(p);
@@ -1248,6 +1291,9 @@ int32_t extmcmc_sync(extmcmc_t h) {
     if (flag == 2)   // sticky until extmcmc_set_state: nothing has been committed since the failed exchange
         return fail(h, EXTMCMC_ENCCL, "peer exchange timed out: a rank did not deliver its partial sums; "
                                       "no step has been committed since (extmcmc_set_state to start over)");
+    if (flag == 3)
+        return fail(h, EXTMCMC_ECUDA, "a persistent block kernel timed out waiting for its own CTAs (EXTMCMC_P2P_TIMEOUT_MS); "
+                                      "the chain state is undefined (extmcmc_set_state to start over)");
     if (flag) {
         CK(h, cudaMemset(h->d.err_flag, 0, sizeof flag));
         return fail(h, EXTMCMC_EDOMAIN,
@@ -1565,7 +1611,7 @@ const char *extmcmc_sweep_variant_name(extmcmc_t h) {
     for (int u = 0; u < h->cfg.n_updates; ++u) all_set = all_set && h->upd_set[u];
     if (all_set && plan_block_kernels(h) == EXTMCMC_OK) {
         if (h->res_ok) {
-            static const char *rn[] = {"", "", "", "", "resident_R4", "resident_R5", "resident_R6", "resident_R7", "resident_R8"};
+            static const char *rn[] = {"", "", "", "", "team_block_R4", "team_block_R5", "team_block_R6", "team_block_R7", "team_block_R8"};
             return rn[h->res_plan.R];
         }
         if (h->obsblk_ok) {

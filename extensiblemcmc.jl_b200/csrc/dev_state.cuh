@@ -66,8 +66,14 @@ struct StepDesc {
 };
 
 struct DevState {
-    int64_t C;              // chains on this rank
+    int64_t C;              // chains on this rank (= the chain stride of every per-chain array below)
     int64_t chain_offset;   // global id of local chain 0
+    // The persistent block kernels stage a CTA's own chains into shared memory and hand the
+    // per-chain functions a VIEW of this struct (pointers into shared memory, C = chains of the CTA,
+    // chain_offset moved).  Arrays that stay in global memory in such a view -- the history ring,
+    // the replay buffers, the sweep partials -- keep the global chain stride gC and start at chain
+    // g0; in the ordinary (global) state gC = C, g0 = 0.
+    int64_t gC, g0;
     int64_t n_obs_total;    // N over all ranks (enters the log-likelihood constant)
     int32_t p, NU, W, H;    // params, updates, rolling window, history ring length
     int32_t law, stats_mode, rng_mode, p_u_max;

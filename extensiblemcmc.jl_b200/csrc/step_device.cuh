@@ -365,7 +365,7 @@ __device__ __forceinline__ void propose_chain(const DevState &d, const StepDesc 
 
     uint32_t used = 0;
     if (d.rng_mode == EXTMCMC_RNG_REPLAY) {
-        for (int i = 0; i < n; ++i) pl[(int64_t)i * C] = d.rp_prop[((int64_t)sd.replay_row * d.p_u_max + i) * C + c];
+        for (int i = 0; i < n; ++i) pl[(int64_t)i * C] = d.rp_prop[((int64_t)sd.replay_row * d.p_u_max + i) * d.gC + d.g0 + c];
     } else {
         ChainStepStream rng(d.seed, (uint64_t)(d.chain_offset + c), sd.mcmciter, sd.pidx);
         for (;;) {
@@ -486,6 +486,7 @@ __device__ __forceinline__ void post_decision(const DevState &d, const StepDesc 
     d.ll[c] = ll_new;
     // history row (state_history / state_proposal_history / ll_history / acceptance_history)
     const int64_t slot = sd.seq % d.H;
+    const int64_t hc = d.g0 + c;       // this chain's column in the arrays that stay global
     const int64_t N = sd.stat_n;
     const double f_old = (double)(N - 1) / (double)N;
     const double f_mean = (double)N / (double)(N + 1);
@@ -509,8 +510,8 @@ __device__ __forceinline__ void post_decision(const DevState &d, const StepDesc 
         for (int q = 0; q < 4; ++q)
             if (j0 + q < d.p) {
                 const int j = j0 + q;
-                d.h_theta[(slot * d.p + j) * C + c] = t[q];
-                d.h_prop[(slot * d.p + j) * C + c] = pr[q];
+                d.h_theta[(slot * d.p + j) * d.gC + hc] = t[q];
+                d.h_prop[(slot * d.p + j) * d.gC + hc] = pr[q];
                 if (cs) cs->t[j * cs->nch + cs->ch] = t[q];
                 if (coop_full || diag) {
                     const double m_new = m[q] * f_mean + t[q] / (double)(N + 1);
@@ -524,9 +525,9 @@ __device__ __forceinline__ void post_decision(const DevState &d, const StepDesc 
                 }
             }
     }
-    d.h_ll[slot * C + c] = ll_new;
-    d.h_llp[slot * C + c] = ll_prop;
-    d.h_acc[slot * C + c] = accepted ? 1 : 0;
+    d.h_ll[slot * d.gC + hc] = ll_new;
+    d.h_llp[slot * d.gC + hc] = ll_prop;
+    d.h_acc[slot * d.gC + hc] = accepted ? 1 : 0;
 
     // full covariance by this thread alone (more than kCoopP parameters, or no spare threads)
     if (d.stats_mode == 0 && !coop_full) {
@@ -622,7 +623,7 @@ __device__ __forceinline__ void post_decision(const DevState &d, const StepDesc 
 }
 
 __device__ __forceinline__ double draw_exp(const DevState &d, const StepDesc &sd, int64_t c) {
-    if (d.rng_mode == EXTMCMC_RNG_REPLAY) return d.rp_exp[(int64_t)sd.replay_row * d.C + c];
+    if (d.rng_mode == EXTMCMC_RNG_REPLAY) return d.rp_exp[(int64_t)sd.replay_row * d.gC + d.g0 + c];
     ChainStepStream rng(d.seed, (uint64_t)(d.chain_offset + c), sd.mcmciter, sd.pidx, d.n_used[c]);
     return -log(rng.next());  // rand(Exponential(1.0)), run.jl:278
 }
@@ -704,12 +705,13 @@ __device__ __forceinline__ bool rw_accept_finish(const DevState &d, const StepDe
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ void grad_finalize_chain(const DevState &d, int64_t c, const double *__restrict__ src,
                                                     double *__restrict__ ll_out, double *__restrict__ grad_out) {
-    const int64_t C = d.C;
+    const int64_t C = d.C, PC = d.gC;
+    const double *part = d.partial + d.g0 + c;   // this chain's column of partial[2][G*S][gC]
     const int G = d.G, S = d.S;
     const int64_t rows = (int64_t)G * S;
     if (d.law == EXTMCMC_LAW_GSN_IID_1D) {
         double s2 = 0.0, s1 = 0.0;
-        for (int i = 0; i < S; ++i) { s2 += d.partial[(int64_t)i * C + c]; s1 += d.partial[(rows + i) * C + c]; }
+        for (int i = 0; i < S; ++i) { s2 += __ldcg(part + (int64_t)i * PC); s1 += __ldcg(part + (rows + i) * PC); }
         const double var = src[C + c];
         ll_out[c] = law_finalize(d, c, s2, src + c);
         grad_out[c] = s1 / var;
@@ -722,8 +724,8 @@ __device__ __forceinline__ void grad_finalize_chain(const DevState &d, int64_t c
         for (int g = 0; g < G; ++g) {
             double s2 = 0.0, s1 = 0.0;
             for (int i = 0; i < S; ++i) {
-                s2 += d.partial[((int64_t)g * S + i) * C + c];
-                s1 += d.partial[(rows + (int64_t)g * S + i) * C + c];
+                s2 += __ldcg(part + ((int64_t)g * S + i) * PC);
+                s1 += __ldcg(part + (rows + (int64_t)g * S + i) * PC);
             }
             s2_tot += s2;
             const double dv = src[(int64_t)g * C + c] - mu;
@@ -764,7 +766,7 @@ __device__ __forceinline__ void mala_propose_chain(const DevState &d, const Step
     }
     if (d.rng_mode == EXTMCMC_RNG_REPLAY) {
         for (int i = 0; i < n; ++i)
-            d.prop_full[(int64_t)u.coords_dev[i] * C + c] = d.rp_prop[((int64_t)sd.replay_row * d.p_u_max + i) * C + c];
+            d.prop_full[(int64_t)u.coords_dev[i] * C + c] = d.rp_prop[((int64_t)sd.replay_row * d.p_u_max + i) * d.gC + d.g0 + c];
         d.n_used[c] = 0;
     } else {
         ChainStepStream rng(d.seed, (uint64_t)(d.chain_offset + c), sd.mcmciter, sd.pidx);

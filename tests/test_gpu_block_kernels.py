@@ -29,12 +29,12 @@ def _clean(rep, rate=True):
 
 
 @pytest.mark.parametrize("n_chains,n_obs,n_iters,block,force,variant", [
-    (64, 10000, 40, None, RESIDENT, "resident_R4"),    # 8 chains per CTA: one chain group of 4 per thread group
-    (37, 3001, 30, 7, RESIDENT, "resident_R"),         # odd everything: ragged CTAs, odd N, blocks of 7 elements
-    (9, 2050, 30, 1, RESIDENT, "resident_R"),          # a CTA whose second group holds a single chain; 1-element blocks
-    (1, 4097, 40, None, RESIDENT, "resident_R4"),      # one chain: the second thread group is empty
-    (1500, 6000, 10, None, 0, "resident_R"),           # what the planner picks by itself for many chains
-    (4200, 20000, 6, 4, 0, "resident_R"),              # 28-29 chains per CTA (the cfg 2 layout), 2 chain groups of 7
+    (64, 10000, 40, None, RESIDENT, "team_block_R"),    # 8 chains per CTA: one chain group of 4 per thread group
+    (37, 3001, 30, 7, RESIDENT, "team_block_R"),         # odd everything: ragged CTAs, odd N, blocks of 7 elements
+    (9, 2050, 30, 1, RESIDENT, "team_block_R"),          # a CTA whose second group holds a single chain; 1-element blocks
+    (1, 4097, 40, None, RESIDENT, "team_block_R"),      # one chain: the second thread group is empty
+    (1500, 6000, 10, None, 0, "team_block_R"),           # what the planner picks by itself for many chains
+    (4200, 20000, 6, 4, 0, "team_block_R"),              # 28-29 chains per CTA (the cfg 2 layout), 2 chain groups of 7
 ])
 def test_resident_replay_parity_gsn1d(n_chains, n_obs, n_iters, block, force, variant):
     rep = replay_compare(_data(n_obs, seed=n_chains), n_chains, n_iters, seed=n_chains + 1, block=block,
@@ -48,7 +48,7 @@ def test_resident_tiny_datasets(n_obs):
     th0 = np.repeat(np.array([[1.0], [2.0]]), 40, axis=1)
     ups = cfg2_updates(eps0=0.8, scale=0.05, k=7, offset=1.0)
     rep = replay_compare(_data(n_obs, seed=9), 40, 50, seed=5, updates=ups, theta_init=th0, sweep_variant=RESIDENT)
-    assert rep["variant"].startswith("resident_R")
+    assert rep["variant"].startswith("team_block_R")
     _clean(rep)
 
 
@@ -74,7 +74,7 @@ def test_resident_cfg4_schedule_replay_parity(n_chains, ragged, force):
     rep = replay_compare(y, n_chains, 24, seed=12, updates=_hier_updates(G), law=em.HierNormalLaw(G), y=grp,
                          theta_init=_hier_theta0(G, n_chains), exclude=[(2, range(5, 9))], block=31,
                          history_window=80, sweep_variant=force)
-    assert rep["variant"].startswith("resident_R"), rep["variant"]
+    assert rep["variant"].startswith("team_block_R"), rep["variant"]
     _clean(rep)
 
 
@@ -127,7 +127,7 @@ def test_block_kernels_and_per_step_kernels_take_the_same_decisions():
     x = _data(30000, seed=2)
     a = _own_stream(x, 96, 40, PER_STEP_CHAINS, 80)
     b = _own_stream(x, 96, 40, RESIDENT, 11)
-    assert a["name"].startswith("gsn1d_chains") and b["name"].startswith("resident_R")
+    assert a["name"].startswith("gsn1d_chains") and b["name"].startswith("team_block_R")
     assert np.array_equal(a["accepted"], b["accepted"])
     assert np.array_equal(a["theta"], b["theta"]) and np.array_equal(a["theta_prop"], b["theta_prop"])
     assert np.allclose(a["ll"][1:], b["ll"][1:], rtol=1e-12, atol=0)
@@ -142,8 +142,10 @@ def test_block_kernels_and_per_step_kernels_take_the_same_decisions():
     kw = dict(law=em.HierNormalLaw(G), ups=_hier_updates(G), th0=_hier_theta0(G, 120), y=grp)
     e = _own_stream(y, 120, 20, PER_STEP_CHAINS, 60, **kw)
     f = _own_stream(y, 120, 20, RESIDENT, 13, **kw)
-    assert f["name"].startswith("resident_R")
-    assert np.array_equal(e["accepted"], f["accepted"]) and np.array_equal(e["theta"], f["theta"])
+    assert f["name"].startswith("team_block_R")
+    # MALA proposals use the gradient, i.e. the observation sums: same decisions, states equal up to
+    # the association of those sums
+    assert np.array_equal(e["accepted"], f["accepted"]) and np.allclose(e["theta"], f["theta"], rtol=1e-9, atol=1e-12)
 
 
 def test_full_size_cfg2_resident_block():
@@ -160,7 +162,7 @@ def test_full_size_cfg2_resident_block():
     ro = o.run(steps, n_threads=8)
     reps = Cn // sub
     g = GpuSession(em.GsnTargetLaw([0.0]), ups, x, np.tile(th_sub, (1, reps)), Cn, seed=3, n_steps_hint=len(steps))
-    assert g.variant() == "resident_R7"
+    assert g.variant() == "team_block_R7"
     rg = g.run(steps, replay=(np.tile(ro["proposals"], (1, 1, reps)), np.tile(ro["exp_draws"], (1, reps))))
     rep = compare_histories(ro, {k: v[..., :sub] for k, v in rg.items() if hasattr(v, "shape")})
     assert rep["accept_mismatch"] == 0 and rep["near_ties"] == 0 and rep["theta_bitexact"], rep
