@@ -33,8 +33,8 @@ def _clean(rep, rate=True):
     (37, 3001, 30, 7, RESIDENT, "team_block_R"),         # odd everything: ragged CTAs, odd N, blocks of 7 elements
     (9, 2050, 30, 1, RESIDENT, "team_block_R"),          # a CTA whose second group holds a single chain; 1-element blocks
     (1, 4097, 40, None, RESIDENT, "team_block_R"),      # one chain: the second thread group is empty
-    (1500, 6000, 10, None, 0, "team_block_R"),           # what the planner picks by itself for many chains
-    (4200, 20000, 6, 4, 0, "team_block_R"),              # 28-29 chains per CTA (the cfg 2 layout), 2 chain groups of 7
+    (1500, 6000, 10, None, RESIDENT, "team_block_R"),    # all 296 CTAs, teams of 4
+    (4200, 20000, 6, 4, RESIDENT, "team_block_R"),       # 56-57 chains per team (the cfg 2 layout)
 ])
 def test_resident_replay_parity_gsn1d(n_chains, n_obs, n_iters, block, force, variant):
     rep = replay_compare(_data(n_obs, seed=n_chains), n_chains, n_iters, seed=n_chains + 1, block=block,
@@ -65,7 +65,7 @@ def test_resident_exclusions_blocks_and_priors():
     _clean(rep)
 
 
-@pytest.mark.parametrize("n_chains,ragged,force", [(200, False, RESIDENT), (7, True, RESIDENT), (1300, False, 0)])
+@pytest.mark.parametrize("n_chains,ragged,force", [(200, False, RESIDENT), (7, True, RESIDENT), (1300, False, RESIDENT)])
 def test_resident_cfg4_schedule_replay_parity(n_chains, ragged, force):
     # BASELINE cfg 4: MALA on theta_1..8 (gradient sweeps), uniform walk on mu, multiplicative walk on
     # tau; full 10 x 10 covariance (cooperative update inside the thread group)
@@ -93,9 +93,9 @@ def test_resident_mala_gsn1d_and_variances_only():
 
 
 @pytest.mark.parametrize("n_chains,n_obs,n_iters,block,force,variant", [
-    (5, 20001, 60, None, 0, "obs_block_C8"),           # picked automatically for a handful of chains
-    (1, 4097, 120, 9, 0, "obs_block_C1"),              # the reference's shape: one chain; 9-element blocks
-    (20, 9000, 40, 1, 0, "obs_block_C32"),             # 1-element blocks: every element through its own launch
+    (5, 20001, 60, None, OBS_BLOCK, "obs_block_C8"),   # a handful of chains
+    (1, 4097, 120, 9, OBS_BLOCK, "obs_block_C1"),      # the reference's shape: one chain; 9-element blocks
+    (20, 9000, 40, 1, OBS_BLOCK, "obs_block_C32"),     # 1-element blocks: every element through its own launch
     (8, 700001, 12, None, OBS_BLOCK, "obs_block_C8"),  # many tiles per segment: the ring wraps across steps
     (3, 5, 30, None, OBS_BLOCK, "obs_block_C4"),       # fewer observations than CTAs
 ])
@@ -161,7 +161,8 @@ def test_full_size_cfg2_resident_block():
     o = orc.Oracle(em.GsnTargetLaw([0.0]), ups, x, th_sub, sub, seed=3)
     ro = o.run(steps, n_threads=8)
     reps = Cn // sub
-    g = GpuSession(em.GsnTargetLaw([0.0]), ups, x, np.tile(th_sub, (1, reps)), Cn, seed=3, n_steps_hint=len(steps))
+    g = GpuSession(em.GsnTargetLaw([0.0]), ups, x, np.tile(th_sub, (1, reps)), Cn, seed=3, n_steps_hint=len(steps),
+                   sweep_variant=RESIDENT)
     assert g.variant() == "team_block_R7"
     rg = g.run(steps, replay=(np.tile(ro["proposals"], (1, 1, reps)), np.tile(ro["exp_draws"], (1, reps))))
     rep = compare_histories(ro, {k: v[..., :sub] for k, v in rg.items() if hasattr(v, "shape")})

@@ -40,10 +40,10 @@ def _assert_clean(rep):
     (300, 3001, 40, 12, "gsn1d_chains_R2"),    # odd N, ragged chain group
     (700, 5000, 25, 14, "gsn1d_chains_R4"),
     (1100, 2050, 25, 18, "gsn1d_chains_R8"),   # 2 chain groups, second one ragged
-    (2100, 60000, 12, 1, "gsn1d_chains_R8"),   # what the per-step planner picks for a mid-size problem
-    (5, 20001, 60, 2, "gsn1d_obs_C8"),         # few chains: observation-mapped kernel
-    (1, 4097, 120, 2, "gsn1d_obs_C1"),         # the reference's shape: one chain
-    (20, 9000, 40, 2, "gsn1d_obs_C32"),
+    (2100, 60000, 12, 0, "gsn1d_chains_R8"),   # what the planner itself picks for a mid-size problem
+    (5, 20001, 60, 0, "gsn1d_obs_C8"),         # few chains: observation-mapped kernel
+    (1, 4097, 120, 0, "gsn1d_obs_C1"),         # the reference's shape: one chain
+    (20, 9000, 40, 0, "gsn1d_obs_C32"),
 ])
 def test_replay_parity(n_chains, n_obs, n_iters, force, variant):
     rep = replay_compare(_data(n_obs, seed=n_chains), n_chains, n_iters, seed=n_chains + 1,
