@@ -63,6 +63,10 @@ class GpuSession:
             self.p_u.append(len(u.coords))
             self.kernels.append(a.kernel)
             self.ck(self.lib.extmcmc_set_update(self.h, i, C.byref(a)))
+            cb = getattr(getattr(u, "adpt", None), "lambda_callback", lambda: None)()
+            if cb is not None:                                  # HaarioTypeAdaptation(...; f = ...)
+                self._keep.append(cb)
+                self.ck(self.lib.extmcmc_set_lambda_fn(self.h, i, cb, None))
         obs = np.ascontiguousarray(obs, dtype=np.float64)
         y = None if y is None else np.ascontiguousarray(y, dtype=np.float64)
         self.ck(self.lib.extmcmc_upload_obs(self.h, _abi.dptr(obs), obs.shape[0], law.obs_dim, _abi.dptr(y)))
