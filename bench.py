@@ -477,7 +477,7 @@ def run_ours(args):
     x = cfg2_data()
     peaks, peak_src = measured_peaks()
 
-    # ---- value: device-resident, one persistent kernel per iteration, L2 flushed between steps ----
+    # ---- value: device-resident, one CUDA graph per iteration, L2 flushed between steps ------------
     ws = make_ws(em, x, C, rank * C, local, block_len=NU, use_graphs=True)
     variant = ws.lib.extmcmc_sweep_variant_name(ws.handle).decode()
     sampler = ClockSampler(local)
@@ -513,13 +513,13 @@ def run_ours(args):
     step_ms_instr = timed_steps(wsi, _abi, C, n_instr, 0)
     wsi._ck(wsi.lib.extmcmc_get_sweep_time(wsi.handle, ctypes.byref(msw), ctypes.byref(nl)))
     kern_ms = msw.value / max(nl.value, 1)
-    sweeps_per_launch = n_instr * NU / max(nl.value, 1)     # 2: one launch runs both update steps of an iteration
+    sweeps_per_launch = n_instr * NU / max(nl.value, 1)     # 1 for the per-step kernels; a block kernel runs several
     sweep_share = msw.value / step_ms_instr if step_ms_instr > 0 else None
     wsi.close()
     flops = 3.0 * C * N_OBS * sweeps_per_launch    # 1 SUB + 1 FMA per chain x observation
     ach_tf = flops / (kern_ms * 1e-3) / 1e12
     fp64_peak = max(fp64_probe, lanes_peak)
-    traffic, traffic_src = ncu_traffic("resident_block_kernel", "ncu_full_resident_r02.csv")
+    traffic, traffic_src = ncu_traffic("sweep_gsn1d_chains_kernel", "ncu_full_chains_r02.csv")
     roofline = {
         "kernel": variant, "bound": "fp64", "achieved": ach_tf, "peak": fp64_peak,
         "unit": "TFLOP/s", "frac": ach_tf / fp64_peak if fp64_peak else None,
@@ -557,7 +557,7 @@ def run_ours(args):
         w5._ck(w5.lib.extmcmc_get_sweep_time(w5.handle, ctypes.byref(msw), ctypes.byref(nl)))
         t5 = msw.value / max(nl.value, 1)
         gbs = 8.0 * n5 / (t5 * 1e-3) / 1e9
-        tr5, tr5_src = ncu_traffic("sweep_gsn1d_obs_kernel", "ncu_full_obs_r01.csv")
+        tr5, tr5_src = ncu_traffic("sweep_gsn1d_obs_kernel", "ncu_full_obs_r02.csv")
         roofline_hbm = {"kernel": w5.lib.extmcmc_sweep_variant_name(w5.handle).decode(),
                         "workload": f"cfg5 shape on 1 GPU: C={c5}, N=2^28 (2 GiB > L2)", "bound": "hbm",
                         "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",

@@ -111,6 +111,9 @@ SIGNATURES = {
     "extmcmc_set_state": (C.c_int32, [Handle, c_double_p]),
     "extmcmc_set_seed": (C.c_int32, [Handle, C.c_uint64]),
     "extmcmc_set_lambda_fn": (C.c_int32, [Handle, C.c_int32, LambdaFn, C.c_void_p]),
+    "extmcmc_checkpoint_size": (C.c_int32, [Handle, c_int64_p]),
+    "extmcmc_checkpoint_save": (C.c_int32, [Handle, C.c_void_p, C.c_int64]),
+    "extmcmc_checkpoint_load": (C.c_int32, [Handle, C.c_void_p, C.c_int64]),
     "extmcmc_comm_unique_id": (C.c_int32, [c_uint8_p]),
     "extmcmc_comm_init": (C.c_int32, [Handle, c_uint8_p]),
     "extmcmc_p2p_export": (C.c_int32, [Handle, c_uint8_p]),

@@ -1189,6 +1189,103 @@ int32_t extmcmc_set_state(extmcmc_t h, const double *theta) {
     return EXTMCMC_OK;
 }
 
+// ---- checkpoint / resume ------------------------------------------------------------------------
+}  // extern "C"
+namespace {
+struct CkptHeader {
+    uint64_t magic;
+    int64_t C, seq_next;
+    int32_t abi, p, NU, W, stats_mode, law, grad_valid, pad;
+};
+constexpr uint64_t kCkptMagic = 0x32544b434d435845ull;   // "EXCMCKT2"
+
+// Visits every piece of the blob in a fixed order: fn(device pointer or nullptr, host pointer or nullptr, bytes).
+template <class F>
+int32_t ckpt_walk(extmcmc_t h, F fn) {
+    const DevState &d = h->d;
+    const size_t C = (size_t)d.C, p = (size_t)d.p;
+    const size_t covn = d.stats_mode == 0 ? p * p : (d.stats_mode == 1 ? p : 0);
+    int32_t rc;
+    if ((rc = fn(d.theta, nullptr, 8 * p * C)) || (rc = fn(d.ll, nullptr, 8 * C))) return rc;
+    if (d.stats_mode != 2 && ((rc = fn(d.mean, nullptr, 8 * p * C)) || (rc = fn(d.cov, nullptr, 8 * covn * C)))) return rc;
+    if ((rc = fn(nullptr, h->ra_iter.data(), 8 * h->ra_iter.size())) || (rc = fn(nullptr, h->acc_tag.data(), 8 * h->acc_tag.size())) ||
+        (rc = fn(nullptr, h->haario_M.data(), 8 * h->haario_M.size())) || (rc = fn(nullptr, h->lambda.data(), 8 * h->lambda.size())))
+        return rc;
+    for (int u = 0; u < h->cfg.n_updates; ++u) {
+        const DevUpdate &t = h->upd_host[u];
+        const size_t n = (size_t)t.n_coords, nn = n * n;
+        const size_t eps_rows = t.kernel == EXTMCMC_KERNEL_MALA ? 1 : n;
+        if ((rc = fn(t.eps, nullptr, 8 * eps_rows * C)) || (rc = fn(t.adapt_prop, nullptr, 4 * C)) ||
+            (rc = fn(t.adapt_acc, nullptr, 4 * C)) || (rc = fn(t.tot_prop, nullptr, 8 * C)) || (rc = fn(t.tot_acc, nullptr, 8 * C)) ||
+            (rc = fn(t.ra_val, nullptr, 8 * C)) || (rc = fn(t.acc_ring, nullptr, (size_t)d.W * C)))
+            return rc;
+        if (t.sigB && ((rc = fn(t.sigB, nullptr, 8 * nn * C)) || (rc = fn(t.LB, nullptr, 8 * nn * C)))) return rc;
+        if (t.hmean && ((rc = fn(t.hmean, nullptr, 8 * n * C)) || (rc = fn(t.hcov, nullptr, 8 * nn * C)))) return rc;
+    }
+    return EXTMCMC_OK;
+}
+}  // namespace
+extern "C" {
+
+int32_t extmcmc_checkpoint_size(extmcmc_t h, int64_t *bytes_out) {
+    if (!h || !bytes_out) return EXTMCMC_EINVAL;
+    for (int u = 0; u < h->cfg.n_updates; ++u)
+        if (!h->upd_set[u]) return fail(h, EXTMCMC_EINVAL, "update " + std::to_string(u) + " not set");
+    size_t tot = sizeof(CkptHeader);
+    ckpt_walk(h, [&](void *, void *, size_t b) { tot += b; return EXTMCMC_OK; });
+    *bytes_out = (int64_t)tot;
+    return EXTMCMC_OK;
+}
+
+int32_t extmcmc_checkpoint_save(extmcmc_t h, void *blob, int64_t bytes) {
+    int64_t need = 0;
+    int32_t rc = extmcmc_checkpoint_size(h, &need);
+    if (rc) return rc;
+    if (!blob || bytes < need) return fail(h, EXTMCMC_EINVAL, "checkpoint buffer too small");
+    if (!h->state_set) return fail(h, EXTMCMC_EINVAL, "nothing to save: extmcmc_set_state not called");
+    CK(h, cudaSetDevice(h->cfg.device));
+    CK(h, cudaStreamSynchronize(h->stream));
+    CkptHeader hd{kCkptMagic, h->d.C, h->seq_next, EXTMCMC_ABI_VERSION, h->d.p, h->d.NU, h->d.W, h->d.stats_mode, h->d.law,
+                  h->grad_valid ? 1 : 0, 0};
+    char *out = (char *)blob;
+    std::memcpy(out, &hd, sizeof hd);
+    out += sizeof hd;
+    return ckpt_walk(h, [&](void *dev, void *host, size_t b) -> int32_t {
+        if (dev) { CK(h, cudaMemcpy(out, dev, b, cudaMemcpyDeviceToHost)); }
+        else std::memcpy(out, host, b);
+        out += b;
+        return EXTMCMC_OK;
+    });
+}
+
+int32_t extmcmc_checkpoint_load(extmcmc_t h, const void *blob, int64_t bytes) {
+    int64_t need = 0;
+    int32_t rc = extmcmc_checkpoint_size(h, &need);
+    if (rc) return rc;
+    if (!blob || bytes < need) return fail(h, EXTMCMC_EINVAL, "checkpoint blob too small for this configuration");
+    CkptHeader hd;
+    std::memcpy(&hd, blob, sizeof hd);
+    if (hd.magic != kCkptMagic || hd.abi != EXTMCMC_ABI_VERSION || hd.C != h->d.C || hd.p != h->d.p || hd.NU != h->d.NU ||
+        hd.W != h->d.W || hd.stats_mode != h->d.stats_mode || hd.law != h->d.law)
+        return fail(h, EXTMCMC_EINVAL, "checkpoint does not match this handle (chains, parameters, updates, windows, law)");
+    CK(h, cudaSetDevice(h->cfg.device));
+    CK(h, cudaStreamSynchronize(h->stream));
+    const char *in = (const char *)blob + sizeof hd;
+    rc = ckpt_walk(h, [&](void *dev, void *host, size_t b) -> int32_t {
+        if (dev) { CK(h, cudaMemcpy(dev, in, b, cudaMemcpyHostToDevice)); }
+        else std::memcpy(host, in, b);
+        in += b;
+        return EXTMCMC_OK;
+    });
+    if (rc) return rc;
+    h->seq_next = hd.seq_next;
+    h->grad_valid = false;          // (the gradient buffers are not part of the blob: recomputed on demand)
+    h->state_set = true;
+    h->fetch_active = false;
+    CK(h, cudaMemset(h->d.err_flag, 0, sizeof(int32_t)));
+    return EXTMCMC_OK;
+}
+
 int32_t extmcmc_comm_unique_id(uint8_t id_out[128]) {
     std::string err;
     if (!id_out) return EXTMCMC_EINVAL;

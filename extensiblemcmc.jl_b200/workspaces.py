@@ -262,6 +262,20 @@ class CUDAGlobalWorkspace(GlobalWorkspace):
         self._ck(self.lib.extmcmc_get_adapt_state(self.handle, u - 1, _abi.dptr(mean), _abi.dptr(cov)))
         return mean, cov
 
+    def checkpoint(self):
+        """Everything a continued run depends on (state, step sizes, counters, moments, bookkeeping) as
+        bytes; restore() puts it into a workspace created with the same configuration."""
+        n = C.c_int64()
+        self._ck(self.lib.extmcmc_checkpoint_size(self.handle, C.byref(n)))
+        buf = (C.c_uint8 * n.value)()
+        self._ck(self.lib.extmcmc_checkpoint_save(self.handle, buf, n.value))
+        return bytes(buf)
+
+    def restore(self, blob):
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        self._ck(self.lib.extmcmc_checkpoint_load(self.handle, buf, len(blob)))
+        self.refresh_state()
+
     def eval_loglik(self):
         out = np.empty(self.C)
         self._ck(self.lib.extmcmc_eval_loglik(self.handle, _abi.dptr(out)))

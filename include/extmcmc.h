@@ -239,6 +239,18 @@ int32_t extmcmc_set_seed(extmcmc_t h, uint64_t seed);
 typedef double (*extmcmc_lambda_fn)(double lambda, int64_t N, int64_t mcmc_iter, void *user);
 int32_t extmcmc_set_lambda_fn(extmcmc_t h, int32_t u, extmcmc_lambda_fn f, void *user);
 
+/* ---- checkpoint / resume ---------------------------------------------------
+ * Everything a later extmcmc_run_block depends on: chain state and log-likelihood, step sizes
+ * (eps / Sigma_B and its factor / tau), adaptation counters, acceptance totals and rings, running
+ * moments, Haario state, the lambda of every mixture walk, and the host bookkeeping (executed-step
+ * count, rolling-acceptance tags).  The RNG has no state: a resumed run continues the same Philox
+ * streams, so `run 2M` and `run M, save, load into a fresh handle with the same configuration,
+ * updates and observations, run M with MCMCSchedule(...; start = ...)` (src/schedule.jl:28) are
+ * bit-identical.  The history ring is not part of the blob.  _load checks the shape header. */
+int32_t extmcmc_checkpoint_size(extmcmc_t h, int64_t *bytes_out);
+int32_t extmcmc_checkpoint_save(extmcmc_t h, void *blob, int64_t bytes);
+int32_t extmcmc_checkpoint_load(extmcmc_t h, const void *blob, int64_t bytes);
+
 /* ---- multi-rank (one process per GPU) ------------------------------------ */
 /* Fills 128 bytes with an NCCL unique id (rank 0 calls it and ships the bytes
  * to the other ranks with any host transport, e.g. torch.distributed/gloo). */

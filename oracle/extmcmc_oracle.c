@@ -17,6 +17,7 @@
 #include <pthread.h>
 
 #define ORC_MAX_D 16 /* obs_dim limit of the general-d Gaussian law in the oracle */
+#define ORC_MAX_P 512 /* parameter-vector limit of the oracle (d = 16: 272 parameters) */
 
 static __thread char g_err[512];
 static char g_err_global[512];
@@ -136,8 +137,8 @@ int32_t oracle_create(const extmcmc_config_t *cfg, const extmcmc_update_t *updat
         set_err("GSN_MV needs n_params = d(d+1), 1 <= d <= 16");
         return EXTMCMC_EINVAL;
     }
-    if (cfg->n_params > 256 || cfg->n_params < 1 || cfg->n_chains < 1 || cfg->n_updates < 1) {
-        set_err("oracle: need 1 <= n_params <= 256, n_chains >= 1, n_updates >= 1");
+    if (cfg->n_params > ORC_MAX_P || cfg->n_params < 1 || cfg->n_chains < 1 || cfg->n_updates < 1) {
+        set_err("oracle: need 1 <= n_params <= 512, n_chains >= 1, n_updates >= 1");
         return EXTMCMC_EINVAL;
     }
     for (int u = 0; u < cfg->n_updates; ++u)
@@ -619,8 +620,8 @@ static void chain_step(struct oracle_handle *h, int64_t c, const extmcmc_step_t 
     /* update_workspaces! src/run.jl:101-112: local state <- global state[coords];
      * local ll <- ll_history of the previously executed update (here: the carried
      * ll); on the very first element prev is `nothing` and ll stays -Inf. */
-    double th_loc[256], th_prop[256];
-    double g_cur[256], g_prop[256];
+    double th_loc[ORC_MAX_P], th_prop[ORC_MAX_P];
+    double g_cur[ORC_MAX_P], g_prop[ORC_MAX_P];
     for (int i = 0; i < n; ++i) th_loc[i] = theta[u->coords[i]];
     double ll_cur = (st->prev_pidx < 0) ? -INFINITY : h->ll[c];
     if (st->prev_pidx < 0) h->ll[c] = -INFINITY;
@@ -695,7 +696,7 @@ static void chain_step(struct oracle_handle *h, int64_t c, const extmcmc_step_t 
 
     /* set_proposal! src/run.jl:221-240: full proposal = global state with the
      * update's coordinates replaced; pushed into P° (gsn_target.jl:15-21) */
-    double full_prop[256];
+    double full_prop[ORC_MAX_P];
     for (int k = 0; k < p; ++k) full_prop[k] = theta[k];
     for (int i = 0; i < n; ++i) full_prop[u->coords[i]] = th_prop[i];
 
@@ -762,7 +763,7 @@ static void chain_step(struct oracle_handle *h, int64_t c, const extmcmc_step_t 
         double f_old = (double)(N - 1) / (double)N;
         double f_mean = (double)N / (double)(N + 1);
         double f_new = (double)(N + 1) / (double)N;
-        double old_mean[256];
+        double old_mean[ORC_MAX_P];
         for (int k = 0; k < p; ++k) old_mean[k] = mean[k];
         for (int k = 0; k < p; ++k) mean[k] = old_mean[k] * f_mean + theta[k] / (double)(N + 1);
         for (int b = 0; b < p; ++b)
@@ -901,7 +902,7 @@ static void run_worker(void *a, int64_t c) {
 
 static void loglik_worker(void *a, int64_t c) {
     run_job_t *j = a;
-    double th[256];
+    double th[ORC_MAX_P];
     for (int k = 0; k < j->h->p; ++k) th[k] = j->theta_eval[(int64_t)k * j->n_eval + c];
     int bad = 0;
     j->ll_out[c] = law_loglik(j->h, th, &bad);
@@ -967,9 +968,9 @@ int32_t oracle_get_eps(oracle_t h, int32_t u, double *eps) {
 
 int32_t oracle_loglik_grad(oracle_t h, const double *theta, int64_t n_eval, double *ll_out, double *grad_out) {
     if (h->cfg.law == EXTMCMC_LAW_GSN_MV) return EXTMCMC_EUNSUPPORTED;
-    if (h->p < 1 || h->p > 256) return EXTMCMC_EINVAL;
+    if (h->p < 1 || h->p > ORC_MAX_P) return EXTMCMC_EINVAL;
     for (int64_t c = 0; c < n_eval; ++c) {
-        double th[256] = {0.0}, g[256] = {0.0};
+        double th[ORC_MAX_P] = {0.0}, g[ORC_MAX_P] = {0.0};
         int bad = 0;
         for (int k = 0; k < h->p; ++k) th[k] = theta[(int64_t)k * n_eval + c];
         ll_out[c] = law_loglik_grad(h, th, g, &bad);

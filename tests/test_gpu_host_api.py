@@ -107,3 +107,40 @@ def test_reschedule_from_a_callback():
     assert not np.isnan(h[3, 1]).any() and np.isnan(h[4:, 1]).all() and not np.isnan(h[:, 0]).any()
     assert (ws.stats()["n_prop"][:, 0] == [12, 4]).all()
     ws.close()
+
+
+def test_checkpoint_resume_continues_the_same_chains_bit_for_bit():
+    """extmcmc_checkpoint_save / _load + MCMCSchedule(...; start = ...) (src/schedule.jl:28): a run cut in
+    two, with the second half in a FRESH handle, equals the uninterrupted run -- state, step sizes,
+    running moments, rolling acceptance rates and decision counts, bit for bit."""
+    from tests.parity import GpuSession, cfg2_updates, theta_init_for
+    x = 1.5 + 2.0 * np.random.default_rng(5).standard_normal(3000)
+    Cn, M = 70, 60
+    th0 = theta_init_for(x, Cn)
+    mk = lambda: cfg2_updates(eps0=0.05, scale=5e-3, k=7, offset=2.0)
+    steps = list(em.MCMCSchedule(M, 2, [(2, range(20, 35))]))
+    full = GpuSession(em.GsnTargetLaw([0.0]), mk(), x, th0, Cn, seed=21, n_steps_hint=len(steps), roll_window=10)
+    rf = full.run(steps)
+    cut = 47                                                    # in the middle of an iteration
+    a = GpuSession(em.GsnTargetLaw([0.0]), mk(), x, th0, Cn, seed=21, n_steps_hint=len(steps), roll_window=10)
+    ra = a.run(steps[:cut])
+    n = C.c_int64()
+    a.ck(a.lib.extmcmc_checkpoint_size(a.h, C.byref(n)))
+    blob = (C.c_uint8 * n.value)()
+    a.ck(a.lib.extmcmc_checkpoint_save(a.h, blob, n.value))
+    a.close()
+    b = GpuSession(em.GsnTargetLaw([0.0]), mk(), x, th0 * 0 + 1.0, Cn, seed=21, n_steps_hint=len(steps), roll_window=10)
+    b.ck(b.lib.extmcmc_checkpoint_load(b.h, blob, n.value))
+    b.seq = cut
+    rb = b.run(steps[cut:])
+    for k in ("theta", "theta_prop", "ll", "accepted"):
+        assert np.array_equal(rf[k], np.concatenate([ra[k], rb[k]])), k
+    sf, sb = full.stats(), b.stats()
+    for k in ("mean", "cov", "rolling_ar", "n_accept", "n_prop"):
+        assert np.array_equal(sf[k], sb[k]), k
+    assert np.array_equal(full.eps(1), b.eps(1)) and np.array_equal(full.eps(2), b.eps(2))
+    # a blob of another shape is refused
+    c = GpuSession(em.GsnTargetLaw([0.0]), mk(), x, th0[:, :8], 8, seed=21)
+    assert c.lib.extmcmc_checkpoint_load(c.h, blob, n.value) == _abi.EINVAL
+    for s in (full, b, c):
+        s.close()

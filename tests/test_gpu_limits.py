@@ -62,12 +62,14 @@ def test_gaussian_mixture_walk_with_haario_on_16_coordinates():
     law = em.GsnTargetLaw(mu, Sig)
     SA = 0.002 * (np.eye(d) + 0.1 * np.ones((d, d)))
     ups = [em.RandomWalkUpdate(em.GaussianRandomWalkMix(SA, 2.0 * SA, 0.4), list(range(1, d + 1)),
-                               adpt=em.HaarioTypeAdaptation(np.zeros(d), adapt_every_k_steps=6)),
+                               adpt=em.HaarioTypeAdaptation(np.zeros(d), adapt_every_k_steps=60)),
            em.RandomWalkUpdate(em.UniformRandomWalk([0.05], [True]), [d + 1], prior=em.ImproperPosPrior())]
-    rep = replay_compare(X, 40, 40, seed=3, updates=ups, law=law, theta_init=_theta_init(law, 40), stats_mode=1,
-                         history_window=96)
+    # (k = 60 own turns: by then the chain has visited more than 16 distinct states, so the adapted
+    # 16 x 16 Sigma_B is positive definite; with fewer the reference throws PosDefException)
+    rep = replay_compare(X, 24, 120, seed=3, updates=ups, law=law, theta_init=_theta_init(law, 24), stats_mode=1,
+                         history_window=256)
     _clean(rep, eps=False)
-    assert rep["eps_max_rel"] < 1e-9, rep      # Sigma_B after six readjustments (no positive coordinates: exact up to libm)
+    assert rep["eps_max_rel"] < 1e-9, rep      # Sigma_B after two readjustments (no positive coordinates)
 
 
 def test_uniform_walk_on_32_coordinates_and_the_limit():
@@ -129,7 +131,7 @@ def test_haario_lambda_schedule_is_called_back_on_the_host():
 def test_device_philox_proposals_match_the_oracle_stream():
     """Own Philox stream (no replay): the first proposal of every chain, computed by the DEVICE's draw
     arithmetic -- theta * exp(U) for positive coordinates, Box-Muller (sincospi) + cached Cholesky
-    factor for Gaussian walks -- against the oracle's (cos / sin of 2 pi u): within 2 ulp."""
+    factor for Gaussian walks -- against the oracle's (cos / sin of 2 pi u): within 2 ulp (uniform walk) / 4 ulp (Gaussian walks)."""
     x = 1.5 + 2.0 * np.random.default_rng(3).standard_normal(300)
     Cn = 200
     th0 = theta_init_for(x, Cn)
@@ -139,7 +141,7 @@ def test_device_philox_proposals_match_the_oracle_stream():
         [em.RandomWalkUpdate(em.GaussianRandomWalk(S, [False, True]), [1, 2], prior=em.ImproperPosPrior())],
         [em.RandomWalkUpdate(em.GaussianRandomWalkMix(S, 3 * S, 0.5, [False, True]), [1, 2], prior=em.ImproperPosPrior())],
     ]
-    for ups in cases:
+    for ups, max_ulp in zip(cases, (2.0, 4.0, 4.0)):     # exp / log / sincospi vs cos, sin of libm, chained
         steps = list(em.MCMCSchedule(1, 1))
         o = orc.Oracle(em.GsnTargetLaw([0.0]), ups, x, th0, Cn, seed=99, chain_offset=11)
         ro = o.run(steps)
@@ -147,6 +149,6 @@ def test_device_philox_proposals_match_the_oracle_stream():
         rg = g.run(steps)
         a, b = ro["theta_prop"][0], rg["theta_prop"][0]
         ulp = np.abs(a - b) / np.spacing(np.abs(a))
-        assert ulp.max() <= 2.0, ulp.max()
+        assert ulp.max() <= max_ulp, ulp.max()
         assert np.array_equal(ro["accepted"], rg["accepted"])
         g.close()
