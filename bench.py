@@ -33,9 +33,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 # stdout carries exactly one JSON line.  NCCL's INFO log (communicator lines with `nranks N`) goes
 # to stderr instead of being silenced, so the ranks of every communicator stay observable.
-os.environ.setdefault("NCCL_DEBUG", os.environ.get("EXTMCMC_NCCL_DEBUG", "INFO"))
+# (the image presets NCCL_DEBUG=VERSION, so this is an override, not a default; EXTMCMC_NCCL_DEBUG picks another level)
+os.environ["NCCL_DEBUG"] = os.environ.get("EXTMCMC_NCCL_DEBUG", "INFO")
 os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
 
 N_OBS = 1_000_000
 CHAINS_PER_GPU = 4096

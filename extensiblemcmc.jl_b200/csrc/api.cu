@@ -269,10 +269,10 @@ int32_t plan_block_kernels(extmcmc_t h) {
             }
         }
     }
-    // The observation-mapped block kernel: automatic where the per-step fixed cost matters, i.e. when
-    // observations are sharded over ranks and the library's own peer exchange is on; opt-in
-    // (sweep_variant 4) on a single rank, where the sweep itself dominates.
-    const bool obs_auto = sv == 0 && obs_sharded(h) && h->d.p2p && h->plan.variant == SWEEP_VARIANT_OBS;
+    // The observation-mapped block kernel is opt-in too (sweep_variant 4): with 125 M observations per
+    // GPU it gains 2 % over the per-step kernels with the fused exchange, with 500 M per GPU it loses
+    // 6 % (two CTAs of 128 registers per SM stream HBM less well than three of 80).
+    const bool obs_auto = false;
     if (!h->res_ok && all_unif && h->cfg.law == EXTMCMC_LAW_GSN_IID_1D && h->d.C <= 32 && (sv == 4 || obs_auto) &&
         (!obs_sharded(h) || h->d.p2p)) {
         cudaError_t e = plan_obs_block(h->d, h->upd_host.data(), h->num_sms, h->n_obs_local, &h->obsblk_plan);

@@ -178,8 +178,10 @@ def compare_histories(o, g, tie_tol=1e-12):
             near_tie += 1
     hard = int((first_bad < n).sum()) - near_tie
     vt = np.broadcast_to(valid[:, None, :], o["theta"].shape)
-    theta_ok = bool(np.array_equal(o["theta"][vt], g["theta"][vt]) and
-                    np.array_equal(o["theta_prop"][vt], g["theta_prop"][vt]))
+    # (NaN proposals -- a Sigma_B that is not positive definite: PosDefException in the reference --
+    # must be NaN on both sides)
+    theta_ok = bool(np.array_equal(o["theta"][vt], g["theta"][vt], equal_nan=True) and
+                    np.array_equal(o["theta_prop"][vt], g["theta_prop"][vt], equal_nan=True))
     fin = np.isfinite(o["ll_prop"]) & valid
     rel = np.abs(o["ll_prop"][fin] - g["ll_prop"][fin]) / np.maximum(np.abs(o["ll_prop"][fin]), 1e-300)
     fin2 = np.isfinite(o["ll"]) & valid

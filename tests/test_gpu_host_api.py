@@ -1,4 +1,5 @@
 """The reference-facing host API (MCMC / run! / callbacks / workspaces) on the GPU path."""
+import ctypes as C
 import io
 import os
 
@@ -6,6 +7,7 @@ import numpy as np
 import pytest
 
 import extensiblemcmc_jl_b200 as em
+from extensiblemcmc_jl_b200 import _abi
 from tests.parity import GpuSession
 
 pytestmark = pytest.mark.gpu
