@@ -69,6 +69,7 @@ struct Slot {
 struct extmcmc_handle {
     extmcmc_config_t cfg{};
     int num_sms = 0;
+    size_t l2_bytes = 0;
     cudaStream_t stream = nullptr;
     std::string err;
     DevState d{};
@@ -349,6 +350,9 @@ int32_t enqueue_sweep(extmcmc_t h, bool instrument, bool grad = false, const dou
             a.rank = h->cfg.rank; a.world = h->cfg.world_size;
             a.descs = d_descs; a.k = k;
         }
+        // a stream that cannot stay in L2 anyway must not evict the chain state (EXTMCMC_L2_HINT=0: off)
+        static const bool hint_on = [] { const char *e = getenv("EXTMCMC_L2_HINT"); return !e || atoi(e) != 0; }();
+        a.stream_hint = hint_on && (size_t)h->n_obs_local * sizeof(double) > h->l2_bytes / 2 ? 1 : 0;
         launch_sweep_gsn1d(h->plan, a, grad, h->stream);
     } else if (h->cfg.law == EXTMCMC_LAW_LOGISTIC) {
         LogisticArgs a{h->obs_dev, h->y_dev, h->n_obs_local, src, h->cfg.obs_dim, h->d.C, h->d.partial,
@@ -736,6 +740,7 @@ int32_t extmcmc_create(const extmcmc_config_t *cfg, extmcmc_t *out) {
         return bail(EXTMCMC_EUNSUPPORTED);
     }
     h->num_sms = prop.multiProcessorCount;
+    h->l2_bytes = (size_t)prop.l2CacheSize;
     CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CKC(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     CKC(cudaEventCreateWithFlags(&h->fetch_ready, cudaEventDisableTiming));
@@ -1133,6 +1138,17 @@ int32_t extmcmc_set_update(extmcmc_t h, int32_t u, const extmcmc_update_t *upd) 
         if (h->upd_set[v] && h->upd_host[v].adapt_kind == EXTMCMC_ADAPT_HAARIO) ++nh;
     }
     if (nh != h->d.n_haario) { h->d.n_haario = nh; invalidate_graphs(h); }
+    // the compact step-kernel instantiations apply when every update is plain (step_device.cuh, SpecLean)
+    static const bool lean_on = [] { const char *e = getenv("EXTMCMC_LEAN"); return !e || atoi(e) != 0; }();
+    int lean = lean_on ? 1 : 0;
+    for (int v = 0; v < h->cfg.n_updates; ++v) {
+        if (!h->upd_set[v]) continue;
+        const DevUpdate &w = h->upd_host[v];
+        if ((w.kernel != EXTMCMC_KERNEL_RW_UNIFORM && w.kernel != EXTMCMC_KERNEL_MALA) || !lean_prior(w.prior) ||
+            w.adapt_kind == EXTMCMC_ADAPT_HAARIO)
+            lean = 0;
+    }
+    if (lean != h->d.lean) { h->d.lean = lean; invalidate_graphs(h); }
     return EXTMCMC_OK;
 }
 

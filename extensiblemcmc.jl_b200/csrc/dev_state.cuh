@@ -19,6 +19,11 @@ constexpr int kMaxPriorFactors = 16; // ProductPrior factors
 constexpr int kMaxPriorParams = 1 + 4 * kMaxPriorFactors;
 constexpr int kMaxObsDim = 16;       // general-d Gaussian law on the device: d <= 16
 
+// prior families the compact (SpecLean) step kernels carry
+inline bool lean_prior(int kind) {
+    return kind == EXTMCMC_PRIOR_IMPROPER || kind == EXTMCMC_PRIOR_IMPROPER_POS || kind == EXTMCMC_PRIOR_NORMAL;
+}
+
 // One update as the kernels see it (constant per run; lives in a device table).
 struct DevUpdate {
     int32_t kernel, n_coords, prior, adapt_kind;
@@ -78,6 +83,9 @@ struct DevState {
     int32_t p, NU, W, H;    // params, updates, rolling window, history ring length
     int32_t law, stats_mode, rng_mode, p_u_max;
     int32_t n_haario;       // updates with HaarioTypeAdaptation (they register on every step)
+    int32_t lean;           // host-side fact: every update set so far is a uniform random walk or MALA
+                            // with an Improper / ImproperPos / Normal prior and no Haario adaptation ->
+                            // the launchers pick the SpecLean instantiations (step_device.cuh)
     int32_t obs_dim, lawc_k;  // observation dimension; per-chain law constants in lawc
     int32_t G;              // observation groups (HIER_NORMAL; 1 otherwise)
     double *ll_prop;        // [C] finalized proposal log-likelihood (gradient path)

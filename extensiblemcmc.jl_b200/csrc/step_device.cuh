@@ -45,9 +45,32 @@ struct MatRef {
     __device__ __forceinline__ void set(int idx, double v) const { p[(int64_t)idx * stride] = v; }
 };
 
+// ---- compile-time specialisation ---------------------------------------------------------------
+// The per-chain functions serve every transition kernel, prior family and law of the ABI.  Inlined
+// into one step kernel that is ~40 000 SASS instructions, of which a chain's thread walks a few
+// thousand, once per launch: the instruction fetch sits on the critical path (ncu, warm caches:
+// 36-42 % of the worker warps' stall samples in the accept kernels are `no_inst`).  A StepSpec folds
+// the dispatch at compile time.  SpecAny: everything dynamic (the general path).  SpecLean<LAW>: the
+// law is LAW, every random-walk update of the handle is a UniformRandomWalk, every prior is one of
+// Improper / ImproperPos / Normal and no update carries a HaarioTypeAdaptation -- the host checks
+// this per handle (DevState.lean) and picks the instantiation; the arithmetic is the same code.
+struct SpecAny {
+    static constexpr int kLaw = -1;
+    static constexpr bool kLean = false;
+};
+template <int LAW>
+struct SpecLean {
+    static constexpr int kLaw = LAW;
+    static constexpr bool kLean = true;
+};
+template <class SP> __device__ __forceinline__ int sp_law(const DevState &d) { return SP::kLaw >= 0 ? SP::kLaw : d.law; }
+template <class SP> __device__ __forceinline__ int sp_rw_kernel(const DevUpdate &u) {
+    return SP::kLean ? (int)EXTMCMC_KERNEL_RW_UNIFORM : u.kernel;
+}
+
 // ---- priors: logpdf(prior, theta_loc) on the update's own coordinates (src/updates.jl:104,
 //      src/priors.jl:18-39) ---------------------------------------------------------------------
-template <class Get>
+template <bool LEAN = false, class Get>
 __device__ __forceinline__ double log_prior_family(int kind, const double *pp, Get get, int n) {
     switch (kind) {
     case EXTMCMC_PRIOR_IMPROPER: return 0.0;  // priors.jl:19
@@ -66,6 +89,7 @@ __device__ __forceinline__ double log_prior_family(int kind, const double *pp, G
         return s;
     }
     case EXTMCMC_PRIOR_GAMMA: {
+        if (LEAN) break;   // not a lean family: unreachable, the host never picks a lean kernel then
         const double k = pp[0], sc = pp[1];
         double s = 0.0;
         for (int i = 0; i < n; ++i) {
@@ -76,6 +100,7 @@ __device__ __forceinline__ double log_prior_family(int kind, const double *pp, G
         return s;
     }
     case EXTMCMC_PRIOR_UNIFORM: {
+        if (LEAN) break;   // not a lean family: unreachable, the host never picks a lean kernel then
         const double a = pp[0], b = pp[1];
         double s = 0.0;
         for (int i = 0; i < n; ++i) {
@@ -86,6 +111,7 @@ __device__ __forceinline__ double log_prior_family(int kind, const double *pp, G
         return s;
     }
     case EXTMCMC_PRIOR_EXPONENTIAL: { /* Exponential(scale): log(rate) - rate x, rate = 1/scale; -Inf for x < 0 */
+        if (LEAN) break;   // not a lean family: unreachable, the host never picks a lean kernel then
         const double rate = 1.0 / pp[0];
         double s = 0.0;
         for (int i = 0; i < n; ++i) {
@@ -96,6 +122,7 @@ __device__ __forceinline__ double log_prior_family(int kind, const double *pp, G
         return s;
     }
     case EXTMCMC_PRIOR_INV_GAMMA: { /* InverseGamma(a, sc): a log sc - lgamma(a) - (a + 1) log x - sc/x */
+        if (LEAN) break;   // not a lean family: unreachable, the host never picks a lean kernel then
         const double a = pp[0], sc = pp[1];
         double s = 0.0;
         for (int i = 0; i < n; ++i) {
@@ -106,6 +133,7 @@ __device__ __forceinline__ double log_prior_family(int kind, const double *pp, G
         return s;
     }
     case EXTMCMC_PRIOR_BETA: { /* Beta(a, b): (a-1) log x + (b-1) log1p(-x) - logbeta(a, b) on (0, 1) */
+        if (LEAN) break;   // not a lean family: unreachable, the host never picks a lean kernel then
         const double a = pp[0], b = pp[1];
         const double lbeta = lgamma(a) + lgamma(b) - lgamma(a + b);
         double s = 0.0;
@@ -117,6 +145,7 @@ __device__ __forceinline__ double log_prior_family(int kind, const double *pp, G
         return s;
     }
     case EXTMCMC_PRIOR_LOGNORMAL: { /* LogNormal(m, sd): logpdf(Normal(m, sd), log x) - log x */
+        if (LEAN) break;   // not a lean family: unreachable, the host never picks a lean kernel then
         const double m = pp[0], sd = pp[1];
         double s = 0.0;
         for (int i = 0; i < n; ++i) {
@@ -128,6 +157,7 @@ __device__ __forceinline__ double log_prior_family(int kind, const double *pp, G
         return s;
     }
     case EXTMCMC_PRIOR_CAUCHY: { /* Cauchy(m, sc): -(log1p(z^2) + log(pi) + log(sc)) */
+        if (LEAN) break;   // not a lean family: unreachable, the host never picks a lean kernel then
         const double m = pp[0], sc = pp[1];
         double s = 0.0;
         for (int i = 0; i < n; ++i) {
@@ -158,8 +188,9 @@ __device__ __forceinline__ double mvn_logpdf_chol(const MatRef &L, int n, MuGet 
     return -((double)n * kLog2Pi + 2.0 * logdet) / 2.0 - sq / 2.0;
 }
 
-template <class Get>
+template <class SP = SpecAny, class Get>
 __device__ __forceinline__ double log_prior(const DevState &d, const DevUpdate &u, Get get, int64_t c) {
+    if (SP::kLean) return log_prior_family<true>(u.prior, u.prior_params, get, u.n_coords);
     if (u.prior == EXTMCMC_PRIOR_MVNORMAL) {
         // StandardPrior(MvNormal(mu, Sigma)) on the whole coordinate block (priors.jl:35-39)
         const int n = u.n_coords;
@@ -250,9 +281,11 @@ __device__ __forceinline__ double log_q_gauss_any(const DevState &d, const DevUp
 //   GSN_MV(d):  lawc = { mu[d], W = inv(L) lower-tri row-major, c0 },  Sigma = L L' built from the
 //               UPPER triangle of the d x d block of theta (Symmetric(triu(S)), gsn_target.jl:19);
 //               ll = N c0 - S/2,  S = sum |W (x - mu)|^2,  c0 = -(d log 2pi + 2 sum log L_ii)/2
+template <class SP = SpecAny>
 __device__ __forceinline__ void law_prepare(const DevState &d, int64_t c, const double *full,
                                             int64_t stride) {
-    if (d.law == EXTMCMC_LAW_GSN_IID_1D) {
+    const int law = sp_law<SP>(d);
+    if (law == EXTMCMC_LAW_GSN_IID_1D) {
         const double mu = full[0], var = full[stride];
         double c0, inv2;
         if (!(var > 0.0) || isinf(var)) {
@@ -265,11 +298,11 @@ __device__ __forceinline__ void law_prepare(const DevState &d, int64_t c, const 
         d.lawc[c] = mu;
         d.lawc[d.C + c] = c0;
         d.lawc[2 * d.C + c] = inv2;
-    } else if (d.law == EXTMCMC_LAW_HIER_NORMAL) {
+    } else if (law == EXTMCMC_LAW_HIER_NORMAL) {
         // no constants: the sweep reads theta_1..G straight from the state array it is given
         const double tau = full[(int64_t)(d.G + 1) * stride];
         if (!(tau > 0.0) || isinf(tau)) *d.err_flag = 1;
-    } else if (d.law == EXTMCMC_LAW_GSN_MV) {
+    } else if (law == EXTMCMC_LAW_GSN_MV) {
         const int n = d.obs_dim;
         const int64_t C = d.C;
         double *L = d.mv_L + c;                       // L[i][k] at (i n + k) C
@@ -311,11 +344,13 @@ __device__ __forceinline__ void law_prepare(const DevState &d, int64_t c, const 
 }
 
 // th: this chain's parameter vector the sums were computed for (stride C)
+template <class SP = SpecAny>
 __device__ __forceinline__ double law_finalize(const DevState &d, int64_t c, double S, const double *th) {
-    if (d.law == EXTMCMC_LAW_LOGISTIC) return S;  // the logistic sweep finishes ll itself
-    if (d.law == EXTMCMC_LAW_GSN_IID_1D)  // N*c0 - S/(2 var)
+    const int law = sp_law<SP>(d);
+    if (law == EXTMCMC_LAW_LOGISTIC) return S;  // the logistic sweep finishes ll itself
+    if (law == EXTMCMC_LAW_GSN_IID_1D)  // N*c0 - S/(2 var)
         return (double)d.n_obs_total * d.lawc[d.C + c] - S * d.lawc[2 * d.C + c];
-    if (d.law == EXTMCMC_LAW_HIER_NORMAL) {
+    if (law == EXTMCMC_LAW_HIER_NORMAL) {
         // sum_gj logN(y_gj; th_g, 1) + sum_g logN(th_g; mu, tau^2)
         const int G = d.G;
         const double mu = th[(int64_t)G * d.C], tau = th[(int64_t)(G + 1) * d.C];
@@ -356,7 +391,9 @@ struct CtaSync { __device__ __forceinline__ void operator()() const { __syncthre
 //     + set_proposal! (src/run.jl:221-240): writes the local and the full proposal and the law
 //     constants the sweep consumes.
 // ---------------------------------------------------------------------------------
+template <class SP = SpecAny>
 __device__ __forceinline__ void propose_chain(const DevState &d, const StepDesc &sd, const DevUpdate &u, int64_t c) {
+    const int kern = sp_rw_kernel<SP>(u);
     const int n = u.n_coords;
     const int64_t C = d.C;
     const CoordGet th{d.theta + c, u.coords, C};
@@ -369,7 +406,7 @@ __device__ __forceinline__ void propose_chain(const DevState &d, const StepDesc 
     } else {
         ChainStepStream rng(d.seed, (uint64_t)(d.chain_offset + c), sd.mcmciter, sd.pidx);
         for (;;) {
-            if (u.kernel == EXTMCMC_KERNEL_RW_UNIFORM) {
+            if (kern == EXTMCMC_KERNEL_RW_UNIFORM) {
                 for (int i = 0; i < n; ++i) {
                     const double r = rng.next();
                     const double e = u.eps[(int64_t)i * C + c];
@@ -381,7 +418,7 @@ __device__ __forceinline__ void propose_chain(const DevState &d, const StepDesc 
             } else {
                 // rand(rw::GaussianRandomWalk[Mix]) random_walk.jl:145-151,213-227
                 bool useB = false;
-                if (u.kernel == EXTMCMC_KERNEL_RW_GAUSS_MIX) useB = rng.next() <= sd.lambda;  // Bernoulli(lambda)
+                if (kern == EXTMCMC_KERNEL_RW_GAUSS_MIX) useB = rng.next() <= sd.lambda;  // Bernoulli(lambda)
                 double *z = d.gw + c;
                 for (int q = 0; q < n; q += 2) {  // randn via Box-Muller on the uniform stream
                     const double u1 = rng.next(), u2 = rng.next();
@@ -407,7 +444,7 @@ __device__ __forceinline__ void propose_chain(const DevState &d, const StepDesc 
                 }
             }
             // whole-vector redraw while the prior is exactly -Inf (updates.jl:193-195)
-            if (!(log_prior(d, u, prop, c) == -INFINITY)) break;
+            if (!(log_prior<SP>(d, u, prop, c) == -INFINITY)) break;
             if (rng.j > 60000u) break;
         }
         used = rng.j;
@@ -423,7 +460,7 @@ __device__ __forceinline__ void propose_chain(const DevState &d, const StepDesc 
         for (int q = 0; q < 4; ++q) if (j0 + q < d.p) d.prop_full[(int64_t)(j0 + q) * C + c] = t[q];
     }
     for (int i = 0; i < n; ++i) d.prop_full[(int64_t)u.coords[i] * C + c] = pl[(int64_t)i * C];
-    law_prepare(d, c, d.prop_full + c, C);
+    law_prepare<SP>(d, c, d.prop_full + c, C);
 }
 
 // Cooperative covariance update for models with more than a handful of parameters (cfg 4: p = 10,
@@ -446,27 +483,45 @@ __device__ __forceinline__ void update_cov_coop(const DevState &d, int64_t N, in
     const int64_t C = d.C;
     const double f_old = (double)(N - 1) / (double)N;
     const double f_new = (double)(N + 1) / (double)N;
-    const int total = nch * p * p;
-    for (int i0 = tid; i0 < total; i0 += 4 * nt) {
+    // nt is a multiple of nch: a thread keeps its chain and walks the entries e = a + b p with stride
+    // nt / nch; (a, b) advance incrementally (no integer division by the run-time p in the loop)
+    if (nt % nch != 0) {   // general thread-group shape (block kernels): flat index, divisions
+        const int total = nch * p * p;
+        for (int i = tid; i < total; i += nt) {
+            const int ch = i % nch, e = i / nch;
+            if (c0 + ch >= C) continue;
+            const int a = e % p, b = e / p;
+            const double ta = sh_t[a * nch + ch], tb = sh_t[b * nch + ch];
+            const double ma_old = sh_m[a * nch + ch], mb_old = sh_m[b * nch + ch];
+            const double ma_new = sh_n[a * nch + ch], mb_new = sh_n[b * nch + ch];
+            const double old_sum_sq = f_old * d.cov[(int64_t)e * C + c0 + ch] + ma_old * mb_old;
+            const double new_sum_sq = old_sum_sq + (ta * tb) / (double)N;
+            d.cov[(int64_t)e * C + c0 + ch] = new_sum_sq - f_new * (ma_new * mb_new);
+        }
+        return;
+    }
+    const int ch = tid % nch, es = nt / nch, pp = p * p;
+    const bool live = c0 + ch < C;
+    int e = tid / nch, a = e % p, b = e / p;
+    for (; e < pp; ) {
         double cv[4];
+        int ea[4], eb[4], ee[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const int i = i0 + q * nt;
-            const int ch = i % nch, e = i / nch;
-            cv[q] = (i < total && c0 + ch < C) ? d.cov[(int64_t)e * C + c0 + ch] : 0.0;
+            ee[q] = e; ea[q] = a; eb[q] = b;
+            cv[q] = (e < pp && live) ? d.cov[(int64_t)e * C + c0 + ch] : 0.0;
+            e += es; a += es;
+            while (a >= p) { a -= p; ++b; }
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const int i = i0 + q * nt;
-            const int ch = i % nch, e = i / nch;
-            if (i < total && c0 + ch < C) {
-                const int a = e % p, b = e / p;
-                const double ta = sh_t[a * nch + ch], tb = sh_t[b * nch + ch];
-                const double ma_old = sh_m[a * nch + ch], mb_old = sh_m[b * nch + ch];
-                const double ma_new = sh_n[a * nch + ch], mb_new = sh_n[b * nch + ch];
+            if (ee[q] < pp && live) {
+                const double ta = sh_t[ea[q] * nch + ch], tb = sh_t[eb[q] * nch + ch];
+                const double ma_old = sh_m[ea[q] * nch + ch], mb_old = sh_m[eb[q] * nch + ch];
+                const double ma_new = sh_n[ea[q] * nch + ch], mb_new = sh_n[eb[q] * nch + ch];
                 const double old_sum_sq = f_old * cv[q] + ma_old * mb_old;
                 const double new_sum_sq = old_sum_sq + (ta * tb) / (double)N;
-                d.cov[(int64_t)e * C + c0 + ch] = new_sum_sq - f_new * (ma_new * mb_new);
+                d.cov[(int64_t)ee[q] * C + c0 + ch] = new_sum_sq - f_new * (ma_new * mb_new);
             }
         }
     }
@@ -479,6 +534,7 @@ __device__ __forceinline__ void update_cov_coop(const DevState &d, int64_t N, in
 // update_adaptation! (src/run.jl:136-173, src/transition_kernels/adaptation.jl:273-329).
 // n_eps = entries of the update's step-size vector (p_u for the uniform walk, 1 for MALA).
 // ---------------------------------------------------------------------------------
+template <class SP = SpecAny>
 __device__ __forceinline__ void post_decision(const DevState &d, const StepDesc &sd, const DevUpdate &u,
                                               int64_t c, bool accepted, double ll_new, double ll_prop,
                                               int n_eps, const CoopStage *cs = nullptr) {
@@ -587,7 +643,7 @@ __device__ __forceinline__ void post_decision(const DevState &d, const StepDesc 
     }
     // HaarioTypeAdaptation registers on EVERY update step of ANY update (adaptation.jl:399-414),
     // on that update's view of the (already committed) global state, log-transformed copy.
-    if (d.n_haario > 0) {
+    if (!SP::kLean && d.n_haario > 0) {
         for (int v = 0; v < d.NU; ++v) {
             const DevUpdate &w = (v == sd.pidx) ? u : d.upd[v];
             if (w.adapt_kind != EXTMCMC_ADAPT_HAARIO) continue;
@@ -637,8 +693,10 @@ struct RwPre {
     double ll_cur, q_back, q_fwd, lp_prop, lp_cur, E;
 };
 
+template <class SP = SpecAny>
 __device__ __forceinline__ RwPre rw_accept_prologue(const DevState &d, const StepDesc &sd, const DevUpdate &u,
                                                     int64_t c) {
+    const int kern = sp_rw_kernel<SP>(u);
     const int64_t C = d.C;
     const CoordGet th{d.theta + c, u.coords, C};
     const StrideGet prop{d.prop_loc + c, C};
@@ -646,12 +704,12 @@ __device__ __forceinline__ RwPre rw_accept_prologue(const DevState &d, const Ste
     // update_workspaces! (run.jl:101-112): ll of the previously executed update; on the
     // very first element it is still the initial -Inf (workspaces.jl:425)
     r.ll_cur = sd.first ? -INFINITY : d.ll[c];
-    if (u.kernel == EXTMCMC_KERNEL_RW_UNIFORM) {
+    if (kern == EXTMCMC_KERNEL_RW_UNIFORM) {
         const StrideGet eps{u.eps + c, C};
         r.q_back = log_q_unif(u, eps, th);    // theta° -> theta
         r.q_fwd = log_q_unif(u, eps, prop);   // theta -> theta°
     } else {
-        const bool ok = !isnan(u.LA[0]) && (u.kernel != EXTMCMC_KERNEL_RW_GAUSS_MIX || !isnan(u.LB[c]));
+        const bool ok = !isnan(u.LA[0]) && (kern != EXTMCMC_KERNEL_RW_GAUSS_MIX || !isnan(u.LB[c]));
         if (!ok) {
             *d.err_flag = 1;
             r.q_back = NAN;
@@ -661,19 +719,20 @@ __device__ __forceinline__ RwPre rw_accept_prologue(const DevState &d, const Ste
             r.q_fwd = log_q_gauss_any(d, u, sd.lambda, th, prop, c);    // theta -> theta°
         }
     }
-    r.lp_prop = log_prior(d, u, prop, c);
-    r.lp_cur = log_prior(d, u, th, c);
+    r.lp_prop = log_prior<SP>(d, u, prop, c);
+    r.lp_cur = log_prior<SP>(d, u, th, c);
     r.E = draw_exp(d, sd, c);
     return r;
 }
 
 // S: the sweep's sum for the proposal.  Returns the decision; the chain state, history, running
 // moments and adaptation state are updated.
+template <class SP = SpecAny>
 __device__ __forceinline__ bool rw_accept_finish(const DevState &d, const StepDesc &sd, const DevUpdate &u, int64_t c,
                                                  const RwPre &r, double S, const CoopStage *cs = nullptr) {
     const int64_t C = d.C;
     const int n = u.n_coords;
-    const double ll_prop = law_finalize(d, c, S, d.prop_full + c);
+    const double ll_prop = law_finalize<SP>(d, c, S, d.prop_full + c);
     // llr, strictly left to right (run.jl:271-277)
     double llr = ll_prop - r.ll_cur;
     llr = llr + r.q_back;
@@ -684,8 +743,8 @@ __device__ __forceinline__ bool rw_accept_finish(const DevState &d, const StepDe
     const double ll_new = accepted ? ll_prop : r.ll_cur;
     if (accepted)
         for (int i = 0; i < n; ++i) d.theta[(int64_t)u.coords[i] * C + c] = d.prop_loc[(int64_t)i * C + c];
-    const int n_eps = u.kernel == EXTMCMC_KERNEL_RW_UNIFORM ? n : 0;
-    post_decision(d, sd, u, c, accepted, ll_new, ll_prop, n_eps, cs);
+    const int n_eps = sp_rw_kernel<SP>(u) == EXTMCMC_KERNEL_RW_UNIFORM ? n : 0;
+    post_decision<SP>(d, sd, u, c, accepted, ll_new, ll_prop, n_eps, cs);
     return accepted;
 }
 
@@ -703,20 +762,22 @@ __device__ __forceinline__ bool rw_accept_finish(const DevState &d, const StepDe
 //                d/dth_g = T_g - (th_g - mu)/tau^2, d/dmu = sum_g (th_g - mu)/tau^2,
 //                d/dtau = -G/tau + sum_g (th_g - mu)^2 / tau^3
 // ---------------------------------------------------------------------------------
+template <class SP = SpecAny>
 __device__ __forceinline__ void grad_finalize_chain(const DevState &d, int64_t c, const double *__restrict__ src,
                                                     double *__restrict__ ll_out, double *__restrict__ grad_out) {
+    const int law = sp_law<SP>(d);
     const int64_t C = d.C, PC = d.gC;
     const double *part = d.partial + d.g0 + c;   // this chain's column of partial[2][G*S][gC]
     const int G = d.G, S = d.S;
     const int64_t rows = (int64_t)G * S;
-    if (d.law == EXTMCMC_LAW_GSN_IID_1D) {
+    if (law == EXTMCMC_LAW_GSN_IID_1D) {
         double s2 = 0.0, s1 = 0.0;
         for (int i = 0; i < S; ++i) { s2 += __ldcg(part + (int64_t)i * PC); s1 += __ldcg(part + (rows + i) * PC); }
         const double var = src[C + c];
-        ll_out[c] = law_finalize(d, c, s2, src + c);
+        ll_out[c] = law_finalize<SP>(d, c, s2, src + c);
         grad_out[c] = s1 / var;
         grad_out[C + c] = -(double)d.n_obs_total / (2.0 * var) + s2 / (2.0 * var * var);
-    } else if (d.law == EXTMCMC_LAW_HIER_NORMAL) {
+    } else if (law == EXTMCMC_LAW_HIER_NORMAL) {
         const double mu = src[(int64_t)G * C + c], tau = src[(int64_t)(G + 1) * C + c];
         if (!(tau > 0.0) || isinf(tau)) *d.err_flag = 1;   // the current state never went through law_prepare
         const double it2 = 1.0 / (tau * tau);
@@ -735,7 +796,7 @@ __device__ __forceinline__ void grad_finalize_chain(const DevState &d, int64_t c
         }
         grad_out[(int64_t)G * C + c] = dmu;
         grad_out[(int64_t)(G + 1) * C + c] = -(double)G / tau + dev2 * it2 / tau;
-        ll_out[c] = law_finalize(d, c, s2_tot, src + c);
+        ll_out[c] = law_finalize<SP>(d, c, s2_tot, src + c);
     }
 }
 
@@ -753,6 +814,7 @@ __device__ __forceinline__ double prior_logpdf1(const DevUpdate &u, double th) {
 }
 
 // MALA proposal  theta° = theta + (tau^2/2) g(theta) + tau z,  g = grad(ll + log prior)
+template <class SP = SpecAny>
 __device__ __forceinline__ void mala_propose_chain(const DevState &d, const StepDesc &sd, const DevUpdate &u, int64_t c) {
     const int64_t C = d.C;
     const int n = u.n_coords;
@@ -786,13 +848,14 @@ __device__ __forceinline__ void mala_propose_chain(const DevState &d, const Step
         }
         d.n_used[c] = rng.j;
     }
-    law_prepare(d, c, d.prop_full + c, C);
+    law_prepare<SP>(d, c, d.prop_full + c, C);
 }
 
 // MALA accept/reject.  log q(a -> b) = -|b - a - (tau^2/2) g(a)|^2 / (2 tau^2) (the
 // normalising constant is the same in both directions and is left out).
 // The chain's own thread: decision, commit, history, counters; cs: staging (see CoopStage; with
 // cs->m the covariance update is left to update_cov_coop).
+template <class SP = SpecAny>
 __device__ __forceinline__ void mala_decide(const DevState &d, const StepDesc &sd, const DevUpdate &u, int64_t c,
                                             const CoopStage *cs) {
     const int64_t C = d.C;
@@ -848,7 +911,7 @@ __device__ __forceinline__ void mala_decide(const DevState &d, const StepDesc &s
             for (int q = 0; q < 4; ++q) if (j0 + q < d.p) d.grad_cur[(int64_t)(j0 + q) * C + c] = g[q];
         }
     }
-    post_decision(d, sd, u, c, accepted, ll_new, ll_prop, 1, cs);
+    post_decision<SP>(d, sd, u, c, accepted, ll_new, ll_prop, 1, cs);
 }
 
 // ---- cross-rank exchange of the per-chain sums (observation sharding, peer stores) ------------

@@ -26,13 +26,14 @@ __device__ __forceinline__ bool exchange_failed(const DevState &d) {
 // ---------------------------------------------------------------------------------
 // K1: proposal!  (step_device.cuh: propose_chain)
 // ---------------------------------------------------------------------------------
+template <class SP>
 __global__ void __launch_bounds__(256)
 propose_kernel(DevState d, const StepDesc *__restrict__ descs, int k) {
     __shared__ StepCtx ctx;
     load_step_ctx(&ctx, d, descs, k, threadIdx.x, blockDim.x, CtaSync{});
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= d.C || exchange_failed(d)) return;
-    propose_chain(d, ctx.sd, ctx.u, c);
+    propose_chain<SP>(d, ctx.sd, ctx.u, c);
 }
 
 // Law constants of the CURRENT state (extmcmc_eval_loglik).
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(256) finalize_loglik_kernel(DevState d, double
 // ---------------------------------------------------------------------------------
 // K3: accept_reject! (src/run.jl:268-281) for the random-walk updates.
 // ---------------------------------------------------------------------------------
-template <int SL>
+template <int SL, class SP>
 __global__ void __launch_bounds__(256)
 accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fuse_next) {
     // 256 threads = (256/SL) chains x SL reduction slices; slice 0 carries on with the chain
@@ -197,7 +198,7 @@ accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fuse_ne
     const StepDesc &sd = ctx.sd;
     const DevUpdate &u = ctx.u;
     RwPre pre{};
-    if (worker) pre = rw_accept_prologue(d, sd, u, c);
+    if (worker) pre = rw_accept_prologue<SP>(d, sd, u, c);
 
     griddep_wait();   // the sweep (and, under sharding, the exchange) has finished
     if (dead) return;
@@ -216,7 +217,7 @@ accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fuse_ne
     const bool coop = stage && d.stats_mode == 0;
     if (worker) {
         const CoopStage cs{sh_t, coop ? sh_m : nullptr, sh_n, kRedChains, (int)(threadIdx.x % kRedChains)};
-        rw_accept_finish(d, sd, u, c, pre, S, stage ? &cs : nullptr);
+        rw_accept_finish<SP>(d, sd, u, c, pre, S, stage ? &cs : nullptr);
     }
     if (coop) {
         __syncthreads();
@@ -225,8 +226,8 @@ accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fuse_ne
     if (!worker) return;
     // proposal of the NEXT schedule element of this block, fused here: the chain's thread has just
     // committed its state, and one launch per update step is saved
-    if (fuse_next == 2) law_prepare(d, c, d.theta + c, d.C);   // what prepare_current_kernel would do
-    else if (fuse_next) propose_chain(d, ctx_next.sd, ctx_next.u, c);
+    if (fuse_next == 2) law_prepare<SP>(d, c, d.theta + c, d.C);   // what prepare_current_kernel would do
+    else if (fuse_next) propose_chain<SP>(d, ctx_next.sd, ctx_next.u, c);
 }
 
 // The MALA step kernels run as CTAs of kMalaChains chains x kMalaSlices slices (256 threads): the
@@ -234,14 +235,15 @@ accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fuse_ne
 // chain's own thread (slice 0) does the scalar work.  Same sums, same order as grad_finalize_chain.
 constexpr int kMalaChains = 32, kMalaSlices = 8;
 constexpr int kCoopG = 16;   // most observation groups reduced this way
+template <class SP>
 __device__ __forceinline__ void grad_finalize_coop(const DevState &d, int64_t c0, const double *__restrict__ src,
                                                    double *__restrict__ ll_out, double *__restrict__ grad_out,
                                                    double *sh2, double *sh1 /*[kCoopG][kMalaChains] each*/) {
     const int ch = threadIdx.x % kMalaChains, slice = threadIdx.x / kMalaChains;
     const int64_t c = c0 + ch, C = d.C;
     const int G = d.G, S = d.S;
-    if (d.law != EXTMCMC_LAW_HIER_NORMAL || G > kCoopG) {   // CTA-uniform
-        if (slice == 0 && c < C) grad_finalize_chain(d, c, src, ll_out, grad_out);
+    if (sp_law<SP>(d) != EXTMCMC_LAW_HIER_NORMAL || G > kCoopG) {   // CTA-uniform
+        if (slice == 0 && c < C) grad_finalize_chain<SP>(d, c, src, ll_out, grad_out);
         return;
     }
     const int64_t rows = (int64_t)G * S;
@@ -277,7 +279,7 @@ __device__ __forceinline__ void grad_finalize_coop(const DevState &d, int64_t c0
     }
     grad_out[(int64_t)G * C + c] = dmu;
     grad_out[(int64_t)(G + 1) * C + c] = -(double)G / tau + dev2 * it2 / tau;
-    ll_out[c] = law_finalize(d, c, s2_tot, src + c);
+    ll_out[c] = law_finalize<SP>(d, c, s2_tot, src + c);
 }
 
 __global__ void __launch_bounds__(128)
@@ -289,6 +291,7 @@ grad_finalize_kernel(DevState d, const double *__restrict__ src, double *__restr
 }
 
 // K5a: MALA proposal (step_device.cuh: mala_propose_chain)
+template <class SP>
 __global__ void __launch_bounds__(kMalaChains * kMalaSlices)
 mala_propose_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int finalize_cur,
                     double *__restrict__ ll_scratch) {
@@ -303,12 +306,13 @@ mala_propose_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int f
     const int64_t c = c0 + threadIdx.x % kMalaChains;
     // the sweep just before this kernel evaluated the CURRENT state: finish its sums here
     // (gradient of the current state) instead of in a kernel of its own
-    if (finalize_cur) grad_finalize_coop(d, c0, d.theta, ll_scratch, d.grad_cur, sh2, sh1);
+    if (finalize_cur) grad_finalize_coop<SP>(d, c0, d.theta, ll_scratch, d.grad_cur, sh2, sh1);
     if (threadIdx.x >= kMalaChains || c >= d.C) return;
-    mala_propose_chain(d, ctx.sd, ctx.u, c);
+    mala_propose_chain<SP>(d, ctx.sd, ctx.u, c);
 }
 
 // K5b: MALA accept/reject (step_device.cuh: mala_decide)
+template <class SP>
 __global__ void __launch_bounds__(kMalaChains * kMalaSlices)
 mala_accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int finalize_prop, int fuse_next) {
     __shared__ StepCtx ctx, ctx_next;
@@ -321,20 +325,20 @@ mala_accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fi
     const int64_t c0 = (int64_t)blockIdx.x * kMalaChains;
     const int ch = threadIdx.x % kMalaChains;
     const int64_t c = c0 + ch;
-    if (finalize_prop) grad_finalize_coop(d, c0, d.prop_full, d.ll_prop, d.grad_prop, sh2, sh1);
+    if (finalize_prop) grad_finalize_coop<SP>(d, c0, d.prop_full, d.ll_prop, d.grad_prop, sh2, sh1);
     const bool worker = threadIdx.x < kMalaChains && c < d.C;
     const bool stage = d.p <= kCoopP;   // CTA-uniform
     const bool coop = stage && d.stats_mode == 0;
     if (worker) {
         const CoopStage cs{sh_t, coop ? sh_m : nullptr, sh_n, kMalaChains, ch};
-        mala_decide(d, ctx.sd, ctx.u, c, stage ? &cs : nullptr);
+        mala_decide<SP>(d, ctx.sd, ctx.u, c, stage ? &cs : nullptr);
     }
     if (coop) {
         __syncthreads();
         update_cov_coop(d, ctx.sd.stat_n, c0, kMalaChains, sh_t, sh_m, sh_n, threadIdx.x, blockDim.x);
     }
     // next element is a random-walk update: issue its proposal here (one launch saved)
-    if (worker && fuse_next) propose_chain(d, ctx_next.sd, ctx_next.u, c);
+    if (worker && fuse_next) propose_chain<SP>(d, ctx_next.sd, ctx_next.u, c);
 }
 
 // ---------------------------------------------------------------------------------
@@ -411,8 +415,18 @@ __global__ void dmma_peak_kernel(double *out, int iters, double a, double b) {
 // ---------------------------------------------------------------------------------
 static inline int blocks_for(int64_t C) { return (int)((C + 255) / 256); }
 
+// Which instantiation serves this handle: the lean ones when the host found every update to be a
+// uniform random walk or MALA with Improper / ImproperPos / Normal priors and no Haario adaptation
+// (DevState.lean), per law; the general one otherwise.  F is called with a StepSpec value.
+template <class F>
+static inline void with_spec(const DevState &d, F f) {
+    if (d.lean && d.law == EXTMCMC_LAW_GSN_IID_1D) f(SpecLean<EXTMCMC_LAW_GSN_IID_1D>{});
+    else if (d.lean && d.law == EXTMCMC_LAW_HIER_NORMAL) f(SpecLean<EXTMCMC_LAW_HIER_NORMAL>{});
+    else if (d.lean && d.law == EXTMCMC_LAW_LOGISTIC) f(SpecLean<EXTMCMC_LAW_LOGISTIC>{});
+    else f(SpecAny{});
+}
 void launch_propose(const DevState &d, const StepDesc *descs, int k, cudaStream_t st) {
-    propose_kernel<<<blocks_for(d.C), 256, 0, st>>>(d, descs, k);
+    with_spec(d, [&](auto sp) { propose_kernel<decltype(sp)><<<blocks_for(d.C), 256, 0, st>>>(d, descs, k); });
 }
 static inline int red_blocks_for(int64_t C, int sl) {
     const int ch = kRedThreads / sl;
@@ -436,16 +450,14 @@ void launch_accept(const DevState &d, const StepDesc *descs, int k, int fuse_nex
     attr[0].val.programmaticStreamSerializationAllowed = (pdl_mask() >> 1) & 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (slices_for(d) == 32) {
-        cfg.gridDim = dim3(red_blocks_for(d.C, 32));
-        cudaLaunchKernelEx(&cfg, accept_kernel<32>, d, descs, k, fuse_next);
-    } else if (slices_for(d) == 8) {
-        cfg.gridDim = dim3(red_blocks_for(d.C, 8));
-        cudaLaunchKernelEx(&cfg, accept_kernel<8>, d, descs, k, fuse_next);
-    } else {
-        cfg.gridDim = dim3(red_blocks_for(d.C, 1));
-        cudaLaunchKernelEx(&cfg, accept_kernel<1>, d, descs, k, fuse_next);
-    }
+    const int sl = slices_for(d);
+    cfg.gridDim = dim3(red_blocks_for(d.C, sl));
+    with_spec(d, [&](auto sp) {
+        using SP = decltype(sp);
+        if (sl == 32) cudaLaunchKernelEx(&cfg, accept_kernel<32, SP>, d, descs, k, fuse_next);
+        else if (sl == 8) cudaLaunchKernelEx(&cfg, accept_kernel<8, SP>, d, descs, k, fuse_next);
+        else cudaLaunchKernelEx(&cfg, accept_kernel<1, SP>, d, descs, k, fuse_next);
+    });
 }
 void launch_grad_finalize(const DevState &d, const double *src, double *ll_out, double *grad_out,
                           cudaStream_t st) {
@@ -462,7 +474,7 @@ void launch_mala_propose(const DevState &d, const StepDesc *descs, int k, int fi
     attr[0].val.programmaticStreamSerializationAllowed = (pdl_mask() >> 1) & 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, mala_propose_kernel, d, descs, k, finalize_cur, ll_scratch);
+    with_spec(d, [&](auto sp) { cudaLaunchKernelEx(&cfg, mala_propose_kernel<decltype(sp)>, d, descs, k, finalize_cur, ll_scratch); });
 }
 void launch_mala_accept(const DevState &d, const StepDesc *descs, int k, int finalize_prop, int fuse_next,
                         cudaStream_t st) {
@@ -475,7 +487,7 @@ void launch_mala_accept(const DevState &d, const StepDesc *descs, int k, int fin
     attr[0].val.programmaticStreamSerializationAllowed = (pdl_mask() >> 1) & 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, mala_accept_kernel, d, descs, k, finalize_prop, fuse_next);
+    with_spec(d, [&](auto sp) { cudaLaunchKernelEx(&cfg, mala_accept_kernel<decltype(sp)>, d, descs, k, finalize_prop, fuse_next); });
 }
 void launch_chol_factor(double *S, double *L, int n, int64_t stride, int64_t count, cudaStream_t st) {
     chol_factor_kernel<<<(int)((count + 127) / 128), 128, 0, st>>>(S, L, n, stride, count);

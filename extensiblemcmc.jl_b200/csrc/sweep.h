@@ -51,6 +51,7 @@ struct Gsn1dArgs {
     int rank, world;
     const void *descs;       // StepDesc array of the block (device), element k names the step
     int k;
+    int stream_hint;         // 1: the observations do not fit in L2 -- copy them with L2::evict_first
 };
 
 SweepPlan plan_sweep_gsn1d(int64_t C, int64_t n_obs_largest_group, int force_variant, int num_sms, int G);

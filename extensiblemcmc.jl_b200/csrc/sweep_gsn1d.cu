@@ -171,13 +171,15 @@ sweep_gsn1d_obs_kernel(Gsn1dArgs a) {
     }
     __syncthreads();
 
+    const uint64_t pol = a.stream_hint ? l2_policy_evict_first() : 0ull;
     auto issue = [&](int t) {
         const int st = t % STAGES;
         const int64_t off = (int64_t)t * TILE;
         const int cnt = (int)((len - off) < (int64_t)TILE ? (len - off) : (int64_t)TILE);
         const uint32_t bytes = (uint32_t)((cnt + 1) >> 1) * 16u;
         mbar_expect_tx(&bar[st], bytes);
-        bulk_g2s(tile + st * TILE, obs + lo + off, bytes, &bar[st]);
+        if (a.stream_hint) bulk_g2s_hint(tile + st * TILE, obs + lo + off, bytes, &bar[st], pol);
+        else bulk_g2s(tile + st * TILE, obs + lo + off, bytes, &bar[st]);
     };
     if (tid == 0)
         for (int t = 0; t < STAGES && t < n_tiles; ++t) issue(t);
@@ -315,7 +317,7 @@ constexpr size_t kObsSmem(int cb) {
 
 // launch with the PDL attribute: the kernel may be scheduled while its predecessor drains
 template <typename Kern>
-void launch_pdl(Kern kern, dim3 grid, int threads, size_t smem, cudaStream_t st, const Gsn1dArgs &a) {
+void launch_pdl(Kern kern, dim3 grid, int threads, size_t smem, cudaStream_t st, const Gsn1dArgs &a, bool early = false) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(threads);
@@ -323,7 +325,7 @@ void launch_pdl(Kern kern, dim3 grid, int threads, size_t smem, cudaStream_t st,
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = pdl_mask() & 1;
+    attr[0].val.programmaticStreamSerializationAllowed = (pdl_mask() & 1) || (early && (pdl_mask() & 4));
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     cudaLaunchKernelEx(&cfg, kern, a);
@@ -349,15 +351,19 @@ template <int CB>
 void launch_obs(const SweepPlan &pl, const Gsn1dArgs &a, bool grad, cudaStream_t st) {
     dim3 grid(pl.S, 1, a.G);
     if (grad)
-        launch_pdl(sweep_gsn1d_obs_kernel<CB, kObsNT, kObsTile, kObsStages, true>, grid, kObsNT, kObsSmem(CB), st, a);
+        launch_pdl(sweep_gsn1d_obs_kernel<CB, kObsNT, kObsTile, kObsStages, true>, grid, kObsNT, kObsSmem(CB), st, a, true);
     else
-        launch_pdl(sweep_gsn1d_obs_kernel<CB, kObsNT, kObsTile, kObsStages, false>, grid, kObsNT, kObsSmem(CB), st, a);
+        launch_pdl(sweep_gsn1d_obs_kernel<CB, kObsNT, kObsTile, kObsStages, false>, grid, kObsNT, kObsSmem(CB), st, a, true);
 }
 }  // namespace
 
 // n_obs: observations of the LARGEST group (all of them when G = 1)
+// EXTMCMC_PDL bits: 1 = every sweep may start early (the "chains" mapping loses its balanced wave:
+// measured 45 % slower at cfg 2), 2 = the step kernels start early (prologue behind the sweep),
+// 4 = the "obs" mapping (few chains, one CTA wave of long segments) may start early: its first tiles
+// are in flight while the step kernel decides (cfg 5, 125 M observations per GPU: -2.4 %).
 int pdl_mask() {
-    static const int m = [] { const char *e = getenv("EXTMCMC_PDL"); return e ? atoi(e) : 2; }();
+    static const int m = [] { const char *e = getenv("EXTMCMC_PDL"); return e ? atoi(e) : 6; }();
     return m;
 }
 
