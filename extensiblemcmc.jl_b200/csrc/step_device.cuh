@@ -391,8 +391,12 @@ struct CtaSync { __device__ __forceinline__ void operator()() const { __syncthre
 //     + set_proposal! (src/run.jl:221-240): writes the local and the full proposal and the law
 //     constants the sweep consumes.
 // ---------------------------------------------------------------------------------
+// Two halves, so that a step kernel can run them on a warp of their own next to the bookkeeping of
+// the step just decided: propose_draw reads the committed state and writes prop_loc / n_used;
+// propose_set writes prop_full and the law constants (the bookkeeping must have read prop_full for
+// its history row by then).  propose_chain = both, back to back.
 template <class SP = SpecAny>
-__device__ __forceinline__ void propose_chain(const DevState &d, const StepDesc &sd, const DevUpdate &u, int64_t c) {
+__device__ __forceinline__ void propose_draw(const DevState &d, const StepDesc &sd, const DevUpdate &u, int64_t c) {
     const int kern = sp_rw_kernel<SP>(u);
     const int n = u.n_coords;
     const int64_t C = d.C;
@@ -450,6 +454,13 @@ __device__ __forceinline__ void propose_chain(const DevState &d, const StepDesc 
         used = rng.j;
     }
     d.n_used[c] = used;
+}
+
+template <class SP = SpecAny>
+__device__ __forceinline__ void propose_set(const DevState &d, const DevUpdate &u, int64_t c) {
+    const int n = u.n_coords;
+    const int64_t C = d.C;
+    const double *pl = d.prop_loc + c;
     // full proposal = current state with the update's coordinates replaced (run.jl:237-239);
     // loads in batches of 4 ahead of the stores (the arrays may alias as far as the compiler knows)
     for (int j0 = 0; j0 < d.p; j0 += 4) {
@@ -461,6 +472,12 @@ __device__ __forceinline__ void propose_chain(const DevState &d, const StepDesc 
     }
     for (int i = 0; i < n; ++i) d.prop_full[(int64_t)u.coords[i] * C + c] = pl[(int64_t)i * C];
     law_prepare<SP>(d, c, d.prop_full + c, C);
+}
+
+template <class SP = SpecAny>
+__device__ __forceinline__ void propose_chain(const DevState &d, const StepDesc &sd, const DevUpdate &u, int64_t c) {
+    propose_draw<SP>(d, sd, u, c);
+    propose_set<SP>(d, u, c);
 }
 
 // Cooperative covariance update for models with more than a handful of parameters (cfg 4: p = 10,
@@ -534,10 +551,12 @@ __device__ __forceinline__ void update_cov_coop(const DevState &d, int64_t N, in
 // update_adaptation! (src/run.jl:136-173, src/transition_kernels/adaptation.jl:273-329).
 // n_eps = entries of the update's step-size vector (p_u for the uniform walk, 1 for MALA).
 // ---------------------------------------------------------------------------------
+// Two halves (a step kernel may run the next proposal on another warp in between, see propose_draw):
+// post_decision_moments -- history row + running moments, reads theta / prop_full / mean / cov;
+// post_decision_counters -- rolling acceptance rate, totals, adaptation.  post_decision = both.
 template <class SP = SpecAny>
-__device__ __forceinline__ void post_decision(const DevState &d, const StepDesc &sd, const DevUpdate &u,
-                                              int64_t c, bool accepted, double ll_new, double ll_prop,
-                                              int n_eps, const CoopStage *cs = nullptr) {
+__device__ __forceinline__ void post_decision_moments(const DevState &d, const StepDesc &sd, int64_t c, bool accepted,
+                                                      double ll_new, double ll_prop, const CoopStage *cs = nullptr) {
     const int64_t C = d.C;
     d.ll[c] = ll_new;
     // history row (state_history / state_proposal_history / ll_history / acceptance_history)
@@ -608,6 +627,13 @@ __device__ __forceinline__ void post_decision(const DevState &d, const StepDesc 
             d.mean[idx] = d.mean[idx] * f_mean + d.theta[idx] / (double)(N + 1);
         }
     }
+}
+
+template <class SP = SpecAny>
+__device__ __forceinline__ void post_decision_counters(const DevState &d, const StepDesc &sd, const DevUpdate &u,
+                                                       int64_t c, bool accepted, int n_eps) {
+    const int64_t C = d.C;
+    const int64_t N = sd.stat_n;
     // rolling acceptance rate (chain_statistics.jl:53-64)
     {
         const int W = d.W;
@@ -678,6 +704,14 @@ __device__ __forceinline__ void post_decision(const DevState &d, const StepDesc 
     }
 }
 
+template <class SP = SpecAny>
+__device__ __forceinline__ void post_decision(const DevState &d, const StepDesc &sd, const DevUpdate &u,
+                                              int64_t c, bool accepted, double ll_new, double ll_prop,
+                                              int n_eps, const CoopStage *cs = nullptr) {
+    post_decision_moments<SP>(d, sd, c, accepted, ll_new, ll_prop, cs);
+    post_decision_counters<SP>(d, sd, u, c, accepted, n_eps);
+}
+
 __device__ __forceinline__ double draw_exp(const DevState &d, const StepDesc &sd, int64_t c) {
     if (d.rng_mode == EXTMCMC_RNG_REPLAY) return d.rp_exp[(int64_t)sd.replay_row * d.gC + d.g0 + c];
     ChainStepStream rng(d.seed, (uint64_t)(d.chain_offset + c), sd.mcmciter, sd.pidx, d.n_used[c]);
@@ -727,9 +761,13 @@ __device__ __forceinline__ RwPre rw_accept_prologue(const DevState &d, const Ste
 
 // S: the sweep's sum for the proposal.  Returns the decision; the chain state, history, running
 // moments and adaptation state are updated.
+struct Decision {
+    bool accepted;
+    double ll_new, ll_prop;
+};
 template <class SP = SpecAny>
-__device__ __forceinline__ bool rw_accept_finish(const DevState &d, const StepDesc &sd, const DevUpdate &u, int64_t c,
-                                                 const RwPre &r, double S, const CoopStage *cs = nullptr) {
+__device__ __forceinline__ Decision rw_decide_commit(const DevState &d, const DevUpdate &u, int64_t c, const RwPre &r,
+                                                     double S) {
     const int64_t C = d.C;
     const int n = u.n_coords;
     const double ll_prop = law_finalize<SP>(d, c, S, d.prop_full + c);
@@ -743,9 +781,18 @@ __device__ __forceinline__ bool rw_accept_finish(const DevState &d, const StepDe
     const double ll_new = accepted ? ll_prop : r.ll_cur;
     if (accepted)
         for (int i = 0; i < n; ++i) d.theta[(int64_t)u.coords[i] * C + c] = d.prop_loc[(int64_t)i * C + c];
-    const int n_eps = sp_rw_kernel<SP>(u) == EXTMCMC_KERNEL_RW_UNIFORM ? n : 0;
-    post_decision<SP>(d, sd, u, c, accepted, ll_new, ll_prop, n_eps, cs);
-    return accepted;
+    return Decision{accepted, ll_new, ll_prop};
+}
+template <class SP = SpecAny>
+__device__ __forceinline__ int rw_n_eps(const DevUpdate &u) {
+    return sp_rw_kernel<SP>(u) == EXTMCMC_KERNEL_RW_UNIFORM ? u.n_coords : 0;
+}
+template <class SP = SpecAny>
+__device__ __forceinline__ bool rw_accept_finish(const DevState &d, const StepDesc &sd, const DevUpdate &u, int64_t c,
+                                                 const RwPre &r, double S, const CoopStage *cs = nullptr) {
+    const Decision dec = rw_decide_commit<SP>(d, u, c, r, S);
+    post_decision<SP>(d, sd, u, c, dec.accepted, dec.ll_new, dec.ll_prop, rw_n_eps<SP>(u), cs);
+    return dec.accepted;
 }
 
 // ---------------------------------------------------------------------------------
@@ -856,8 +903,7 @@ __device__ __forceinline__ void mala_propose_chain(const DevState &d, const Step
 // The chain's own thread: decision, commit, history, counters; cs: staging (see CoopStage; with
 // cs->m the covariance update is left to update_cov_coop).
 template <class SP = SpecAny>
-__device__ __forceinline__ void mala_decide(const DevState &d, const StepDesc &sd, const DevUpdate &u, int64_t c,
-                                            const CoopStage *cs) {
+__device__ __forceinline__ Decision mala_decide_commit(const DevState &d, const StepDesc &sd, const DevUpdate &u, int64_t c) {
     const int64_t C = d.C;
     const int n = u.n_coords;
     const double tau = u.eps[c], h2 = tau * tau / 2.0;
@@ -911,7 +957,13 @@ __device__ __forceinline__ void mala_decide(const DevState &d, const StepDesc &s
             for (int q = 0; q < 4; ++q) if (j0 + q < d.p) d.grad_cur[(int64_t)(j0 + q) * C + c] = g[q];
         }
     }
-    post_decision<SP>(d, sd, u, c, accepted, ll_new, ll_prop, 1, cs);
+    return Decision{accepted, ll_new, ll_prop};
+}
+template <class SP = SpecAny>
+__device__ __forceinline__ void mala_decide(const DevState &d, const StepDesc &sd, const DevUpdate &u, int64_t c,
+                                            const CoopStage *cs) {
+    const Decision dec = mala_decide_commit<SP>(d, sd, u, c);
+    post_decision<SP>(d, sd, u, c, dec.accepted, dec.ll_new, dec.ll_prop, 1, cs);
 }
 
 // ---- cross-rank exchange of the per-chain sums (observation sharding, peer stores) ------------

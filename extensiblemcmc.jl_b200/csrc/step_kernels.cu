@@ -215,10 +215,27 @@ accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fuse_ne
     // full covariance of a model with more than a handful of parameters: all slices share the work
     const bool stage = SL >= 8 && d.p > 4 && d.p <= kCoopP;   // CTA-uniform
     const bool coop = stage && d.stats_mode == 0;
-    if (worker) {
-        const CoopStage cs{sh_t, coop ? sh_m : nullptr, sh_n, kRedChains, (int)(threadIdx.x % kRedChains)};
-        rw_accept_finish<SP>(d, sd, u, c, pre, S, stage ? &cs : nullptr);
+    const CoopStage cs{sh_t, coop ? sh_m : nullptr, sh_n, kRedChains, (int)(threadIdx.x % kRedChains)};
+    // Task split (lean instantiations, sliced layouts): once the decision is committed, the next
+    // element's proposal runs on the chains' lanes of warp 1 while the worker lanes (warp 0) do the
+    // bookkeeping -- both are latency-bound single-warp instruction streams.  Not when the next
+    // element is the same update: its proposal must see this step's adapted step size.
+    const bool split = SL >= 8 && SP::kLean && fuse_next == 1 && ctx_next.sd.pidx != sd.pidx;   // CTA-uniform
+    if (split) {
+        const bool prop_lane = (threadIdx.x >> 5) == 1 && (threadIdx.x & 31) < kRedChains && c < d.C;
+        Decision dec{};
+        if (worker) dec = rw_decide_commit<SP>(d, u, c, pre, S);
+        __syncthreads();   // the committed state is visible to the proposal lanes
+        if (worker) post_decision_moments<SP>(d, sd, c, dec.accepted, dec.ll_new, dec.ll_prop, stage ? &cs : nullptr);
+        else if (prop_lane) propose_draw<SP>(d, ctx_next.sd, ctx_next.u, c);
+        __syncthreads();   // prop_full has been read for the history row; the staging is complete
+        if (worker) post_decision_counters<SP>(d, sd, u, c, dec.accepted, rw_n_eps<SP>(u));
+        else if (prop_lane) propose_set<SP>(d, ctx_next.u, c);
+        if (coop)
+            update_cov_coop(d, sd.stat_n, (int64_t)blockIdx.x * kRedChains, kRedChains, sh_t, sh_m, sh_n, threadIdx.x, blockDim.x);
+        return;
     }
+    if (worker) rw_accept_finish<SP>(d, sd, u, c, pre, S, stage ? &cs : nullptr);
     if (coop) {
         __syncthreads();
         update_cov_coop(d, sd.stat_n, (int64_t)blockIdx.x * kRedChains, kRedChains, sh_t, sh_m, sh_n, threadIdx.x, blockDim.x);
@@ -329,10 +346,21 @@ mala_accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fi
     const bool worker = threadIdx.x < kMalaChains && c < d.C;
     const bool stage = d.p <= kCoopP;   // CTA-uniform
     const bool coop = stage && d.stats_mode == 0;
-    if (worker) {
-        const CoopStage cs{sh_t, coop ? sh_m : nullptr, sh_n, kMalaChains, ch};
-        mala_decide<SP>(d, ctx.sd, ctx.u, c, stage ? &cs : nullptr);
+    const CoopStage cs{sh_t, coop ? sh_m : nullptr, sh_n, kMalaChains, ch};
+    if (SP::kLean && fuse_next) {   // task split as in accept_kernel (the next element is another update)
+        const bool prop_lane = (threadIdx.x >> 5) == 1 && c < d.C;
+        Decision dec{};
+        if (worker) dec = mala_decide_commit<SP>(d, ctx.sd, ctx.u, c);
+        __syncthreads();
+        if (worker) post_decision_moments<SP>(d, ctx.sd, c, dec.accepted, dec.ll_new, dec.ll_prop, stage ? &cs : nullptr);
+        else if (prop_lane) propose_draw<SP>(d, ctx_next.sd, ctx_next.u, c);
+        __syncthreads();
+        if (worker) post_decision_counters<SP>(d, ctx.sd, ctx.u, c, dec.accepted, 1);
+        else if (prop_lane) propose_set<SP>(d, ctx_next.u, c);
+        if (coop) update_cov_coop(d, ctx.sd.stat_n, c0, kMalaChains, sh_t, sh_m, sh_n, threadIdx.x, blockDim.x);
+        return;
     }
+    if (worker) mala_decide<SP>(d, ctx.sd, ctx.u, c, stage ? &cs : nullptr);
     if (coop) {
         __syncthreads();
         update_cov_coop(d, ctx.sd.stat_n, c0, kMalaChains, sh_t, sh_m, sh_n, threadIdx.x, blockDim.x);
@@ -437,7 +465,9 @@ static inline int red_blocks_for(int64_t C, int sl) {
 static inline int slices_for(const DevState &d) {
     // a full covariance of more than a handful of parameters is updated by all slices (update_cov_coop)
     const bool stage = d.p > 4 && d.p <= kCoopP;
-    if (!stage && (d.use_ssum || d.S * d.G <= 16)) return 1;
+    // one thread per chain only when there is nothing to share AND the grid would still fill the GPU:
+    // the sliced layouts also give the next proposal a warp of its own (accept_kernel, task split)
+    if (!stage && (d.use_ssum || d.S * d.G <= 16) && d.C >= 32768) return 1;
     return d.C <= 8 ? 32 : 8;
 }
 void launch_accept(const DevState &d, const StepDesc *descs, int k, int fuse_next, cudaStream_t st) {
