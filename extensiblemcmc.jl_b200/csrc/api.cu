@@ -136,7 +136,7 @@ struct extmcmc_handle {
     int64_t fetch_lo = 0, fetch_hi = 0;
     bool fetch_active = false;
     // fused peer exchange
-    void *p2p_region = nullptr;                 // rx[2][W][C] doubles followed by flag[2][W] u64
+    void *p2p_region = nullptr;                 // rx[2][W][C] tagged 16-byte cells (exchange.cuh)
     std::vector<void *> p2p_opened;             // peer mappings to close
     // multi-rank
     ncclComm_t comm = nullptr;
@@ -346,7 +346,7 @@ int32_t enqueue_sweep(extmcmc_t h, bool instrument, bool grad = false, const dou
             const bool push = obs_sharded(h) && h->d.p2p && d_descs;
             a.tail_mode = push ? 2 : 1;
             a.tail_counter = h->tail_counter; a.ssum = h->d.ssum;
-            a.peer_rx = h->d.peer_rx; a.peer_flag = h->d.peer_flag;
+            a.peer_rx = h->d.peer_rx;
             a.rank = h->cfg.rank; a.world = h->cfg.world_size;
             a.descs = d_descs; a.k = k;
         }
@@ -1327,7 +1327,7 @@ int32_t extmcmc_comm_init(extmcmc_t h, const uint8_t id_in[128]) {
 
 static size_t p2p_region_bytes(extmcmc_t h) {
     const size_t W = (size_t)h->cfg.world_size;
-    return 2 * W * (size_t)h->d.C * sizeof(double) + 2 * W * sizeof(unsigned long long);
+    return 2 * W * (size_t)h->d.C * 2 * sizeof(unsigned long long);   // rx[2][W][C] cells of two tagged words
 }
 
 int32_t extmcmc_p2p_export(extmcmc_t h, uint8_t handle_out[64]) {
@@ -1352,9 +1352,7 @@ int32_t extmcmc_p2p_import(extmcmc_t h, const uint8_t *handles) {
     if (!h->p2p_region) return fail(h, EXTMCMC_EINVAL, "call extmcmc_p2p_export first");
     CK(h, cudaSetDevice(h->cfg.device));
     const int W = h->cfg.world_size;
-    const size_t rx_bytes = 2 * (size_t)W * h->d.C * sizeof(double);
-    std::vector<double *> rx(W);
-    std::vector<unsigned long long *> fl(W);
+    std::vector<unsigned long long *> rx(W);
     for (int q = 0; q < W; ++q) {
         void *base = nullptr;
         if (q == h->cfg.rank) {
@@ -1365,18 +1363,12 @@ int32_t extmcmc_p2p_import(extmcmc_t h, const uint8_t *handles) {
             CK(h, cudaIpcOpenMemHandle(&base, hd, cudaIpcMemLazyEnablePeerAccess));
             h->p2p_opened.push_back(base);
         }
-        rx[q] = (double *)base;
-        fl[q] = (unsigned long long *)((char *)base + rx_bytes);
+        rx[q] = (unsigned long long *)base;
     }
     int32_t rc;
-    if ((rc = dev_alloc(h, &h->d.peer_rx, (size_t)W)) || (rc = dev_alloc(h, &h->d.peer_flag, (size_t)W)) ||
-        (rc = dev_alloc(h, &h->d.push_counter, 1)))
-        return rc;
-    CK(h, cudaMemcpy(h->d.peer_rx, rx.data(), sizeof(double *) * W, cudaMemcpyHostToDevice));
-    CK(h, cudaMemcpy(h->d.peer_flag, fl.data(), sizeof(unsigned long long *) * W, cudaMemcpyHostToDevice));
-    CK(h, cudaMemset(h->d.push_counter, 0, sizeof(unsigned int)));
+    if ((rc = dev_alloc(h, &h->d.peer_rx, (size_t)W))) return rc;
+    CK(h, cudaMemcpy(h->d.peer_rx, rx.data(), sizeof(unsigned long long *) * W, cudaMemcpyHostToDevice));
     h->d.my_rx = rx[h->cfg.rank];
-    h->d.my_flag = fl[h->cfg.rank];
     h->d.rank = h->cfg.rank;
     h->d.world = W;
     h->d.p2p = 1;

@@ -754,26 +754,20 @@ obs_block_kernel(ObsBlockArgs a) {
             // cross-rank exchange: store this rank's totals into every rank's slot, raise the flag
             // there, wait for everybody's flag here, add the slots in rank order
             const int parity = (int)(xseq & 1);
+            const uint32_t tag = (uint32_t)(xseq + 1);
+            int mine = 1;
             if (tid < CB && tid < C) {
-                const int64_t slot = ((int64_t)parity * d.world + d.rank) * C + tid;
-                for (int q = 0; q < d.world; ++q) d.peer_rx[q][slot] = tot;
-            }
-            __threadfence_system();
-            __syncthreads();
-            if (tid == 0) {
-                const unsigned long long tag = (unsigned long long)(xseq + 1);
-                for (int q = 0; q < d.world; ++q) {
-                    unsigned long long *f = d.peer_flag[q] + (parity * d.world + d.rank);
-                    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(tag) : "memory");
-                }
-                sh_alive = wait_peer_flags(d, parity, tag) ? 1 : 0;
-            }
-            __syncthreads();
-            alive = sh_alive != 0;
-            if (alive && tid < CB && tid < C) {
+                const int64_t cell = ll_cell(parity, d.world, d.rank, C, tid);
+                for (int q = 0; q < d.world; ++q) ll_store(d.peer_rx[q] + cell, tot, tag);
+                const unsigned long long t0 = global_timer_ns();
                 tot = 0.0;
-                for (int r = 0; r < d.world; ++r) tot += __ldcg(d.my_rx + ((int64_t)parity * d.world + r) * C + tid);
+                for (int r = 0; r < d.world && mine; ++r) {
+                    double v;
+                    if (ll_load(d.my_rx + ll_cell(parity, d.world, r, C, tid), tag, v, t0, d.p2p_timeout_ns)) tot += v;
+                    else { atomicExch(d.err_flag, 2); mine = 0; }
+                }
             }
+            alive = __syncthreads_and(mine) != 0;
         }
         const bool more = k + 1 < a.n_steps;
         if (alive) {

@@ -123,18 +123,16 @@ struct DevState {
     const double *rp_prop;  // [rows][p_u_max][C]
     const double *rp_exp;   // [rows][C]
     // fused cross-GPU exchange of the per-chain sums under observation sharding (no NCCL on the
-    // hot path): every rank pushes its sums into slot [parity][rank] of every peer's rx buffer
-    // over NVLink peer mappings and raises a sequence flag; the consumer waits for all flags and
-    // adds the slots in rank order (identical totals on every rank).  parity = xseq & 1,
-    // tag = xseq + 1: xseq is never reset, so a slot is only reused two exchanges later, after
-    // every rank has consumed it.
+    // hot path): every rank stores its sums into cell [parity][rank][chain] of every rank's rx
+    // buffer over NVLink peer mappings; a cell is two 8-byte words that each carry the exchange's
+    // sequence tag (exchange.cuh), so there is no fence and no flag; the consumer polls the cells and
+    // adds them in rank order (identical totals on every rank).  parity = xseq & 1, tag = xseq + 1:
+    // xseq is never reset, so a cell is only rewritten two exchanges later, after every rank has
+    // consumed it.
     int32_t p2p, rank, world;
-    double **peer_rx;                   // [world] -> rx[2][world][C] of each rank
-    unsigned long long **peer_flag;     // [world] -> flag[2][world] of each rank
-    double *my_rx;
-    unsigned long long *my_flag;
-    unsigned int *push_counter;
-    unsigned long long p2p_timeout_ns;  // bounded wait for the peers' flags
+    unsigned long long **peer_rx;       // [world] -> rx[2][world][C][2] of each rank
+    unsigned long long *my_rx;
+    unsigned long long p2p_timeout_ns;  // bounded wait for the peers' cells
     int32_t *err_flag;      // sticky: 1 = a chain left the law's domain, 2 = peer exchange timed out
                             // (2: every later step is a no-op until the host has seen it)
     DevUpdate *upd;         // [NU]

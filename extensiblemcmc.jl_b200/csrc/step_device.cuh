@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 #include "dev_state.cuh"
 #include "philox.cuh"
+#include "exchange.cuh"
 
 namespace extmcmc {
 
@@ -964,31 +965,6 @@ __device__ __forceinline__ void mala_decide(const DevState &d, const StepDesc &s
                                             const CoopStage *cs) {
     const Decision dec = mala_decide_commit<SP>(d, sd, u, c);
     post_decision<SP>(d, sd, u, c, dec.accepted, dec.ll_new, dec.ll_prop, 1, cs);
-}
-
-// ---- cross-rank exchange of the per-chain sums (observation sharding, peer stores) ------------
-__device__ __forceinline__ unsigned long long global_timer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
-// One thread: wait until every rank's flag of this exchange has reached `tag`.  false on timeout
-// (the sticky error flag is raised: nobody commits anything any more until the host has seen it).
-__device__ __forceinline__ bool wait_peer_flags(const DevState &d, int parity, unsigned long long tag) {
-    const unsigned long long t0 = global_timer_ns();
-    for (int r = 0; r < d.world; ++r) {
-        const unsigned long long *f = d.my_flag + (parity * d.world + r);
-        unsigned long long v;
-        for (;;) {
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
-            if (v >= tag) break;
-            if (global_timer_ns() - t0 > d.p2p_timeout_ns) {
-                atomicExch(d.err_flag, 2);
-                return false;
-            }
-        }
-    }
-    return true;
 }
 
 }  // namespace extmcmc

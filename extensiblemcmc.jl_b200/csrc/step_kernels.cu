@@ -14,6 +14,7 @@
 #include "step_device.cuh"
 #include "step_kernels.h"
 #include "tma.cuh"
+#include "exchange.cuh"
 #include "sweep.h"
 
 namespace extmcmc {
@@ -118,12 +119,11 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(DevState d) {
 }
 
 // Reduce this rank's partial sums and push them to every rank (itself included) through peer
-// pointers; the last CTA to finish raises this rank's flag on every peer (threadfence pattern).
+// pointers, as tagged cells (exchange.cuh): nothing else to signal.
 template <int SL>
 __global__ void __launch_bounds__(256)
 reduce_push_kernel(DevState d, const StepDesc *__restrict__ descs, int k) {
     __shared__ double sh[kRedThreads];
-    __shared__ bool last;
     constexpr int kRedChains = kRedThreads / SL;
     // PDL chain sweep -> reduce_push -> accept: start early, let the accept kernel start early
     // too (its prologue then overlaps the sweep), and wait for the sweep before touching its sums
@@ -134,35 +134,29 @@ reduce_push_kernel(DevState d, const StepDesc *__restrict__ descs, int k) {
     const double tot = reduce_segments<SL>(d, sh);
     const int64_t c = (int64_t)blockIdx.x * kRedChains + (threadIdx.x % kRedChains);
     if ((threadIdx.x / kRedChains) == 0 && c < d.C) {
-        const int64_t slot = ((int64_t)parity * d.world + d.rank) * d.C + c;
-        for (int q = 0; q < d.world; ++q) d.peer_rx[q][slot] = tot;
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) last = atomicAdd(d.push_counter, 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (last && threadIdx.x == 0) {
-        *d.push_counter = 0;
-        __threadfence_system();
-        const unsigned long long tag = (unsigned long long)(sd.xseq + 1);
-        for (int q = 0; q < d.world; ++q) {
-            unsigned long long *f = d.peer_flag[q] + (parity * d.world + d.rank);
-            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(tag) : "memory");
-        }
+        const int64_t cell = ll_cell(parity, d.world, d.rank, d.C, c);
+        const uint32_t tag = (uint32_t)(sd.xseq + 1);
+        for (int q = 0; q < d.world; ++q) ll_store(d.peer_rx[q] + cell, tot, tag);
     }
 }
 
 // Wait until every rank's sums of this step have landed, then add them in rank order.  ok = false
 // (CTA-uniform) when the wait timed out: the caller must not commit anything.
-__device__ __forceinline__ double wait_and_combine(const DevState &d, const StepDesc &sd, int64_t c, bool &ok) {
-    __shared__ int sh_ok;
+// `reader`: the threads that need the sum (one per chain).
+__device__ __forceinline__ double wait_and_combine(const DevState &d, const StepDesc &sd, int64_t c, bool reader, bool &ok) {
     const int parity = (int)(sd.xseq & 1);
-    if (threadIdx.x == 0) sh_ok = wait_peer_flags(d, parity, (unsigned long long)(sd.xseq + 1)) ? 1 : 0;
-    __syncthreads();
-    ok = sh_ok != 0;
+    const uint32_t tag = (uint32_t)(sd.xseq + 1);
     double s = 0.0;
-    if (ok && c < d.C)
-        for (int r = 0; r < d.world; ++r) s += __ldcg(d.my_rx + ((int64_t)parity * d.world + r) * d.C + c);
+    int mine = 1;
+    if (reader && c < d.C) {
+        const unsigned long long t0 = global_timer_ns();
+        for (int r = 0; r < d.world && mine; ++r) {
+            double v;
+            if (ll_load(d.my_rx + ll_cell(parity, d.world, r, d.C, c), tag, v, t0, d.p2p_timeout_ns)) s += v;
+            else { atomicExch(d.err_flag, 2); mine = 0; }
+        }
+    }
+    ok = __syncthreads_and(mine) != 0;
     return s;
 }
 
@@ -205,7 +199,7 @@ accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fuse_ne
     double S;
     if (d.p2p) {
         bool ok;
-        S = wait_and_combine(d, ctx.sd, c, ok);
+        S = wait_and_combine(d, ctx.sd, c, (threadIdx.x / kRedChains) == 0 && !dead, ok);
         if (!ok) return;   // nothing is committed; the sticky flag turns the steps to come into no-ops
     } else if (d.use_ssum) {
         S = c < d.C ? d.ssum[c] : 0.0;

@@ -46,8 +46,7 @@ struct Gsn1dArgs {
     int tail_mode;
     unsigned int *tail_counter;
     double *ssum;
-    double **peer_rx;
-    unsigned long long **peer_flag;
+    unsigned long long **peer_rx;   // [world] -> rx[2][world][C][2] of each rank (exchange.cuh)
     int rank, world;
     const void *descs;       // StepDesc array of the block (device), element k names the step
     int k;

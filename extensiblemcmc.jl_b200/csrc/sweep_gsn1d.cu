@@ -32,6 +32,7 @@
 #include "dev_state.cuh"
 #include "sweep.h"
 #include "tma.cuh"
+#include "exchange.cuh"
 
 namespace extmcmc {
 
@@ -277,29 +278,22 @@ sweep_gsn1d_obs_kernel(Gsn1dArgs a) {
     double *sh = reinterpret_cast<double *>(smem_raw);   // the tile ring is free now
     sh[sl * CB + ch] = acc2;
     __syncthreads();
-    if (tid < CB && tid < C) {
-        double tot = 0.0;
+    double tot = 0.0;
+    if (tid < CB && tid < C)
         for (int j = 0; j < NS; ++j) tot += sh[j * CB + tid];
-        if (a.tail_mode == 1) {
-            a.ssum[tid] = tot;
-        } else {
-            const StepDesc *sd = reinterpret_cast<const StepDesc *>(a.descs) + a.k;
-            const int parity = (int)(sd->xseq & 1);
-            const int64_t slot = ((int64_t)parity * a.world + a.rank) * C + tid;
-            for (int q = 0; q < a.world; ++q) a.peer_rx[q][slot] = tot;   // stores into peer memory
-        }
-    }
-    if (a.tail_mode == 2) {
-        __threadfence_system();
+    if (a.tail_mode == 1) {
+        if (tid < CB && tid < C) a.ssum[tid] = tot;
+    } else {
+        // one thread per (peer, chain): a tagged 16-byte cell straight into that rank's buffer
         __syncthreads();
-        if (tid == 0) {
-            const StepDesc *sd = reinterpret_cast<const StepDesc *>(a.descs) + a.k;
-            const int parity = (int)(sd->xseq & 1);
-            const unsigned long long tag = (unsigned long long)(sd->xseq + 1);
-            for (int q = 0; q < a.world; ++q) {
-                unsigned long long *f = a.peer_flag[q] + (parity * a.world + a.rank);
-                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(tag) : "memory");
-            }
+        if (tid < CB) sh[tid] = tot;
+        __syncthreads();
+        const StepDesc *sd = reinterpret_cast<const StepDesc *>(a.descs) + a.k;
+        const int parity = (int)(sd->xseq & 1);
+        const uint32_t tag = (uint32_t)(sd->xseq + 1);
+        for (int i = tid; i < a.world * CB; i += NT) {
+            const int q = i / CB, ch = i % CB;
+            if (ch < C) ll_store(a.peer_rx[q] + ll_cell(parity, a.world, a.rank, C, ch), sh[ch], tag);
         }
     }
     if (tid == 0) *a.tail_counter = 0u;
