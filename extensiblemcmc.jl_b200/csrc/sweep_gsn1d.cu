@@ -377,7 +377,11 @@ SweepPlan plan_sweep_gsn1d(int64_t C, int64_t n_obs, int force_variant, int num_
         int R = 8, S = 1, groups = 1;
         for (;; R >>= 1) {
             groups = (int)((C + (int64_t)kChainsNT * R - 1) / ((int64_t)kChainsNT * R));
-            S = (num_sms * 4 + groups * G - 1) / (groups * G);
+            // 8 CTAs of 128 threads x 62 registers fill an SM's register file: 8 warps per scheduler hide
+            // the DADD -> DFMA latency that ptxas's register-minimal schedule leaves exposed (measured at
+            // cfg 2: 0.4724 ms per sweep with 4 CTAs per SM, 0.4643 with 8; EXTMCMC_CHAINS_CTAS overrides)
+            static const int ctas_per_sm = [] { const char *e = getenv("EXTMCMC_CHAINS_CTAS"); return e && atoi(e) > 0 ? atoi(e) : 8; }();
+            S = (num_sms * ctas_per_sm + groups * G - 1) / (groups * G);
             if (S > max_S) S = (int)max_S;
             if (S < 1) S = 1;
             // The FP64 pipe of an SM is shared by its resident CTAs, so the sweep lasts as long as
