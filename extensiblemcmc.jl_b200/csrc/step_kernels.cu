@@ -1,9 +1,10 @@
 // K1 (proposal), K3 (accept / commit / statistics / adaptation) and the MALA kernels of the
-// per-step path: one kernel per stage of an update step.  This is the general path (any law, any
-// transition kernel, any shape); the shapes BASELINE names run through the persistent block
-// kernels of block_kernels.cu instead.  One thread owns a chain's scalar work (step_device.cuh);
-// the reductions of the sweep's partial sums and the covariance update of mid-sized models are
-// shared by the 8 "slices" (threads) a CTA assigns to every chain.  Compiled with -fmad=false: the
+// per-step path: one kernel per stage of an update step -- the default path for every law, transition
+// kernel and shape (the persistent block kernels of block_kernels.cu are opt-in variants).  Every
+// kernel exists in a general instantiation (SpecAny) and in lean ones (SpecLean<LAW>, step_device.cuh)
+// the host picks per handle.  One thread owns a chain's scalar work; the reductions of the sweep's
+// partial sums and the covariance update of mid-sized models are shared by the 8 "slices" (threads) a
+// CTA assigns to every chain, and the next element's proposal runs on the lanes of a second warp.  Compiled with -fmad=false: the
 // reference never contracts a*b+c, and the replay parity tests compare eps, running moments and
 // trajectories bit-for-bit against the CPU oracle.
 #include <cmath>

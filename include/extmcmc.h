@@ -259,8 +259,9 @@ int32_t extmcmc_comm_unique_id(uint8_t id_out[128]);
 int32_t extmcmc_comm_init(extmcmc_t h, const uint8_t id[128]);
 
 /* Optional, on top of extmcmc_comm_init: the library's own exchange of the per-chain sums
- * (peer stores over NVLink + sequence flags, combined inside the accept kernel) instead of
- * ncclAllReduce on the hot path.  Every rank exports a 64-byte CUDA IPC handle, the host ships
+ * (self-validating tagged cells stored straight into every peer's buffer over NVLink, polled and
+ * combined in rank order inside the accept kernel: no fence, no flag) instead of ncclAllReduce on
+ * the hot path.  Every rank exports a 64-byte CUDA IPC handle, the host ships
  * all of them to every rank (handles[world][64], rank order), every rank imports.  All ranks
  * must then call set_state / run_block in lock-step (they do: state and schedule are replicated). */
 int32_t extmcmc_p2p_export(extmcmc_t h, uint8_t handle_out[64]);
