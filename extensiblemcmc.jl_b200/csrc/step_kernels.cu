@@ -217,15 +217,22 @@ accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fuse_ne
     // element is the same update: its proposal must see this step's adapted step size.
     const bool split = SL >= 8 && SP::kLean && fuse_next == 1 && ctx_next.sd.pidx != sd.pidx;   // CTA-uniform
     if (split) {
-        const bool prop_lane = (threadIdx.x >> 5) == 1 && (threadIdx.x & 31) < kRedChains && c < d.C;
+        // lanes of warp 1: the next proposal; lanes of warp 2: rolling acceptance rate, totals, adaptation
+        const bool lane_ok = (threadIdx.x & 31) < kRedChains && c < d.C;
+        const bool prop_lane = (threadIdx.x >> 5) == 1 && lane_ok;
+        const bool cnt_lane = (threadIdx.x >> 5) == 2 && lane_ok;
+        __shared__ uint8_t sh_acc[kRedChains];
         Decision dec{};
-        if (worker) dec = rw_decide_commit<SP>(d, u, c, pre, S);
-        __syncthreads();   // the committed state is visible to the proposal lanes
+        if (worker) {
+            dec = rw_decide_commit<SP>(d, u, c, pre, S);
+            sh_acc[threadIdx.x % kRedChains] = dec.accepted ? 1 : 0;
+        }
+        __syncthreads();   // the committed state and the decisions are visible to the other warps
         if (worker) post_decision_moments<SP>(d, sd, c, dec.accepted, dec.ll_new, dec.ll_prop, stage ? &cs : nullptr);
         else if (prop_lane) propose_draw<SP>(d, ctx_next.sd, ctx_next.u, c);
+        else if (cnt_lane) post_decision_counters<SP>(d, sd, u, c, sh_acc[threadIdx.x % kRedChains] != 0, rw_n_eps<SP>(u));
         __syncthreads();   // prop_full has been read for the history row; the staging is complete
-        if (worker) post_decision_counters<SP>(d, sd, u, c, dec.accepted, rw_n_eps<SP>(u));
-        else if (prop_lane) propose_set<SP>(d, ctx_next.u, c);
+        if (prop_lane) propose_set<SP>(d, ctx_next.u, c);
         if (coop)
             update_cov_coop(d, sd.stat_n, (int64_t)blockIdx.x * kRedChains, kRedChains, sh_t, sh_m, sh_n, threadIdx.x, blockDim.x);
         return;
@@ -319,6 +326,45 @@ mala_propose_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int f
     // the sweep just before this kernel evaluated the CURRENT state: finish its sums here
     // (gradient of the current state) instead of in a kernel of its own
     if (finalize_cur) grad_finalize_coop<SP>(d, c0, d.theta, ll_scratch, d.grad_cur, sh2, sh1);
+    if (SP::kLean && d.rng_mode != EXTMCMC_RNG_REPLAY) {   // CTA-uniform
+        // The Box-Muller pairs of a chain's proposal are independent (counter-based stream: pair q
+        // reads Philox block q): slice q % 8 draws pair q while the slices also share the copy of the
+        // state into prop_full.  Same expressions as mala_propose_chain, coordinate by coordinate.
+        if (finalize_cur) __syncthreads();   // grad_cur of this CTA's chains is complete
+        const int slice = threadIdx.x / kMalaChains;
+        const DevUpdate &u = ctx.u;
+        const StepDesc &sd = ctx.sd;
+        const int n = u.n_coords;
+        const int64_t C = d.C;
+        const bool live = c < C;
+        if (live)
+            for (int j = slice; j < d.p; j += kMalaSlices) d.prop_full[(int64_t)j * C + c] = d.theta[(int64_t)j * C + c];
+        __syncthreads();   // the copy of the state is complete: the update's coordinates may be overwritten
+        const double tau = live ? u.eps[c] : 1.0, h2 = tau * tau / 2.0;
+        const int n_pairs = (n + 1) / 2;
+        if (live)
+            for (int q = slice; q < n_pairs; q += kMalaSlices) {
+                ChainStepStream rng(d.seed, (uint64_t)(d.chain_offset + c), sd.mcmciter, sd.pidx, (uint32_t)(2 * q));
+                const double u1 = rng.next(), u2 = rng.next();
+                const double rad = sqrt(-2.0 * log(u1));
+                double sn, cs;
+                sincospi(2.0 * u2, &sn, &cs);
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int i = 2 * q + e;
+                    if (i >= n) break;
+                    const int64_t j = u.coords_dev[i];
+                    const double th = d.theta[j * C + c];
+                    const double g = d.grad_cur[j * C + c] + prior_grad(u, th);
+                    d.prop_full[j * C + c] = th + h2 * g + tau * (rad * (e ? sn : cs));
+                }
+            }
+        __syncthreads();
+        if (slice != 0 || !live) return;
+        d.n_used[c] = (uint32_t)(2 * n_pairs);
+        law_prepare<SP>(d, c, d.prop_full + c, C);
+        return;
+    }
     if (threadIdx.x >= kMalaChains || c >= d.C) return;
     mala_propose_chain<SP>(d, ctx.sd, ctx.u, c);
 }
@@ -344,14 +390,19 @@ mala_accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fi
     const CoopStage cs{sh_t, coop ? sh_m : nullptr, sh_n, kMalaChains, ch};
     if (SP::kLean && fuse_next) {   // task split as in accept_kernel (the next element is another update)
         const bool prop_lane = (threadIdx.x >> 5) == 1 && c < d.C;
+        const bool cnt_lane = (threadIdx.x >> 5) == 2 && c < d.C;
+        __shared__ uint8_t sh_acc[kMalaChains];
         Decision dec{};
-        if (worker) dec = mala_decide_commit<SP>(d, ctx.sd, ctx.u, c);
+        if (worker) {
+            dec = mala_decide_commit<SP>(d, ctx.sd, ctx.u, c);
+            sh_acc[ch] = dec.accepted ? 1 : 0;
+        }
         __syncthreads();
         if (worker) post_decision_moments<SP>(d, ctx.sd, c, dec.accepted, dec.ll_new, dec.ll_prop, stage ? &cs : nullptr);
         else if (prop_lane) propose_draw<SP>(d, ctx_next.sd, ctx_next.u, c);
+        else if (cnt_lane) post_decision_counters<SP>(d, ctx.sd, ctx.u, c, sh_acc[ch] != 0, 1);
         __syncthreads();
-        if (worker) post_decision_counters<SP>(d, ctx.sd, ctx.u, c, dec.accepted, 1);
-        else if (prop_lane) propose_set<SP>(d, ctx_next.u, c);
+        if (prop_lane) propose_set<SP>(d, ctx_next.u, c);
         if (coop) update_cov_coop(d, ctx.sd.stat_n, c0, kMalaChains, sh_t, sh_m, sh_n, threadIdx.x, blockDim.x);
         return;
     }
