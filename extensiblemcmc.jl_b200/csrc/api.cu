@@ -420,6 +420,8 @@ int32_t enqueue_steps(extmcmc_t h, const StepDesc *d_descs, const int *kinds, in
     bool cur_prepared = false;  // accept(k-1) already wrote the law constants of the current state
     for (int k = 0; k < n_steps; ++k) {
         int32_t rc;
+        // deferred bookkeeping between consecutive elements of this block (step_kernels.cu, run_deferred)
+        const int dflags = step_deferral_flags(h->d, k, n_steps);
         const bool next_mala = k + 1 < n_steps && kinds[k + 1] == EXTMCMC_KERNEL_MALA;
         const bool next_rw = k + 1 < n_steps && kinds[k + 1] != EXTMCMC_KERNEL_MALA;
         if (kinds[k] == EXTMCMC_KERNEL_MALA) {
@@ -437,14 +439,14 @@ int32_t enqueue_steps(extmcmc_t h, const StepDesc *d_descs, const int *kinds, in
                 }
             }
             const DevState gv = grad_view(h);
-            launch_mala_propose(gv, d_descs, k, finalize_cur, h->scratch_ll, h->stream);
+            launch_mala_propose(gv, d_descs, k, finalize_cur, h->scratch_ll, dflags, h->stream);
             if (logi) {
                 if ((rc = enqueue_sweep(h, instrument, true, h->d.prop_full, h->d.ll_prop, h->d.grad_prop))) return rc;
             } else {
                 if ((rc = enqueue_sweep(h, instrument, true, h->d.prop_full))) return rc;   // finished inside mala_accept
             }
             fused = next_rw;   // the next random-walk proposal rides on this accept kernel
-            launch_mala_accept(gv, d_descs, k, logi ? 0 : 1, fused ? 1 : 0, h->stream);
+            launch_mala_accept(gv, d_descs, k, logi ? 0 : 1, fused ? 1 : 0, dflags, h->stream);
             h->launches += 2;
             grad_valid = true;
             cur_prepared = false;
@@ -455,7 +457,7 @@ int32_t enqueue_steps(extmcmc_t h, const StepDesc *d_descs, const int *kinds, in
             // a MALA element follows and will need the law constants of the (then) current state for
             // its gradient sweep: let this accept kernel write them (fuse_next = 2)
             cur_prepared = next_mala && h->cfg.law != EXTMCMC_LAW_LOGISTIC && h->cfg.law != EXTMCMC_LAW_HIER_NORMAL;
-            launch_accept(h->d, d_descs, k, fused ? 1 : (cur_prepared ? 2 : 0), h->stream);
+            launch_accept(h->d, d_descs, k, fused ? 1 : (cur_prepared ? 2 : 0), dflags, h->stream);
             h->launches += 1;
             grad_valid = false;
         }

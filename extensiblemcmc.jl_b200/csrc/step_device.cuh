@@ -555,11 +555,15 @@ __device__ __forceinline__ void update_cov_coop(const DevState &d, int64_t N, in
 // Two halves (a step kernel may run the next proposal on another warp in between, see propose_draw):
 // post_decision_moments -- history row + running moments, reads theta / prop_full / mean / cov;
 // post_decision_counters -- rolling acceptance rate, totals, adaptation.  post_decision = both.
-template <class SP = SpecAny>
+// HIST / MOM select the two parts of the first half: the history row (+ the carried ll) and the running
+// moments.  A step kernel that DEFERS its bookkeeping writes only the history row (the full proposal is
+// about to be overwritten by the next one); moments and counters are then run by the next step kernel
+// in its prologue, behind the next sweep (step_kernels.cu, "deferred bookkeeping").
+template <class SP = SpecAny, bool HIST = true, bool MOM = true>
 __device__ __forceinline__ void post_decision_moments(const DevState &d, const StepDesc &sd, int64_t c, bool accepted,
                                                       double ll_new, double ll_prop, const CoopStage *cs = nullptr) {
     const int64_t C = d.C;
-    d.ll[c] = ll_new;
+    if (HIST) d.ll[c] = ll_new;
     // history row (state_history / state_proposal_history / ll_history / acceptance_history)
     const int64_t slot = sd.seq % d.H;
     const int64_t hc = d.g0 + c;       // this chain's column in the arrays that stay global
@@ -567,8 +571,8 @@ __device__ __forceinline__ void post_decision_moments(const DevState &d, const S
     const double f_old = (double)(N - 1) / (double)N;
     const double f_mean = (double)N / (double)(N + 1);
     const double f_new = (double)(N + 1) / (double)N;
-    const bool coop_full = cs && cs->m;        // full covariance left to update_cov_coop
-    const bool diag = d.stats_mode == 1;
+    const bool coop_full = MOM && cs && cs->m;        // full covariance left to update_cov_coop
+    const bool diag = MOM && d.stats_mode == 1;
     // History row, staging and -- diagonal statistics / cooperative path -- update_stats!
     // (chain_statistics.jl:46-51, verbatim arithmetic); loads in batches of 4 ahead of the stores
     // (the stores may alias the loads as far as the compiler knows, so a plain loop serialises).
@@ -578,7 +582,7 @@ __device__ __forceinline__ void post_decision_moments(const DevState &d, const S
         for (int q = 0; q < 4; ++q)
             if (j0 + q < d.p) {
                 t[q] = d.theta[(int64_t)(j0 + q) * C + c];
-                pr[q] = d.prop_full[(int64_t)(j0 + q) * C + c];
+                if (HIST) pr[q] = d.prop_full[(int64_t)(j0 + q) * C + c];
                 if (coop_full || diag) m[q] = d.mean[(int64_t)(j0 + q) * C + c];
                 if (diag) cv[q] = d.cov[(int64_t)(j0 + q) * C + c];
             }
@@ -586,9 +590,11 @@ __device__ __forceinline__ void post_decision_moments(const DevState &d, const S
         for (int q = 0; q < 4; ++q)
             if (j0 + q < d.p) {
                 const int j = j0 + q;
-                d.h_theta[(slot * d.p + j) * d.gC + hc] = t[q];
-                d.h_prop[(slot * d.p + j) * d.gC + hc] = pr[q];
-                if (cs) cs->t[j * cs->nch + cs->ch] = t[q];
+                if (HIST) {
+                    d.h_theta[(slot * d.p + j) * d.gC + hc] = t[q];
+                    d.h_prop[(slot * d.p + j) * d.gC + hc] = pr[q];
+                }
+                if (MOM && cs) cs->t[j * cs->nch + cs->ch] = t[q];
                 if (coop_full || diag) {
                     const double m_new = m[q] * f_mean + t[q] / (double)(N + 1);
                     if (coop_full) { cs->m[j * cs->nch + cs->ch] = m[q]; cs->mn[j * cs->nch + cs->ch] = m_new; }
@@ -601,12 +607,14 @@ __device__ __forceinline__ void post_decision_moments(const DevState &d, const S
                 }
             }
     }
-    d.h_ll[slot * d.gC + hc] = ll_new;
-    d.h_llp[slot * d.gC + hc] = ll_prop;
-    d.h_acc[slot * d.gC + hc] = accepted ? 1 : 0;
+    if (HIST) {
+        d.h_ll[slot * d.gC + hc] = ll_new;
+        d.h_llp[slot * d.gC + hc] = ll_prop;
+        d.h_acc[slot * d.gC + hc] = accepted ? 1 : 0;
+    }
 
     // full covariance by this thread alone (more than kCoopP parameters, or no spare threads)
-    if (d.stats_mode == 0 && !coop_full) {
+    if (MOM && d.stats_mode == 0 && !coop_full) {
         const int p = d.p;
         // covariance first (it needs the old mean), column by column
         for (int b = 0; b < p; ++b) {

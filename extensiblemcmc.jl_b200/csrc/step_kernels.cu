@@ -168,15 +168,52 @@ __global__ void __launch_bounds__(256) finalize_loglik_kernel(DevState d, double
 }
 
 // ---------------------------------------------------------------------------------
+// Deferred bookkeeping.  What feeds the next sweep is the decision, the commit and the next proposal;
+// running moments, rolling acceptance rate, totals and adaptation of a step feed nothing before the
+// SAME update's next turn.  In the lean, sliced instantiations the kernel that decides step k - 1
+// therefore writes only the history row and leaves the rest to the first step kernel of step k, which
+// runs it in its prologue -- resident through PDL while the sweep of step k is still streaming -- on
+// warps of its own: moments on the chains' lanes of warp 3, counters on those of warp 2, then the
+// cooperative covariance update by all threads.  Both sides evaluate the same predicate: the host says
+// whether a producer / consumer exists (flags, from the block's kernel kinds), the device checks that
+// the two elements name different updates (the next proposal of the same update must see its adapted
+// step size, so that case stays in place).  The last element of a block is never deferred.
+// ---------------------------------------------------------------------------------
+constexpr int kFlagConsume = 1, kFlagDefer = 2;
+
+template <class SP>
+__device__ __forceinline__ void run_deferred(const DevState &d, const StepCtx &prev, int64_t c0, int nch, bool stage,
+                                             double *sh_t, double *sh_m, double *sh_n) {
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int64_t c = c0 + (tid % nch);
+    const bool lane_ok = lane < nch && c < d.C;
+    const bool coop = stage && d.stats_mode == 0;   // CTA-uniform
+    const CoopStage cs{sh_t, coop ? sh_m : nullptr, sh_n, nch, tid % nch};
+    if (w == 3 && lane_ok) {
+        post_decision_moments<SP, false, true>(d, prev.sd, c, false, 0.0, 0.0, stage ? &cs : nullptr);
+    } else if (w == 2 && lane_ok) {
+        const bool acc = d.h_acc[(prev.sd.seq % d.H) * d.gC + d.g0 + c] != 0;
+        const int n_eps = prev.u.kernel == EXTMCMC_KERNEL_MALA ? 1 : prev.u.n_coords;   // lean: uniform walk or MALA
+        post_decision_counters<SP>(d, prev.sd, prev.u, c, acc, n_eps);
+    }
+    if (coop) {
+        __syncthreads();
+        update_cov_coop(d, prev.sd.stat_n, c0, nch, sh_t, sh_m, sh_n, tid, blockDim.x);
+    }
+    // the deferred work has read the state of step k - 1 (and the staging): only now may this step commit
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------
 // K3: accept_reject! (src/run.jl:268-281) for the random-walk updates.
 // ---------------------------------------------------------------------------------
 template <int SL, class SP>
 __global__ void __launch_bounds__(256)
-accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fuse_next) {
+accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fuse_next, int flags) {
     // 256 threads = (256/SL) chains x SL reduction slices; slice 0 carries on with the chain
     constexpr int kRedChains = kRedThreads / SL;
     __shared__ double sh[kRedThreads];
-    __shared__ StepCtx ctx, ctx_next;
+    __shared__ StepCtx ctx, ctx_next, ctx_prev;
     // staging of the cooperative covariance update (only the sliced layouts have spare threads)
     constexpr int kStage = SL >= 8 ? kCoopP * kRedChains : 1;
     __shared__ double sh_t[kStage], sh_m[kStage], sh_n[kStage];
@@ -185,15 +222,24 @@ accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fuse_ne
     // (chain state, proposal, step sizes, law constants, RNG counters) -- the transition-density
     // and prior terms and the Exp(1) draw are computed here, hidden behind the sweep.
     griddep_launch_dependents();
+    constexpr bool kCanDefer = SL >= 8 && SP::kLean;
+    const bool may_defer = kCanDefer && (flags & kFlagDefer), may_consume = kCanDefer && (flags & kFlagConsume);
     load_step_ctx(&ctx, d, descs, k, threadIdx.x, blockDim.x, CtaSync{});
-    if (fuse_next == 1) load_step_ctx(&ctx_next, d, descs, k + 1, threadIdx.x, blockDim.x, CtaSync{});
+    if (fuse_next == 1 || may_defer) load_step_ctx(&ctx_next, d, descs, k + 1, threadIdx.x, blockDim.x, CtaSync{});
+    if (may_consume) load_step_ctx(&ctx_prev, d, descs, k - 1, threadIdx.x, blockDim.x, CtaSync{});
     const int64_t c = (int64_t)blockIdx.x * kRedChains + (threadIdx.x % kRedChains);
     const bool dead = exchange_failed(d);   // CTA-uniform
     const bool worker = (threadIdx.x / kRedChains) == 0 && c < d.C && !dead;
     const StepDesc &sd = ctx.sd;
     const DevUpdate &u = ctx.u;
+    // full covariance of a model with more than a handful of parameters: all slices share the work
+    const bool stage = SL >= 8 && d.p > 4 && d.p <= kCoopP;   // CTA-uniform
+    const bool coop = stage && d.stats_mode == 0;
     RwPre pre{};
     if (worker) pre = rw_accept_prologue<SP>(d, sd, u, c);
+    // bookkeeping the previous element left to us (other warps; the worker lanes join when they are done)
+    if (may_consume && !dead && ctx_prev.sd.pidx != sd.pidx)
+        run_deferred<SP>(d, ctx_prev, (int64_t)blockIdx.x * kRedChains, kRedChains, stage, sh_t, sh_m, sh_n);
 
     griddep_wait();   // the sweep (and, under sharding, the exchange) has finished
     if (dead) return;
@@ -207,15 +253,29 @@ accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fuse_ne
     } else {
         S = reduce_segments<SL>(d, sh);
     }
-    // full covariance of a model with more than a handful of parameters: all slices share the work
-    const bool stage = SL >= 8 && d.p > 4 && d.p <= kCoopP;   // CTA-uniform
-    const bool coop = stage && d.stats_mode == 0;
     const CoopStage cs{sh_t, coop ? sh_m : nullptr, sh_n, kRedChains, (int)(threadIdx.x % kRedChains)};
     // Task split (lean instantiations, sliced layouts): once the decision is committed, the next
     // element's proposal runs on the chains' lanes of warp 1 while the worker lanes (warp 0) do the
     // bookkeeping -- both are latency-bound single-warp instruction streams.  Not when the next
     // element is the same update: its proposal must see this step's adapted step size.
     const bool split = SL >= 8 && SP::kLean && fuse_next == 1 && ctx_next.sd.pidx != sd.pidx;   // CTA-uniform
+    const bool defer = may_defer && ctx_next.sd.pidx != sd.pidx;                                  // CTA-uniform
+    if (defer) {
+        // only what the next sweep and the history need: decision, commit, history row, next proposal
+        const bool prop_lane = fuse_next == 1 && (threadIdx.x >> 5) == 1 && (threadIdx.x & 31) < kRedChains && c < d.C;
+        Decision dec{};
+        if (worker) dec = rw_decide_commit<SP>(d, u, c, pre, S);
+        if (fuse_next == 1) __syncthreads();   // the committed state is visible to the proposal lanes
+        if (worker) post_decision_moments<SP, true, false>(d, sd, c, dec.accepted, dec.ll_new, dec.ll_prop);
+        else if (prop_lane) propose_draw<SP>(d, ctx_next.sd, ctx_next.u, c);
+        if (fuse_next == 1) {
+            __syncthreads();   // prop_full has been read for the history row
+            if (prop_lane) propose_set<SP>(d, ctx_next.u, c);
+        } else if (fuse_next == 2 && worker) {
+            law_prepare<SP>(d, c, d.theta + c, d.C);
+        }
+        return;
+    }
     if (split) {
         // lanes of warp 1: the next proposal; lanes of warp 2: rolling acceptance rate, totals, adaptation
         const bool lane_ok = (threadIdx.x & 31) < kRedChains && c < d.C;
@@ -313,16 +373,25 @@ grad_finalize_kernel(DevState d, const double *__restrict__ src, double *__restr
 template <class SP>
 __global__ void __launch_bounds__(kMalaChains * kMalaSlices)
 mala_propose_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int finalize_cur,
-                    double *__restrict__ ll_scratch) {
-    __shared__ StepCtx ctx;
+                    double *__restrict__ ll_scratch, int flags) {
+    __shared__ StepCtx ctx, ctx_prev;
     __shared__ double sh2[kCoopG * kMalaChains], sh1[kCoopG * kMalaChains];
+    __shared__ double sh_t[kCoopP * kMalaChains], sh_m[kCoopP * kMalaChains], sh_n[kCoopP * kMalaChains];
     // PDL (as in accept_kernel): the schedule element and update entry are staged while the
     // preceding sweep is still running; nothing the predecessor writes is read before the wait
     griddep_launch_dependents();
     load_step_ctx(&ctx, d, descs, k, threadIdx.x, blockDim.x, CtaSync{});
-    griddep_wait();
     const int64_t c0 = (int64_t)blockIdx.x * kMalaChains;
     const int64_t c = c0 + threadIdx.x % kMalaChains;
+    // bookkeeping the previous element left to us (see run_deferred).  Behind the current-state gradient
+    // sweep when there is one (that sweep started after the previous step kernel had finished); otherwise
+    // our predecessor IS that step kernel and we must wait for it first.
+    const bool may_consume = SP::kLean && (flags & kFlagConsume);
+    if (may_consume) load_step_ctx(&ctx_prev, d, descs, k - 1, threadIdx.x, blockDim.x, CtaSync{});
+    const bool consume = may_consume && ctx_prev.sd.pidx != ctx.sd.pidx;
+    if (consume && finalize_cur) run_deferred<SP>(d, ctx_prev, c0, kMalaChains, d.p <= kCoopP, sh_t, sh_m, sh_n);
+    griddep_wait();
+    if (consume && !finalize_cur) run_deferred<SP>(d, ctx_prev, c0, kMalaChains, d.p <= kCoopP, sh_t, sh_m, sh_n);
     // the sweep just before this kernel evaluated the CURRENT state: finish its sums here
     // (gradient of the current state) instead of in a kernel of its own
     if (finalize_cur) grad_finalize_coop<SP>(d, c0, d.theta, ll_scratch, d.grad_cur, sh2, sh1);
@@ -372,13 +441,14 @@ mala_propose_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int f
 // K5b: MALA accept/reject (step_device.cuh: mala_decide)
 template <class SP>
 __global__ void __launch_bounds__(kMalaChains * kMalaSlices)
-mala_accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int finalize_prop, int fuse_next) {
+mala_accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int finalize_prop, int fuse_next, int flags) {
     __shared__ StepCtx ctx, ctx_next;
     __shared__ double sh2[kCoopG * kMalaChains], sh1[kCoopG * kMalaChains];
     __shared__ double sh_t[kCoopP * kMalaChains], sh_m[kCoopP * kMalaChains], sh_n[kCoopP * kMalaChains];
     griddep_launch_dependents();
+    const bool may_defer = SP::kLean && (flags & kFlagDefer);
     load_step_ctx(&ctx, d, descs, k, threadIdx.x, blockDim.x, CtaSync{});
-    if (fuse_next) load_step_ctx(&ctx_next, d, descs, k + 1, threadIdx.x, blockDim.x, CtaSync{});
+    if (fuse_next || may_defer) load_step_ctx(&ctx_next, d, descs, k + 1, threadIdx.x, blockDim.x, CtaSync{});
     griddep_wait();   // the gradient sweep of the proposal has finished
     const int64_t c0 = (int64_t)blockIdx.x * kMalaChains;
     const int ch = threadIdx.x % kMalaChains;
@@ -388,6 +458,19 @@ mala_accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fi
     const bool stage = d.p <= kCoopP;   // CTA-uniform
     const bool coop = stage && d.stats_mode == 0;
     const CoopStage cs{sh_t, coop ? sh_m : nullptr, sh_n, kMalaChains, ch};
+    if (may_defer && ctx_next.sd.pidx != ctx.sd.pidx) {   // deferred bookkeeping (see run_deferred)
+        const bool prop_lane = fuse_next && (threadIdx.x >> 5) == 1 && c < d.C;
+        Decision dec{};
+        if (worker) dec = mala_decide_commit<SP>(d, ctx.sd, ctx.u, c);
+        if (fuse_next) __syncthreads();
+        if (worker) post_decision_moments<SP, true, false>(d, ctx.sd, c, dec.accepted, dec.ll_new, dec.ll_prop);
+        else if (prop_lane) propose_draw<SP>(d, ctx_next.sd, ctx_next.u, c);
+        if (fuse_next) {
+            __syncthreads();
+            if (prop_lane) propose_set<SP>(d, ctx_next.u, c);
+        }
+        return;
+    }
     if (SP::kLean && fuse_next) {   // task split as in accept_kernel (the next element is another update)
         const bool prop_lane = (threadIdx.x >> 5) == 1 && c < d.C;
         const bool cnt_lane = (threadIdx.x >> 5) == 2 && c < d.C;
@@ -516,7 +599,14 @@ static inline int slices_for(const DevState &d) {
     if (!stage && (d.use_ssum || d.S * d.G <= 16) && d.C >= 32768) return 1;
     return d.C <= 8 ? 32 : 8;
 }
-void launch_accept(const DevState &d, const StepDesc *descs, int k, int fuse_next, cudaStream_t st) {
+// Deferral flags of element k of an n_steps block (see run_deferred): needs the lean instantiations and
+// the sliced layout on both sides; d is the handle's state (not a gradient view).  EXTMCMC_DEFER=0: off.
+int step_deferral_flags(const DevState &d, int k, int n_steps) {
+    static const bool on = [] { const char *e = getenv("EXTMCMC_DEFER"); return !e || atoi(e) != 0; }();
+    if (!(on && d.lean && slices_for(d) >= 8)) return 0;
+    return (k > 0 ? kFlagConsume : 0) | (k + 1 < n_steps ? kFlagDefer : 0);
+}
+void launch_accept(const DevState &d, const StepDesc *descs, int k, int fuse_next, int flags, cudaStream_t st) {
     // PDL attribute: the accept kernel's prologue overlaps the tail of the sweep
     cudaLaunchConfig_t cfg{};
     cfg.blockDim = dim3(256);
@@ -530,9 +620,9 @@ void launch_accept(const DevState &d, const StepDesc *descs, int k, int fuse_nex
     cfg.gridDim = dim3(red_blocks_for(d.C, sl));
     with_spec(d, [&](auto sp) {
         using SP = decltype(sp);
-        if (sl == 32) cudaLaunchKernelEx(&cfg, accept_kernel<32, SP>, d, descs, k, fuse_next);
-        else if (sl == 8) cudaLaunchKernelEx(&cfg, accept_kernel<8, SP>, d, descs, k, fuse_next);
-        else cudaLaunchKernelEx(&cfg, accept_kernel<1, SP>, d, descs, k, fuse_next);
+        if (sl == 32) cudaLaunchKernelEx(&cfg, accept_kernel<32, SP>, d, descs, k, fuse_next, flags);
+        else if (sl == 8) cudaLaunchKernelEx(&cfg, accept_kernel<8, SP>, d, descs, k, fuse_next, flags);
+        else cudaLaunchKernelEx(&cfg, accept_kernel<1, SP>, d, descs, k, fuse_next, flags);
     });
 }
 void launch_grad_finalize(const DevState &d, const double *src, double *ll_out, double *grad_out,
@@ -540,7 +630,7 @@ void launch_grad_finalize(const DevState &d, const double *src, double *ll_out, 
     grad_finalize_kernel<<<(int)((d.C + 127) / 128), 128, 0, st>>>(d, src, ll_out, grad_out);
 }
 void launch_mala_propose(const DevState &d, const StepDesc *descs, int k, int finalize_cur, double *ll_scratch,
-                         cudaStream_t st) {
+                         int flags, cudaStream_t st) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)((d.C + kMalaChains - 1) / kMalaChains));
     cfg.blockDim = dim3(kMalaChains * kMalaSlices);
@@ -550,10 +640,10 @@ void launch_mala_propose(const DevState &d, const StepDesc *descs, int k, int fi
     attr[0].val.programmaticStreamSerializationAllowed = (pdl_mask() >> 1) & 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    with_spec(d, [&](auto sp) { cudaLaunchKernelEx(&cfg, mala_propose_kernel<decltype(sp)>, d, descs, k, finalize_cur, ll_scratch); });
+    with_spec(d, [&](auto sp) { cudaLaunchKernelEx(&cfg, mala_propose_kernel<decltype(sp)>, d, descs, k, finalize_cur, ll_scratch, flags); });
 }
 void launch_mala_accept(const DevState &d, const StepDesc *descs, int k, int finalize_prop, int fuse_next,
-                        cudaStream_t st) {
+                        int flags, cudaStream_t st) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)((d.C + kMalaChains - 1) / kMalaChains));
     cfg.blockDim = dim3(kMalaChains * kMalaSlices);
@@ -563,7 +653,7 @@ void launch_mala_accept(const DevState &d, const StepDesc *descs, int k, int fin
     attr[0].val.programmaticStreamSerializationAllowed = (pdl_mask() >> 1) & 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    with_spec(d, [&](auto sp) { cudaLaunchKernelEx(&cfg, mala_accept_kernel<decltype(sp)>, d, descs, k, finalize_prop, fuse_next); });
+    with_spec(d, [&](auto sp) { cudaLaunchKernelEx(&cfg, mala_accept_kernel<decltype(sp)>, d, descs, k, finalize_prop, fuse_next, flags); });
 }
 void launch_chol_factor(double *S, double *L, int n, int64_t stride, int64_t count, cudaStream_t st) {
     chol_factor_kernel<<<(int)((count + 127) / 128), 128, 0, st>>>(S, L, n, stride, count);

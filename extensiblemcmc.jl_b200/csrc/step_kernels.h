@@ -6,15 +6,16 @@
 
 namespace extmcmc {
 void launch_propose(const DevState &d, const StepDesc *descs, int k, cudaStream_t st);
-void launch_accept(const DevState &d, const StepDesc *descs, int k, int fuse_next, cudaStream_t st);
+int step_deferral_flags(const DevState &d, int k, int n_steps);   // see run_deferred in step_kernels.cu
+void launch_accept(const DevState &d, const StepDesc *descs, int k, int fuse_next, int flags, cudaStream_t st);
 void launch_prepare_current(const DevState &d, cudaStream_t st);
 // lower Cholesky factors of `count` column-major n x n matrices (element stride `stride`, matrix c at + c)
 void launch_chol_factor(double *S, double *L, int n, int64_t stride, int64_t count, cudaStream_t st);
 void launch_grad_finalize(const DevState &d, const double *src, double *ll_out, double *grad_out, cudaStream_t st);
 void launch_mala_propose(const DevState &d, const StepDesc *descs, int k, int finalize_cur, double *ll_scratch,
-                         cudaStream_t st);
+                         int flags, cudaStream_t st);
 void launch_mala_accept(const DevState &d, const StepDesc *descs, int k, int finalize_prop, int fuse_next,
-                        cudaStream_t st);
+                        int flags, cudaStream_t st);
 void launch_reduce_partials(const DevState &d, cudaStream_t st);
 void launch_reduce_group_sums(const DevState &d, double *out, cudaStream_t st);
 void launch_reduce_push(const DevState &d, const StepDesc *descs, int k, cudaStream_t st);

@@ -70,5 +70,5 @@ def _run(env_extra):
 def test_launch_variants_are_bit_identical():
     base = _run({})
     assert len(base) == 3
-    for env in ({"EXTMCMC_LEAN": "0"}, {"EXTMCMC_L2_HINT": "0"}, {"EXTMCMC_PDL": "0"}, {"EXTMCMC_PDL": "7"}):
+    for env in ({"EXTMCMC_LEAN": "0"}, {"EXTMCMC_DEFER": "0"}, {"EXTMCMC_L2_HINT": "0"}, {"EXTMCMC_PDL": "0"}, {"EXTMCMC_PDL": "7"}):
         assert _run(env) == base, env
