@@ -391,9 +391,15 @@ def measure_cfg34(args, workload, em, _abi, local, steps):
         # per iteration: 2 gradient sweeps (3 FP64 instructions per chain x observation: x - mu, the
         # square and the first-order sum) + 2 plain sweeps (2 instructions) = 10 issue slots = 20 "flop"
         # at the FMA rate the peak is quoted in
-        n_obs, flops_per_iter, sweeps_per_iter = G * ng, 2.0 * 10.0 * C * G * ng, 4
+        # With the data-sum cache (default; EXTMCMC_DATA_CACHE=0 turns it off) the mu / tau elements and
+        # the current-state gradient reuse the per-group sums: ONE gradient sweep per iteration (3 slots).
+        cache_on = os.environ.get("EXTMCMC_DATA_CACHE", "1") != "0"
+        slots = 3.0 if cache_on else 10.0
+        n_obs, flops_per_iter, sweeps_per_iter = G * ng, 2.0 * slots * C * G * ng, 1 if cache_on else 4
         desc = (f"BASELINE cfg4: hierarchical normal, {G} groups x {ng} obs, {C} chains/GPU, "
-                "schedule MALA(theta_1..8) + RW(mu) + RW-pos(tau), full 10 x 10 running covariance")
+                "schedule MALA(theta_1..8) + RW(mu) + RW-pos(tau), full 10 x 10 running covariance; "
+                + ("data-sum cache on: the sums over the observations are recomputed only when theta_1..8 move "
+                   "(1 sweep per iteration)" if cache_on else "data-sum cache off: every element sweeps (4 per iteration)"))
     NUc = len(ups)
 
     def make(instrument):
@@ -603,6 +609,14 @@ def run_ours(args):
     cfg3 = cfg4 = None
     if rank == 0 and world == 1 and not args.skip_extras:
         cfg4 = measure_cfg34(args, "cfg4", em, _abi, local, args.cfg4_steps)
+        if "EXTMCMC_DATA_CACHE" not in os.environ:
+            # the same workload with every element streaming the observations (round-1 / early round-2 path)
+            os.environ["EXTMCMC_DATA_CACHE"] = "0"
+            try:
+                off = measure_cfg34(args, "cfg4", em, _abi, local, args.cfg4_steps)
+            finally:
+                del os.environ["EXTMCMC_DATA_CACHE"]
+            cfg4["without_data_cache"] = {k: off[k] for k in ("workload", "ms_per_step", "value", "unit", "roofline", "gpu_launches")}
         cfg3 = measure_cfg34(args, "cfg3", em, _abi, local, args.cfg3_steps)
 
     # ---- BASELINE cfg 5 (observations sharded, strong scaling, cross-rank exchange) ----------------

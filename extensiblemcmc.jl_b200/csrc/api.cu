@@ -85,6 +85,11 @@ struct extmcmc_handle {
     unsigned int *tail_counter = nullptr; // CTA counter of the fused sweep tail
     bool tail = false;                   // the obs-mapped sweep finishes the reduction itself
     bool grad_valid = false;             // grad_cur holds d ll/d theta of the CURRENT state
+    // Data-sum cache (dev_state.cuh: dsum_cur / dsum_prop).  dcache: the handle keeps one (HIER_NORMAL,
+    // observations not sharded, EXTMCMC_DATA_CACHE != 0); dc_valid: dsum_cur holds the per-group data
+    // sums of the CURRENT state.
+    bool dcache = false, dc_valid = false;
+    double *dsum_buf[2] = {nullptr, nullptr};   // the allocations behind d.dsum_cur / d.dsum_prop
     bool any_mala = false;
     bool state_set = false;
     SweepPlan plan{};
@@ -225,10 +230,56 @@ int32_t ensure_plan(extmcmc_t h) {
     if (obs_sharded(h) && !h->gsum &&
         (h->cfg.law == EXTMCMC_LAW_GSN_IID_1D || h->cfg.law == EXTMCMC_LAW_HIER_NORMAL))
         if ((rc = dev_alloc(h, &h->gsum, (size_t)2 * h->d.G * h->d.C))) return rc;
+    {
+        const char *e = getenv("EXTMCMC_DATA_CACHE");   // read per plan, so that one process can compare both
+        const bool on = !e || atoi(e) != 0;
+        h->dcache = on && h->cfg.law == EXTMCMC_LAW_HIER_NORMAL && !obs_sharded(h) && h->d.G <= kDataCacheMaxG;
+        if (h->dcache && !h->dsum_buf[0])
+            if ((rc = dev_alloc(h, &h->dsum_buf[0], (size_t)2 * h->d.G * h->d.C)) ||
+                (rc = dev_alloc(h, &h->dsum_buf[1], (size_t)2 * h->d.G * h->d.C)))
+                return rc;
+        h->d.dsum_cur = h->dcache ? h->dsum_buf[0] : nullptr;
+        h->d.dsum_prop = h->dcache ? h->dsum_buf[1] : nullptr;
+        h->dc_valid = false;
+    }
     h->plan_valid = true;
     h->blk_planned = false;
     invalidate_graphs(h);
     return EXTMCMC_OK;
+}
+
+// ---- data-sum cache: which elements need no sweep ------------------------------------------------
+// The data term of HIER_NORMAL depends on theta_1..G only.  An element whose update moves none of
+// them (mu, tau) proposes a state with the data sums of the current one; a MALA element that follows
+// such elements finds the sums of its current state still in the cache.  kinds[] carries the fact as
+// kDataFree on top of the transition kernel id; step_advance is the one place that says what an
+// element does to (grad_valid, dc_valid) and is used by the descriptor loop, the graph key, the
+// kernel sequence and the end-of-block state alike.
+constexpr int kDataFree = 0x100;
+int step_kind(extmcmc_t h, int u) {
+    const DevUpdate &t = h->upd_host[u];
+    int kind = t.kernel;
+    if (h->dcache && kind != EXTMCMC_KERNEL_MALA && t.n_coords <= kMaxCoords) {
+        bool moves_data = false;
+        for (int i = 0; i < t.n_coords; ++i) moves_data = moves_data || t.coords[i] < h->d.G;
+        if (!moves_data) kind |= kDataFree;
+    }
+    return kind;
+}
+inline bool kind_is_mala(int kind) { return (kind & 0xff) == EXTMCMC_KERNEL_MALA; }
+// MALA: returns how the gradient of the current state is obtained (0 = still valid, 1 = sweep,
+// 2 = from the cache).  Random walk: returns 1 when the element runs without a sweep.
+int step_advance(bool dcache, int kind, bool &gv, bool &dc) {
+    if (kind_is_mala(kind)) {
+        const int mode = gv ? 0 : (dc ? 2 : 1);
+        if (mode == 1 && dcache) dc = true;   // mala_propose stores the sums it finishes
+        gv = true;                            // (an accepted proposal hands its sums over: mala_decide_commit)
+        return mode;
+    }
+    gv = false;
+    if (kind & kDataFree) return dc ? 1 : 0;
+    dc = false;
+    return 0;
 }
 
 // Which schedule blocks run as ONE persistent kernel (block_kernels.cu) instead of a kernel sequence
@@ -415,19 +466,21 @@ DevState grad_view(extmcmc_t h) {
 }
 
 int32_t enqueue_steps(extmcmc_t h, const StepDesc *d_descs, const int *kinds, int n_steps,
-                      bool instrument, bool &grad_valid) {
+                      bool instrument, bool &grad_valid, bool &dc_valid) {
     bool fused = false;      // the proposal of element k was already issued by accept(k-1)
     bool cur_prepared = false;  // accept(k-1) already wrote the law constants of the current state
     for (int k = 0; k < n_steps; ++k) {
         int32_t rc;
         // deferred bookkeeping between consecutive elements of this block (step_kernels.cu, run_deferred)
         const int dflags = step_deferral_flags(h->d, k, n_steps);
-        const bool next_mala = k + 1 < n_steps && kinds[k + 1] == EXTMCMC_KERNEL_MALA;
-        const bool next_rw = k + 1 < n_steps && kinds[k + 1] != EXTMCMC_KERNEL_MALA;
-        if (kinds[k] == EXTMCMC_KERNEL_MALA) {
+        const bool next_mala = k + 1 < n_steps && kind_is_mala(kinds[k + 1]);
+        const bool next_rw = k + 1 < n_steps && !kind_is_mala(kinds[k + 1]);
+        const int mode = step_advance(h->dcache, kinds[k], grad_valid, dc_valid);
+        if (kind_is_mala(kinds[k])) {
             const bool logi = h->cfg.law == EXTMCMC_LAW_LOGISTIC;
             int finalize_cur = 0;
-            if (!grad_valid) {
+            DevState gv = grad_view(h);
+            if (mode == 1) {
                 if (logi) {
                     if ((rc = enqueue_sweep(h, instrument, true, h->d.theta, h->scratch_ll, h->d.grad_cur))) return rc;
                 } else {
@@ -437,9 +490,13 @@ int32_t enqueue_steps(extmcmc_t h, const StepDesc *d_descs, const int *kinds, in
                     if ((rc = enqueue_sweep(h, instrument, true, h->d.theta))) return rc;
                     finalize_cur = 1;
                 }
+            } else if (mode == 2) {
+                // the sums of the current state are in the cache: mala_propose finishes them from there
+                gv.partial = h->d.dsum_cur; gv.S = 1;
+                finalize_cur = 2;
             }
-            const DevState gv = grad_view(h);
             launch_mala_propose(gv, d_descs, k, finalize_cur, h->scratch_ll, dflags, h->stream);
+            gv = grad_view(h);
             if (logi) {
                 if ((rc = enqueue_sweep(h, instrument, true, h->d.prop_full, h->d.ll_prop, h->d.grad_prop))) return rc;
             } else {
@@ -448,18 +505,18 @@ int32_t enqueue_steps(extmcmc_t h, const StepDesc *d_descs, const int *kinds, in
             fused = next_rw;   // the next random-walk proposal rides on this accept kernel
             launch_mala_accept(gv, d_descs, k, logi ? 0 : 1, fused ? 1 : 0, dflags, h->stream);
             h->launches += 2;
-            grad_valid = true;
             cur_prepared = false;
         } else {
             if (!fused) { launch_propose(h->d, d_descs, k, h->stream); h->launches += 1; }
-            if ((rc = enqueue_sweep(h, instrument, false, h->d.prop_full, h->d.ssum, nullptr, d_descs, k))) return rc;
+            const bool from_cache = mode == 1;
+            if (!from_cache)
+                if ((rc = enqueue_sweep(h, instrument, false, h->d.prop_full, h->d.ssum, nullptr, d_descs, k))) return rc;
             fused = next_rw;
             // a MALA element follows and will need the law constants of the (then) current state for
             // its gradient sweep: let this accept kernel write them (fuse_next = 2)
             cur_prepared = next_mala && h->cfg.law != EXTMCMC_LAW_LOGISTIC && h->cfg.law != EXTMCMC_LAW_HIER_NORMAL;
-            launch_accept(h->d, d_descs, k, fused ? 1 : (cur_prepared ? 2 : 0), dflags, h->stream);
+            launch_accept(h->d, d_descs, k, fused ? 1 : (cur_prepared ? 2 : 0), dflags, h->stream, from_cache);
             h->launches += 1;
-            grad_valid = false;
         }
     }
     CK(h, cudaGetLastError());
@@ -499,6 +556,10 @@ int32_t run_block_impl(extmcmc_t h, const extmcmc_step_t *steps, int32_t n_steps
     if ((rc = upload_updates(h))) return rc;
     if ((rc = ensure_total_obs(h))) return rc;
     if ((rc = plan_block_kernels(h))) return rc;
+    if ((h->res_ok || h->obsblk_ok) && h->dcache) {   // the persistent block kernels sweep for every element
+        h->dcache = h->dc_valid = false;
+        h->d.dsum_cur = h->d.dsum_prop = nullptr;
+    }
     // a history fetch still in flight reads ring slots this block is about to overwrite: order the
     // block after the copy (callers that keep 2 x block_len rows never get here)
     if (h->fetch_active && h->seq_next + n_steps - h->d.H > h->fetch_lo)
@@ -549,7 +610,7 @@ int32_t run_block_impl(extmcmc_t h, const extmcmc_step_t *steps, int32_t n_steps
     const int W = h->d.W;
     int n_sweeps = 0;
     {
-        bool gv = h->grad_valid;
+        bool gv = h->grad_valid, dc = h->dc_valid;
         for (int s = 0; s < n_steps; ++s) {
             StepDesc &sd = sl.h_descs[s];
             const int u = steps[s].pidx;
@@ -580,8 +641,8 @@ int32_t run_block_impl(extmcmc_t h, const extmcmc_step_t *steps, int32_t n_steps
             }
             const bool mala = h->upd_host[u].kernel == EXTMCMC_KERNEL_MALA;
             sd.need_cur_grad = (mala && !gv) ? 1 : 0;
-            n_sweeps += mala ? 1 + sd.need_cur_grad : 1;
-            gv = mala;
+            const int mode = step_advance(h->dcache, step_kind(h, u), gv, dc);
+            n_sweeps += mala ? 1 + (mode == 1 ? 1 : 0) : 1 - mode;
             h->ra_iter[u] = it;
             tag = it;
         }
@@ -590,10 +651,10 @@ int32_t run_block_impl(extmcmc_t h, const extmcmc_step_t *steps, int32_t n_steps
     std::vector<int> kinds(n_steps);
     unsigned long long hash = 1469598103934665603ull;  // FNV-1a over the kernel-kind sequence
     for (int s = 0; s < n_steps; ++s) {
-        kinds[s] = h->upd_host[steps[s].pidx].kernel;
+        kinds[s] = step_kind(h, steps[s].pidx);
         hash = (hash ^ (unsigned long long)kinds[s]) * 1099511628211ull;
     }
-    hash = (hash ^ (unsigned long long)(h->grad_valid ? 7 : 3)) * 1099511628211ull;
+    hash = (hash ^ (unsigned long long)((h->grad_valid ? 7 : 3) + (h->dc_valid ? 16 : 0))) * 1099511628211ull;
     hash = (hash ^ (unsigned long long)n_steps) * 1099511628211ull;
     const bool instrument = h->cfg.instrument != 0;
     const bool use_graph = h->cfg.use_graphs && !instrument && rng_mode == EXTMCMC_RNG_PHILOX;
@@ -608,6 +669,7 @@ int32_t run_block_impl(extmcmc_t h, const extmcmc_step_t *steps, int32_t n_steps
         if (h->res_ok) {
             TeamArgs a{};
             a.d = h->d;
+            a.d.dsum_cur = a.d.dsum_prop = nullptr;
             a.d.S = h->res_plan.ts;        // the members of a team are the "segments" of the partial sums
             a.descs = sl.d_descs; a.n_steps = n_steps; a.n_sweeps = n_sweeps;
             a.obs = h->obs_dev; a.goff = h->goff_dev; a.glen = h->glen_dev; a.G = h->d.G;
@@ -621,6 +683,7 @@ int32_t run_block_impl(extmcmc_t h, const extmcmc_step_t *steps, int32_t n_steps
         } else {
             ObsBlockArgs a{};
             a.d = h->d;
+            a.d.dsum_cur = a.d.dsum_prop = nullptr;
             a.descs = sl.d_descs; a.n_steps = n_steps;
             a.obs = h->obs_dev; a.n_obs = h->n_obs_local;
             a.go = h->blk_go; a.counter = h->blk_counter;
@@ -632,11 +695,12 @@ int32_t run_block_impl(extmcmc_t h, const extmcmc_step_t *steps, int32_t n_steps
             CK(h, cudaEventRecord(ev.second, h->stream));
             h->ev_pending.push_back(ev);
         }
-        h->grad_valid = kinds[n_steps - 1] == EXTMCMC_KERNEL_MALA;
+        h->grad_valid = kind_is_mala(kinds[n_steps - 1]);
+        h->dc_valid = false;
     } else if (!use_graph) {
         CK(h, cudaMemcpyAsync(sl.d_descs, sl.h_descs, sizeof(StepDesc) * n_steps,
                               cudaMemcpyHostToDevice, h->stream));
-        if ((rc = enqueue_steps(h, sl.d_descs, kinds.data(), n_steps, instrument, h->grad_valid))) return rc;
+        if ((rc = enqueue_steps(h, sl.d_descs, kinds.data(), n_steps, instrument, h->grad_valid, h->dc_valid))) return rc;
     } else {
         // the kernel sequence depends on the kinds of the block's updates (and on whether the
         // current-state gradient is fresh), not on which update each element names
@@ -644,12 +708,12 @@ int32_t run_block_impl(extmcmc_t h, const extmcmc_step_t *steps, int32_t n_steps
         auto it = h->graphs.find(key);
         if (it == h->graphs.end()) {
             const int64_t launches_before = h->launches;
-            bool gv = h->grad_valid;
+            bool gv = h->grad_valid, dc = h->dc_valid;
             cudaGraph_t g = nullptr;
             CK(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
             cudaError_t e1 = cudaMemcpyAsync(sl.d_descs, sl.h_descs, sizeof(StepDesc) * n_steps,
                                              cudaMemcpyHostToDevice, h->stream);
-            int32_t rc2 = e1 == cudaSuccess ? enqueue_steps(h, sl.d_descs, kinds.data(), n_steps, false, gv) : EXTMCMC_ECUDA;
+            int32_t rc2 = e1 == cudaSuccess ? enqueue_steps(h, sl.d_descs, kinds.data(), n_steps, false, gv, dc) : EXTMCMC_ECUDA;
             cudaError_t e2 = cudaStreamEndCapture(h->stream, &g);
             h->graph_launches[key] = h->launches - launches_before;
             h->launches = launches_before;
@@ -666,7 +730,7 @@ int32_t run_block_impl(extmcmc_t h, const extmcmc_step_t *steps, int32_t n_steps
         }
         CK(h, cudaGraphLaunch(it->second, h->stream));
         h->launches += h->graph_launches[key];
-        h->grad_valid = kinds[n_steps - 1] == EXTMCMC_KERNEL_MALA;
+        for (int s = 0; s < n_steps; ++s) step_advance(h->dcache, kinds[s], h->grad_valid, h->dc_valid);
     }
     CK(h, cudaEventRecord(sl.done, h->stream));
     sl.in_flight = true;
@@ -889,6 +953,7 @@ static int32_t install_obs(extmcmc_t h, int64_t n_obs, const std::vector<int64_t
     h->plan_valid = false;
     h->n_total_known = false;
     h->grad_valid = false;
+    h->dc_valid = false;
     return EXTMCMC_OK;
 }
 
@@ -919,6 +984,7 @@ int32_t extmcmc_upload_obs(extmcmc_t h, const double *obs, int64_t n_obs, int32_
         h->plan_valid = false;
         h->n_total_known = false;
         h->grad_valid = false;
+        h->dc_valid = false;
         return EXTMCMC_OK;
     }
     std::vector<int64_t> glen(h->d.G, 0);
@@ -1200,6 +1266,7 @@ int32_t extmcmc_set_state(extmcmc_t h, const double *theta) {
     std::fill(h->haario_M.begin(), h->haario_M.end(), 0);
     h->seq_next = 0;
     h->grad_valid = false;
+    h->dc_valid = false;
     if (h->fetch_active) { cudaEventSynchronize(h->fetch_done); h->fetch_active = false; }
     std::fill(h->ra_iter.begin(), h->ra_iter.end(), 0);
     std::fill(h->acc_tag.begin(), h->acc_tag.end(), 0);
@@ -1297,6 +1364,7 @@ int32_t extmcmc_checkpoint_load(extmcmc_t h, const void *blob, int64_t bytes) {
     });
     if (rc) return rc;
     h->seq_next = hd.seq_next;
+    h->dc_valid = false;
     h->grad_valid = false;          // (the gradient buffers are not part of the blob: recomputed on demand)
     h->state_set = true;
     h->fetch_active = false;

@@ -17,6 +17,7 @@ namespace extmcmc {
 constexpr int kMaxCoords = 32;       // p_u limit of the random-walk updates (MALA: unlimited, coords_dev)
 constexpr int kMaxPriorFactors = 16; // ProductPrior factors
 constexpr int kMaxPriorParams = 1 + 4 * kMaxPriorFactors;
+constexpr int kDataCacheMaxG = 16;   // most observation groups the data-sum cache serves (= kCoopG, step_kernels.cu)
 constexpr int kMaxObsDim = 16;       // general-d Gaussian law on the device: d <= 16
 
 // prior families the compact (SpecLean) step kernels carry
@@ -91,6 +92,11 @@ struct DevState {
     double *ll_prop;        // [C] finalized proposal log-likelihood (gradient path)
     double *grad_cur;       // [p][C] d ll / d theta at the current state
     double *grad_prop;      // [p][C] ... at the proposal
+    // Data-sum cache (HIER_NORMAL, api.cu: data_cache_on): the per-group sums of both orders of the
+    // CURRENT state and of the proposal in flight, laid out like a partial buffer with one segment per
+    // group ([2][G][C]).  They depend on theta_1..G only, so an update of mu / tau reuses them instead
+    // of streaming the observations again.  NULL: no cache.
+    double *dsum_cur, *dsum_prop;
     uint64_t seed;
     // current state
     double *theta;          // [p][C]

@@ -965,6 +965,16 @@ __device__ __forceinline__ Decision mala_decide_commit(const DevState &d, const 
 #pragma unroll
             for (int q = 0; q < 4; ++q) if (j0 + q < d.p) d.grad_cur[(int64_t)(j0 + q) * C + c] = g[q];
         }
+        if (d.dsum_cur) {   // data-sum cache: the proposal's per-group sums become the current state's
+            const int rows = 2 * d.G;
+            for (int r0 = 0; r0 < rows; r0 += 4) {
+                double g[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) if (r0 + q < rows) g[q] = d.dsum_prop[(int64_t)(r0 + q) * C + c];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) if (r0 + q < rows) d.dsum_cur[(int64_t)(r0 + q) * C + c] = g[q];
+            }
+        }
     }
     return Decision{accepted, ll_new, ll_prop};
 }

@@ -180,6 +180,10 @@ __global__ void __launch_bounds__(256) finalize_loglik_kernel(DevState d, double
 // step size, so that case stays in place).  The last element of a block is never deferred.
 // ---------------------------------------------------------------------------------
 constexpr int kFlagConsume = 1, kFlagDefer = 2;
+// kFlagNoSweep: no likelihood sweep precedes this step kernel (data-sum cache, dev_state.cuh): its
+// stream predecessor is the step kernel of the previous element, whose writes it must wait for
+// before it reads anything but the descriptors.
+constexpr int kFlagNoSweep = 4;
 
 template <class SP>
 __device__ __forceinline__ void run_deferred(const DevState &d, const StepCtx &prev, int64_t c0, int nch, bool stage,
@@ -228,6 +232,7 @@ accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fuse_ne
     if (fuse_next == 1 || may_defer) load_step_ctx(&ctx_next, d, descs, k + 1, threadIdx.x, blockDim.x, CtaSync{});
     if (may_consume) load_step_ctx(&ctx_prev, d, descs, k - 1, threadIdx.x, blockDim.x, CtaSync{});
     const int64_t c = (int64_t)blockIdx.x * kRedChains + (threadIdx.x % kRedChains);
+    if (flags & kFlagNoSweep) griddep_wait();   // the predecessor is a step kernel, not a sweep
     const bool dead = exchange_failed(d);   // CTA-uniform
     const bool worker = (threadIdx.x / kRedChains) == 0 && c < d.C && !dead;
     const StepDesc &sd = ctx.sd;
@@ -314,10 +319,12 @@ accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fuse_ne
 // chain's own thread (slice 0) does the scalar work.  Same sums, same order as grad_finalize_chain.
 constexpr int kMalaChains = 32, kMalaSlices = 8;
 constexpr int kCoopG = 16;   // most observation groups reduced this way
+static_assert(kCoopG == kDataCacheMaxG, "the data-sum cache is filled by grad_finalize_coop");
 template <class SP>
 __device__ __forceinline__ void grad_finalize_coop(const DevState &d, int64_t c0, const double *__restrict__ src,
                                                    double *__restrict__ ll_out, double *__restrict__ grad_out,
-                                                   double *sh2, double *sh1 /*[kCoopG][kMalaChains] each*/) {
+                                                   double *sh2, double *sh1 /*[kCoopG][kMalaChains] each*/,
+                                                   double *__restrict__ dsum_out = nullptr /*[2][G][C] or NULL*/) {
     const int ch = threadIdx.x % kMalaChains, slice = threadIdx.x / kMalaChains;
     const int64_t c = c0 + ch, C = d.C;
     const int G = d.G, S = d.S;
@@ -342,6 +349,7 @@ __device__ __forceinline__ void grad_finalize_coop(const DevState &d, int64_t c0
             for (; i < S; ++i) { s2 += p2[(int64_t)i * C]; s1 += p1[(int64_t)i * C]; }
             sh2[g * kMalaChains + ch] = s2;
             sh1[g * kMalaChains + ch] = s1;
+            if (dsum_out) { dsum_out[(int64_t)g * C + c] = s2; dsum_out[((int64_t)G + g) * C + c] = s1; }
         }
     __syncthreads();
     if (slice != 0 || c >= C) return;
@@ -389,12 +397,17 @@ mala_propose_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int f
     const bool may_consume = SP::kLean && (flags & kFlagConsume);
     if (may_consume) load_step_ctx(&ctx_prev, d, descs, k - 1, threadIdx.x, blockDim.x, CtaSync{});
     const bool consume = may_consume && ctx_prev.sd.pidx != ctx.sd.pidx;
-    if (consume && finalize_cur) run_deferred<SP>(d, ctx_prev, c0, kMalaChains, d.p <= kCoopP, sh_t, sh_m, sh_n);
+    // finalize_cur: 1 = a sweep of the current state precedes this kernel; 2 = its sums come from the
+    // data-sum cache (d.partial is the cache, one segment per group): no sweep, the predecessor is a
+    // step kernel like with 0
+    const bool behind_sweep = finalize_cur == 1;
+    if (consume && behind_sweep) run_deferred<SP>(d, ctx_prev, c0, kMalaChains, d.p <= kCoopP, sh_t, sh_m, sh_n);
     griddep_wait();
-    if (consume && !finalize_cur) run_deferred<SP>(d, ctx_prev, c0, kMalaChains, d.p <= kCoopP, sh_t, sh_m, sh_n);
+    if (consume && !behind_sweep) run_deferred<SP>(d, ctx_prev, c0, kMalaChains, d.p <= kCoopP, sh_t, sh_m, sh_n);
     // the sweep just before this kernel evaluated the CURRENT state: finish its sums here
     // (gradient of the current state) instead of in a kernel of its own
-    if (finalize_cur) grad_finalize_coop<SP>(d, c0, d.theta, ll_scratch, d.grad_cur, sh2, sh1);
+    if (finalize_cur)
+        grad_finalize_coop<SP>(d, c0, d.theta, ll_scratch, d.grad_cur, sh2, sh1, behind_sweep ? d.dsum_cur : nullptr);
     if (SP::kLean && d.rng_mode != EXTMCMC_RNG_REPLAY) {   // CTA-uniform
         // The Box-Muller pairs of a chain's proposal are independent (counter-based stream: pair q
         // reads Philox block q): slice q % 8 draws pair q while the slices also share the copy of the
@@ -453,7 +466,7 @@ mala_accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fi
     const int64_t c0 = (int64_t)blockIdx.x * kMalaChains;
     const int ch = threadIdx.x % kMalaChains;
     const int64_t c = c0 + ch;
-    if (finalize_prop) grad_finalize_coop<SP>(d, c0, d.prop_full, d.ll_prop, d.grad_prop, sh2, sh1);
+    if (finalize_prop) grad_finalize_coop<SP>(d, c0, d.prop_full, d.ll_prop, d.grad_prop, sh2, sh1, d.dsum_prop);
     const bool worker = threadIdx.x < kMalaChains && c < d.C;
     const bool stage = d.p <= kCoopP;   // CTA-uniform
     const bool coop = stage && d.stats_mode == 0;
@@ -606,7 +619,13 @@ int step_deferral_flags(const DevState &d, int k, int n_steps) {
     if (!(on && d.lean && slices_for(d) >= 8)) return 0;
     return (k > 0 ? kFlagConsume : 0) | (k + 1 < n_steps ? kFlagDefer : 0);
 }
-void launch_accept(const DevState &d, const StepDesc *descs, int k, int fuse_next, int flags, cudaStream_t st) {
+void launch_accept(const DevState &d0, const StepDesc *descs, int k, int fuse_next, int flags, cudaStream_t st,
+                   bool from_cache) {
+    // from_cache: no sweep ran for this element; the sums of its proposal are the cached per-group sums
+    // of the current state, read as a partial buffer with one segment per group.  The thread layout is
+    // the one the handle's real state gives (the deferral flags were derived from it).
+    DevState d = d0;
+    if (from_cache) { d.partial = d0.dsum_cur; d.S = 1; d.use_ssum = 0; d.p2p = 0; flags |= kFlagNoSweep; }
     // PDL attribute: the accept kernel's prologue overlaps the tail of the sweep
     cudaLaunchConfig_t cfg{};
     cfg.blockDim = dim3(256);
@@ -616,7 +635,7 @@ void launch_accept(const DevState &d, const StepDesc *descs, int k, int fuse_nex
     attr[0].val.programmaticStreamSerializationAllowed = (pdl_mask() >> 1) & 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    const int sl = slices_for(d);
+    const int sl = slices_for(d0);
     cfg.gridDim = dim3(red_blocks_for(d.C, sl));
     with_spec(d, [&](auto sp) {
         using SP = decltype(sp);

@@ -7,7 +7,8 @@
 namespace extmcmc {
 void launch_propose(const DevState &d, const StepDesc *descs, int k, cudaStream_t st);
 int step_deferral_flags(const DevState &d, int k, int n_steps);   // see run_deferred in step_kernels.cu
-void launch_accept(const DevState &d, const StepDesc *descs, int k, int fuse_next, int flags, cudaStream_t st);
+void launch_accept(const DevState &d, const StepDesc *descs, int k, int fuse_next, int flags, cudaStream_t st,
+                   bool from_cache = false);
 void launch_prepare_current(const DevState &d, cudaStream_t st);
 // lower Cholesky factors of `count` column-major n x n matrices (element stride `stride`, matrix c at + c)
 void launch_chol_factor(double *S, double *L, int n, int64_t stride, int64_t count, cudaStream_t st);

@@ -214,3 +214,55 @@ def test_full_size_cfg4_replay_parity():
     assert np.array_equal(full, np.broadcast_to(full[..., :1, :], full.shape))
     assert np.array_equal(g.eps(1)[:, :sub], o.eps(1))
     g.close()
+
+
+def _hier_own_stream(cache, use_graphs, block, n_chains=130, n_iters=36):
+    """cfg 4 schedule plus a fourth update (a random walk on theta_1, which DOES move the data term)
+    with exclusions, on the device's own Philox stream; EXTMCMC_DATA_CACHE is read when the sweep is
+    planned, i.e. per handle."""
+    import os
+    G = 5
+    y, grp, _ = _hier_data(G, 300, seed=21, ragged=True)
+    ups = _hier_updates(G) + [em.RandomWalkUpdate(em.UniformRandomWalk([0.2]), [1])]
+    steps = list(em.MCMCSchedule(n_iters, len(ups), [(1, range(4, 7)), (4, range(9, 30, 2)), (3, range(20, 24))]))
+    old = os.environ.get("EXTMCMC_DATA_CACHE")
+    os.environ["EXTMCMC_DATA_CACHE"] = "1" if cache else "0"
+    try:
+        g = GpuSession(em.HierNormalLaw(G), ups, y, _hier_theta0(G, n_chains), n_chains, seed=31,
+                       n_steps_hint=len(steps), use_graphs=use_graphs, y=grp)
+        l0 = g.lib.extmcmc_launch_count(g.h)
+        parts = [g.run(steps[b:b + block]) for b in range(0, len(steps), block)]
+        launches = int(g.lib.extmcmc_launch_count(g.h) - l0)
+    finally:
+        if old is None:
+            del os.environ["EXTMCMC_DATA_CACHE"]
+        else:
+            os.environ["EXTMCMC_DATA_CACHE"] = old
+    assert all(q["rc"] == 0 for q in parts)
+    out = {k: np.concatenate([q[k] for q in parts]) for k in ("theta", "theta_prop", "ll", "accepted")}
+    out["eps"] = [g.eps(u + 1) for u in range(len(ups))]
+    out["stats"] = g.stats()
+    out["launches"] = launches
+    g.close()
+    return out
+
+
+def test_data_sum_cache_reuses_the_sums_and_changes_nothing_else():
+    """HIER_NORMAL: elements that move only mu / tau run without a sweep, a MALA element after them
+    finishes its current-state gradient from the cached per-group sums.  Same proposals, decisions,
+    trajectories, step sizes and moments as with every element sweeping (the log-likelihood differs only
+    by the association of the observation sums), whatever the block length, graphs or not."""
+    ref = _hier_own_stream(cache=False, use_graphs=0, block=1000)
+    for use_graphs, block in ((0, 1000), (1, 7), (1, 4), (0, 1)):
+        got = _hier_own_stream(cache=True, use_graphs=use_graphs, block=block)
+        assert np.array_equal(got["accepted"], ref["accepted"]), (use_graphs, block)
+        assert np.array_equal(got["theta"], ref["theta"]) and np.array_equal(got["theta_prop"], ref["theta_prop"])
+        assert np.allclose(got["ll"][1:], ref["ll"][1:], rtol=1e-12, atol=0)
+        assert all(np.array_equal(p, q) for p, q in zip(got["eps"], ref["eps"]))
+        for k in ("mean", "cov", "n_accept", "n_prop"):
+            assert np.array_equal(got["stats"][k], ref["stats"][k]), k
+        assert block < 1000 or got["launches"] < ref["launches"]
+    # the two cached runs with different block lengths are bit-identical, log-likelihoods included
+    a = _hier_own_stream(cache=True, use_graphs=1, block=7)
+    b = _hier_own_stream(cache=True, use_graphs=0, block=1000)
+    assert np.array_equal(a["ll"], b["ll"])
