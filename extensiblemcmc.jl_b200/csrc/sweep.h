@@ -77,6 +77,7 @@ struct LogisticArgs {
     double *g_part;
     int S;        // partial slots per chain block
     int n_cta;    // persistent CTAs sharing the flattened (chain block, tile) units
+    int pair_mode = 0;   // phase-1 variant (set by launch_sweep_logistic; see the kernel)
 };
 int logistic_padded_dim(int d);
 cudaError_t sweep_logistic_init();

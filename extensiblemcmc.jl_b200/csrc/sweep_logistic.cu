@@ -21,6 +21,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include "sweep.h"
 #include "tma.cuh"
@@ -92,7 +93,7 @@ __device__ __forceinline__ void softplus_sigmoid(double z, double &sp, double &s
 
 template <int D>
 constexpr size_t logistic_smem() {
-    return (size_t)kBN * (D + kPadT) * 8 + (size_t)2 * kBM * (D + kPad) * 8 + (size_t)kBM * kRPad * 8 +
+    return (size_t)kBN * (D + kPadT) * 8 + (size_t)2 * kBM * (D + kPad) * 8 + (size_t)2 * kBM * kRPad * 8 +
            (size_t)(kNT / 32) * 64 * 8 + 2 * kBM * 8 + kTabN * 8 + 4 * 8;
 }
 
@@ -116,30 +117,32 @@ __device__ __forceinline__ void pair_sync(int id) {  // named barrier for the tw
 }  // namespace
 
 // 16 warps: warp (w8 = w % 8, h = w / 8).  The two warps of a pair share chain block w8 (8 chains):
-//   phase 1  each takes half of the feature range (k in [h D/2, (h+1) D/2)) for the whole 16 x 8
-//            Z block, the halves are exchanged through shared memory (the partner's half of the
-//            sum for MY 8 observations), pair barrier;
-//   epilogue each handles its own 8 observations (rows 8h .. 8h+7), writes its R rows, pair barrier;
+//   phase 1  PM = 2 (default): each contracts its own 8 observations (rows 8h .. 8h+7) with the 8 chains
+//            over the whole feature range -- no exchange, no barrier;
+//            PM = 0: each takes half of the feature range for the whole 16 x 8 Z block and the halves are
+//            exchanged through shared memory (pair barrier);
+//   epilogue each handles its own 8 observations, writes its R rows, pair barrier;
 //   phase 2  each accumulates G for its half of the feature columns over all 16 observations.
 // Four warps per SM sub-partition instead of two: while one pair sits in its epilogue or at a
 // barrier, the others keep the MMA pipe busy.  G costs 64 registers per thread (D = 256), which is
 // what makes 512 threads x 128 registers possible.
-template <int D>
+template <int D, int PM>
 __global__ void __launch_bounds__(kNT, 1) sweep_logistic_kernel(LogisticArgs a) {
     constexpr int LD = D + kPad, LDT = D + kPadT;
     constexpr int NW = kNT / 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *Th = reinterpret_cast<double *>(smem_raw);   // [kBN][LDT]  Theta block, row = chain
     double *Xs = Th + kBN * LDT;                          // [2][kBM][LD] observation tiles
-    double *Rs = Xs + 2 * kBM * LD;                       // [kBM][kRPad] residuals y - sigmoid(z)
-    double *Zp = Rs + kBM * kRPad;                        // [NW][64]     partial Z handed to the partner
+    double *Rs = Xs + 2 * kBM * LD;                       // [2][kBM][kRPad] residuals y - sigmoid(z), by tile parity (PM >= 2)
+    double *Zp = Rs + 2 * kBM * kRPad;                    // [NW][64]     partial Z handed to the partner
     double *ys = Zp + NW * 64;                            // [2][kBM]
     double *tab = ys + 2 * kBM;                           // [kTabN]      softplus/sigmoid tables
     uint64_t *bar = reinterpret_cast<uint64_t *>(tab + kTabN);   // [2] full (TMA landed)
     unsigned int *done = reinterpret_cast<unsigned int *>(bar + 2);  // [2] warps done with a stage
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const int w8 = w & 7, h = w >> 3;
+    const int w8 = w & 7, h = w >> 3;   // partners w and w + 8 sit on the same SM sub-partition (w % 4): measured
+                                        // 9 % faster than partners on neighbouring sub-partitions (2 w8, 2 w8 + 1)
     const int gq = lane >> 2, tq = lane & 3;  // mma fragment coordinates: group id, thread in group
     const int64_t C = a.C;
     const int64_t T = (a.n_obs + kBM - 1) / kBM;            // tiles per chain block
@@ -201,12 +204,46 @@ __global__ void __launch_bounds__(kNT, 1) sweep_logistic_kernel(LogisticArgs a) 
         mbar_wait(&bar[st], (uint32_t)((tt + t) >> 1) & 1u);
         const double *X = Xs + st * kBM * LD;
         const int64_t row0 = (t0 + t) * kBM;
+        const int tile_no = tt + t;   // tiles this CTA has consumed before this one
+        // PM >= 2 has no barrier between phase 2 of a tile and the epilogue of the next one: the R tile is
+        // double-buffered by tile parity (a buffer is rewritten two tiles later, when the partner has passed
+        // the hand-over of the tile in between, i.e. finished reading it)
+        double *R = Rs + (PM >= 2 ? (tile_no & 1) * kBM * kRPad : 0);
 
         // ---- phase 1: half of the k range for Z[16 x 8(w8)] ---------------------------------------
         // The k index of the MMA fragments is a relabelling of the real feature index: fragment slot
         // tq of MMA e (e = 0, 1) of pair s stands for feature 8s + 2 tq + e, so that one LDS.128 per
         // operand feeds two MMAs, and the two MMAs go to independent accumulators.
         constexpr int MB = kBM / 8, KH = D / 2;
+        double z[2];
+      if (PM >= 2) {
+        // ---- phase 1 (default): my own 8 observations over the FULL feature range -- no exchange with the
+        // partner, one pair barrier less per tile, at 16 more operand loads per warp and tile; four
+        // independent accumulator pairs, added in a fixed order ----------
+        double zc[4][2];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) zc[m][0] = zc[m][1] = 0.0;
+        const double *Bq = Th + (8 * w8 + gq) * LDT + 2 * tq;
+        const double *Aq = X + (8 * h + rq) * LD + 2 * tq;
+        double2 b_cur = *reinterpret_cast<const double2 *>(Bq);
+        double2 a_cur = *reinterpret_cast<const double2 *>(Aq);
+#pragma unroll 8
+        for (int k0 = 0; k0 < D; k0 += 16) {
+            const double2 b_mid = *reinterpret_cast<const double2 *>(Bq + k0 + 8);
+            const double2 a_mid = *reinterpret_cast<const double2 *>(Aq + k0 + 8);
+            const int kn = k0 + 16 < D ? k0 + 16 : k0;
+            const double2 b_nxt = *reinterpret_cast<const double2 *>(Bq + kn);
+            const double2 a_nxt = *reinterpret_cast<const double2 *>(Aq + kn);
+            dmma(zc[0][0], zc[0][1], a_cur.x, b_cur.x);
+            dmma(zc[1][0], zc[1][1], a_cur.y, b_cur.y);
+            dmma(zc[2][0], zc[2][1], a_mid.x, b_mid.x);
+            dmma(zc[3][0], zc[3][1], a_mid.y, b_mid.y);
+            b_cur = b_nxt;
+            a_cur = a_nxt;
+        }
+        z[0] = (zc[0][0] + zc[1][0]) + (zc[2][0] + zc[3][0]);
+        z[1] = (zc[0][1] + zc[1][1]) + (zc[2][1] + zc[3][1]);
+      } else {
         double za[MB][2], zb[MB][2];
 #pragma unroll
         for (int m = 0; m < MB; ++m) za[m][0] = za[m][1] = zb[m][0] = zb[m][1] = 0.0;
@@ -243,12 +280,12 @@ __global__ void __launch_bounds__(kNT, 1) sweep_logistic_kernel(LogisticArgs a) 
             *reinterpret_cast<double2 *>(Zp + w * 64 + gq * 8 + 2 * tq) = v;
         }
         pair_sync(1 + w8);
-        double z[2];
         {
             const double2 v = *reinterpret_cast<const double2 *>(Zp + (w ^ 8) * 64 + gq * 8 + 2 * tq);
             z[0] = (h ? s10 : s00) + v.x;
             z[1] = (h ? s11 : s01) + v.y;
         }
+      }
         // ---- epilogue: residuals and log-likelihood of my 8 observations ---------------------------
         {
             const int r = 8 * h + rq;
@@ -262,7 +299,7 @@ __global__ void __launch_bounds__(kNT, 1) sweep_logistic_kernel(LogisticArgs a) 
             softplus_sigmoid(z[1], sp, sg, tab);
             res.y = live ? yv - sg : 0.0;
             ll1 += live ? yv * z[1] - sp : 0.0;
-            *reinterpret_cast<double2 *>(Rs + r * kRPad + 8 * w8 + 2 * tq) = res;
+            *reinterpret_cast<double2 *>(R + r * kRPad + 8 * w8 + 2 * tq) = res;
         }
         pair_sync(1 + w8);   // both halves of R[:, 8 w8 ..] are in place
 
@@ -271,7 +308,7 @@ __global__ void __launch_bounds__(kNT, 1) sweep_logistic_kernel(LogisticArgs a) 
         // (one LDS.128 of X feeds two MMAs); undone when the partials are written.
 #pragma unroll
         for (int i0 = 0; i0 < kBM; i0 += 4) {
-            const double af = Rs[(i0 + tq) * kRPad + 8 * w8 + gq];
+            const double af = R[(i0 + tq) * kRPad + 8 * w8 + gq];
             const double *Xr = X + (i0 + tq) * LD + 16 * NPH * h + 2 * gq;
             constexpr int AH = NPH < 4 ? NPH : 4;   // X fragments fetched AH pairs ahead of their MMAs
             double2 xq[AH];
@@ -351,12 +388,22 @@ logistic_finalize_kernel(LogisticArgs a, double *__restrict__ ll_out, double *__
 namespace {
 template <int D>
 cudaError_t prep() {
-    return cudaFuncSetAttribute(sweep_logistic_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(sweep_logistic_kernel<D, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)logistic_smem<D>());
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(sweep_logistic_kernel<D, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)logistic_smem<D>());
 }
 template <int D>
-void launch(const SweepPlan &pl, const LogisticArgs &a, cudaStream_t st) {
-    sweep_logistic_kernel<D><<<a.n_cta, kNT, logistic_smem<D>(), st>>>(a);
+void launch(const SweepPlan &pl, const LogisticArgs &a0, cudaStream_t st) {
+    // EXTMCMC_LOGI_PHASE1: 2 (default) = every warp contracts its own 8 observations over all features;
+    // 0 = the two warps of a pair split the feature range and exchange half-sums (one more pair barrier
+    // per tile): 34.19 -> 33.92 ms per launch at cfg 3 with 2
+    static const int pair_mode = [] { const char *e = getenv("EXTMCMC_LOGI_PHASE1"); return e ? atoi(e) : 2; }();
+    LogisticArgs a = a0;
+    a.pair_mode = pair_mode;
+    if (pair_mode == 2) sweep_logistic_kernel<D, 2><<<a.n_cta, kNT, logistic_smem<D>(), st>>>(a);
+    else sweep_logistic_kernel<D, 0><<<a.n_cta, kNT, logistic_smem<D>(), st>>>(a);
 }
 }  // namespace
 
