@@ -16,8 +16,10 @@ e2e      the whole cfg 2 job through the reference-facing API `run_(mcmc, M, dat
          history row back to the host are inside the timed region.
 extra    sub-records of the same JSON line: `strong_cfg5` (BASELINE cfg 5: N = 1e9 observations
          sharded over the ranks, NCCL all-reduce and the library's fused NVLink exchange, with an
-         in-run cross-rank parity check), and at N = 1 `cfg3` / `cfg4` (logistic regression on the
-         FP64 tensor path; hierarchical model with the mixed MALA / random-walk schedule).
+         in-run cross-rank parity check), `cfg4` (hierarchical model with the mixed MALA /
+         random-walk schedule, 8192 chains per GPU, i.e. BASELINE's 65536 chains at N = 8; at
+         N = 1 with and without the data-sum cache) and at N = 1 `cfg3` (logistic regression on
+         the FP64 tensor path).
 """
 import argparse
 import json
@@ -360,7 +362,7 @@ def measure_cfg5(args, em, _abi, par, dist, rank, world, local, peaks, peak_src)
     return out
 
 
-def measure_cfg34(args, workload, em, _abi, local, steps):
+def measure_cfg34(args, workload, em, _abi, local, steps, chain_offset=0):
     """BASELINE cfg 3 (logistic regression d = 256, N = 1e6, 1024 chains, MALA, FP64 tensor-core GEMMs)
     or cfg 4 (hierarchical normal, 8 groups x 4096 observations, MALA + 2 random-walk updates, 8192
     chains per GPU) on one GPU: ms per iteration and the roofline of its dominant kernel."""
@@ -404,7 +406,8 @@ def measure_cfg34(args, workload, em, _abi, local, steps):
 
     def make(instrument):
         mcmc = em.MCMC(ups, backend=em.CUDAMCMCBackend(n_chains=C, device=local, seed=7, history="none", block_len=NUc,
-                                                       use_graphs=not instrument, instrument=instrument))
+                                                       use_graphs=not instrument, instrument=instrument,
+                                                       chain_offset=chain_offset))
         init_(mcmc, 1, data, th0)
         return mcmc.workspace
     K, Wm = steps, 3
@@ -618,6 +621,18 @@ def run_ours(args):
                 del os.environ["EXTMCMC_DATA_CACHE"]
             cfg4["without_data_cache"] = {k: off[k] for k in ("workload", "ms_per_step", "value", "unit", "roofline", "gpu_launches")}
         cfg3 = measure_cfg34(args, "cfg3", em, _abi, local, args.cfg3_steps)
+    elif world > 1 and not args.skip_extras:
+        # BASELINE cfg 4 as it is stated: 8192 chains per GPU (65536 over 8 GPUs), chains sharded, no
+        # collective.  Every rank runs its own shard at the same time; the time is the max over ranks.
+        barrier()
+        rec = measure_cfg34(args, "cfg4", em, _abi, local, args.cfg4_steps, chain_offset=rank * 8192)
+        t = torch.tensor([rec["ms_per_step"]], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            per_gpu = rec["value"] * rec["ms_per_step"] / t.item()
+            cfg4 = dict(rec, ms_per_step=t.item(), value=per_gpu * world, n_gpus=world, chains_total=8192 * world,
+                        timing="every rank times its own shard with CUDA events; max over ranks",
+                        roofline_of="rank 0")
 
     # ---- BASELINE cfg 5 (observations sharded, strong scaling, cross-rank exchange) ----------------
     strong_cfg5 = None
@@ -791,7 +806,7 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-hbm", action="store_true")
     ap.add_argument("--skip-cfg5", action="store_true", help="no strong_cfg5 sub-record")
-    ap.add_argument("--skip-extras", action="store_true", help="no cfg3 / cfg4 sub-records (N = 1 only anyway)")
+    ap.add_argument("--skip-extras", action="store_true", help="no cfg3 / cfg4 sub-records (cfg3: N = 1 only; cfg4: every N, 8192 chains per GPU)")
     ap.add_argument("--skip-ess", action="store_true", help="reference arm: no ESS/s trace")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--cfg5-n-obs", type=int, default=1_000_000_000, help="cfg5: total observations over all ranks")
