@@ -268,7 +268,11 @@ int step_kind(extmcmc_t h, int u) {
 }
 inline bool kind_is_mala(int kind) { return (kind & 0xff) == EXTMCMC_KERNEL_MALA; }
 // MALA: returns how the gradient of the current state is obtained (0 = still valid, 1 = sweep,
-// 2 = from the cache).  Random walk: returns 1 when the element runs without a sweep.
+// 2 = from the cache).  Random walk: 0 = the element sweeps its proposal; 1 = it runs from the cache;
+// 2 = the cache is refilled first (gradient sweep of the CURRENT state + per-group reduction -- the
+// kernels and the association that fill it on the MALA path, so a data-free element sees the same
+// bits whether the sums were kept or recomputed: start of a run, after a checkpoint load, after an
+// element that moved a theta_g), then as 1.
 int step_advance(bool dcache, int kind, bool &gv, bool &dc) {
     if (kind_is_mala(kind)) {
         const int mode = gv ? 0 : (dc ? 2 : 1);
@@ -277,7 +281,11 @@ int step_advance(bool dcache, int kind, bool &gv, bool &dc) {
         return mode;
     }
     gv = false;
-    if (kind & kDataFree) return dc ? 1 : 0;
+    if (kind & kDataFree) {
+        const int mode = dc ? 1 : 2;
+        dc = true;
+        return mode;
+    }
     dc = false;
     return 0;
 }
@@ -508,7 +516,12 @@ int32_t enqueue_steps(extmcmc_t h, const StepDesc *d_descs, const int *kinds, in
             cur_prepared = false;
         } else {
             if (!fused) { launch_propose(h->d, d_descs, k, h->stream); h->launches += 1; }
-            const bool from_cache = mode == 1;
+            const bool from_cache = mode != 0;
+            if (mode == 2) {
+                if ((rc = enqueue_sweep(h, instrument, true, h->d.theta))) return rc;
+                launch_reduce_group_sums(h->d, h->d.dsum_cur, h->stream);
+                h->launches += 1;
+            }
             if (!from_cache)
                 if ((rc = enqueue_sweep(h, instrument, false, h->d.prop_full, h->d.ssum, nullptr, d_descs, k))) return rc;
             fused = next_rw;
@@ -642,7 +655,7 @@ int32_t run_block_impl(extmcmc_t h, const extmcmc_step_t *steps, int32_t n_steps
             const bool mala = h->upd_host[u].kernel == EXTMCMC_KERNEL_MALA;
             sd.need_cur_grad = (mala && !gv) ? 1 : 0;
             const int mode = step_advance(h->dcache, step_kind(h, u), gv, dc);
-            n_sweeps += mala ? 1 + (mode == 1 ? 1 : 0) : 1 - mode;
+            n_sweeps += mala ? 1 + (mode == 1 ? 1 : 0) : (mode == 1 ? 0 : 1);
             h->ra_iter[u] = it;
             tag = it;
         }

@@ -246,7 +246,9 @@ int32_t extmcmc_set_lambda_fn(extmcmc_t h, int32_t u, extmcmc_lambda_fn f, void 
  * count, rolling-acceptance tags).  The RNG has no state: a resumed run continues the same Philox
  * streams, so `run 2M` and `run M, save, load into a fresh handle with the same configuration,
  * updates and observations, run M with MCMCSchedule(...; start = ...)` (src/schedule.jl:28) are
- * bit-identical.  The history ring is not part of the blob.  _load checks the shape header. */
+ * bit-identical.  The history ring is not part of the blob.  _load checks the shape header.
+ * (Gradients and the data-sum cache of HIER_NORMAL are not part of the blob either: they are
+ * recomputed on demand by the kernels that produced them, to the same bits.) */
 int32_t extmcmc_checkpoint_size(extmcmc_t h, int64_t *bytes_out);
 int32_t extmcmc_checkpoint_save(extmcmc_t h, void *blob, int64_t bytes);
 int32_t extmcmc_checkpoint_load(extmcmc_t h, const void *blob, int64_t bytes);

@@ -266,3 +266,39 @@ def test_data_sum_cache_reuses_the_sums_and_changes_nothing_else():
     a = _hier_own_stream(cache=True, use_graphs=1, block=7)
     b = _hier_own_stream(cache=True, use_graphs=0, block=1000)
     assert np.array_equal(a["ll"], b["ll"])
+
+
+def test_checkpoint_resume_hier_with_the_data_sum_cache():
+    """The data-sum cache is not part of the checkpoint blob: a handle that resumes in the middle of an
+    iteration -- right after the MALA element, in front of the mu / tau elements that would have read
+    the cache -- refills it with the kernels that produced it and continues bit for bit, log-likelihoods
+    included.  The same for a schedule that starts with a data-free element."""
+    import ctypes as C
+    G, n_chains = 5, 90
+    y, grp, _ = _hier_data(G, 200, seed=4)
+    ups = _hier_updates(G)
+    th0 = _hier_theta0(G, n_chains)
+    steps = list(em.MCMCSchedule(20, len(ups), [(1, range(1, 3))]))   # the first two iterations start at mu
+    mk = lambda th: GpuSession(em.HierNormalLaw(G), _hier_updates(G), y, th, n_chains, seed=17,
+                               n_steps_hint=len(steps), y=grp, roll_window=10)
+    full = mk(th0)
+    rf = full.run(steps)
+    cut = next(i for i, s in enumerate(steps) if s.mcmciter == 9 and s.pidx == 1) + 1   # after the MALA element
+    a = mk(th0)
+    ra = a.run(steps[:cut])
+    n = C.c_int64()
+    a.ck(a.lib.extmcmc_checkpoint_size(a.h, C.byref(n)))
+    blob = (C.c_uint8 * n.value)()
+    a.ck(a.lib.extmcmc_checkpoint_save(a.h, blob, n.value))
+    a.close()
+    b = mk(th0 * 0 + 1.0)
+    b.ck(b.lib.extmcmc_checkpoint_load(b.h, blob, n.value))
+    b.seq = cut
+    rb = b.run(steps[cut:])
+    for k in ("theta", "theta_prop", "ll", "accepted"):
+        assert np.array_equal(rf[k], np.concatenate([ra[k], rb[k]])), k
+    sf, sb = full.stats(), b.stats()
+    for k in ("mean", "cov", "rolling_ar", "n_accept", "n_prop"):
+        assert np.array_equal(sf[k], sb[k]), k
+    assert all(np.array_equal(full.eps(u + 1), b.eps(u + 1)) for u in range(len(ups)))
+    full.close(); b.close()
