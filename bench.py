@@ -611,24 +611,35 @@ def run_ours(args):
     # its power limit, and a short cfg 4 run right after them is timed at a capped clock) -------------
     cfg3 = cfg4 = None
     if rank == 0 and world == 1 and not args.skip_extras:
-        cfg4 = measure_cfg34(args, "cfg4", em, _abi, local, args.cfg4_steps)
-        if "EXTMCMC_DATA_CACHE" not in os.environ:
+        def guarded(fn):   # a failed sub-record is reported as such and never costs the headline line
+            try:
+                return fn()
+            except Exception as e:
+                return {"error": repr(e)}
+        cfg4 = guarded(lambda: measure_cfg34(args, "cfg4", em, _abi, local, args.cfg4_steps))
+        if "EXTMCMC_DATA_CACHE" not in os.environ and "error" not in cfg4:
             # the same workload with every element streaming the observations (round-1 / early round-2 path)
             os.environ["EXTMCMC_DATA_CACHE"] = "0"
             try:
-                off = measure_cfg34(args, "cfg4", em, _abi, local, args.cfg4_steps)
+                off = guarded(lambda: measure_cfg34(args, "cfg4", em, _abi, local, args.cfg4_steps))
             finally:
                 del os.environ["EXTMCMC_DATA_CACHE"]
-            cfg4["without_data_cache"] = {k: off[k] for k in ("workload", "ms_per_step", "value", "unit", "roofline", "gpu_launches")}
-        cfg3 = measure_cfg34(args, "cfg3", em, _abi, local, args.cfg3_steps)
+            cfg4["without_data_cache"] = {k: off[k] for k in ("workload", "ms_per_step", "value", "unit", "roofline", "gpu_launches", "error")
+                                          if k in off}
+        cfg3 = guarded(lambda: measure_cfg34(args, "cfg3", em, _abi, local, args.cfg3_steps))
     elif world > 1 and not args.skip_extras:
         # BASELINE cfg 4 as it is stated: 8192 chains per GPU (65536 over 8 GPUs), chains sharded, no
         # collective.  Every rank runs its own shard at the same time; the time is the max over ranks.
         barrier()
-        rec = measure_cfg34(args, "cfg4", em, _abi, local, args.cfg4_steps, chain_offset=rank * 8192)
+        try:
+            rec = measure_cfg34(args, "cfg4", em, _abi, local, args.cfg4_steps, chain_offset=rank * 8192)
+        except Exception as e:   # a failed sub-record must not take the collective (and the headline) down
+            rec = {"error": repr(e), "ms_per_step": float("inf")}
         t = torch.tensor([rec["ms_per_step"]], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        if rank == 0:
+        if rank == 0 and not np.isfinite(t.item()):
+            cfg4 = {"error": rec.get("error", "the sub-record failed on another rank")}
+        elif rank == 0:
             per_gpu = rec["value"] * rec["ms_per_step"] / t.item()
             cfg4 = dict(rec, ms_per_step=t.item(), value=per_gpu * world, n_gpus=world, chains_total=8192 * world,
                         timing="every rank times its own shard with CUDA events; max over ranks",
