@@ -1,0 +1,14 @@
+#!/bin/bash
+# last session of round 2 (1 GPU): GPU test log and bench line of the final build; resident-CTA target of the
+# chain-mapped sweep at cfg 4 (informational)
+set -u
+O=gpurun_out; mkdir -p $O
+T=${1:-r02g}
+timeout 600 python -m pytest tests -m gpu -q > $O/${T}_pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/${T}_pytest_gpu.log
+tail -3 $O/${T}_pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/${T}_smoke.log 2>&1; echo "smoke rc=$?" >> $O/${T}_smoke.log
+( time timeout 900 python bench.py > $O/${T}_bench_1gpu.json 2> $O/${T}_bench_1gpu.err ) 2> $O/${T}_bench_1gpu.time
+tail -3 $O/${T}_bench_1gpu.time
+for n in 4 6 8 12 16; do
+  EXTMCMC_CHAINS_CTAS=$n timeout 200 python bench.py --workload cfg4 --steps 400 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.readlines()[-1]); print('ctas $n', d['ms_per_step'], d['roofline']['avg_launch_ms'])" | tee -a $O/${T}_cfg4_ctas.txt
+done
