@@ -518,28 +518,35 @@ __device__ __forceinline__ void update_cov_coop(const DevState &d, int64_t N, in
         }
         return;
     }
-    const int ch = tid % nch, es = nt / nch, pp = p * p;
+    // The recursion is symmetric in (a, b) -- every product in it commutes, and the matrix starts
+    // symmetric -- so entry (b, a) is bit for bit entry (a, b): only the p (p + 1) / 2 entries with
+    // a <= b are computed (one division each) and stored to both places.  They are walked column by
+    // column, e = a + b (b + 1) / 2.
+    const int ch = tid % nch, es = nt / nch, tri = p * (p + 1) / 2;
     const bool live = c0 + ch < C;
-    int e = tid / nch, a = e % p, b = e / p;
-    for (; e < pp; ) {
+    int e = tid / nch, a = e, b = 0;
+    while (a > b) { a -= b + 1; ++b; }
+    for (; e < tri; ) {
         double cv[4];
         int ea[4], eb[4], ee[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             ee[q] = e; ea[q] = a; eb[q] = b;
-            cv[q] = (e < pp && live) ? d.cov[(int64_t)e * C + c0 + ch] : 0.0;
+            cv[q] = (e < tri && live) ? d.cov[(int64_t)(a + b * p) * C + c0 + ch] : 0.0;
             e += es; a += es;
-            while (a >= p) { a -= p; ++b; }
+            while (a > b) { a -= b + 1; ++b; }
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            if (ee[q] < pp && live) {
+            if (ee[q] < tri && live) {
                 const double ta = sh_t[ea[q] * nch + ch], tb = sh_t[eb[q] * nch + ch];
                 const double ma_old = sh_m[ea[q] * nch + ch], mb_old = sh_m[eb[q] * nch + ch];
                 const double ma_new = sh_n[ea[q] * nch + ch], mb_new = sh_n[eb[q] * nch + ch];
                 const double old_sum_sq = f_old * cv[q] + ma_old * mb_old;
                 const double new_sum_sq = old_sum_sq + (ta * tb) / (double)N;
-                d.cov[(int64_t)ee[q] * C + c0 + ch] = new_sum_sq - f_new * (ma_new * mb_new);
+                const double v = new_sum_sq - f_new * (ma_new * mb_new);
+                d.cov[(int64_t)(ea[q] + eb[q] * p) * C + c0 + ch] = v;
+                if (ea[q] != eb[q]) d.cov[(int64_t)(eb[q] + ea[q] * p) * C + c0 + ch] = v;
             }
         }
     }
