@@ -918,7 +918,9 @@ __device__ __forceinline__ void mala_propose_chain(const DevState &d, const Step
 // normalising constant is the same in both directions and is left out).
 // The chain's own thread: decision, commit, history, counters; cs: staging (see CoopStage; with
 // cs->m the covariance update is left to update_cov_coop).
-template <class SP = SpecAny>
+// HANDOVER = false: the caller passes grad_prop / dsum_prop on to grad_cur / dsum_cur itself
+// (mala_handover_coop: the rows are shared by the threads that have nothing else to do).
+template <class SP = SpecAny, bool HANDOVER = true>
 __device__ __forceinline__ Decision mala_decide_commit(const DevState &d, const StepDesc &sd, const DevUpdate &u, int64_t c) {
     const int64_t C = d.C;
     const int n = u.n_coords;
@@ -965,14 +967,14 @@ __device__ __forceinline__ Decision mala_decide_commit(const DevState &d, const 
             const int64_t j = u.coords_dev[i];
             d.theta[j * C + c] = d.prop_full[j * C + c];
         }
-        for (int j0 = 0; j0 < d.p; j0 += 4) {   // grad_cur <- grad_prop
+        for (int j0 = 0; HANDOVER && j0 < d.p; j0 += 4) {   // grad_cur <- grad_prop
             double g[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) if (j0 + q < d.p) g[q] = d.grad_prop[(int64_t)(j0 + q) * C + c];
 #pragma unroll
             for (int q = 0; q < 4; ++q) if (j0 + q < d.p) d.grad_cur[(int64_t)(j0 + q) * C + c] = g[q];
         }
-        if (d.dsum_cur) {   // data-sum cache: the proposal's per-group sums become the current state's
+        if (HANDOVER && d.dsum_cur) {   // data-sum cache: the proposal's per-group sums become the current state's
             const int rows = 2 * d.G;
             for (int r0 = 0; r0 < rows; r0 += 4) {
                 double g[4];
@@ -984,6 +986,21 @@ __device__ __forceinline__ Decision mala_decide_commit(const DevState &d, const 
         }
     }
     return Decision{accepted, ll_new, ll_prop};
+}
+// What an accepted MALA proposal hands over to the current state -- the gradient and, with the data-sum
+// cache, the per-group sums: p + 2 G rows per chain, copied by the threads of slices [s0, s0 + ns) of an
+// nch-chains-per-slice CTA (acc[ch] = the chain's decision, written before a CTA barrier).
+__device__ __forceinline__ void mala_handover_coop(const DevState &d, int64_t c0, int nch, const uint8_t *acc,
+                                                   int tid, int s0, int ns) {
+    const int ch = tid % nch, slice = tid / nch - s0;
+    const int64_t C = d.C, c = c0 + ch;
+    if (slice < 0 || slice >= ns || c >= C || !acc[ch]) return;
+    const int rows = d.p + (d.dsum_cur ? 2 * d.G : 0);
+#pragma unroll 2
+    for (int r = slice; r < rows; r += ns) {
+        if (r < d.p) d.grad_cur[(int64_t)r * C + c] = d.grad_prop[(int64_t)r * C + c];
+        else d.dsum_cur[(int64_t)(r - d.p) * C + c] = d.dsum_prop[(int64_t)(r - d.p) * C + c];
+    }
 }
 template <class SP = SpecAny>
 __device__ __forceinline__ void mala_decide(const DevState &d, const StepDesc &sd, const DevUpdate &u, int64_t c,

@@ -471,13 +471,20 @@ mala_accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fi
     const bool stage = d.p <= kCoopP;   // CTA-uniform
     const bool coop = stage && d.stats_mode == 0;
     const CoopStage cs{sh_t, coop ? sh_m : nullptr, sh_n, kMalaChains, ch};
+    // the decisions, for the threads that hand the proposal's gradient and data sums over (slices 3..7:
+    // warps with no other task, next to the worker's bookkeeping and the next proposal)
+    __shared__ uint8_t sh_acc[kMalaChains];
     if (may_defer && ctx_next.sd.pidx != ctx.sd.pidx) {   // deferred bookkeeping (see run_deferred)
         const bool prop_lane = fuse_next && (threadIdx.x >> 5) == 1 && c < d.C;
         Decision dec{};
-        if (worker) dec = mala_decide_commit<SP>(d, ctx.sd, ctx.u, c);
-        if (fuse_next) __syncthreads();
+        if (worker) {
+            dec = mala_decide_commit<SP, false>(d, ctx.sd, ctx.u, c);
+            sh_acc[ch] = dec.accepted ? 1 : 0;
+        }
+        __syncthreads();
         if (worker) post_decision_moments<SP, true, false>(d, ctx.sd, c, dec.accepted, dec.ll_new, dec.ll_prop);
         else if (prop_lane) propose_draw<SP>(d, ctx_next.sd, ctx_next.u, c);
+        else mala_handover_coop(d, c0, kMalaChains, sh_acc, threadIdx.x, 3, kMalaSlices - 3);
         if (fuse_next) {
             __syncthreads();
             if (prop_lane) propose_set<SP>(d, ctx_next.u, c);
@@ -487,16 +494,16 @@ mala_accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fi
     if (SP::kLean && fuse_next) {   // task split as in accept_kernel (the next element is another update)
         const bool prop_lane = (threadIdx.x >> 5) == 1 && c < d.C;
         const bool cnt_lane = (threadIdx.x >> 5) == 2 && c < d.C;
-        __shared__ uint8_t sh_acc[kMalaChains];
         Decision dec{};
         if (worker) {
-            dec = mala_decide_commit<SP>(d, ctx.sd, ctx.u, c);
+            dec = mala_decide_commit<SP, false>(d, ctx.sd, ctx.u, c);
             sh_acc[ch] = dec.accepted ? 1 : 0;
         }
         __syncthreads();
         if (worker) post_decision_moments<SP>(d, ctx.sd, c, dec.accepted, dec.ll_new, dec.ll_prop, stage ? &cs : nullptr);
         else if (prop_lane) propose_draw<SP>(d, ctx_next.sd, ctx_next.u, c);
         else if (cnt_lane) post_decision_counters<SP>(d, ctx.sd, ctx.u, c, sh_acc[ch] != 0, 1);
+        else mala_handover_coop(d, c0, kMalaChains, sh_acc, threadIdx.x, 3, kMalaSlices - 3);
         __syncthreads();
         if (prop_lane) propose_set<SP>(d, ctx_next.u, c);
         if (coop) update_cov_coop(d, ctx.sd.stat_n, c0, kMalaChains, sh_t, sh_m, sh_n, threadIdx.x, blockDim.x);
