@@ -566,11 +566,16 @@ __device__ __forceinline__ void update_cov_coop(const DevState &d, int64_t N, in
 // moments.  A step kernel that DEFERS its bookkeeping writes only the history row (the full proposal is
 // about to be overwritten by the next one); moments and counters are then run by the next step kernel
 // in its prologue, behind the next sweep (step_kernels.cu, "deferred bookkeeping").
+// grp / n_grp: the per-parameter part (history row, staging, mean, diagonal statistics) is independent from
+// parameter to parameter, so several threads may share a chain -- thread `grp` of `n_grp` takes the
+// parameters [4 grp, 4 grp + 4), [4 (grp + n_grp), ...); the per-chain scalars belong to grp 0.  Only where
+// nothing else follows the loop: not with the thread-alone full covariance (stats_mode 0 without cs->m).
 template <class SP = SpecAny, bool HIST = true, bool MOM = true>
 __device__ __forceinline__ void post_decision_moments(const DevState &d, const StepDesc &sd, int64_t c, bool accepted,
-                                                      double ll_new, double ll_prop, const CoopStage *cs = nullptr) {
+                                                      double ll_new, double ll_prop, const CoopStage *cs = nullptr,
+                                                      int grp = 0, int n_grp = 1) {
     const int64_t C = d.C;
-    if (HIST) d.ll[c] = ll_new;
+    if (HIST && grp == 0) d.ll[c] = ll_new;
     // history row (state_history / state_proposal_history / ll_history / acceptance_history)
     const int64_t slot = sd.seq % d.H;
     const int64_t hc = d.g0 + c;       // this chain's column in the arrays that stay global
@@ -583,7 +588,7 @@ __device__ __forceinline__ void post_decision_moments(const DevState &d, const S
     // History row, staging and -- diagonal statistics / cooperative path -- update_stats!
     // (chain_statistics.jl:46-51, verbatim arithmetic); loads in batches of 4 ahead of the stores
     // (the stores may alias the loads as far as the compiler knows, so a plain loop serialises).
-    for (int j0 = 0; j0 < d.p; j0 += 4) {
+    for (int j0 = 4 * grp; j0 < d.p; j0 += 4 * n_grp) {
         double t[4], pr[4], m[4], cv[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q)
@@ -614,14 +619,14 @@ __device__ __forceinline__ void post_decision_moments(const DevState &d, const S
                 }
             }
     }
-    if (HIST) {
+    if (HIST && grp == 0) {
         d.h_ll[slot * d.gC + hc] = ll_new;
         d.h_llp[slot * d.gC + hc] = ll_prop;
         d.h_acc[slot * d.gC + hc] = accepted ? 1 : 0;
     }
 
     // full covariance by this thread alone (more than kCoopP parameters, or no spare threads)
-    if (MOM && d.stats_mode == 0 && !coop_full) {
+    if (MOM && d.stats_mode == 0 && !coop_full && grp == 0) {
         const int p = d.p;
         // covariance first (it needs the old mean), column by column
         for (int b = 0; b < p; ++b) {

@@ -193,8 +193,13 @@ __device__ __forceinline__ void run_deferred(const DevState &d, const StepCtx &p
     const bool lane_ok = lane < nch && c < d.C;
     const bool coop = stage && d.stats_mode == 0;   // CTA-uniform
     const CoopStage cs{sh_t, coop ? sh_m : nullptr, sh_n, nch, tid % nch};
-    if (w == 3 && lane_ok) {
-        post_decision_moments<SP, false, true>(d, prev.sd, c, false, 0.0, 0.0, stage ? &cs : nullptr);
+    // moments: per-parameter work only (cooperative covariance, variances or no statistics) is shared by
+    // warps 3.. in groups of four parameters; the thread-alone full covariance stays on warp 3
+    const bool multi = coop || d.stats_mode != 0;   // CTA-uniform
+    const int nw = (int)(blockDim.x >> 5);
+    if (w >= 3 && lane_ok && (multi || w == 3)) {
+        post_decision_moments<SP, false, true>(d, prev.sd, c, false, 0.0, 0.0, stage ? &cs : nullptr,
+                                               multi ? w - 3 : 0, multi ? nw - 3 : 1);
     } else if (w == 2 && lane_ok) {
         const bool acc = d.h_acc[(prev.sd.seq % d.H) * d.gC + d.g0 + c] != 0;
         const int n_eps = prev.u.kernel == EXTMCMC_KERNEL_MALA ? 1 : prev.u.n_coords;   // lean: uniform walk or MALA
@@ -270,9 +275,14 @@ accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fuse_ne
         const bool prop_lane = fuse_next == 1 && (threadIdx.x >> 5) == 1 && (threadIdx.x & 31) < kRedChains && c < d.C;
         Decision dec{};
         if (worker) dec = rw_decide_commit<SP>(d, u, c, pre, S);
-        if (fuse_next == 1) __syncthreads();   // the committed state is visible to the proposal lanes
-        if (worker) post_decision_moments<SP, true, false>(d, sd, c, dec.accepted, dec.ll_new, dec.ll_prop);
+        __syncthreads();   // the committed state is visible to the proposal lanes and to the history lanes
+        // history row: the chain's thread writes the scalars and the first four parameters, the chains'
+        // lanes of warps 2.. the other groups of four
+        const int wv = threadIdx.x >> 5, n_grp = (int)(blockDim.x >> 5) - 1;
+        const bool hist_lane = wv >= 2 && (threadIdx.x & 31) < kRedChains && c < d.C;
+        if (worker) post_decision_moments<SP, true, false>(d, sd, c, dec.accepted, dec.ll_new, dec.ll_prop, nullptr, 0, n_grp);
         else if (prop_lane) propose_draw<SP>(d, ctx_next.sd, ctx_next.u, c);
+        else if (hist_lane) post_decision_moments<SP, true, false>(d, sd, c, false, 0.0, 0.0, nullptr, wv - 1, n_grp);
         if (fuse_next == 1) {
             __syncthreads();   // prop_full has been read for the history row
             if (prop_lane) propose_set<SP>(d, ctx_next.u, c);
@@ -482,9 +492,14 @@ mala_accept_kernel(DevState d, const StepDesc *__restrict__ descs, int k, int fi
             sh_acc[ch] = dec.accepted ? 1 : 0;
         }
         __syncthreads();
-        if (worker) post_decision_moments<SP, true, false>(d, ctx.sd, c, dec.accepted, dec.ll_new, dec.ll_prop);
+        const int wv = threadIdx.x >> 5;
+        if (worker) post_decision_moments<SP, true, false>(d, ctx.sd, c, dec.accepted, dec.ll_new, dec.ll_prop, nullptr, 0, kMalaSlices - 1);
         else if (prop_lane) propose_draw<SP>(d, ctx_next.sd, ctx_next.u, c);
-        else mala_handover_coop(d, c0, kMalaChains, sh_acc, threadIdx.x, 3, kMalaSlices - 3);
+        else {
+            if (wv >= 2 && c < d.C)   // history row: groups of four parameters on the lanes of warps 2..
+                post_decision_moments<SP, true, false>(d, ctx.sd, c, false, 0.0, 0.0, nullptr, wv - 1, kMalaSlices - 1);
+            mala_handover_coop(d, c0, kMalaChains, sh_acc, threadIdx.x, 3, kMalaSlices - 3);
+        }
         if (fuse_next) {
             __syncthreads();
             if (prop_lane) propose_set<SP>(d, ctx_next.u, c);
