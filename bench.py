@@ -403,25 +403,30 @@ def measure_cfg34(args, workload, em, _abi, local, steps, chain_offset=0):
                 + ("data-sum cache on: the sums over the observations are recomputed only when theta_1..8 move "
                    "(1 sweep per iteration)" if cache_on else "data-sum cache off: every element sweeps (4 per iteration)"))
     NUc = len(ups)
+    # iterations per extmcmc_run_block: cfg 4 runs blocks of 10 iterations (30 schedule elements, like the
+    # cfg 5 sub-record and well below run_()'s default block of 128 elements) -- the last element of a block
+    # cannot leave its bookkeeping to the next element's kernels, which costs ~4 us per block; cfg 3: 1
+    IPB = 10 if workload == "cfg4" else 1
 
     def make(instrument):
-        mcmc = em.MCMC(ups, backend=em.CUDAMCMCBackend(n_chains=C, device=local, seed=7, history="none", block_len=NUc,
+        mcmc = em.MCMC(ups, backend=em.CUDAMCMCBackend(n_chains=C, device=local, seed=7, history="none", block_len=NUc * IPB,
                                                        use_graphs=not instrument, instrument=instrument,
                                                        chain_offset=chain_offset))
         init_(mcmc, 1, data, th0)
         return mcmc.workspace
-    K, Wm = steps, 3
+    up = lambda n: -(-n // IPB) * IPB            # whole blocks
+    K, Wm = up(steps), up(3)
     ws = make(False)
     sampler = ClockSampler(local)
-    _generic_timed(ws, _abi, NUc, 0, Wm)
+    _generic_timed(ws, _abi, NUc, 0, Wm, ipb=IPB)
     sampler.start()
     l0 = ws.lib.extmcmc_launch_count(ws.handle)
-    ms_total = _generic_timed(ws, _abi, NUc, K, 0, it0=Wm + 1)
+    ms_total = _generic_timed(ws, _abi, NUc, K, 0, it0=Wm + 1, ipb=IPB)
     launches = int(ws.lib.extmcmc_launch_count(ws.handle) - l0)
     ext = [Wm + 1 + K]
 
     def hold():
-        _generic_timed(ws, _abi, NUc, 5, 0, it0=ext[0]); ext[0] += 5
+        _generic_timed(ws, _abi, NUc, up(5), 0, it0=ext[0], ipb=IPB); ext[0] += up(5)
     clocks = sampler.stop(extend=hold)
     variant = ws.lib.extmcmc_sweep_variant_name(ws.handle).decode()
     pk64, lanes = fp64_peaks(ws, clocks)
@@ -430,10 +435,10 @@ def measure_cfg34(args, workload, em, _abi, local, steps, chain_offset=0):
     acc = ws.stats()["n_accept"].sum(axis=1) / np.maximum(ws.stats()["n_prop"].sum(axis=1), 1)
     ws.close()
     wi = make(True)
-    _generic_timed(wi, _abi, NUc, 0, Wm)
+    _generic_timed(wi, _abi, NUc, 0, Wm, ipb=IPB)
     msw, nl = ctypes.c_float(), ctypes.c_int64()
     wi._ck(wi.lib.extmcmc_get_sweep_time(wi.handle, ctypes.byref(msw), ctypes.byref(nl)))
-    step_ms = _generic_timed(wi, _abi, NUc, min(K, 20), 0)
+    step_ms = _generic_timed(wi, _abi, NUc, min(K, 20), 0, it0=Wm + 1, ipb=IPB)
     wi._ck(wi.lib.extmcmc_get_sweep_time(wi.handle, ctypes.byref(msw), ctypes.byref(nl)))
     kern_ms = msw.value / max(nl.value, 1)
     wi.close()
@@ -442,6 +447,7 @@ def measure_cfg34(args, workload, em, _abi, local, steps, chain_offset=0):
     ach = flops_per_iter / launches_per_iter / (kern_ms * 1e-3) / 1e12
     return {
         "workload": desc, "ms_per_step": ms_total / K, "steps": K,
+        "block": f"{IPB} iteration(s) ({IPB * NUc} schedule elements) per extmcmc_run_block, one CUDA event pair per block",
         "value": float(C) * K * NUc * n_obs / (ms_total * 1e-3), "unit": "chain-step*obs/s",
         "roofline": {"kernel": variant, "bound": "tensor" if workload == "cfg3" else "fp64",
                      "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None,
@@ -624,7 +630,7 @@ def run_ours(args):
                 off = guarded(lambda: measure_cfg34(args, "cfg4", em, _abi, local, args.cfg4_steps))
             finally:
                 del os.environ["EXTMCMC_DATA_CACHE"]
-            cfg4["without_data_cache"] = {k: off[k] for k in ("workload", "ms_per_step", "value", "unit", "roofline", "gpu_launches", "error")
+            cfg4["without_data_cache"] = {k: off[k] for k in ("workload", "ms_per_step", "block", "value", "unit", "roofline", "gpu_launches", "error")
                                           if k in off}
         cfg3 = guarded(lambda: measure_cfg34(args, "cfg3", em, _abi, local, args.cfg3_steps))
     elif world > 1 and not args.skip_extras:
@@ -685,27 +691,32 @@ def run_ours(args):
     print(json.dumps(out))
 
 
-def _generic_timed(ws, _abi, n_updates, K, W, it0=1):
-    """W warm-up + K timed MCMC iterations of an n_updates-element schedule (one block per
-    iteration, one CUDA event pair per iteration)."""
+def _generic_timed(ws, _abi, n_updates, K, W, it0=1, ipb=1):
+    """W warm-up + K timed MCMC iterations of an n_updates-element schedule, `ipb` iterations per
+    extmcmc_run_block (one CUDA event pair per block; K and W are rounded up to whole blocks by the
+    caller).  Returns the summed milliseconds of the K timed iterations."""
     import ctypes
     lib, h = ws.lib, ws.handle
+    assert K % ipb == 0 and W % ipb == 0
 
     def block(it):
-        arr = (_abi.Step * n_updates)()
-        for pj in range(n_updates):
-            first = it == 1 and pj == 0
-            arr[pj].mcmciter, arr[pj].pidx = it, pj
-            arr[pj].prev_pidx = -1 if first else (pj - 1 if pj else n_updates - 1)
-            arr[pj].prev_mcmciter = 0 if first else (it if pj else it - 1)
+        arr = (_abi.Step * (n_updates * ipb))()
+        for i in range(ipb):
+            for pj in range(n_updates):
+                e = arr[i * n_updates + pj]
+                first = it + i == 1 and pj == 0
+                e.mcmciter, e.pidx = it + i, pj
+                e.prev_pidx = -1 if first else (pj - 1 if pj else n_updates - 1)
+                e.prev_mcmciter = 0 if first else (it + i if pj else it + i - 1)
         return arr
     it = it0
-    for _ in range(W):
-        ws._ck(lib.extmcmc_run_block(h, block(it), n_updates)); it += 1
+    for _ in range(W // ipb):
+        ws._ck(lib.extmcmc_run_block(h, block(it), n_updates * ipb)); it += ipb
     ws.sync()
+    K = K // ipb
     for k in range(K):
         ws._ck(lib.extmcmc_event_record(h, 2 * k))
-        ws._ck(lib.extmcmc_run_block(h, block(it), n_updates)); it += 1
+        ws._ck(lib.extmcmc_run_block(h, block(it), n_updates * ipb)); it += ipb
         ws._ck(lib.extmcmc_event_record(h, 2 * k + 1))
     ws.sync()
     ms, total = ctypes.c_float(), 0.0
